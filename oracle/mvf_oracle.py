@@ -195,9 +195,15 @@ def _batch_norm_train(x: Tensor, w: Tensor, b: Tensor, eps: float) -> Tuple[Tens
     return y, mean, var
 
 
+# Test hook: a callable (x, weight, bias, eps) -> (y, mean, biased_var) replacing the train-mode BatchNorm, used by
+# the gloo tests to plug in a cross-rank (SyncBatchNorm-semantics) implementation.
+BN_TRAIN_HOOK = None
+
+
 def _bn(x, P, buf, pre, cfg: HeadCfg, training: bool, new_buf: Dict[str, Tensor]):
     if training:
-        y, mean, var = _batch_norm_train(x, P[pre + ".weight"], P[pre + ".bias"], cfg.bn_eps)
+        fn = BN_TRAIN_HOOK or _batch_norm_train
+        y, mean, var = fn(x, P[pre + ".weight"], P[pre + ".bias"], cfg.bn_eps)
         if buf is not None:
             n = x.shape[0]
             m = cfg.bn_momentum

@@ -1,0 +1,168 @@
+"""CPU: the host-side mirror of the reference's models/ + algos/ interface (construction, names, init, ckpt)."""
+import copy
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import mvf_oracle as O
+from oracle import ref_shim as R
+from video_rep_learning_b200 import engine
+from video_rep_learning_b200.algos import SCL, get_algo
+from video_rep_learning_b200.config import Cfg, mvf_cfg
+from video_rep_learning_b200.models import (MLPHead, MultiEntityTransformerEmbModel, TransformerModel, build_model,
+                                            load_checkpoint, save_checkpoint)
+
+
+class DummyBackbone(nn.Module):
+    """frames [n,3,H,W] -> (tokens [n,1+P,C], cls [n,C]); stands in for the frozen timm ViT (upstream producer)."""
+
+    def __init__(self, c_out=48, patch=56):
+        super().__init__()
+        self.proj = nn.Conv2d(3, c_out, patch, patch)
+
+    def forward(self, x):
+        t = self.proj(x).flatten(2).transpose(1, 2)
+        cls = t.mean(1, keepdim=True)
+        return torch.cat([cls, t], 1), cls[:, 0]
+
+
+def small_cfg(**kw):
+    base = dict(c_in=48, num_frames=8, entities=3, capacity=1, emb=16, hidden=32, d_ff=64, heads=4, layers=2,
+                fc_layers=((64, True), (64, True)), projection_size=16, pool_channels=32)
+    base.update(kw)
+    return mvf_cfg(**base)
+
+
+def test_state_dict_keys_match_reference_names():
+    cfg = small_cfg()
+    model = build_model(cfg, backbone=DummyBackbone())
+    hc = O.HeadCfg(c_in=48, n_entities=3, pool_channels=32, fc_channels=(64, 64), hidden=32, d_ff=64, n_heads=4,
+                   n_layers=2, emb=16, proj=16, train_frames=8)
+    sd = {k: v for k, v in model.state_dict().items() if not k.startswith("backbone")}
+    want = dict(O.param_shapes(hc))
+    for pre, ch in zip(O.bn_buffer_names(hc), list(hc.fc_channels) + [hc.proj]):
+        want[pre + ".running_mean"] = (ch,)
+        want[pre + ".running_var"] = (ch,)
+        want[pre + ".num_batches_tracked"] = ()
+    assert set(sd.keys()) == set(want.keys())
+    for k, shp in want.items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+    # canonical (C ABI) order == module lookup order
+    assert model.embed.head_param_names() == [k[len("embed."):] for k in O.param_shapes(hc) if k.startswith("embed.")]
+    assert [p.shape for p in model.ssl_projection.proj_params()] == [torch.Size(s) for k, s in O.param_shapes(hc).items()
+                                                                     if k.startswith("ssl_projection.")]
+    # optimizer contract (utils/optimizer.py:29-42 skips names containing 'backbone')
+    assert all(not p.requires_grad for p in model.backbone.parameters())
+    assert model.embedding_size == 16 and hasattr(model, "res_finetune")
+
+
+def test_encoder_layers_start_identical_like_reference_clone():
+    head = MultiEntityTransformerEmbModel(small_cfg(layers=3))
+    l0 = head.video_encoder.enc_layers[0].state_dict()
+    for l in (1, 2):
+        for k, v in head.video_encoder.enc_layers[l].state_dict().items():
+            assert torch.equal(v, l0[k])
+
+
+@pytest.mark.skipif(not R.available(), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("yml_like", ["penn", "fg99"])
+def test_seeded_init_identical_to_reference(yml_like):
+    """Same constructor order -> same RNG stream -> bit-identical initial parameters (checkpoints interchange)."""
+    ref = R.load_reference()
+    yml = "penn_mvf.yml" if yml_like == "penn" else "fg99_mvf.yml"
+    rcfg = R.reference_cfg(yml, c_in=96, T=8)
+    if yml_like == "penn":
+        ours = mvf_cfg(c_in=96, num_frames=8)
+    else:
+        ours = mvf_cfg(c_in=96, num_frames=8, entities=6, capacity=6, emb=256, final="avg", smart_feats="9,10,11")
+    import contextlib, io
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rhead = ref.MultiEntityTransformerEmbModel(rcfg)
+        rproj = ref.MLPHead(rcfg)
+    torch.manual_seed(1)
+    head = MultiEntityTransformerEmbModel(ours)
+    proj = MLPHead(ours)
+    a, b = rhead.state_dict(), head.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    a, b = rproj.state_dict(), proj.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # and a reference state_dict loads strictly
+    head.load_state_dict(rhead.state_dict(), strict=True)
+
+
+def test_unsupported_branches_fail_loudly():
+    for key, val in (("SMART_DYNAMIC_TOKENS", 2), ("VAL_PASS", True), ("SMART_DISJOINT", True), ("SMART_LN_KEYS", True),
+                     ("FIXED_WIDTH_BASELINE", True)):
+        cfg = small_cfg()
+        cfg.MODEL.EMBEDDER_MODEL[key] = val
+        with pytest.raises(NotImplementedError):
+            MultiEntityTransformerEmbModel(cfg)
+    with pytest.raises(NotImplementedError):
+        MultiEntityTransformerEmbModel(small_cfg(one_hot="enc"))
+    cfg = small_cfg()
+    cfg.MODEL.EMBEDDER_MODEL.FUSION_TYPE = "late"
+    with pytest.raises(NotImplementedError):
+        TransformerModel(cfg, backbone=DummyBackbone())
+    cfg = small_cfg(negative_type="all")
+    with pytest.raises(NotImplementedError):
+        SCL(cfg)
+    cfg = small_cfg()
+    cfg.TRAINING_ALGO = "tcc"
+    with pytest.raises(ValueError):
+        get_algo(cfg)
+
+
+def test_submodules_are_containers_not_silent_torch_paths():
+    head = MultiEntityTransformerEmbModel(small_cfg())
+    with pytest.raises(RuntimeError, match="parameter container"):
+        head.video_encoder(torch.zeros(1, 4, 32))
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        head(torch.zeros(2, 8, 48, 3, 3))          # CPU tensor: must not fall back to PyTorch math
+
+
+def test_head_spec_from_cfg_defaults():
+    cfg = small_cfg()
+    del cfg.MODEL.EMBEDDER_MODEL["SMART_POOL_CHANNELS"]
+    head = MultiEntityTransformerEmbModel(cfg)
+    assert head.spec.pool_channels == 384 and head.spec.fc_channels == (64, 64) and head.spec.final == "one"
+    assert head.spec == engine.HeadSpec(c_in=48, n_entities=3, pool_channels=384, fc_channels=(64, 64), hidden=32, d_ff=64,
+                                        n_heads=4, n_layers=2, emb=16, proj=16, one_hot="pool", final="one", train_frames=8,
+                                        drop_p=0.1)
+
+
+def test_to_token_major_is_the_inverse_of_the_reference_permute():
+    x = torch.arange(2 * 3 * 5 * 2 * 2, dtype=torch.float32).view(2, 3, 5, 2, 2)        # [BV,T,C,h,w]
+    t = MultiEntityTransformerEmbModel.to_token_major(x)
+    assert t.shape == (2, 3, 4, 5)
+    assert torch.equal(t[1, 2, 3], x[1, 2, :, 1, 1])
+    assert torch.equal(R.tokens_to_nchw(t), x)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    cfg = small_cfg()
+    cfg.LOGDIR = str(tmp_path)
+    model = build_model(cfg, backbone=DummyBackbone())
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+    save_checkpoint(cfg, model, opt, 3)
+    assert os.path.exists(os.path.join(str(tmp_path), "checkpoints", "checkpoint_epoch_00003.pth"))
+    model2 = build_model(copy.deepcopy(cfg), backbone=DummyBackbone())
+    opt2 = torch.optim.Adam([p for p in model2.parameters() if p.requires_grad], lr=1e-3)
+    assert load_checkpoint(cfg, model2, opt2) == 4
+    for (k, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_cfg_container_semantics():
+    cfg = Cfg({"A": {"B": 1}})
+    assert cfg.A.B == 1 and "B" in cfg.A and "C" not in cfg.A
+    cfg.A.C = {"D": 2}
+    assert cfg.A.C.D == 2
+    with pytest.raises(AttributeError):
+        _ = cfg.missing

@@ -1,0 +1,283 @@
+// Temporal multi-head self-attention core (models/utils.py:11-44, 87-103): softmax(Q K^T / sqrt(dk) + keymask) V
+// per (view, head), streaming over key tiles with an online softmax so the [S,S] score matrix never reaches
+// HBM (the reference materialises [BV,8,S,S]).  fp32 math on CUDA cores: with dk = 32 the exp, not the MMA, is
+// the bound; a tcgen05 version only pays at S >= ~1k and is a later-round item.
+//
+// Layout: qkv [B*S, 3*H] rows = (view, token), columns Q | K | V with head h at [h*dk, (h+1)*dk).
+// One thread owns one query row (forward, dQ) or one key row (dK/dV); key/query tiles are staged in shared
+// memory and read as warp-wide broadcasts.
+#include "kernels.cuh"
+
+namespace mvf {
+
+constexpr int ATT_THREADS = 64;  // rows per CTA
+constexpr int ATT_TILE = 32;     // keys (or queries) per shared-memory tile
+
+template <typename T, int DK>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_fwd_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict__ keymask, T* __restrict__ ctx,
+                float* __restrict__ lse) {
+  __shared__ float Ks[ATT_TILE][DK];
+  __shared__ float Vs[ATT_TILE][DK];
+  __shared__ float Ms[ATT_TILE];
+  const int b = blockIdx.z, h = blockIdx.y, heads = gridDim.y;
+  const int i = blockIdx.x * ATT_THREADS + threadIdx.x;
+  const bool active = i < S;
+  const int64_t ld = 3 * (int64_t)H;
+  const T* base = qkv + (int64_t)b * S * ld + h * DK;
+  const float scale = 1.0f / sqrtf((float)DK);
+
+  float q[DK], o[DK];
+#pragma unroll
+  for (int d = 0; d < DK; ++d) {
+    q[d] = active ? to_f<T>(base[(int64_t)i * ld + d]) : 0.f;
+    o[d] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+
+  for (int j0 = 0; j0 < S; j0 += ATT_TILE) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ATT_TILE * DK; idx += ATT_THREADS) {
+      const int jj = idx / DK, d = idx % DK;
+      const int j = j0 + jj;
+      float kvv = 0.f, vvv = 0.f;
+      if (j < S) {
+        kvv = to_f<T>(base[(int64_t)j * ld + H + d]);
+        vvv = to_f<T>(base[(int64_t)j * ld + 2 * H + d]);
+      }
+      Ks[jj][d] = kvv;
+      Vs[jj][d] = vvv;
+    }
+    if (threadIdx.x < ATT_TILE) {
+      const int j = j0 + threadIdx.x;
+      Ms[threadIdx.x] = (j < S && (keymask == nullptr || keymask[(int64_t)b * S + j] != 0.f)) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    float s[ATT_TILE];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < ATT_TILE; ++jj) {
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < DK; ++d) acc = fmaf(q[d], Ks[jj][d], acc);
+      acc = Ms[jj] != 0.f ? acc * scale : -INFINITY;
+      s[jj] = acc;
+      tmax = fmaxf(tmax, acc);
+    }
+    const float m_new = fmaxf(m, tmax);
+    if (m_new == -INFINITY) continue;  // every key so far is masked
+    const float alpha = (m == -INFINITY) ? 0.f : expf(m - m_new);
+    l *= alpha;
+#pragma unroll
+    for (int d = 0; d < DK; ++d) o[d] *= alpha;
+#pragma unroll
+    for (int jj = 0; jj < ATT_TILE; ++jj) {
+      const float p = expf(s[jj] - m_new);  // exp(-inf) = 0 for masked keys
+      l += p;
+#pragma unroll
+      for (int d = 0; d < DK; ++d) o[d] = fmaf(p, Vs[jj][d], o[d]);
+    }
+    m = m_new;
+  }
+  if (active) {
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    T* out = ctx + ((int64_t)b * S + i) * H + h * DK;
+#pragma unroll
+    for (int d = 0; d < DK; ++d) out[d] = from_f<T>(o[d] * inv);
+    lse[((int64_t)b * heads + h) * S + i] = m + logf(l);
+  }
+}
+
+// dQ (and delta = rowsum(dO * O), written for the dK/dV kernel)
+template <typename T, int DK>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dq_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict__ keymask,
+                   const T* __restrict__ ctx, const float* __restrict__ lse, const T* __restrict__ d_ctx,
+                   T* __restrict__ d_qkv, float* __restrict__ delta) {
+  __shared__ float Ks[ATT_TILE][DK];
+  __shared__ float Vs[ATT_TILE][DK];
+  __shared__ float Ms[ATT_TILE];
+  const int b = blockIdx.z, h = blockIdx.y, heads = gridDim.y;
+  const int i = blockIdx.x * ATT_THREADS + threadIdx.x;
+  const bool active = i < S;
+  const int64_t ld = 3 * (int64_t)H;
+  const T* base = qkv + (int64_t)b * S * ld + h * DK;
+  const float scale = 1.0f / sqrtf((float)DK);
+
+  float q[DK], go[DK], dq[DK];
+  float dl = 0.f;
+#pragma unroll
+  for (int d = 0; d < DK; ++d) {
+    q[d] = active ? to_f<T>(base[(int64_t)i * ld + d]) : 0.f;
+    go[d] = active ? to_f<T>(d_ctx[((int64_t)b * S + i) * H + h * DK + d]) : 0.f;
+    float ov = active ? to_f<T>(ctx[((int64_t)b * S + i) * H + h * DK + d]) : 0.f;
+    dl = fmaf(go[d], ov, dl);
+    dq[d] = 0.f;
+  }
+  const float lse_i = active ? lse[((int64_t)b * heads + h) * S + i] : 0.f;
+  if (active) delta[((int64_t)b * heads + h) * S + i] = dl;
+
+  for (int j0 = 0; j0 < S; j0 += ATT_TILE) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ATT_TILE * DK; idx += ATT_THREADS) {
+      const int jj = idx / DK, d = idx % DK;
+      const int j = j0 + jj;
+      float kvv = 0.f, vvv = 0.f;
+      if (j < S) {
+        kvv = to_f<T>(base[(int64_t)j * ld + H + d]);
+        vvv = to_f<T>(base[(int64_t)j * ld + 2 * H + d]);
+      }
+      Ks[jj][d] = kvv;
+      Vs[jj][d] = vvv;
+    }
+    if (threadIdx.x < ATT_TILE) {
+      const int j = j0 + threadIdx.x;
+      Ms[threadIdx.x] = (j < S && (keymask == nullptr || keymask[(int64_t)b * S + j] != 0.f)) ? 1.f : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int jj = 0; jj < ATT_TILE; ++jj) {
+      if (Ms[jj] == 0.f) continue;  // block-uniform
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < DK; ++d) {
+        s = fmaf(q[d], Ks[jj][d], s);
+        dp = fmaf(go[d], Vs[jj][d], dp);
+      }
+      const float p = expf(s * scale - lse_i);
+      const float ds = p * (dp - dl) * scale;
+#pragma unroll
+      for (int d = 0; d < DK; ++d) dq[d] = fmaf(ds, Ks[jj][d], dq[d]);
+    }
+  }
+  if (active) {
+    T* out = d_qkv + ((int64_t)b * S + i) * ld + h * DK;
+#pragma unroll
+    for (int d = 0; d < DK; ++d) out[d] = from_f<T>(dq[d]);
+  }
+}
+
+// dK, dV: one thread per key row, query tiles broadcast from shared memory
+template <typename T, int DK>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dkv_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict__ keymask,
+                    const float* __restrict__ lse, const T* __restrict__ d_ctx, const float* __restrict__ delta,
+                    T* __restrict__ d_qkv) {
+  __shared__ float Qs[ATT_TILE][DK];
+  __shared__ float Gs[ATT_TILE][DK];
+  __shared__ float Ls[ATT_TILE];
+  __shared__ float Ds[ATT_TILE];
+  const int b = blockIdx.z, h = blockIdx.y, heads = gridDim.y;
+  const int j = blockIdx.x * ATT_THREADS + threadIdx.x;
+  const int64_t ld = 3 * (int64_t)H;
+  const T* base = qkv + (int64_t)b * S * ld + h * DK;
+  const float scale = 1.0f / sqrtf((float)DK);
+  const bool active = j < S && (keymask == nullptr || keymask[(int64_t)b * S + j] != 0.f);
+
+  float k[DK], v[DK], dk[DK], dv[DK];
+#pragma unroll
+  for (int d = 0; d < DK; ++d) {
+    k[d] = active ? to_f<T>(base[(int64_t)j * ld + H + d]) : 0.f;
+    v[d] = active ? to_f<T>(base[(int64_t)j * ld + 2 * H + d]) : 0.f;
+    dk[d] = 0.f;
+    dv[d] = 0.f;
+  }
+  for (int i0 = 0; i0 < S; i0 += ATT_TILE) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ATT_TILE * DK; idx += ATT_THREADS) {
+      const int ii = idx / DK, d = idx % DK;
+      const int i = i0 + ii;
+      float qv = 0.f, gv = 0.f;
+      if (i < S) {
+        qv = to_f<T>(base[(int64_t)i * ld + d]);
+        gv = to_f<T>(d_ctx[((int64_t)b * S + i) * H + h * DK + d]);
+      }
+      Qs[ii][d] = qv;
+      Gs[ii][d] = gv;
+    }
+    if (threadIdx.x < ATT_TILE) {
+      const int i = i0 + threadIdx.x;
+      Ls[threadIdx.x] = i < S ? lse[((int64_t)b * heads + h) * S + i] : INFINITY;  // exp(s - inf) = 0
+      Ds[threadIdx.x] = i < S ? delta[((int64_t)b * heads + h) * S + i] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+#pragma unroll 4
+    for (int ii = 0; ii < ATT_TILE; ++ii) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < DK; ++d) {
+        s = fmaf(Qs[ii][d], k[d], s);
+        dp = fmaf(Gs[ii][d], v[d], dp);
+      }
+      const float p = expf(s * scale - Ls[ii]);
+      const float ds = p * (dp - Ds[ii]) * scale;
+#pragma unroll
+      for (int d = 0; d < DK; ++d) {
+        dv[d] = fmaf(p, Gs[ii][d], dv[d]);
+        dk[d] = fmaf(ds, Qs[ii][d], dk[d]);
+      }
+    }
+  }
+  if (j < S) {
+    T* out = d_qkv + ((int64_t)b * S + j) * ld + h * DK;
+#pragma unroll
+    for (int d = 0; d < DK; ++d) {
+      out[H + d] = from_f<T>(dk[d]);
+      out[2 * H + d] = from_f<T>(dv[d]);
+    }
+  }
+}
+
+template <typename T, int DK>
+static int fwd_launch(int B, int S, int heads, const void* qkv, const float* keymask, void* ctx, float* lse,
+                      cudaStream_t st) {
+  dim3 grid(cdiv(S, ATT_THREADS), heads, B);
+  attn_fwd_kernel<T, DK><<<grid, ATT_THREADS, 0, st>>>(S, heads * DK, (const T*)qkv, keymask, (T*)ctx, lse);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+template <typename T, int DK>
+static int bwd_launch(int B, int S, int heads, const void* qkv, const float* keymask, const void* ctx, const float* lse,
+                      const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st) {
+  dim3 grid(cdiv(S, ATT_THREADS), heads, B);
+  attn_bwd_dq_kernel<T, DK><<<grid, ATT_THREADS, 0, st>>>(S, heads * DK, (const T*)qkv, keymask, (const T*)ctx, lse,
+                                                          (const T*)d_ctx, (T*)d_qkv, delta);
+  MVF_CHECK_LAUNCH();
+  attn_bwd_dkv_kernel<T, DK><<<grid, ATT_THREADS, 0, st>>>(S, heads * DK, (const T*)qkv, keymask, lse, (const T*)d_ctx,
+                                                           delta, (T*)d_qkv);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+#define DISPATCH_DK(FN, ...)                                                                   \
+  do {                                                                                         \
+    if (dtype == MVF_BF16) {                                                                   \
+      if (dk == 8) return FN<bf16, 8>(__VA_ARGS__);                                            \
+      if (dk == 16) return FN<bf16, 16>(__VA_ARGS__);                                          \
+      if (dk == 32) return FN<bf16, 32>(__VA_ARGS__);                                          \
+      if (dk == 64) return FN<bf16, 64>(__VA_ARGS__);                                          \
+    } else {                                                                                   \
+      if (dk == 8) return FN<float, 8>(__VA_ARGS__);                                           \
+      if (dk == 16) return FN<float, 16>(__VA_ARGS__);                                         \
+      if (dk == 32) return FN<float, 32>(__VA_ARGS__);                                         \
+      if (dk == 64) return FN<float, 64>(__VA_ARGS__);                                         \
+    }                                                                                          \
+    set_error("attention: head width %d not supported (8, 16, 32, 64)", dk);                  \
+    return MVF_ERR_UNSUPPORTED;                                                                \
+  } while (0)
+
+int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, void* ctx,
+                  float* lse, cudaStream_t st) {
+  if (B <= 0 || S <= 0) return MVF_OK;
+  MVF_REQUIRE(B <= 65535 && heads <= 65535, MVF_ERR_BAD_ARG, "attention: grid too large");
+  DISPATCH_DK(fwd_launch, B, S, heads, qkv, keymask, ctx, lse, st);
+}
+int attention_bwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, const void* ctx,
+                  const float* lse, const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st) {
+  if (B <= 0 || S <= 0) return MVF_OK;
+  MVF_REQUIRE(B <= 65535 && heads <= 65535, MVF_ERR_BAD_ARG, "attention: grid too large");
+  DISPATCH_DK(bwd_launch, B, S, heads, qkv, keymask, ctx, lse, d_ctx, d_qkv, delta, st);
+}
+
+}  // namespace mvf

@@ -1,0 +1,98 @@
+// Shared device/host helpers for libmvf_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mvf_b200.h"
+
+namespace mvf {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (thread-local message; no exceptions cross the C ABI) ---------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define MVF_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      mvf::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return MVF_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define MVF_CHECK_LAUNCH() MVF_CHECK_CUDA(cudaGetLastError())
+
+#define MVF_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      mvf::set_error(__VA_ARGS__);    \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define MVF_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != MVF_OK) return _s; \
+  } while (0)
+
+// ---- scalar conversion ---------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- counter-based dropout ------------------------------------------------------------------------------
+// keep(seed, site, idx) is a pure function, so forward and backward regenerate the same mask without
+// storing it.  Returns the multiplier (0 or 1/(1-p)).
+__host__ __device__ __forceinline__ uint32_t mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return (uint32_t)(x >> 32) ^ (uint32_t)x;
+}
+__host__ __device__ __forceinline__ float drop_scale(uint64_t seed, int site, uint64_t idx, float p, float inv_keep) {
+  uint32_t h = mix64(seed * 0x9E3779B97F4A7C15ULL + ((uint64_t)(site + 1) << 56) + idx);
+  float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.0f;
+}
+
+enum DropSite { SITE_FC0 = 0, SITE_POS = 8, SITE_ENC0 = 16 };
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- internal launchers (defined across the .cu files) ---------------------------------------------------
+int gemm_simt(int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A,
+              int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias, const void* relu_src,
+              int64_t ld_relu, int flags, cudaStream_t st);
+int gemm_tc(int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+            const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias, const void* relu_src, int64_t ld_relu,
+            int flags, int split_k, cudaStream_t st);
+bool tc_available();
+
+int gemm_dispatch(int backend, int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K,
+                  const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
+                  const void* relu_src, int64_t ld_relu, int flags, int split_k, cudaStream_t st);
+
+}  // namespace mvf

@@ -1,0 +1,637 @@
+// Memory-bound glue kernels of the head: parameter packing, positional encoding, LayerNorm (+residual
+// +dropout), BatchNorm1d (+ReLU +dropout) with split statistics (so the statistics can be all-reduced across
+// ranks between two launches), column sums for bias gradients, entity reduction, L2 normalisation.
+// All fp32 math; outputs optionally bf16 when they feed a tensor-core GEMM.
+#include "kernels.cuh"
+
+namespace mvf {
+
+// =========================================== pack / unpack ===========================================
+constexpr int PACK_CHUNK = 48;
+struct PackTable {
+  int n;
+  PackEntry e[PACK_CHUNK];
+};
+struct UnpackTable {
+  int n;
+  UnpackEntry e[PACK_CHUNK];
+};
+
+__global__ void pack_kernel(const PackTable tab) {
+  const PackEntry& en = tab.e[blockIdx.y];
+  const int64_t total = (int64_t)en.rows * en.ld_dst;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / en.ld_dst), c = (int)(i - (int64_t)r * en.ld_dst);
+    float v = c < en.cols ? en.src[(int64_t)r * en.cols + c] : 0.f;
+    if (en.dst_bf16) ((bf16*)en.dst)[i] = __float2bfloat16_rn(v);
+    else ((float*)en.dst)[i] = v;
+  }
+}
+
+int pack_params(const PackEntry* entries, int n, cudaStream_t st) {
+  for (int base = 0; base < n; base += PACK_CHUNK) {
+    PackTable tab;
+    tab.n = (n - base < PACK_CHUNK) ? n - base : PACK_CHUNK;
+    for (int i = 0; i < tab.n; ++i) tab.e[i] = entries[base + i];
+    pack_kernel<<<dim3(32, tab.n), 256, 0, st>>>(tab);
+    MVF_CHECK_LAUNCH();
+  }
+  return MVF_OK;
+}
+
+__global__ void unpack_kernel(const UnpackTable tab, float scale) {
+  const UnpackEntry& en = tab.e[blockIdx.y];
+  const int64_t total = (int64_t)en.rows * en.cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / en.cols), c = (int)(i - (int64_t)r * en.cols);
+    en.dst[i] = scale * en.src[(int64_t)r * en.ld_src + c];
+  }
+}
+
+int unpack_grads(const UnpackEntry* entries, int n, float scale, cudaStream_t st) {
+  for (int base = 0; base < n; base += PACK_CHUNK) {
+    UnpackTable tab;
+    tab.n = (n - base < PACK_CHUNK) ? n - base : PACK_CHUNK;
+    for (int i = 0; i < tab.n; ++i) tab.e[i] = entries[base + i];
+    unpack_kernel<<<dim3(32, tab.n), 256, 0, st>>>(tab, scale);
+    MVF_CHECK_LAUNCH();
+  }
+  return MVF_OK;
+}
+
+// ======================================== positional encoding ========================================
+// models/utils.py:113-126: sin on even channels, cos on odd, exponent uses the channel index itself;
+// positions 0..T-1 or numpy.linspace(0, train-1, T) when T != train length.  float64 like numpy.
+__global__ void posenc_table_kernel(float* table, int T, int H, int train_frames) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * H) return;
+  int t = i / H, c = i % H;
+  double pos;
+  if (T == train_frames) pos = (double)t;
+  else if (T == 1) pos = 0.0;
+  else {
+    double step = (double)(train_frames - 1) / (double)(T - 1);
+    pos = (t == T - 1) ? (double)(train_frames - 1) : (double)t * step;
+  }
+  double ang = pos / pow(10000.0, (double)c / (double)H);
+  table[i] = (float)((c & 1) ? cos(ang) : sin(ang));
+}
+int posenc_table(float* table, int T, int H, int train_frames, cudaStream_t st) {
+  posenc_table_kernel<<<cdiv((int64_t)T * H, 256), 256, 0, st>>>(table, T, H, train_frames);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+__global__ void posenc_add_kernel(const float* __restrict__ h3, const float* __restrict__ table, float* __restrict__ z,
+                                  int BV, int T, int E, int H, float p, float inv_keep, uint64_t seed) {
+  int64_t total = (int64_t)BV * E * T * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % H);
+    int64_t row = i / H;  // b*E*T + e*T + t
+    int t = (int)(row % T);
+    int e = (int)((row / T) % E);
+    int b = (int)(row / ((int64_t)T * E));
+    float v = h3[(((int64_t)b * T + t) * E + e) * H + c] + table[t * H + c];
+    if (p > 0.f) v *= drop_scale(seed, SITE_POS, (uint64_t)i, p, inv_keep);
+    z[i] = v;
+  }
+}
+int posenc_add(const float* h3, const float* table, float* z, int BV, int T, int E, int H, float p, uint64_t seed,
+               cudaStream_t st) {
+  int64_t total = (int64_t)BV * E * T * H;
+  int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  posenc_add_kernel<<<grid, 256, 0, st>>>(h3, table, z, BV, T, E, H, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+template <typename TO>
+__global__ void posenc_bwd_kernel(const float* __restrict__ dz, TO* __restrict__ dh3, int BV, int T, int E, int H,
+                                  float p, float inv_keep, uint64_t seed) {
+  int64_t total = (int64_t)BV * E * T * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % H);
+    int64_t row = i / H;
+    int t = (int)(row % T);
+    int e = (int)((row / T) % E);
+    int b = (int)(row / ((int64_t)T * E));
+    float v = dz[i];
+    if (p > 0.f) v *= drop_scale(seed, SITE_POS, (uint64_t)i, p, inv_keep);
+    dh3[(((int64_t)b * T + t) * E + e) * H + c] = from_f<TO>(v);
+  }
+}
+int posenc_bwd(int dtype_out, const float* dz, void* dh3, int BV, int T, int E, int H, float p, uint64_t seed,
+               cudaStream_t st) {
+  int64_t total = (int64_t)BV * E * T * H;
+  int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (dtype_out == MVF_BF16) posenc_bwd_kernel<bf16><<<grid, 256, 0, st>>>(dz, (bf16*)dh3, BV, T, E, H, p, ik, seed);
+  else posenc_bwd_kernel<float><<<grid, 256, 0, st>>>(dz, (float*)dh3, BV, T, E, H, p, ik, seed);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+// ============================================ LayerNorm =============================================
+// One warp per row.  z_out = z_in + drop(o); two-pass mean/variance (biased, eps inside the sqrt).
+template <typename TO>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ z_in, const float* __restrict__ o,
+                                                     float* __restrict__ z_out, TO* __restrict__ r,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     int64_t rows, int H, float eps, float p, float inv_keep,
+                                                     uint64_t seed, int site) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* zi = z_in + row * H;
+  float* zo = z_out + row * H;
+  float s = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    float v = zi[c];
+    if (o) {
+      float ov = o[row * H + c];
+      if (p > 0.f) ov *= drop_scale(seed, site, (uint64_t)(row * H + c), p, inv_keep);
+      v += ov;
+    }
+    if (o || zo != zi) zo[c] = v;
+    s += v;
+  }
+  if (r == nullptr) return;
+  s = warp_sum(s);
+  const float mean = s / (float)H;
+  float ss = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    float dv = zo[c] - mean;
+    ss += dv * dv;
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / (float)H + eps);
+  for (int c = lane; c < H; c += 32) r[row * H + c] = from_f<TO>((zo[c] - mean) * rstd * gamma[c] + beta[c]);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+int ln_fwd(int dtype_out, const float* z_in, const float* o, float* z_out, void* r, float* mean, float* rstd,
+           const float* gamma, const float* beta, int64_t rows, int H, float eps, float p, uint64_t seed, int site,
+           cudaStream_t st) {
+  float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  int grid = cdiv(rows, 8);
+  if (dtype_out == MVF_BF16)
+    ln_fwd_kernel<bf16><<<grid, 256, 0, st>>>(z_in, o, z_out, (bf16*)r, mean, rstd, gamma, beta, rows, H, eps, p, ik,
+                                              seed, site);
+  else
+    ln_fwd_kernel<float><<<grid, 256, 0, st>>>(z_in, o, z_out, (float*)r, mean, rstd, gamma, beta, rows, H, eps, p, ik,
+                                               seed, site);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+// dz_out = dz_in + rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dr*gamma; dgamma += dr*xhat; dbeta += dr
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dr, const float* __restrict__ z,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ gamma, const float* __restrict__ dz_in,
+                                                     float* __restrict__ dz_out, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, int64_t rows, int H) {
+  extern __shared__ float acc[];  // [8 warps][2][H]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ag = acc + (size_t)warp * 2 * H;
+  float* ab = ag + H;
+  for (int c = lane; c < H; c += 32) { ag[c] = 0.f; ab[c] = 0.f; }
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
+    const float m = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < H; c += 32) {
+      float d = dr[row * H + c];
+      float xh = (z[row * H + c] - m) * rs;
+      float g = d * gamma[c];
+      s1 += g;
+      s2 += g * xh;
+      ag[c] += d * xh;
+      ab[c] += d;
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+    for (int c = lane; c < H; c += 32) {
+      float d = dr[row * H + c];
+      float xh = (z[row * H + c] - m) * rs;
+      float v = rs * (d * gamma[c] - s1 - xh * s2);
+      if (dz_in) v += dz_in[row * H + c];
+      dz_out[row * H + c] = v;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      g += acc[(size_t)w * 2 * H + c];
+      b += acc[(size_t)w * 2 * H + H + c];
+    }
+    atomicAdd(dgamma + c, g);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
+int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd, const float* gamma,
+           const float* dz_in, float* dz_out, float* dgamma, float* dbeta, int64_t rows, int H, cudaStream_t st) {
+  int grid = cdiv(rows, 8 * 4);
+  if (grid > 296) grid = 296;
+  if (grid < 1) grid = 1;
+  size_t smem = (size_t)8 * 2 * H * sizeof(float);
+  MVF_REQUIRE(smem <= 48 * 1024, MVF_ERR_UNSUPPORTED, "ln_bwd: hidden size %d too large", H);
+  ln_bwd_kernel<<<grid, 256, smem, st>>>(dr, z, mean, rstd, gamma, dz_in, dz_out, dgamma, dbeta, rows, H);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+// ============================================ BatchNorm ==============================================
+// Column statistics: block = 32 columns x 8 row lanes; double partials, double atomics.
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int64_t R, int C,
+                                                       double* __restrict__ sums) {
+  __shared__ double sh[2][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < R; r += (int64_t)gridDim.y * 8) {
+      double v = (double)x[r * C + c];
+      s += v;
+      q += v * v;
+    }
+  }
+  sh[0][ty][tx] = s;
+  sh[1][ty][tx] = q;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) { s += sh[0][j][tx]; q += sh[1][j][tx]; }
+    atomicAdd(sums + c, s);
+    atomicAdd(sums + C + c, q);
+  }
+}
+int bn_stats(const float* x, int64_t R, int C, double* sums, cudaStream_t st) {
+  int gy = cdiv(R, 8 * 16);
+  if (gy > 64) gy = 64;
+  if (gy < 1) gy = 1;
+  bn_stats_kernel<<<dim3(cdiv(C, 32), gy), 256, 0, st>>>(x, R, C, sums);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+// mean / invstd (fp32) from the (possibly all-reduced) double sums; running statistics as nn.BatchNorm1d:
+// running = (1-m)*running + m*batch, with the UNBIASED batch variance.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double n, float eps, int training,
+                                   float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   int64_t* __restrict__ tracked, float* __restrict__ mi) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && tracked) *tracked += 1;
+  if (c >= C) return;
+  if (training) {
+    double mean = sums[c] / n;
+    double var = sums[C + c] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mi[c] = (float)mean;
+    mi[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean) {
+      double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+    }
+  } else {
+    mi[c] = rmean[c];
+    mi[C + c] = 1.0f / sqrtf(rvar[c] + eps);
+  }
+}
+int bn_finalize(const double* sums, int C, double n_global, float eps, int training, float momentum, float* rmean,
+                float* rvar, int64_t* tracked, float* mi, cudaStream_t st) {
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(sums, C, n_global, eps, training, momentum, rmean, rvar, tracked, mi);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+template <typename TO>
+__global__ void bn_apply_kernel(const float* __restrict__ x, int64_t R, int C, const float* __restrict__ mi,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                                TO* __restrict__ out, int64_t ld_out, float p, float inv_keep, uint64_t seed, int site) {
+  int64_t total = R * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t r = i / C;
+    float y = (x[i] - mi[c]) * mi[C + c] * gamma[c] + beta[c];
+    if (relu) y = fmaxf(y, 0.f);
+    if (p > 0.f) y *= drop_scale(seed, site, (uint64_t)i, p, inv_keep);
+    out[r * ld_out + c] = from_f<TO>(y);
+  }
+}
+int bn_apply(int dtype_out, const float* x, int64_t R, int C, const float* mi, const float* gamma, const float* beta,
+             int relu, void* out, int64_t ld_out, float p, uint64_t seed, int site, cudaStream_t st) {
+  int64_t total = R * C;
+  int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+  float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (dtype_out == MVF_BF16)
+    bn_apply_kernel<bf16><<<grid, 256, 0, st>>>(x, R, C, mi, gamma, beta, relu, (bf16*)out, ld_out, p, ik, seed, site);
+  else
+    bn_apply_kernel<float><<<grid, 256, 0, st>>>(x, R, C, mi, gamma, beta, relu, (float*)out, ld_out, p, ik, seed, site);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+// dy = d_out * drop * [y > 0]; bsums[0:C] += sum dy; bsums[C:2C] += sum dy*xhat; dgamma/dbeta += local sums
+__global__ void __launch_bounds__(256)
+bn_bwd_stats_kernel(const float* __restrict__ d_out, int64_t ld_d, const float* __restrict__ x, int64_t R, int C,
+                    const float* __restrict__ mi, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    int relu, float p, float inv_keep, uint64_t seed, int site, double* __restrict__ bsums,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double sh[2][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C) {
+    const float m = mi[c], is = mi[C + c], g = gamma[c], b = beta[c];
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < R; r += (int64_t)gridDim.y * 8) {
+      float xh = (x[r * C + c] - m) * is;
+      float dy = d_out[r * ld_d + c];
+      if (p > 0.f) dy *= drop_scale(seed, site, (uint64_t)(r * C + c), p, inv_keep);
+      if (relu && !(xh * g + b > 0.f)) dy = 0.f;
+      s1 += (double)dy;
+      s2 += (double)dy * (double)xh;
+    }
+  }
+  sh[0][ty][tx] = s1;
+  sh[1][ty][tx] = s2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) { s1 += sh[0][j][tx]; s2 += sh[1][j][tx]; }
+    atomicAdd(bsums + c, s1);
+    atomicAdd(bsums + C + c, s2);
+    atomicAdd(dbeta + c, (float)s1);
+    atomicAdd(dgamma + c, (float)s2);
+  }
+}
+int bn_bwd_stats(const float* d_out, int64_t ld_d, const float* x, int64_t R, int C, const float* mi,
+                 const float* gamma, const float* beta, int relu, float p, uint64_t seed, int site, double* bsums,
+                 float* dgamma, float* dbeta, cudaStream_t st) {
+  int gy = cdiv(R, 8 * 16);
+  if (gy > 64) gy = 64;
+  if (gy < 1) gy = 1;
+  float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  bn_bwd_stats_kernel<<<dim3(cdiv(C, 32), gy), 256, 0, st>>>(d_out, ld_d, x, R, C, mi, gamma, beta, relu, p, ik, seed,
+                                                             site, bsums, dgamma, dbeta);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+// dx = gamma*invstd*(dy - sum(dy)/n - xhat*sum(dy*xhat)/n), n and sums global (torch SyncBatchNorm backward)
+template <typename TO>
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ d_out, int64_t ld_d, const float* __restrict__ x,
+                                    int64_t R, int C, const float* __restrict__ mi, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, int relu, float p, float inv_keep, uint64_t seed,
+                                    int site, const double* __restrict__ bsums, double n, TO* __restrict__ dx,
+                                    int64_t ld_dx) {
+  int64_t total = R * C;
+  const float inv_n = (float)(1.0 / n);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t r = i / C;
+    const float m = mi[c], is = mi[C + c], g = gamma[c], b = beta[c];
+    float xh = (x[i] - m) * is;
+    float dy = d_out[r * ld_d + c];
+    if (p > 0.f) dy *= drop_scale(seed, site, (uint64_t)i, p, inv_keep);
+    if (relu && !(xh * g + b > 0.f)) dy = 0.f;
+    float s1 = (float)bsums[c], s2 = (float)bsums[C + c];
+    dx[r * ld_dx + c] = from_f<TO>(g * is * (dy - s1 * inv_n - xh * s2 * inv_n));
+  }
+}
+int bn_bwd_apply(int dtype_out, const float* d_out, int64_t ld_d, const float* x, int64_t R, int C, const float* mi,
+                 const float* gamma, const float* beta, int relu, float p, uint64_t seed, int site, const double* bsums,
+                 double n_global, void* dx, int64_t ld_dx, cudaStream_t st) {
+  int64_t total = R * C;
+  int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+  float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (dtype_out == MVF_BF16)
+    bn_bwd_apply_kernel<bf16><<<grid, 256, 0, st>>>(d_out, ld_d, x, R, C, mi, gamma, beta, relu, p, ik, seed, site,
+                                                    bsums, n_global, (bf16*)dx, ld_dx);
+  else
+    bn_bwd_apply_kernel<float><<<grid, 256, 0, st>>>(d_out, ld_d, x, R, C, mi, gamma, beta, relu, p, ik, seed, site,
+                                                     bsums, n_global, (float*)dx, ld_dx);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+// =============================================== misc ================================================
+template <typename TI>
+__global__ void __launch_bounds__(256) colsum_kernel(const TI* __restrict__ X, int64_t R, int C, int64_t ld,
+                                                     float* __restrict__ out) {
+  __shared__ float sh[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < C)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < R; r += (int64_t)gridDim.y * 8) s += to_f<TI>(X[r * ld + c]);
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) s += sh[j][tx];
+    atomicAdd(out + c, s);
+  }
+}
+int colsum(int dtype_in, const void* X, int64_t R, int C, int64_t ld, float* out, cudaStream_t st) {
+  int gy = cdiv(R, 8 * 32);
+  if (gy > 128) gy = 128;
+  if (gy < 1) gy = 1;
+  dim3 grid(cdiv(C, 32), gy);
+  if (dtype_in == MVF_BF16) colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)X, R, C, ld, out);
+  else colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)X, R, C, ld, out);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+template <typename TO>
+__global__ void dropout_cast_kernel(const float* __restrict__ in, TO* __restrict__ out, int64_t rows, int cols,
+                                    int64_t ld_out, float p, float inv_keep, uint64_t seed, int site) {
+  int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = in[i];
+    if (p > 0.f) v *= drop_scale(seed, site, (uint64_t)i, p, inv_keep);
+    out[(i / cols) * ld_out + (i % cols)] = from_f<TO>(v);
+  }
+}
+int dropout_cast(int dtype_out, const float* in, void* out, int64_t rows, int cols, int64_t ld_out, float p,
+                 uint64_t seed, int site, cudaStream_t st) {
+  int64_t total = rows * cols;
+  if (total == 0) return MVF_OK;
+  int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+  float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (dtype_out == MVF_BF16)
+    dropout_cast_kernel<bf16><<<grid, 256, 0, st>>>(in, (bf16*)out, rows, cols, ld_out, p, ik, seed, site);
+  else
+    dropout_cast_kernel<float><<<grid, 256, 0, st>>>(in, (float*)out, rows, cols, ld_out, p, ik, seed, site);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+int cast_f32(int dtype_out, const float* in, void* out, int64_t n, cudaStream_t st) {
+  return dropout_cast(dtype_out, in, out, 1, (int)n, n, 0.f, 0, 0, st);
+}
+
+__global__ void dropout_mask_kernel(uint64_t seed, int site, int64_t total, float p, float inv_keep, float* out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = p > 0.f ? drop_scale(seed, site, (uint64_t)i, p, inv_keep) : 1.f;
+}
+int dropout_mask_export(uint64_t seed, int site, int64_t rows, int64_t cols, float p, float* out, cudaStream_t st) {
+  int64_t total = rows * cols;
+  if (total == 0) return MVF_OK;
+  int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+  dropout_mask_kernel<<<grid, 256, 0, st>>>(seed, site, total, p, p > 0.f ? 1.f / (1.f - p) : 1.f, out);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+// entity reduction over e of z[b, e*T+t, c] (mvformer.py:181-190)
+template <typename TO>
+__global__ void entity_reduce_fwd_kernel(const float* __restrict__ z, TO* __restrict__ y, int32_t* __restrict__ argmax,
+                                         int BV, int T, int E, int H, int mode) {
+  int64_t total = (int64_t)BV * T * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % H);
+    int64_t bt = i / H;
+    int t = (int)(bt % T), b = (int)(bt / T);
+    const float* zp = z + ((int64_t)b * E * T + t) * H + c;
+    const int64_t es = (int64_t)T * H;
+    float v;
+    if (mode == MVF_FINAL_ONE) v = zp[0];
+    else if (mode == MVF_FINAL_AVG) {
+      v = 0.f;
+      for (int e = 0; e < E; ++e) v += zp[e * es];
+      v /= (float)E;
+    } else {
+      v = zp[0];
+      int am = 0;
+      for (int e = 1; e < E; ++e) {
+        float w = zp[e * es];
+        if (w > v) { v = w; am = e; }
+      }
+      if (argmax) argmax[i] = am;
+    }
+    y[i] = from_f<TO>(v);
+  }
+}
+int entity_reduce_fwd(int dtype_out, const float* z, void* y, int32_t* argmax, int BV, int T, int E, int H, int mode,
+                      cudaStream_t st) {
+  int64_t total = (int64_t)BV * T * H;
+  int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+  if (dtype_out == MVF_BF16) entity_reduce_fwd_kernel<bf16><<<grid, 256, 0, st>>>(z, (bf16*)y, argmax, BV, T, E, H, mode);
+  else entity_reduce_fwd_kernel<float><<<grid, 256, 0, st>>>(z, (float*)y, argmax, BV, T, E, H, mode);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+__global__ void entity_reduce_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ argmax,
+                                         float* __restrict__ dz, int BV, int T, int E, int H, int mode) {
+  int64_t total = (int64_t)BV * E * T * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % H);
+    int64_t row = i / H;
+    int t = (int)(row % T);
+    int e = (int)((row / T) % E);
+    int b = (int)(row / ((int64_t)T * E));
+    int64_t yi = ((int64_t)b * T + t) * H + c;
+    float g = dy[yi];
+    float v;
+    if (mode == MVF_FINAL_ONE) v = e == 0 ? g : 0.f;
+    else if (mode == MVF_FINAL_AVG) v = g / (float)E;
+    else v = argmax[yi] == e ? g : 0.f;
+    dz[i] = v;
+  }
+}
+int entity_reduce_bwd(const float* dy, const int32_t* argmax, float* dz, int BV, int T, int E, int H, int mode,
+                      cudaStream_t st) {
+  int64_t total = (int64_t)BV * E * T * H;
+  int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+  entity_reduce_bwd_kernel<<<grid, 256, 0, st>>>(dy, argmax, dz, BV, T, E, H, mode);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+// SMART_FINAL 'lin' (mvformer.py:191-195): zl[b*T+t, e*H+c] = z[b, e*T+t, c]
+template <typename TO>
+__global__ void entity_gather_lin_kernel(const float* __restrict__ z, TO* __restrict__ zl, int BV, int T, int E, int H) {
+  int64_t total = (int64_t)BV * E * T * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % H);
+    int64_t row = i / H;
+    int t = (int)(row % T);
+    int e = (int)((row / T) % E);
+    int b = (int)(row / ((int64_t)T * E));
+    zl[(((int64_t)b * T + t) * E + e) * H + c] = from_f<TO>(z[i]);
+  }
+}
+int entity_gather_lin(int dtype_out, const float* z, void* zl, int BV, int T, int E, int H, cudaStream_t st) {
+  int64_t total = (int64_t)BV * E * T * H;
+  int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+  if (dtype_out == MVF_BF16) entity_gather_lin_kernel<bf16><<<grid, 256, 0, st>>>(z, (bf16*)zl, BV, T, E, H);
+  else entity_gather_lin_kernel<float><<<grid, 256, 0, st>>>(z, (float*)zl, BV, T, E, H);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+__global__ void entity_scatter_lin_kernel(const float* __restrict__ dzl, float* __restrict__ dz, int BV, int T, int E,
+                                          int H) {
+  int64_t total = (int64_t)BV * E * T * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % H);
+    int64_t row = i / H;
+    int t = (int)(row % T);
+    int e = (int)((row / T) % E);
+    int b = (int)(row / ((int64_t)T * E));
+    dz[i] = dzl[(((int64_t)b * T + t) * E + e) * H + c];
+  }
+}
+int entity_scatter_lin(const float* dzl, float* dz, int BV, int T, int E, int H, cudaStream_t st) {
+  int64_t total = (int64_t)BV * E * T * H;
+  int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+  entity_scatter_lin_kernel<<<grid, 256, 0, st>>>(dzl, dz, BV, T, E, H);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+// F.normalize(x, dim=-1, eps=1e-12): y = x / max(||x||, eps)   (transformer.py:228)
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                         float* __restrict__ norm, int64_t rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) { float v = x[row * D + c]; s += v * v; }
+  s = warp_sum(s);
+  float n = fmaxf(sqrtf(s), 1e-12f);
+  for (int c = lane; c < D; c += 32) y[row * D + c] = x[row * D + c] / n;
+  if (lane == 0) norm[row] = n;
+}
+int l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int D, cudaStream_t st) {
+  l2norm_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, y, norm, rows, D);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+// dx = (dy - y * <y, dy>) / n   (n = clamped norm; for ||x|| <= eps the clamp is active: dx = dy / eps)
+template <typename TO>
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                         const float* __restrict__ norm, TO* __restrict__ dx,
+                                                         int64_t rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s += y[row * D + c] * dy[row * D + c];
+  s = warp_sum(s);
+  const float n = norm[row];
+  if (n <= 1e-12f) s = 0.f;
+  for (int c = lane; c < D; c += 32) dx[row * D + c] = from_f<TO>((dy[row * D + c] - y[row * D + c] * s) / n);
+}
+int l2norm_bwd(const float* dy, const float* y, const float* norm, void* dx, int dtype_out, int64_t rows, int D,
+               cudaStream_t st) {
+  if (dtype_out == MVF_BF16) l2norm_bwd_kernel<bf16><<<cdiv(rows, 8), 256, 0, st>>>(dy, y, norm, (bf16*)dx, rows, D);
+  else l2norm_bwd_kernel<float><<<cdiv(rows, 8), 256, 0, st>>>(dy, y, norm, (float*)dx, rows, D);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+}  // namespace mvf

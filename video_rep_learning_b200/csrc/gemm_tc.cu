@@ -1,0 +1,490 @@
+// bf16 x bf16 -> fp32 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands
+// staged by TMA (cp.async.bulk.tensor, 128B swizzle) through an mbarrier ring.  sm_100a only.
+//
+//   C[M,N] (+)= opA(A)[M,K] * opB(B)[K,N] (+ bias)           fp32 accumulate in TMEM
+//
+// Operand majors are free: K-major ([rows,K] row-major, the nn.Linear forward) or MN-major ([K,rows]
+// row-major, needed by dX = dY*W and dW = dY^T*X) -- selected per operand through the shared-memory
+// descriptor + instruction descriptor, never by materialising a transpose.
+//
+// Kernel shape: persistent, one CTA per SM, 8 warps:
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      MMA issuer   (one elected lane; tcgen05.mma cta_group::1, M=128, N=BLOCK_N, K=16)
+//   warp 2      TMEM allocator / deallocator
+//   warps 4..7  epilogue: tcgen05.ld (lane quadrant = warp%4) -> bias/ReLU/mask -> global (store or red.add)
+// Two TMEM accumulators (2*BLOCK_N columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Split-K (work item = tile x K-slice, fp32 atomics) fills the machine when M*N is small and K huge
+// (the weight gradient of the K/V projection: 768 x 2304 outputs, K = frames*196).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mvf {
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (sticky CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SPIN_LIMIT) {
+      printf("mvf gemm_tc: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane quadrant base + t).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
+//   K-major : rows of 128 B (64 bf16 along K); 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major: k-rows of 128 B (64 bf16 along M/N); 8-k groups 1024 B apart (SBO); successive 64-element
+//             M/N chunks are separate TMA boxes of BLOCK_K*128 B = 8192 B (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool kmajor) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  uint32_t lbo = kmajor ? 1u : (uint32_t)((BLOCK_K * 128) >> 4);
+  uint32_t sbo = 1024u >> 4;
+  d |= (uint64_t)(lbo & 0x3FFF) << 16;
+  d |= (uint64_t)(sbo & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor for kind::f16: D fp32, A/B bf16, M=128, N=n.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_kmajor, bool b_kmajor) {
+  return (1u << 4)                        // c_format = F32
+         | (1u << 7)                      // a_format = BF16
+         | (1u << 10)                     // b_format = BF16
+         | ((a_kmajor ? 0u : 1u) << 15)   // a_major (1 = MN-major)
+         | ((b_kmajor ? 0u : 1u) << 16)   // b_major
+         | ((uint32_t)(n >> 3) << 17)     // n_dim
+         | ((uint32_t)(BLOCK_M >> 4) << 24);  // m_dim
+}
+
+struct Params {
+  int M, N, K;
+  int tiles_m, tiles_n, split_k, kb_per_split, num_kb;
+  int a_kmajor, b_kmajor;
+  int c_bf16;
+  int flags;
+  void* C;
+  int64_t ldc;
+  const float* bias;
+  const bf16* relu_src;
+  int64_t ld_relu;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                            : (2 * BLOCK_N <= 256) ? 256 : 512;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A|B)] then barriers
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_work = p.tiles_m * p.tiles_n * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int split = w / (p.tiles_m * p.tiles_n);
+        const int rem = w - split * (p.tiles_m * p.tiles_n);
+        const int tm = rem / p.tiles_n, tn = rem - tm * p.tiles_n;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const int k = kb * BLOCK_K;
+          if (p.a_kmajor) {
+            tma_load_2d(&map_a, &full_bar[stage], sa, k, tm * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_2d(&map_a, &full_bar[stage], sa + c * (BLOCK_K * 128), tm * BLOCK_M + c * 64, k);
+          }
+          if (p.b_kmajor) {
+            tma_load_2d(&map_b, &full_bar[stage], sb, k, tn * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              tma_load_2d(&map_b, &full_bar[stage], sb + c * (BLOCK_K * 128), tn * BLOCK_N + c * 64, k);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_N, p.a_kmajor != 0, p.b_kmajor != 0);
+      // start-address advance (in 16 B units) per UMMA_K step inside a stage
+      const uint32_t adv_a = p.a_kmajor ? (UMMA_K * 2) >> 4 : (UMMA_K * 128) >> 4;
+      const uint32_t adv_b = p.b_kmajor ? (UMMA_K * 2) >> 4 : (UMMA_K * 128) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int split = w / (p.tiles_m * p.tiles_n);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t da = make_smem_desc(sa, p.a_kmajor != 0);
+          const uint64_t db = make_smem_desc(sa + A_BYTES, p.b_kmajor != 0);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_bf16(tmem_d, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int split = w / (p.tiles_m * p.tiles_n);
+      const int rem = w - split * (p.tiles_m * p.tiles_n);
+      const int tm = rem / p.tiles_n, tn = rem - tm * p.tiles_n;
+      const int kb0 = split * p.kb_per_split;
+      const bool has_k = kb0 < p.num_kb;
+      mbar_wait(&tmem_full[acc], acc_phase, 4);
+      tcgen05_fence_after();
+      const int row = tm * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool add_bias = p.bias != nullptr && split == 0;
+      const bool atomic = p.split_k > 1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        const int col0 = tn * BLOCK_N + c0;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
+        tmem_ld_wait();
+        if (row_ok && has_k) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (add_bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.flags & MVF_GEMM_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.flags & MVF_GEMM_RELUMASK) {
+            const bf16* rs = p.relu_src + (int64_t)row * p.ld_relu + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] = (__bfloat162float(rs[j]) > 0.f) ? v[j] : 0.f;
+          }
+          const bool full = col0 + 32 <= p.N;
+          if (p.c_bf16) {
+            bf16* cp = (bf16*)p.C + (int64_t)row * p.ldc + col0;
+            if (full && ((p.ldc & 7) == 0) && ((((uintptr_t)p.C) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(cp + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+            }
+          } else {
+            float* cp = (float*)p.C + (int64_t)row * p.ldc + col0;
+            if (atomic) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(cp + j, v[j]);
+            } else if (p.flags & MVF_GEMM_ACCUM) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) cp[j] += v[j];
+            } else if (full && ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) cp[j] = v[j];
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+// rows x cols row-major bf16 matrix with leading dimension ld (elements); box = box_cols x box_rows.
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                    int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  MVF_REQUIRE(fn != nullptr, MVF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  MVF_REQUIRE((((uintptr_t)ptr) & 15) == 0, MVF_ERR_ALIGN, "gemm_tc: operand base %p not 16-byte aligned", ptr);
+  MVF_REQUIRE((ld * 2) % 16 == 0, MVF_ERR_ALIGN, "gemm_tc: leading dimension %lld not a multiple of 8 elements",
+              (long long)ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MVF_REQUIRE(r == CUDA_SUCCESS, MVF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+              (long long)rows, (long long)cols, (long long)ld);
+  return MVF_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int num_sms, cudaStream_t st) {
+  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    MVF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        smem));
+    configured = true;
+  }
+  int work = p.tiles_m * p.tiles_n * p.split_k;
+  int grid = work < num_sms ? work : num_sms;
+  gemm_tc_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+}  // namespace tc
+
+static int g_num_sms = -1;
+static int g_cc_major = -1;
+static void query_device() {
+  if (g_num_sms >= 0) return;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+    g_num_sms = prop.multiProcessorCount;
+    g_cc_major = prop.major;
+  } else {
+    g_num_sms = 0;
+    g_cc_major = 0;
+  }
+}
+
+bool tc_available() {
+  query_device();
+  return g_cc_major == 10 && tc::get_encode_fn() != nullptr;
+}
+
+int gemm_tc(int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+            const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias, const void* relu_src, int64_t ld_relu,
+            int flags, int split_k, cudaStream_t st) {
+  using namespace tc;
+  if (M <= 0 || N <= 0) return MVF_OK;
+  MVF_REQUIRE(tc_available(), MVF_ERR_UNSUPPORTED, "tcgen05 GEMM requested but the device is not sm_100");
+  MVF_REQUIRE(K > 0, MVF_ERR_BAD_ARG, "gemm_tc: K must be positive");
+  MVF_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), MVF_ERR_BAD_ARG, "gemm_tc: dims exceed int32");
+  const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  Params p;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.tiles_m = cdiv(M, BLOCK_M);
+  p.tiles_n = cdiv(N, bn);
+  p.num_kb = cdiv(K, BLOCK_K);
+  if (split_k <= 0) {
+    // auto: split K only when the output tiles cannot fill the machine and K is long
+    int tiles = p.tiles_m * p.tiles_n;
+    split_k = 1;
+    if (dtype_c == MVF_F32 && !(flags & (MVF_GEMM_RELU | MVF_GEMM_RELUMASK)) && tiles < g_num_sms && p.num_kb >= 16) {
+      split_k = (2 * g_num_sms + tiles - 1) / tiles;
+      int max_split = p.num_kb / 8;
+      if (split_k > max_split) split_k = max_split;
+      if (split_k < 1) split_k = 1;
+    }
+  }
+  if (split_k > 1) {
+    MVF_REQUIRE(dtype_c == MVF_F32 && !(flags & (MVF_GEMM_RELU | MVF_GEMM_RELUMASK)), MVF_ERR_BAD_ARG,
+                "gemm_tc: split-K needs an fp32 linear epilogue");
+    if (!(flags & MVF_GEMM_ACCUM)) {
+      // partial sums are accumulated with atomics: C must start from zero
+      MVF_CHECK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
+    }
+  }
+  p.kb_per_split = cdiv(p.num_kb, split_k);
+  p.split_k = cdiv(p.num_kb, p.kb_per_split);
+  p.a_kmajor = a_kmajor; p.b_kmajor = b_kmajor;
+  p.c_bf16 = dtype_c == MVF_BF16;
+  p.flags = flags;
+  p.C = C; p.ldc = ldc; p.bias = bias;
+  p.relu_src = (const bf16*)relu_src; p.ld_relu = ld_relu;
+
+  CUtensorMap ma, mb;
+  if (a_kmajor) MVF_TRY(make_map(&ma, A, M, K, lda, BLOCK_K, BLOCK_M));
+  else MVF_TRY(make_map(&ma, A, K, M, lda, 64, BLOCK_K));
+  if (b_kmajor) MVF_TRY(make_map(&mb, B, N, K, ldb, BLOCK_K, bn));
+  else MVF_TRY(make_map(&mb, B, K, N, ldb, 64, BLOCK_K));
+
+  if (bn == 256) return launch<256, 4>(ma, mb, p, g_num_sms, st);
+  if (bn == 128) return launch<128, 6>(ma, mb, p, g_num_sms, st);
+  return launch<64, 8>(ma, mb, p, g_num_sms, st);
+}
+
+}  // namespace mvf

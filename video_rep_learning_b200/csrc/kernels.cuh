@@ -1,0 +1,99 @@
+// Internal launcher declarations (one per kernel family). All launchers are asynchronous on `st`.
+#pragma once
+#include "common.cuh"
+
+namespace mvf {
+
+// ---- pack / unpack (elementwise.cu) ------------------------------------------------------------------
+struct PackEntry {
+  const float* src;  // fp32 [rows, cols] contiguous
+  void* dst;         // [rows, ld_dst] in dst dtype, zero padded
+  int rows, cols, ld_dst, dst_bf16;
+};
+int pack_params(const PackEntry* entries, int n, cudaStream_t st);
+struct UnpackEntry {
+  const float* src;  // gpack + offset, [rows, ld_src]
+  float* dst;        // [rows, cols] contiguous
+  int rows, cols, ld_src;
+};
+int unpack_grads(const UnpackEntry* entries, int n, float scale, cudaStream_t st);
+
+// ---- positional encoding (models/utils.py:113-145) ---------------------------------------------------
+int posenc_table(float* table, int T, int H, int train_frames, cudaStream_t st);
+// z[b, e*T+t, :] = drop(h3[(b*T+t)*E+e, :] + pe[t, :])
+int posenc_add(const float* h3, const float* table, float* z, int BV, int T, int E, int H, float p, uint64_t seed,
+               cudaStream_t st);
+// dh3[(b*T+t)*E+e, :] = drop'(dz[b, e*T+t, :])   (out dtype)
+int posenc_bwd(int dtype_out, const float* dz, void* dh3, int BV, int T, int E, int H, float p, uint64_t seed,
+               cudaStream_t st);
+
+// ---- LayerNorm with fused residual-add + dropout (models/utils.py:147-159) ----------------------------
+// z_out = z_in + drop(o) (o may be null -> z_out = z_in); r = LN(z_out)*gamma + beta (r may be null -> add only)
+int ln_fwd(int dtype_out, const float* z_in, const float* o, float* z_out, void* r, float* mean, float* rstd,
+           const float* gamma, const float* beta, int64_t rows, int H, float eps, float p, uint64_t seed, int site,
+           cudaStream_t st);
+// dz_out = dz_in + LN'(dr); dgamma/dbeta accumulated (atomics). dz_in may be null (treated as 0).
+int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd, const float* gamma,
+           const float* dz_in, float* dz_out, float* dgamma, float* dbeta, int64_t rows, int H, cudaStream_t st);
+
+// ---- BatchNorm1d (+ReLU +dropout) in training / eval mode ---------------------------------------------
+// The statistics are produced in three launches so that a multi-GPU caller can all-reduce `sums` in between:
+//   bn_stats (local partial sums, float64) -> [all-reduce] -> bn_finalize (mean/invstd + running stats) -> bn_apply
+int bn_stats(const float* x, int64_t R, int C, double* sums, cudaStream_t st);  // sums[0:C]+=sum x, [C:2C]+=sum x^2
+// mi[0:C] = mean, mi[C:2C] = invstd. training: from sums / n_global (+ running-stat update, momentum, unbiased
+// variance, num_batches_tracked += 1); eval: from the running buffers.
+int bn_finalize(const double* sums, int C, double n_global, float eps, int training, float momentum, float* rmean,
+                float* rvar, int64_t* tracked, float* mi, cudaStream_t st);
+// out = drop(relu?(gamma*(x-mean)*invstd+beta))
+int bn_apply(int dtype_out, const float* x, int64_t R, int C, const float* mi, const float* gamma, const float* beta,
+             int relu, void* out, int64_t ld_out, float p, uint64_t seed, int site, cudaStream_t st);
+// dy = d_out*drop*relu'(y); bsums[0:C]+=sum dy, [C:2C]+=sum dy*xhat; dgamma/dbeta accumulated from the LOCAL sums
+int bn_bwd_stats(const float* d_out, int64_t ld_d, const float* x, int64_t R, int C, const float* mi,
+                 const float* gamma, const float* beta, int relu, float p, uint64_t seed, int site, double* bsums,
+                 float* dgamma, float* dbeta, cudaStream_t st);
+// dx = gamma*invstd*(dy - sum(dy)/n - xhat*sum(dy*xhat)/n) with the (all-reduced) bsums and global n
+int bn_bwd_apply(int dtype_out, const float* d_out, int64_t ld_d, const float* x, int64_t R, int C, const float* mi,
+                 const float* gamma, const float* beta, int relu, float p, uint64_t seed, int site, const double* bsums,
+                 double n_global, void* dx, int64_t ld_dx, cudaStream_t st);
+
+// ---- misc ------------------------------------------------------------------------------------------------
+// out[c] += sum_r X[r,c]
+int colsum(int dtype_in, const void* X, int64_t R, int C, int64_t ld, float* out, cudaStream_t st);
+// out = in * dropmask (site) cast to dtype_out; p = 0 -> plain cast
+int dropout_cast(int dtype_out, const float* in, void* out, int64_t rows, int cols, int64_t ld_out, float p,
+                 uint64_t seed, int site, cudaStream_t st);
+int cast_f32(int dtype_out, const float* in, void* out, int64_t n, cudaStream_t st);
+// entity reduction (mvformer.py:181-190): z [BV, E*T, H] -> y [BV*T, H]
+int entity_reduce_fwd(int dtype_out, const float* z, void* y, int32_t* argmax, int BV, int T, int E, int H, int mode,
+                      cudaStream_t st);
+int entity_reduce_bwd(const float* dy, const int32_t* argmax, float* dz, int BV, int T, int E, int H, int mode,
+                      cudaStream_t st);
+// 'lin' gather: zl[b*T+t, e*H + c] = z[b, e*T+t, c] and its transpose-scatter
+int entity_gather_lin(int dtype_out, const float* z, void* zl, int BV, int T, int E, int H, cudaStream_t st);
+int entity_scatter_lin(const float* dzl, float* dz, int BV, int T, int E, int H, cudaStream_t st);
+// F.normalize (eps 1e-12) and its backward; norms saved
+int l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int D, cudaStream_t st);
+int l2norm_bwd(const float* dy, const float* y, const float* norm, void* dx, int dtype_out, int64_t rows, int D,
+               cudaStream_t st);
+int dropout_mask_export(uint64_t seed, int site, int64_t rows, int64_t cols, float p, float* out, cudaStream_t st);
+
+// ---- xattn.cu ----------------------------------------------------------------------------------------------
+int xattn_pool_fwd(int dtype, int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b,
+                   float* attn, void* ent, int64_t ld_ent, int one_hot, float drop_p, uint64_t seed, cudaStream_t st);
+int xattn_pool_bwd(int dtype, int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b,
+                   const float* attn, const void* d_ent, int64_t ld_ent, int one_hot, float drop_p, uint64_t seed,
+                   void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv, cudaStream_t st);
+
+// ---- attention.cu --------------------------------------------------------------------------------------------
+int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, void* ctx,
+                  float* lse, cudaStream_t st);
+int attention_bwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, const void* ctx,
+                  const float* lse, const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st);
+
+// ---- scl.cu ----------------------------------------------------------------------------------------------------
+size_t scl_ws_bytes(int Bv, int T, int D);
+int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps, const float* masks, int Bv, int T,
+                int D, float temperature, float label_variance, int negative_type, int quirk, float* loss_out,
+                float* d_embs, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace mvf
