@@ -79,6 +79,13 @@ int mvf_version(void);
 const char* mvf_last_error(void);
 /* 1 when the library was built with the tcgen05/TMA GEMM and the current device is sm_100. */
 int mvf_has_tcgen05(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t mvf_launch_count(void);
+/* Measurement aid: when enabled, CUDA events are recorded on the launching stream around the dominant kernels
+ * (tag 0: K|V projection GEMM, 1: its weight-gradient GEMM, 2: cross-attention pooling fwd, 3: its bwd).
+ * mvf_profile_read synchronises on the recorded events and returns the durations in milliseconds. */
+int mvf_profile_enable(int on);
+int mvf_profile_read(int tag, float* ms, int cap, int* n);
 
 /* Canonical parameter table (state_dict order of `embed.*` then `ssl_projection.*`).
  * mvf_param_info fills the reference state_dict key and the logical shape of parameter `idx`. */

@@ -1,0 +1,129 @@
+"""GPU: building-block kernels through the C ABI against the oracle / torch autograd (fp64 on the host)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvf_oracle as O
+from tests import helpers as H
+from video_rep_learning_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("F,P,E,SPC,one_hot", [(5, 16, 3, 32, 1), (3, 196, 3, 384, 1), (2, 49, 6, 64, 0), (2, 30, 16, 96, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype):
+    g = torch.Generator().manual_seed(F * P + E)
+    kv = torch.randn(F * P, 2 * SPC, generator=g).to(dtype)
+    q_s = torch.randn(E, SPC, generator=g) * 0.3
+    q_b = torch.randn(SPC, generator=g) * 0.1
+    W = SPC + (E if one_hot else 0)
+    ld = (W + 7) // 8 * 8
+    # host reference in fp64 on the (possibly bf16-rounded) inputs
+    kvd = kv.double().view(F, P, 2 * SPC).requires_grad_(True)
+    qs, qb = q_s.double().requires_grad_(True), q_b.double().requires_grad_(True)
+    K, V = kvd[..., :SPC], kvd[..., SPC:]
+    A = torch.softmax(torch.einsum("fpc,ec->fep", K, qs + qb) / np.sqrt(SPC), -1)
+    ent = torch.einsum("fep,fpc->fec", A, V)
+    d_ent = torch.randn(F, E, SPC, generator=g).double()
+    (ent * d_ent).sum().backward()
+
+    dev = "cuda"
+    kv_d = kv.to(dev)
+    attn = torch.empty(F, E, P, device=dev)
+    out = torch.full((F * E, ld), float("nan"), dtype=dtype, device=dev)
+    md = L.MVF_BF16 if dtype == torch.bfloat16 else L.MVF_F32
+    L.check(L.lib().mvf_xattn_pool_fwd(md, F, P, E, SPC, L.ptr(kv_d), L.ptr(q_s.to(dev)), L.ptr(q_b.to(dev)), L.ptr(attn),
+                                       L.ptr(out), ld, one_hot, 0.0, 0, _stream()))
+    torch.cuda.synchronize()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert float((attn.cpu().double() - A.detach()).abs().max()) < 1e-5
+    got = out.float().cpu().view(F, E, ld)
+    assert float((got[..., :SPC].double() - ent.detach()).abs().max()) < tol
+    if one_hot:
+        assert torch.equal(got[..., SPC:SPC + E], torch.eye(E).expand(F, E, E))
+    assert float(got[..., W:].abs().max()) == 0.0 if ld > W else True
+
+    d_in = torch.zeros(F * E, ld, dtype=dtype)
+    d_in[:, :SPC] = d_ent.view(F * E, SPC).to(dtype)
+    d_kv = torch.empty_like(kv_d)
+    dqs, dqb = torch.zeros(E, SPC, device=dev), torch.zeros(SPC, device=dev)
+    dbk, dbv = torch.zeros(SPC, device=dev), torch.zeros(SPC, device=dev)
+    L.check(L.lib().mvf_xattn_pool_bwd(md, F, P, E, SPC, L.ptr(kv_d), L.ptr(q_s.to(dev)), L.ptr(q_b.to(dev)), L.ptr(attn),
+                                       L.ptr(d_in.to(dev)), ld, one_hot, 0.0, 0, L.ptr(d_kv), L.ptr(dqs), L.ptr(dqb),
+                                       L.ptr(dbk), L.ptr(dbv), _stream()))
+    torch.cuda.synchronize()
+    # with bf16 the incoming gradient was rounded too: compare against the reference of the rounded d_ent
+    if dtype == torch.bfloat16:
+        kvd.grad = None; qs.grad = None; qb.grad = None
+        A2 = torch.softmax(torch.einsum("fpc,ec->fep", kvd[..., :SPC], qs + qb) / np.sqrt(SPC), -1)
+        ent2 = torch.einsum("fep,fpc->fec", A2, kvd[..., SPC:])
+        (ent2 * d_ent.to(dtype).double()).sum().backward()
+    rt = 2e-5 if dtype == torch.float32 else 2e-2
+    assert H.rel_l2(d_kv.float().cpu().view(F, P, 2 * SPC), kvd.grad) < rt
+    assert H.rel_l2(dqs.cpu(), qs.grad) < rt and H.rel_l2(dqb.cpu(), qb.grad) < rt
+    assert H.rel_l2(dbv.cpu(), kvd.grad[..., SPC:].sum((0, 1))) < rt
+    # key bias gradient is analytically zero (softmax shift invariance): only rounding noise may remain
+    assert float(dbk.abs().max()) < 1e-3 * float(kvd.grad.abs().max()) * P * F
+
+
+@pytest.mark.parametrize("B,S,heads,dk,masked", [(2, 24, 4, 8, True), (3, 60, 8, 32, True), (1, 100, 2, 16, False), (2, 70, 2, 64, True)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_temporal_attention_fwd_bwd(B, S, heads, dk, masked, dtype):
+    Hd = heads * dk
+    g = torch.Generator().manual_seed(B * S + heads)
+    qkv = (torch.randn(B * S, 3 * Hd, generator=g) * 0.7).to(dtype)
+    km = None
+    if masked:
+        km = (torch.rand(B, S, generator=g) > 0.25).float()
+        km[:, 0] = 1
+    x = qkv.double().view(B, S, 3, heads, dk).requires_grad_(True)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    sc = q @ k.transpose(-1, -2) / np.sqrt(dk)
+    if km is not None:
+        sc = sc.masked_fill(km[:, None, None, :] == 0, -float("inf"))
+    ctx_ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, Hd)
+    d_ctx = torch.randn(B * S, Hd, generator=g).to(dtype)
+    (ctx_ref * d_ctx.double()).sum().backward()
+
+    dev = "cuda"
+    md = L.MVF_BF16 if dtype == torch.bfloat16 else L.MVF_F32
+    qkv_d = qkv.to(dev)
+    ctx = torch.empty(B * S, Hd, dtype=dtype, device=dev)
+    lse = torch.empty(B, heads, S, device=dev)
+    kmd = None if km is None else km.to(dev)
+    L.check(L.lib().mvf_attention_fwd(md, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse), _stream()))
+    torch.cuda.synchronize()
+    tol = 2e-6 if dtype == torch.float32 else 1.5e-2
+    assert float((ctx.float().cpu().double() - ctx_ref.detach()).abs().max()) < tol * max(1.0, float(ctx_ref.abs().max()))
+    d_qkv = torch.full_like(qkv_d, float("nan"))
+    delta = torch.empty(B, heads, S, device=dev)
+    L.check(L.lib().mvf_attention_bwd(md, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse),
+                                      L.ptr(d_ctx.to(dev)), L.ptr(d_qkv), L.ptr(delta), _stream()))
+    torch.cuda.synchronize()
+    want = x.grad.reshape(B * S, 3 * Hd)
+    assert H.rel_l2(d_qkv.float().cpu(), want) < (2e-5 if dtype == torch.float32 else 3e-2)
+
+
+def test_dropout_mask_is_counter_based_and_unbiased():
+    n_r, n_c, p = 1000, 257, 0.1
+    a = torch.empty(n_r, n_c, device="cuda")
+    b = torch.empty(n_r, n_c, device="cuda")
+    L.check(L.lib().mvf_dropout_mask(1234, 3, n_r, n_c, p, L.ptr(a), _stream()))
+    L.check(L.lib().mvf_dropout_mask(1234, 3, n_r, n_c, p, L.ptr(b), _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    vals = torch.unique(a).cpu()
+    assert torch.allclose(vals, torch.tensor([0.0, 1.0 / 0.9]))
+    keep = float((a > 0).float().mean())
+    assert abs(keep - 0.9) < 0.005
+    L.check(L.lib().mvf_dropout_mask(1235, 3, n_r, n_c, p, L.ptr(b), _stream()))
+    torch.cuda.synchronize()
+    assert 0.7 < float(((a > 0) == (b > 0)).float().mean()) < 0.9       # a different seed decorrelates (~0.82)
+    L.check(L.lib().mvf_dropout_mask(1234, 3, n_r, n_c, 0.0, L.ptr(b), _stream()))
+    torch.cuda.synchronize()
+    assert float(b.min()) == 1.0 and float(b.max()) == 1.0

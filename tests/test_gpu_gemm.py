@@ -1,0 +1,110 @@
+"""GPU: the two GEMM engines through the C ABI.  SIMT fp32 vs torch fp64; tcgen05 (bf16) vs the same product of
+the bf16-rounded operands in fp64 -- every operand-major combination, ragged sizes, epilogue flags, split-K."""
+import pytest
+import torch
+
+from video_rep_learning_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(backend, A, B, a_k, b_k, M, N, K, c_dtype, bias=None, relu_src=None, flags=0, split_k=1, C=None):
+    dev = A.device
+    ab = L.MVF_BF16 if A.dtype == torch.bfloat16 else L.MVF_F32
+    if C is None:
+        C = torch.full((M, N), float("nan"), dtype=c_dtype, device=dev)
+    cd = L.MVF_BF16 if c_dtype == torch.bfloat16 else L.MVF_F32
+    st = L.lib().mvf_gemm(backend, ab, cd, int(a_k), int(b_k), M, N, K, L.ptr(A), A.stride(0), L.ptr(B), B.stride(0),
+                          L.ptr(C), C.stride(0), L.ptr(bias), L.ptr(relu_src), relu_src.stride(0) if relu_src is not None else 0,
+                          flags, split_k, torch.cuda.current_stream().cuda_stream)
+    L.check(st, "mvf_gemm")
+    torch.cuda.synchronize()
+    return C
+
+
+def _operands(M, N, K, a_k, b_k, dtype, pad=0):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((M, K + pad) if a_k else (K, M + pad), generator=g, device="cuda").to(dtype)
+    B = torch.randn((N, K + pad) if b_k else (K, N + pad), generator=g, device="cuda").to(dtype)
+    Av = A[:, :K] if a_k else A[:, :M]
+    Bv = B[:, :K] if b_k else B[:, :N]
+    Am = Av.double() if a_k else Av.double().t()
+    Bm = Bv.double().t() if b_k else Bv.double()
+    return A, B, Am @ Bm
+
+
+@pytest.mark.parametrize("a_k,b_k", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 16), (130, 70, 37), (257, 129, 300)])
+def test_simt_fp32(a_k, b_k, M, N, K):
+    A, B, ref = _operands(M, N, K, a_k, b_k, torch.float32)
+    bias = torch.randn(N, device="cuda")
+    C = _gemm(L.GEMM_SIMT, A, B, a_k, b_k, M, N, K, torch.float32, bias=bias)
+    err = (C.double() - (ref + bias.double())).abs().max() / ref.abs().max()
+    assert float(err) < 2e-6
+    C2 = _gemm(L.GEMM_SIMT, A, B, a_k, b_k, M, N, K, torch.float32, flags=L.GEMM_RELU)
+    assert float((C2.double() - ref.clamp_min(0)).abs().max() / ref.abs().max()) < 2e-6
+    base = torch.randn(M, N, device="cuda")
+    C3 = _gemm(L.GEMM_SIMT, A, B, a_k, b_k, M, N, K, torch.float32, flags=L.GEMM_ACCUM, C=base.clone())
+    assert float((C3.double() - (ref + base.double())).abs().max() / ref.abs().max()) < 2e-6
+    mask_src = torch.randn(M, N, device="cuda")
+    C4 = _gemm(L.GEMM_SIMT, A, B, a_k, b_k, M, N, K, torch.float32, relu_src=mask_src, flags=L.GEMM_RELUMASK)
+    assert float((C4.double() - ref * (mask_src > 0)).abs().max() / ref.abs().max()) < 2e-6
+
+
+TC_SHAPES = [(128, 64, 64), (128, 256, 128), (256, 128, 192), (200, 72, 100), (384, 768, 320), (1000, 520, 72),
+             (3840, 1024, 256), (130, 392, 512)]
+
+
+@pytest.mark.parametrize("a_k,b_k", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+def test_tcgen05_bf16(a_k, b_k, M, N, K):
+    assert L.lib().mvf_has_tcgen05() == 1, "tcgen05 path unavailable on this device"
+    # leading dimensions must be multiples of 8 elements (16-byte TMA rows): pad when the logical size is not
+    padA = (-(K if a_k else M)) % 8
+    padB = (-(K if b_k else N)) % 8
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn((M, K + padA) if a_k else (K, M + padA), generator=g, device="cuda").to(torch.bfloat16)
+    B = torch.randn((N, K + padB) if b_k else (K, N + padB), generator=g, device="cuda").to(torch.bfloat16)
+    Am = A[:, :K].double() if a_k else A[:, :M].double().t()
+    Bm = B[:, :K].double().t() if b_k else B[:, :N].double()
+    ref = Am @ Bm
+    bias = torch.randn(N, device="cuda")
+    C = _gemm(L.GEMM_TCGEN05, A, B, a_k, b_k, M, N, K, torch.float32, bias=bias)
+    err = float((C.double() - (ref + bias.double())).abs().max() / ref.abs().max())
+    assert err < 1e-5, f"fp32-out error {err}"
+    Cb = _gemm(L.GEMM_TCGEN05, A, B, a_k, b_k, M, N, K, torch.bfloat16, flags=L.GEMM_RELU)
+    errb = float((Cb.double() - ref.clamp_min(0)).abs().max() / ref.abs().max())
+    assert errb < 8e-3, f"bf16-out error {errb}"
+    # cross-check against the SIMT engine on identical bf16 operands
+    Cs = _gemm(L.GEMM_SIMT, A, B, a_k, b_k, M, N, K, torch.float32, bias=bias)
+    assert float((C - Cs).abs().max() / ref.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("split", [0, 2, 7])
+def test_tcgen05_split_k_weight_gradient_shape(split):
+    """dW = dY^T X with a long contraction and few output tiles: both operands MN-major, fp32 atomics."""
+    M, N, K = 768, 264, 196 * 40
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dY = (torch.randn(K, M, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    X = torch.randn(K, N, generator=g, device="cuda").to(torch.bfloat16)
+    ref = dY.double().t() @ X.double()
+    base = torch.randn(M, N, device="cuda")
+    C = _gemm(L.GEMM_TCGEN05, dY, X, 0, 0, M, N, K, torch.float32, flags=L.GEMM_ACCUM, split_k=split, C=base.clone())
+    err = float((C.double() - (ref + base.double())).abs().max() / ref.abs().max())
+    assert err < 2e-5
+    C0 = _gemm(L.GEMM_TCGEN05, dY, X, 0, 0, M, N, K, torch.float32, split_k=split)
+    assert float((C0.double() - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+def test_tcgen05_relumask_and_alignment_errors():
+    M, N, K = 256, 128, 64
+    A, B, ref = _operands(M, N, K, 1, 1, torch.bfloat16)
+    src = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    C = _gemm(L.GEMM_TCGEN05, A, B, 1, 1, M, N, K, torch.bfloat16, relu_src=src, flags=L.GEMM_RELUMASK)
+    want = ref * (src.double() > 0)
+    assert float((C.double() - want).abs().max() / ref.abs().max()) < 8e-3
+    A2 = torch.randn(M, K + 4, device="cuda").to(torch.bfloat16)      # row stride 136 B: not a multiple of 16
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        _gemm(L.GEMM_TCGEN05, A2, B, 1, 1, M, N, K, torch.float32)
+    with pytest.raises(RuntimeError, match="bf16"):
+        _gemm(L.GEMM_TCGEN05, A.float(), B.float(), 1, 1, M, N, K, torch.float32)

@@ -1,0 +1,176 @@
+"""GPU: the whole hot path (head + projection + normalise + SCL, forward and backward) through the public API
+against the reference-generated goldens and the oracle; stage-by-stage comparison of every saved activation."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvf_oracle as O
+from tests import helpers as H
+from video_rep_learning_b200 import _lib as L
+from video_rep_learning_b200 import engine
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["tiny_penn", "tiny_fg_avg", "tiny_max_nohot", "tiny_lin", "tiny_batch_noself", "tiny_e1"]
+# parameters whose gradient is analytically zero (bias in front of a train-mode BatchNorm / key bias under softmax):
+# the reference's values are rounding noise, so they are compared with an absolute floor
+ZERO_GRAD = ("linear_K2d.bias", "linear_V2d.bias", "fc_layers.1.bias", "fc_layers.5.bias", "embedding_layer.bias",
+             "ssl_projection.net.0.bias")
+
+
+def _inputs(z):
+    return (torch.from_numpy(z["tokens"]), torch.from_numpy(z["masks"]), torch.from_numpy(z["seq_lens"]),
+            torch.from_numpy(z["steps"]))
+
+
+def _check_grads(got, ref, keys, tol, floor_scale):
+    gmax = max(float(ref[k].abs().max()) for k in keys)
+    worst = 0.0
+    for k in keys:
+        a, b = got[k].double(), ref[k].double()
+        if any(k.endswith(s) for s in ZERO_GRAD) or ("feed_forward.fc2.bias" in k and float(b.abs().max()) < 1e-6 * gmax):
+            assert float((a - b).abs().max()) <= floor_scale * gmax, k
+            continue
+        err = float((a - b).norm() / (b.norm() + 1e-30))
+        worst = max(worst, err)
+        assert err < tol, f"{k}: rel err {err:.3e}"
+    return worst
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_step_matches_reference_golden(name):
+    m, hc, z, P, G, B = H.load_case(name)
+    tokens, masks, seq_lens, steps = _inputs(z)
+    r = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.float32, negative_type=m["negative_type"])
+    assert float((r["emb"] - torch.from_numpy(z["ref_emb"])).abs().max()) < 2e-5
+    assert float((r["e"] - torch.from_numpy(z["ref_e"])).abs().max()) < 1e-5
+    assert abs(float(r["loss"]) - float(z["ref_loss"])) / float(z["ref_loss"]) < 1e-5
+    keys = list(P.keys())
+    # whole gradient vector and every tensor on its own: 1e-5 relative (fp32 tolerance of the north star)
+    assert H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(G, keys)) < 1e-5
+    _check_grads(r["grads"], G, keys, 2e-5, 1e-5)
+    for k, v in r["bufs"].items():
+        assert float((v.double() - B[k].double()).abs().max()) < 1e-5, k
+    assert int(r["bufs"]["embed.fc_layers.2.num_batches_tracked"]) == 1
+
+
+@pytest.mark.parametrize("name", ["tiny_penn", "tiny_fg_avg"])
+def test_every_stage_against_the_oracle(name):
+    """Localises a wrong kernel: each named region of the save buffer vs the oracle's intermediate (fp64)."""
+    m, hc, z, P, G, B = H.load_case(name)
+    tokens, masks, seq_lens, steps = _inputs(z)
+    r = H.run_cuda(hc, P, None, tokens, masks, None, None, dtype=torch.float32)
+    o = H.run_oracle(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.float64)
+    cs, plan = r["cs"], r["cs"].plan
+    BV, T, Pt, _ = tokens.shape
+    E = hc.n_entities
+    reg = lambda n: plan.region(cs.head_save, n).float().cpu().double()
+    assert float((reg("attn").view(BV, T, E, Pt) - o["aux"]["attn"]).abs().max()) < 1e-6
+    assert float((reg("h0")[:, :hc.pool_channels].view(BV, T, E, -1) - o["aux"]["ent"]).abs().max()) < 1e-5
+    assert float((reg("h3").view(BV, T, E, -1) - o["aux"]["h3"]).abs().max()) < 2e-5
+    pe = torch.from_numpy(O.pos_table_for(hc, T, hc.hidden))
+    assert float((reg("pe") - pe).abs().max()) < 1e-6
+    zl = reg("z" + str(2 * hc.n_layers)).view(BV, E * T, -1)
+    assert float((zl - o["aux"]["z"]).abs().max()) < 5e-5
+    assert float((r["e"].double() - o["e"]).abs().max()) < 1e-5
+
+
+def test_bf16_step_within_north_star_tolerance():
+    """bf16 operands / fp32 accumulate through the tcgen05 GEMMs vs the fp32 reference golden: 2e-2 relative."""
+    m, hc, z, P, G, B = H.load_case("tiny_fg_avg")
+    tokens, masks, seq_lens, steps = _inputs(z)
+    r = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16)
+    assert H.rel_l2(r["e"], torch.from_numpy(z["ref_e"])) < 2e-2
+    assert abs(float(r["loss"]) - float(z["ref_loss"])) / float(z["ref_loss"]) < 2e-2
+    keys = list(P.keys())
+    err = H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(G, keys))
+    print("bf16 concatenated-gradient rel err", err)
+    assert err < 6e-2        # the reference's own bf16-autocast run is 1.7e-1 off its fp32 run
+    # same bf16 inputs through the SIMT engine: isolates tensor-core GEMM error from bf16 rounding of operands
+    r2 = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16, backend=L.GEMM_SIMT)
+    assert H.rel_l2(r["e"], r2["e"]) < 2e-3
+    assert H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(r2["grads"], keys)) < 1e-2
+
+
+def test_penn_cfg1_shape_fp32_digest():
+    """BASELINE configs[0]: 2 videos x 20 frames, ViT-S/16 x 3 layers (C_in 1152), real penn_mvf.yml head sizes."""
+    m = H.meta()["penn_cfg1"]
+    z = np.load(os.path.join(H.GOLDEN, "penn_cfg1.npz"))
+    kw = dict(m["head_cfg"]); kw["fc_channels"] = tuple(kw["fc_channels"])
+    hc = O.HeadCfg(**kw)
+    P = O.init_params(hc, seed=m["seed"])
+    tokens, seq_lens, steps, masks = O.synth_batch(m["Bv"], m["T"], m["Ptok"], hc.c_in, seed=m["seed"])
+    assert torch.equal(tokens.reshape(-1)[:64], torch.from_numpy(z["tokens_head"]))       # same synthetic stream
+    assert torch.equal(steps, torch.from_numpy(z["steps"])) and torch.equal(masks, torch.from_numpy(z["masks"]))
+    r = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.float32)
+    assert float((r["emb"] - torch.from_numpy(z["ref_emb"])).abs().max()) < 5e-5
+    assert float((r["e"] - torch.from_numpy(z["ref_e"])).abs().max()) < 1e-5
+    assert abs(float(r["loss"]) - float(z["ref_loss"])) / float(z["ref_loss"]) < 1e-5
+    gmax = max(v["absmax"] for v in m["grad_digest"].values())
+    tot = 0.0
+    for k, dg in m["grad_digest"].items():
+        g = r["grads"][k].double().reshape(-1)
+        if dg["l2"] < 1e-6 * gmax:                       # analytically-zero gradients: absolute floor
+            assert float(g.abs().max()) < 1e-5 * gmax, k
+            continue
+        assert abs(float(g.norm()) - dg["l2"]) / dg["l2"] < 1e-5, k
+        head = torch.tensor(dg["head"], dtype=torch.float64)
+        assert float((g[:6] - head).abs().max()) < 1e-5 * dg["absmax"] + 1e-9, k
+        tot += float(g.norm()) ** 2
+    # bf16 / tcgen05 at the same shape against the fp32 reference
+    rb = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16)
+    assert H.rel_l2(rb["e"], torch.from_numpy(z["ref_e"])) < 2e-2
+    assert abs(float(rb["loss"]) - float(z["ref_loss"])) / float(z["ref_loss"]) < 2e-2
+    keys = list(r["grads"].keys())
+    eb = H.rel_l2(H.grad_vector(rb["grads"], keys), H.grad_vector(r["grads"], keys))
+    print("cfg1 bf16-vs-fp32 concatenated gradient rel err", eb)
+    assert eb < 6e-2
+
+
+def test_eval_forward_golden():
+    """evaluate.py:58-62: no masks, project=False, L2 normalise, BatchNorm running stats, T != TRAIN.NUM_FRAMES."""
+    m = H.meta()["cases"]["tiny_eval"]
+    z = np.load(os.path.join(H.GOLDEN, "tiny_eval.npz"))
+    kw = dict(m["head_cfg"]); kw["fc_channels"] = tuple(kw["fc_channels"])
+    hc = O.HeadCfg(**kw)
+    P = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param:")}
+    B = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("buf:")}
+    r = H.run_cuda(hc, P, B, torch.from_numpy(z["tokens"]), None, None, None, dtype=torch.float32, training=False,
+                   project=False)
+    assert float((r["e"] - torch.from_numpy(z["ref_out"])).abs().max()) < 1e-5
+    for k, v in r["bufs"].items():          # eval mode must not touch the running statistics
+        assert torch.equal(v, B[k]), k
+
+
+def test_dropout_forward_backward_consistent_with_exported_masks():
+    """Training-mode dropout (FC_DROPOUT_RATE 0.1, 9 sites): feed the kernels' own masks to the oracle."""
+    m, hc, z, P, G, B = H.load_case("tiny_penn")
+    tokens, masks, seq_lens, steps = _inputs(z)
+    p, seed = 0.1, 987654321
+    r = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.float32, drop_p=p, seed=seed)
+    BV, T = tokens.shape[0], tokens.shape[1]
+    E, Hh = hc.n_entities, hc.hidden
+    R = BV * T * E
+
+    def mask(site, rows, cols):
+        t = torch.empty(rows, cols, device="cuda")
+        L.check(L.lib().mvf_dropout_mask(seed, site, rows, cols, p, L.ptr(t), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return t.cpu().double()
+
+    dm = {"fc0": mask(L.SITE_FC0, R, hc.pool_channels + E), "fc1": mask(L.SITE_FC0 + 1, R, hc.fc_channels[0]),
+          "pos": mask(L.SITE_POS, BV * E * T, Hh)}
+    for l in range(hc.n_layers):
+        dm[f"enc{l}_0"] = mask(L.SITE_ENC0 + 2 * l, BV * E * T, Hh).view(BV, E * T, Hh)
+        dm[f"enc{l}_1"] = mask(L.SITE_ENC0 + 2 * l + 1, BV * E * T, Hh).view(BV, E * T, Hh)
+    assert 0.85 < float((dm["pos"] > 0).double().mean()) < 0.95
+    o = H.run_oracle(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.float64, drop_masks=dm)
+    assert float((r["e"].double() - o["e"]).abs().max()) < 2e-5
+    assert abs(float(r["loss"]) - float(o["loss"])) / float(o["loss"]) < 1e-5
+    keys = list(P.keys())
+    assert H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(o["grads"], keys)) < 2e-5
+    # and dropout really changes the result
+    r0 = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.float32, drop_p=0.0)
+    assert H.rel_l2(r["e"], r0["e"]) > 1e-3

@@ -47,6 +47,9 @@ _PROTOS = {
     "mvf_version": (C.c_int, []),
     "mvf_last_error": (C.c_char_p, []),
     "mvf_has_tcgen05": (C.c_int, []),
+    "mvf_launch_count": (C.c_uint64, []),
+    "mvf_profile_enable": (C.c_int, [C.c_int]),
+    "mvf_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
     "mvf_num_params": (C.c_int, [_pd]),
     "mvf_param_info": (C.c_int, [_pd, C.c_int, C.c_char_p, _sz, C.POINTER(_i64), C.POINTER(_i64)]),
     "mvf_num_bn": (C.c_int, [_pd]),

@@ -25,7 +25,12 @@ const char* get_error();
     }                                                                                         \
   } while (0)
 
-#define MVF_CHECK_LAUNCH() MVF_CHECK_CUDA(cudaGetLastError())
+void count_launch();  // library-wide kernel launch counter (mvf_launch_count)
+#define MVF_CHECK_LAUNCH()                  \
+  do {                                      \
+    mvf::count_launch();                    \
+    MVF_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
 
 #define MVF_REQUIRE(cond, code, ...)  \
   do {                                \

@@ -24,6 +24,39 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 // ------------------------------------------------------------------------------------------------------------
+// launch counter + optional CUDA-event timing of the dominant kernels (bench.py's roofline numbers)
+// ------------------------------------------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+constexpr int PROF_TAGS = 6, PROF_CAP = 512;
+static int g_prof_on = 0;
+static cudaEvent_t g_prof_ev[PROF_TAGS][PROF_CAP][2];
+static int g_prof_n[PROF_TAGS] = {0};
+static bool g_prof_init[PROF_TAGS][PROF_CAP] = {{false}};
+struct ProfScope {
+  int tag, slot;
+  cudaStream_t st;
+  ProfScope(int tag_, cudaStream_t st_) : tag(tag_), slot(-1), st(st_) {
+    if (!g_prof_on || tag < 0 || tag >= PROF_TAGS || g_prof_n[tag] >= PROF_CAP) return;
+    slot = g_prof_n[tag];
+    if (!g_prof_init[tag][slot]) {
+      if (cudaEventCreate(&g_prof_ev[tag][slot][0]) != cudaSuccess || cudaEventCreate(&g_prof_ev[tag][slot][1]) != cudaSuccess) {
+        slot = -1;
+        return;
+      }
+      g_prof_init[tag][slot] = true;
+    }
+    cudaEventRecord(g_prof_ev[tag][slot][0], st);
+  }
+  ~ProfScope() {
+    if (slot < 0) return;
+    cudaEventRecord(g_prof_ev[tag][slot][1], st);
+    g_prof_n[tag] = slot + 1;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
 // parameter table (canonical order == reference state_dict order of embed.* then ssl_projection.*)
 // ------------------------------------------------------------------------------------------------------------
 struct ParamInfo {
@@ -463,11 +496,17 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
     if (ph == 0) {
       MVF_TRY(pack_head_weights(c));
       // a4: K|V projection of every patch token -- the dominant contraction
-      MVF_TRY(c.linear(A, m.F * d.P, 2 * d.SPC, d.C_in, tokens, d.C_in, c.S.p("w.kv"), c.S.ld("w.kv"), c.S.f("b.kv"),
-                       c.S.p("kv"), 2 * d.SPC));
+      {
+        ProfScope ps(0, st);
+        MVF_TRY(c.linear(A, m.F * d.P, 2 * d.SPC, d.C_in, tokens, d.C_in, c.S.p("w.kv"), c.S.ld("w.kv"), c.S.f("b.kv"),
+                         c.S.p("kv"), 2 * d.SPC));
+      }
       float* attn = c.S.f("attn");
-      MVF_TRY(xattn_pool_fwd(A, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], attn, c.S.p("h0"), m.ld0,
-                             d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, st));
+      {
+        ProfScope ps(2, st);
+        MVF_TRY(xattn_pool_fwd(A, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], attn, c.S.p("h0"), m.ld0,
+                               d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, st));
+      }
       if (attn_out)
         MVF_CHECK_CUDA(cudaMemcpyAsync(attn_out, attn, (size_t)m.F * d.E * d.P * 4, cudaMemcpyDeviceToDevice, st));
     }
@@ -678,12 +717,18 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
       // ---- entity cross-attention pooling and the K|V projection weight gradient ----
       const int o_spc = d.SPC;
       float* gbkv = c.G.f("g.b.kv");
-      MVF_TRY(xattn_pool_bwd(A, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], c.S.f("attn"), c.W.p("dh0"),
-                             m.ld0, d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, c.W.p("dkv"), c.G.f("g.Qs"), c.G.f("g.Qb"),
-                             gbkv, gbkv + o_spc, st));
+      {
+        ProfScope ps(3, st);
+        MVF_TRY(xattn_pool_bwd(A, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], c.S.f("attn"),
+                               c.W.p("dh0"), m.ld0, d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, c.W.p("dkv"), c.G.f("g.Qs"),
+                               c.G.f("g.Qb"), gbkv, gbkv + o_spc, st));
+      }
       // dW_kv = dKV^T X : 2*SPC x C_in outputs, K = frames*tokens -> split-K across the machine
-      MVF_TRY(c.gemm(MVF_F32, 0, 0, 2 * d.SPC, d.C_in, m.F * d.P, c.W.p("dkv"), 2 * d.SPC, tokens, d.C_in, c.G.f("g.w.kv"),
-                     c.Lg.find("g.w.kv")->ld, nullptr, nullptr, 0, MVF_GEMM_ACCUM, 0));
+      {
+        ProfScope ps(1, st);
+        MVF_TRY(c.gemm(MVF_F32, 0, 0, 2 * d.SPC, d.C_in, m.F * d.P, c.W.p("dkv"), 2 * d.SPC, tokens, d.C_in,
+                       c.G.f("g.w.kv"), c.Lg.find("g.w.kv")->ld, nullptr, nullptr, 0, MVF_GEMM_ACCUM, 0));
+      }
     }
   }
   return MVF_OK;
@@ -842,6 +887,22 @@ extern "C" {
 int mvf_version(void) { return MVF_ABI_VERSION; }
 const char* mvf_last_error(void) { return get_error(); }
 int mvf_has_tcgen05(void) { return tc_available() ? 1 : 0; }
+uint64_t mvf_launch_count(void) { return (uint64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+int mvf_profile_enable(int on) {
+  g_prof_on = on ? 1 : 0;
+  for (int t = 0; t < PROF_TAGS; ++t) g_prof_n[t] = 0;
+  return MVF_OK;
+}
+int mvf_profile_read(int tag, float* ms, int cap, int* n) {
+  MVF_REQUIRE(tag >= 0 && tag < PROF_TAGS && ms != nullptr && n != nullptr, MVF_ERR_BAD_ARG, "profile_read: bad argument");
+  int cnt = g_prof_n[tag] < cap ? g_prof_n[tag] : cap;
+  for (int i = 0; i < cnt; ++i) {
+    MVF_CHECK_CUDA(cudaEventSynchronize(g_prof_ev[tag][i][1]));
+    MVF_CHECK_CUDA(cudaEventElapsedTime(&ms[i], g_prof_ev[tag][i][0], g_prof_ev[tag][i][1]));
+  }
+  *n = cnt;
+  return MVF_OK;
+}
 
 int mvf_num_params(const mvf_head_desc* d) {
   Model m;

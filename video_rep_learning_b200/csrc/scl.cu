@@ -375,13 +375,16 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
   const int T2 = 2 * T;
   const bool batch = negative_type == MVF_NEG_BATCH_NOSELF;
   // Z extras
-  if (quirk)
+  if (quirk) {
     scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.masked, w.counts + 1,
                                                     nullptr, 1.f, nullptr, 1e-6f, 0, w.zext, nullptr);
-  if (batch)
+    MVF_CHECK_LAUNCH();
+  }
+  if (batch) {
     scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.valid, w.counts,
                                                     nullptr, 1.f, nullptr, 1.f, 1, w.zext, nullptr);
-  MVF_CHECK_LAUNCH();
+    MVF_CHECK_LAUNCH();
+  }
 
   const int pair_grid = Bv * 2 * cdiv(T, 8);
   scl_pair_kernel<0><<<pair_grid, 256, smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature,
@@ -395,17 +398,20 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
       // rows valid i, columns masked k: dE_i += c_i 1e-6 e^{l_ik} e_k / tau
       scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.masked,
                                                       w.counts + 1, w.c, 1.f, nullptr, 1e-6f, 0, nullptr, d_embs);
+      MVF_CHECK_LAUNCH();
       // rows masked k, columns valid i: dE_k += 1e-6 sum_i c_i e^{l_ik} e_i / tau
       scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.masked, w.counts + 1, w.valid,
                                                       w.counts, nullptr, 1e-6f, w.c, 1.f, 0, nullptr, d_embs);
+      MVF_CHECK_LAUNCH();
     }
     if (batch) {
       scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.valid, w.counts,
                                                       w.c, 1.f, nullptr, 1.f, 1, nullptr, d_embs);
+      MVF_CHECK_LAUNCH();
       scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.valid, w.counts,
                                                       nullptr, 1.f, w.c, 1.f, 1, nullptr, d_embs);
+      MVF_CHECK_LAUNCH();
     }
-    MVF_CHECK_LAUNCH();
   }
   return MVF_OK;
 }
