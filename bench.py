@@ -254,60 +254,64 @@ def run_ours(args):
     value = world * Bv / (ms_step / 1e3)
     final_loss = float(loss.item())
 
-    # ---- timed region 2: end to end from pinned host memory through the public API --------------------------
-    n_host = 2
-    host_tokens = [torch.empty(BV, T, P, C_in, dtype=torch.bfloat16).pin_memory() for _ in range(n_host)]
-    for h in host_tokens:
-        h.copy_(tokens_dev.cpu())
-    host_meta = [(seq_lens.pin_memory(), steps.pin_memory(), masks.pin_memory()) for _ in range(n_host)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    dev_tok = [torch.empty_like(tokens_dev) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    e2e_value = e2e_ms = None
+    h2d = d2h = 0
+    k2 = 0
+    if not args.no_e2e:
+        # ---- timed region 2: end to end from pinned host memory through the public API --------------------------
+        n_host = 2
+        host_tokens = [torch.empty(BV, T, P, C_in, dtype=torch.bfloat16).pin_memory() for _ in range(n_host)]
+        for h in host_tokens:
+            h.copy_(tokens_dev.cpu())
+        host_meta = [(seq_lens.pin_memory(), steps.pin_memory(), masks.pin_memory()) for _ in range(n_host)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        dev_tok = [torch.empty_like(tokens_dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def prefetch(i):
-        slot = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            dev_tok[slot].copy_(host_tokens[i % n_host], non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    def e2e_loop(k):
-        losses = []
-        for c in consumed:
-            c.record()
-        prefetch(0)
-        for i in range(k):
+        def prefetch(i):
             slot = i % 2
-            if i + 1 < k:
-                prefetch(i + 1)
-            torch.cuda.current_stream().wait_event(ready[slot])
-            sl, st_, mk = host_meta[i % n_host]
-            sl_d, st_d, mk_d = sl.to(dev, non_blocking=True), st_.to(dev, non_blocking=True), mk.to(dev, non_blocking=True)
-            for p in params:
-                p.grad = None
-            embs = model.forward_tokens(dev_tok[slot], video_masks=mk_d, project=True)
-            loss = algo.compute_sequence_loss(embs.view(Bv, 2, T, -1), sl_d, st_d, mk_d)["loss"]
-            loss.backward()
-            consumed[slot].record()
-            losses.append(loss.item())            # D2H read of the step's result
-        return losses
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                dev_tok[slot].copy_(host_tokens[i % n_host], non_blocking=True)
+                ready[slot].record(copy_stream)
 
-    e2e_loop(2)
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k2 = max(3, min(args.steps, 10))
-    e0.record()
-    e2e_loop(k2)
-    e1.record()
-    sync_all()
-    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t2.item()) / k2
-    e2e_value = world * Bv / (e2e_ms / 1e3)
-    h2d = tokens_dev.numel() * 2 + seq_lens.numel() * 8 + steps.numel() * 8 + masks.numel() * 4
-    d2h = 4
+        def e2e_loop(k):
+            losses = []
+            for c in consumed:
+                c.record()
+            prefetch(0)
+            for i in range(k):
+                slot = i % 2
+                if i + 1 < k:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[slot])
+                sl, st_, mk = host_meta[i % n_host]
+                sl_d, st_d, mk_d = sl.to(dev, non_blocking=True), st_.to(dev, non_blocking=True), mk.to(dev, non_blocking=True)
+                for p in params:
+                    p.grad = None
+                embs = model.forward_tokens(dev_tok[slot], video_masks=mk_d, project=True)
+                loss = algo.compute_sequence_loss(embs.view(Bv, 2, T, -1), sl_d, st_d, mk_d)["loss"]
+                loss.backward()
+                consumed[slot].record()
+                losses.append(loss.item())            # D2H read of the step's result
+            return losses
+
+        e2e_loop(2)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k2 = max(3, min(args.steps, 10))
+        e0.record()
+        e2e_loop(k2)
+        e1.record()
+        sync_all()
+        t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2.item()) / k2
+        e2e_value = world * Bv / (e2e_ms / 1e3)
+        h2d = tokens_dev.numel() * 2 + seq_lens.numel() * 8 + steps.numel() * 8 + masks.numel() * 4
+        d2h = 4
 
     if rank == 0:
         fl = flops_per_video()
@@ -336,7 +340,7 @@ def run_ours(args):
                                          xattn_bwd=(statistics.mean(prof["xattn_bwd"]) / ms_step) if prof["xattn_bwd"] else None)
         whole = fl["total"] * Bv * world / (ms_step * 1e-3) / 1e12
         cpu = None
-        if world == 1 or True:
+        if not args.no_cpu:
             threads = os.cpu_count() or 1
             sample = 2
             times = cpu_step_time(sample, 2, threads)
@@ -353,8 +357,9 @@ def run_ours(args):
                    whole_step_tflops=whole, whole_step_frac_of_peak=whole / peaks["tflops"],
                    gflop_per_video=fl["total"] / 1e9, loss=final_loss,
                    roofline=roof, cpu_baseline=cpu,
-                   e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                            steps=k2, note="pinned host tokens -> HBM on a copy stream (double buffered) + loss.item() per step"),
+                   e2e=None if args.no_e2e else dict(
+                       value=e2e_value, unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=k2,
+                       note="pinned host tokens -> HBM on a copy stream (double buffered) + loss.item() per step"),
                    gpu_launches=launches, clocks=clk)
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -364,9 +369,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-to-device leg")
+    ap.add_argument("--no-cpu", action="store_true", help="profiling runs: skip the CPU baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

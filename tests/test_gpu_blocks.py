@@ -33,11 +33,11 @@ def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype):
     (ent * d_ent).sum().backward()
 
     dev = "cuda"
-    kv_d = kv.to(dev)
+    kv_d, qs_d, qb_d = kv.to(dev), q_s.to(dev), q_b.to(dev)      # keep references: raw pointers cross the C ABI
     attn = torch.empty(F, E, P, device=dev)
     out = torch.full((F * E, ld), float("nan"), dtype=dtype, device=dev)
     md = L.MVF_BF16 if dtype == torch.bfloat16 else L.MVF_F32
-    L.check(L.lib().mvf_xattn_pool_fwd(md, F, P, E, SPC, L.ptr(kv_d), L.ptr(q_s.to(dev)), L.ptr(q_b.to(dev)), L.ptr(attn),
+    L.check(L.lib().mvf_xattn_pool_fwd(md, F, P, E, SPC, L.ptr(kv_d), L.ptr(qs_d), L.ptr(qb_d), L.ptr(attn),
                                        L.ptr(out), ld, one_hot, 0.0, 0, _stream()))
     torch.cuda.synchronize()
     tol = 1e-5 if dtype == torch.float32 else 1e-2
@@ -50,11 +50,12 @@ def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype):
 
     d_in = torch.zeros(F * E, ld, dtype=dtype)
     d_in[:, :SPC] = d_ent.view(F * E, SPC).to(dtype)
+    d_in_d = d_in.to(dev)
     d_kv = torch.empty_like(kv_d)
     dqs, dqb = torch.zeros(E, SPC, device=dev), torch.zeros(SPC, device=dev)
     dbk, dbv = torch.zeros(SPC, device=dev), torch.zeros(SPC, device=dev)
-    L.check(L.lib().mvf_xattn_pool_bwd(md, F, P, E, SPC, L.ptr(kv_d), L.ptr(q_s.to(dev)), L.ptr(q_b.to(dev)), L.ptr(attn),
-                                       L.ptr(d_in.to(dev)), ld, one_hot, 0.0, 0, L.ptr(d_kv), L.ptr(dqs), L.ptr(dqb),
+    L.check(L.lib().mvf_xattn_pool_bwd(md, F, P, E, SPC, L.ptr(kv_d), L.ptr(qs_d), L.ptr(qb_d), L.ptr(attn),
+                                       L.ptr(d_in_d), ld, one_hot, 0.0, 0, L.ptr(d_kv), L.ptr(dqs), L.ptr(dqb),
                                        L.ptr(dbk), L.ptr(dbv), _stream()))
     torch.cuda.synchronize()
     # with bf16 the incoming gradient was rounded too: compare against the reference of the rounded d_ent
@@ -102,8 +103,9 @@ def test_temporal_attention_fwd_bwd(B, S, heads, dk, masked, dtype):
     assert float((ctx.float().cpu().double() - ctx_ref.detach()).abs().max()) < tol * max(1.0, float(ctx_ref.abs().max()))
     d_qkv = torch.full_like(qkv_d, float("nan"))
     delta = torch.empty(B, heads, S, device=dev)
+    d_ctx_d = d_ctx.to(dev)
     L.check(L.lib().mvf_attention_bwd(md, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse),
-                                      L.ptr(d_ctx.to(dev)), L.ptr(d_qkv), L.ptr(delta), _stream()))
+                                      L.ptr(d_ctx_d), L.ptr(d_qkv), L.ptr(delta), _stream()))
     torch.cuda.synchronize()
     want = x.grad.reshape(B * S, 3 * Hd)
     assert H.rel_l2(d_qkv.float().cpu(), want) < (2e-5 if dtype == torch.float32 else 3e-2)

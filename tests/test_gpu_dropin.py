@@ -94,6 +94,8 @@ def test_separate_modules_equal_fused_node():
     emb = model.embed(nchw, video_masks=masks)
     sep = torch.nn.functional.normalize(model.ssl_projection(emb), dim=-1)
     (sep * w).sum().backward()
+    gmax = max(float(g.abs().max()) for g in gs.values())
     for k, v in model.named_parameters():
         if v.grad is not None and k in gs:
-            assert float((v.grad - gs[k]).abs().max()) <= 2e-5 * float(gs[k].abs().max()) + 1e-7, k
+            # analytically-zero gradients (biases in front of BatchNorm) are rounding noise: absolute floor
+            assert float((v.grad - gs[k]).abs().max()) <= 2e-5 * float(gs[k].abs().max()) + 1e-5 * gmax, k
