@@ -175,13 +175,15 @@ int mvf_gemm(int backend, int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor,
              const void* relu_src, int64_t ld_relu, int flags, int split_k, mvf_stream_t stream);
 
 /* a3-a5 alone (mvformer.py:243-266, 352-414; utils.py:11-44): kv [F*P, 2*SPC] (K | V), q_s [E,SPC],
- * q_b [SPC] -> attn [F,E,P] fp32, ent [F*E, ld_ent] (dtype), one-hot columns appended when one_hot = 1. */
+ * q_b [SPC] -> attn [F,E,P] fp32, ent [F*E, ld_ent] (dtype), one-hot columns appended when one_hot = 1.
+ * ent_f32 (optional, [F*E, SPC] fp32): pooled entities before dropout; when given for bf16 and E <= 4 the
+ * single-pass kernels run (each K|V row read once); backward needs the same buffer back. */
 int mvf_xattn_pool_fwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t SPC, const void* kv, const float* q_s,
-                       const float* q_b, float* attn, void* ent, int64_t ld_ent, int one_hot, float drop_p,
-                       uint64_t seed, mvf_stream_t stream);
+                       const float* q_b, float* attn, void* ent, int64_t ld_ent, float* ent_f32, int one_hot,
+                       float drop_p, uint64_t seed, mvf_stream_t stream);
 int mvf_xattn_pool_bwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t SPC, const void* kv, const float* q_s,
-                       const float* q_b, const float* attn, const void* d_ent, int64_t ld_ent, int one_hot,
-                       float drop_p, uint64_t seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk,
+                       const float* q_b, const float* attn, const void* d_ent, int64_t ld_ent, const float* ent_f32,
+                       int one_hot, float drop_p, uint64_t seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk,
                        float* d_bv, mvf_stream_t stream);
 
 /* a5/a8 temporal self-attention core (utils.py:11-44 with the [B,1,1,S] key mask): qkv [B*S, 3*H]

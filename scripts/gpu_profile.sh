@@ -8,7 +8,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
 echo "launch list exit $?"
 for k in kv_fwd kv_dw xattn_fwd xattn_bwd; do
   pat="gemm_tc_kernel"; skip=1
-  case $k in xattn_fwd) pat="xattn_fwd_kernel";; xattn_bwd) pat="xattn_bwd_kernel";; esac
+  case $k in xattn_fwd) pat="xattn_fwd";; xattn_bwd) pat="xattn_bwd";; esac
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$pat -s $skip -c 1 -f -o gpurun_out/prof_$k \
       python scripts/prof_kernels.py $k > gpurun_out/prof_$k.log 2>&1
   echo "$k exit $?"

@@ -28,13 +28,14 @@ elif which in ("xattn_fwd", "xattn_bwd"):
     qb = torch.zeros(SPC, device="cuda")
     attn = torch.empty(F, E, P, device="cuda")
     ent = torch.empty(F * E, 392, dtype=torch.bfloat16, device="cuda")
+    ent32 = torch.empty(F * E, SPC, device="cuda")
     for _ in range(3):
-        L.check(lib.mvf_xattn_pool_fwd(1, F, P, E, SPC, L.ptr(KV), L.ptr(qs), L.ptr(qb), L.ptr(attn), L.ptr(ent), 392, 1, 0.1, 7, st))
+        L.check(lib.mvf_xattn_pool_fwd(1, F, P, E, SPC, L.ptr(KV), L.ptr(qs), L.ptr(qb), L.ptr(attn), L.ptr(ent), 392, L.ptr(ent32), 1, 0.1, 7, st))
     if which == "xattn_bwd":
         dkv = torch.empty_like(KV)
         dq, dqb, dbk, dbv = torch.zeros(E, SPC, device="cuda"), torch.zeros(SPC, device="cuda"), torch.zeros(SPC, device="cuda"), torch.zeros(SPC, device="cuda")
         for _ in range(3):
-            L.check(lib.mvf_xattn_pool_bwd(1, F, P, E, SPC, L.ptr(KV), L.ptr(qs), L.ptr(qb), L.ptr(attn), L.ptr(ent), 392, 1, 0.1, 7,
+            L.check(lib.mvf_xattn_pool_bwd(1, F, P, E, SPC, L.ptr(KV), L.ptr(qs), L.ptr(qb), L.ptr(attn), L.ptr(ent), 392, L.ptr(ent32), 1, 0.1, 7,
                                            L.ptr(dkv), L.ptr(dq), L.ptr(dqb), L.ptr(dbk), L.ptr(dbv), st))
 torch.cuda.synchronize()
 print("done", which)

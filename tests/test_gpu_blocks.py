@@ -14,9 +14,13 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-@pytest.mark.parametrize("F,P,E,SPC,one_hot", [(5, 16, 3, 32, 1), (3, 196, 3, 384, 1), (2, 49, 6, 64, 0), (2, 30, 16, 96, 1)])
+@pytest.mark.parametrize("F,P,E,SPC,one_hot", [(5, 16, 3, 32, 1), (3, 196, 3, 384, 1), (2, 49, 6, 64, 0), (2, 30, 16, 96, 1),
+                                                (4, 50, 4, 128, 1), (3, 9, 1, 256, 0), (2, 784, 2, 384, 1)])
+@pytest.mark.parametrize("single_pass", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype):
+def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype, single_pass):
+    """single_pass=True hands the fp32 pooled-entity buffer to the kernels, which selects the one-pass bf16 kernels
+    (E <= 4); otherwise (and for fp32 / E > 4) the generic kernels run."""
     g = torch.Generator().manual_seed(F * P + E)
     kv = torch.randn(F * P, 2 * SPC, generator=g).to(dtype)
     q_s = torch.randn(E, SPC, generator=g) * 0.3
@@ -36,9 +40,10 @@ def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype):
     kv_d, qs_d, qb_d = kv.to(dev), q_s.to(dev), q_b.to(dev)      # keep references: raw pointers cross the C ABI
     attn = torch.empty(F, E, P, device=dev)
     out = torch.full((F * E, ld), float("nan"), dtype=dtype, device=dev)
+    ent32 = torch.full((F * E, SPC), float("nan"), device=dev) if single_pass else None
     md = L.MVF_BF16 if dtype == torch.bfloat16 else L.MVF_F32
     L.check(L.lib().mvf_xattn_pool_fwd(md, F, P, E, SPC, L.ptr(kv_d), L.ptr(qs_d), L.ptr(qb_d), L.ptr(attn),
-                                       L.ptr(out), ld, one_hot, 0.0, 0, _stream()))
+                                       L.ptr(out), ld, L.ptr(ent32), one_hot, 0.0, 0, _stream()))
     torch.cuda.synchronize()
     tol = 1e-5 if dtype == torch.float32 else 1e-2
     assert float((attn.cpu().double() - A.detach()).abs().max()) < 1e-5
@@ -47,6 +52,8 @@ def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype):
     if one_hot:
         assert torch.equal(got[..., SPC:SPC + E], torch.eye(E).expand(F, E, E))
     assert float(got[..., W:].abs().max()) == 0.0 if ld > W else True
+    if single_pass and dtype == torch.bfloat16 and E <= 4:
+        assert float((ent32.cpu().double().view(F, E, SPC) - ent.detach()).abs().max()) < 1e-5
 
     d_in = torch.zeros(F * E, ld, dtype=dtype)
     d_in[:, :SPC] = d_ent.view(F * E, SPC).to(dtype)
@@ -55,7 +62,7 @@ def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype):
     dqs, dqb = torch.zeros(E, SPC, device=dev), torch.zeros(SPC, device=dev)
     dbk, dbv = torch.zeros(SPC, device=dev), torch.zeros(SPC, device=dev)
     L.check(L.lib().mvf_xattn_pool_bwd(md, F, P, E, SPC, L.ptr(kv_d), L.ptr(qs_d), L.ptr(qb_d), L.ptr(attn),
-                                       L.ptr(d_in_d), ld, one_hot, 0.0, 0, L.ptr(d_kv), L.ptr(dqs), L.ptr(dqb),
+                                       L.ptr(d_in_d), ld, L.ptr(ent32), one_hot, 0.0, 0, L.ptr(d_kv), L.ptr(dqs), L.ptr(dqb),
                                        L.ptr(dbk), L.ptr(dbv), _stream()))
     torch.cuda.synchronize()
     # with bf16 the incoming gradient was rounded too: compare against the reference of the rounded d_ent

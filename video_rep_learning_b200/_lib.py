@@ -71,8 +71,8 @@ _PROTOS = {
     "mvf_scl_fwd_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "mvf_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
                            _vp, _vp, _i64, C.c_int, C.c_int, _vp]),
-    "mvf_xattn_pool_fwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int, _f32, _u64, _vp]),
-    "mvf_xattn_pool_bwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int, _f32, _u64,
+    "mvf_xattn_pool_fwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_int, _f32, _u64, _vp]),
+    "mvf_xattn_pool_bwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_int, _f32, _u64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvf_attention_fwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mvf_attention_bwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -33,7 +33,7 @@ int pack_params(const PackEntry* entries, int n, cudaStream_t st) {
     PackTable tab;
     tab.n = (n - base < PACK_CHUNK) ? n - base : PACK_CHUNK;
     for (int i = 0; i < tab.n; ++i) tab.e[i] = entries[base + i];
-    pack_kernel<<<dim3(32, tab.n), 256, 0, st>>>(tab);
+    pack_kernel<<<dim3(148, tab.n), 256, 0, st>>>(tab);
     MVF_CHECK_LAUNCH();
   }
   return MVF_OK;
@@ -53,7 +53,7 @@ int unpack_grads(const UnpackEntry* entries, int n, float scale, cudaStream_t st
     UnpackTable tab;
     tab.n = (n - base < PACK_CHUNK) ? n - base : PACK_CHUNK;
     for (int i = 0; i < tab.n; ++i) tab.e[i] = entries[base + i];
-    unpack_kernel<<<dim3(32, tab.n), 256, 0, st>>>(tab, scale);
+    unpack_kernel<<<dim3(148, tab.n), 256, 0, st>>>(tab, scale);
     MVF_CHECK_LAUNCH();
   }
   return MVF_OK;
@@ -189,6 +189,10 @@ int ln_fwd(int dtype_out, const float* z_in, const float* o, float* z_out, void*
 }
 
 // dz_out = dz_in + rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dr*gamma; dgamma += dr*xhat; dbeta += dr
+// One warp per row, each lane owns VPL = H/32 fixed columns: the row is read once into registers, the per-column
+// gamma/beta gradients accumulate in registers across the warp's rows, then warps are merged through shared memory
+// and one atomic per column per CTA reaches the gradient buffer.
+template <int VPL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dr, const float* __restrict__ z,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ dz_in,
@@ -196,30 +200,42 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      float* __restrict__ dbeta, int64_t rows, int H) {
   extern __shared__ float acc[];  // [8 warps][2][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* ag = acc + (size_t)warp * 2 * H;
-  float* ab = ag + H;
-  for (int c = lane; c < H; c += 32) { ag[c] = 0.f; ab[c] = 0.f; }
+  float gam[VPL], ag[VPL], ab[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    gam[k] = gamma[lane + 32 * k];
+    ag[k] = 0.f;
+    ab[k] = 0.f;
+  }
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
     const float m = mean[row], rs = rstd[row];
+    float d[VPL], xh[VPL];
     float s1 = 0.f, s2 = 0.f;
-    for (int c = lane; c < H; c += 32) {
-      float d = dr[row * H + c];
-      float xh = (z[row * H + c] - m) * rs;
-      float g = d * gamma[c];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = lane + 32 * k;
+      d[k] = dr[row * H + c];
+      xh[k] = (z[row * H + c] - m) * rs;
+      const float g = d[k] * gam[k];
       s1 += g;
-      s2 += g * xh;
-      ag[c] += d * xh;
-      ab[c] += d;
+      s2 += g * xh[k];
+      ag[k] += d[k] * xh[k];
+      ab[k] += d[k];
     }
     s1 = warp_sum(s1) / (float)H;
     s2 = warp_sum(s2) / (float)H;
-    for (int c = lane; c < H; c += 32) {
-      float d = dr[row * H + c];
-      float xh = (z[row * H + c] - m) * rs;
-      float v = rs * (d * gamma[c] - s1 - xh * s2);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = lane + 32 * k;
+      float v = rs * (d[k] * gam[k] - s1 - xh[k] * s2);
       if (dz_in) v += dz_in[row * H + c];
       dz_out[row * H + c] = v;
     }
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    acc[(size_t)warp * 2 * H + lane + 32 * k] = ag[k];
+    acc[(size_t)warp * 2 * H + H + lane + 32 * k] = ab[k];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
@@ -236,12 +252,28 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 
 int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd, const float* gamma,
            const float* dz_in, float* dz_out, float* dgamma, float* dbeta, int64_t rows, int H, cudaStream_t st) {
-  int grid = cdiv(rows, 8 * 4);
-  if (grid > 296) grid = 296;
+  int grid = cdiv(rows, 8 * 2);
+  if (grid > 592) grid = 592;
   if (grid < 1) grid = 1;
   size_t smem = (size_t)8 * 2 * H * sizeof(float);
-  MVF_REQUIRE(smem <= 48 * 1024, MVF_ERR_UNSUPPORTED, "ln_bwd: hidden size %d too large", H);
-  ln_bwd_kernel<<<grid, 256, smem, st>>>(dr, z, mean, rstd, gamma, dz_in, dz_out, dgamma, dbeta, rows, H);
+  MVF_REQUIRE(H % 32 == 0 && H <= 1024 && smem <= 48 * 1024, MVF_ERR_UNSUPPORTED,
+              "ln_bwd: hidden size %d must be a multiple of 32 and <= 768", H);
+#define MVF_LNB(V) ln_bwd_kernel<V><<<grid, 256, smem, st>>>(dr, z, mean, rstd, gamma, dz_in, dz_out, dgamma, dbeta, rows, H)
+  switch (H / 32) {
+    case 1: MVF_LNB(1); break;
+    case 2: MVF_LNB(2); break;
+    case 3: MVF_LNB(3); break;
+    case 4: MVF_LNB(4); break;
+    case 6: MVF_LNB(6); break;
+    case 8: MVF_LNB(8); break;
+    case 12: MVF_LNB(12); break;
+    case 16: MVF_LNB(16); break;
+    case 24: MVF_LNB(24); break;
+    default:
+      set_error("ln_bwd: hidden size %d not instantiated (32,64,96,128,192,256,384,512,768)", H);
+      return MVF_ERR_UNSUPPORTED;
+  }
+#undef MVF_LNB
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }

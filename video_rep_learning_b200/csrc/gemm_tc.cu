@@ -443,7 +443,14 @@ int gemm_tc(int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64
   MVF_REQUIRE(tc_available(), MVF_ERR_UNSUPPORTED, "tcgen05 GEMM requested but the device is not sm_100");
   MVF_REQUIRE(K > 0, MVF_ERR_BAD_ARG, "gemm_tc: K must be positive");
   MVF_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), MVF_ERR_BAD_ARG, "gemm_tc: dims exceed int32");
-  const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  // small problems: trade tile size for CTA count so that the 148 SMs are not left idle
+  {
+    const int kb_est = cdiv(K, BLOCK_K);
+    int sk_est = split_k > 0 ? split_k : ((dtype_c == MVF_F32 && !(flags & (MVF_GEMM_RELU | MVF_GEMM_RELUMASK)) && kb_est >= 16) ? kb_est / 8 : 1);
+    if (sk_est < 1) sk_est = 1;
+    while (bn > 64 && (int64_t)cdiv(M, BLOCK_M) * cdiv(N, bn) * sk_est < g_num_sms) bn >>= 1;
+  }
   Params p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.tiles_m = cdiv(M, BLOCK_M);

@@ -234,6 +234,7 @@ static void head_save_layout(const Model& m, Layout& L) {
   L.add("kv", m.F * d.P, 2 * d.SPC, A);
   L.add("attn", m.F * d.E, d.P, RT_F32);
   L.add("h0", m.R, m.W0, A, m.ld0);
+  L.add("ent32", m.R, d.SPC, RT_F32);
   for (int i = 0; i < d.n_fc; ++i) {
     L.add(fname(i, "x"), m.R, d.fc[i], RT_F32);
     L.add(fname(i, "sum"), 1, 2 * d.fc[i], RT_F64);
@@ -505,7 +506,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       {
         ProfScope ps(2, st);
         MVF_TRY(xattn_pool_fwd(A, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], attn, c.S.p("h0"), m.ld0,
-                               d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, st));
+                               c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, st));
       }
       if (attn_out)
         MVF_CHECK_CUDA(cudaMemcpyAsync(attn_out, attn, (size_t)m.F * d.E * d.P * 4, cudaMemcpyDeviceToDevice, st));
@@ -720,8 +721,8 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
       {
         ProfScope ps(3, st);
         MVF_TRY(xattn_pool_bwd(A, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], c.S.f("attn"),
-                               c.W.p("dh0"), m.ld0, d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, c.W.p("dkv"), c.G.f("g.Qs"),
-                               c.G.f("g.Qb"), gbkv, gbkv + o_spc, st));
+                               c.W.p("dh0"), m.ld0, c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, c.W.p("dkv"),
+                               c.G.f("g.Qs"), c.G.f("g.Qb"), gbkv, gbkv + o_spc, st));
       }
       // dW_kv = dKV^T X : 2*SPC x C_in outputs, K = frames*tokens -> split-K across the machine
       {
@@ -1069,19 +1070,20 @@ int mvf_gemm(int backend, int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor,
 }
 
 int mvf_xattn_pool_fwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t SPC, const void* kv, const float* q_s,
-                       const float* q_b, float* attn, void* ent, int64_t ld_ent, int one_hot, float drop_p, uint64_t seed,
-                       mvf_stream_t stream) {
+                       const float* q_b, float* attn, void* ent, int64_t ld_ent, float* ent_f32, int one_hot, float drop_p,
+                       uint64_t seed, mvf_stream_t stream) {
   MVF_REQUIRE(kv && q_s && q_b && ent, MVF_ERR_BAD_ARG, "xattn fwd: null pointer");
-  return xattn_pool_fwd(dtype, F, P, E, SPC, kv, q_s, q_b, attn, ent, ld_ent, one_hot, drop_p, seed, (cudaStream_t)stream);
+  return xattn_pool_fwd(dtype, F, P, E, SPC, kv, q_s, q_b, attn, ent, ld_ent, ent_f32, one_hot, drop_p, seed,
+                        (cudaStream_t)stream);
 }
 int mvf_xattn_pool_bwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t SPC, const void* kv, const float* q_s,
-                       const float* q_b, const float* attn, const void* d_ent, int64_t ld_ent, int one_hot, float drop_p,
-                       uint64_t seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv,
-                       mvf_stream_t stream) {
+                       const float* q_b, const float* attn, const void* d_ent, int64_t ld_ent, const float* ent_f32,
+                       int one_hot, float drop_p, uint64_t seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk,
+                       float* d_bv, mvf_stream_t stream) {
   MVF_REQUIRE(kv && q_s && q_b && attn && d_ent && d_kv && d_q_s && d_q_b && d_bk && d_bv, MVF_ERR_BAD_ARG,
               "xattn bwd: null pointer");
-  return xattn_pool_bwd(dtype, F, P, E, SPC, kv, q_s, q_b, attn, d_ent, ld_ent, one_hot, drop_p, seed, d_kv, d_q_s, d_q_b,
-                        d_bk, d_bv, (cudaStream_t)stream);
+  return xattn_pool_bwd(dtype, F, P, E, SPC, kv, q_s, q_b, attn, d_ent, ld_ent, ent_f32, one_hot, drop_p, seed, d_kv, d_q_s,
+                        d_q_b, d_bk, d_bv, (cudaStream_t)stream);
 }
 
 int mvf_attention_fwd(int dtype, int32_t B, int32_t S, int32_t heads, int32_t dk, const void* qkv, const float* keymask,

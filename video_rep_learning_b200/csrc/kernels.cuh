@@ -78,11 +78,14 @@ int l2norm_bwd(const float* dy, const float* y, const float* norm, void* dx, int
 int dropout_mask_export(uint64_t seed, int site, int64_t rows, int64_t cols, float p, float* out, cudaStream_t st);
 
 // ---- xattn.cu ----------------------------------------------------------------------------------------------
+// ent32 (optional, fp32 [F*E, SPC]): the pooled entities before dropout; when given (and bf16, E <= 4) the single-pass
+// kernels are used -- backward needs it for rowdot[e] = <dEnt[e], ent[e]>.
 int xattn_pool_fwd(int dtype, int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b,
-                   float* attn, void* ent, int64_t ld_ent, int one_hot, float drop_p, uint64_t seed, cudaStream_t st);
+                   float* attn, void* ent, int64_t ld_ent, float* ent32, int one_hot, float drop_p, uint64_t seed,
+                   cudaStream_t st);
 int xattn_pool_bwd(int dtype, int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b,
-                   const float* attn, const void* d_ent, int64_t ld_ent, int one_hot, float drop_p, uint64_t seed,
-                   void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv, cudaStream_t st);
+                   const float* attn, const void* d_ent, int64_t ld_ent, const float* ent32, int one_hot, float drop_p,
+                   uint64_t seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv, cudaStream_t st);
 
 // ---- attention.cu --------------------------------------------------------------------------------------------
 int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, void* ctx,

@@ -105,6 +105,38 @@ __global__ void scl_prep_kernel(const float* __restrict__ masks, int N, SclWs w,
   }
 }
 
+// 4-way unrolled dot product of two shared-memory vectors (16-byte aligned, D % 4 == 0).  Row i vs row j and row j vs
+// row i go through the same sequence of operations, so l_ij == l_ji bit for bit.
+__device__ __forceinline__ float dot4(const float* __restrict__ a, const float* __restrict__ b, int D) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+  for (int d = 0; d < D; d += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(a + d);
+    const float4 y = *reinterpret_cast<const float4*>(b + d);
+    s0 = fmaf(x.x, y.x, s0);
+    s1 = fmaf(x.y, y.y, s1);
+    s2 = fmaf(x.z, y.z, s2);
+    s3 = fmaf(x.w, y.w, s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+// cooperative, 16-byte vectorised load of up to 32 embedding rows into a padded shared-memory tile
+__device__ __forceinline__ void load_tile(float* tile, int Dp, const float* __restrict__ embs, int D, const int* idx_list,
+                                          int first, int count_limit, int base_row) {
+  const int D4 = D >> 2;
+  for (int i = threadIdx.x; i < 32 * D4; i += blockDim.x) {
+    const int jj = i / D4, d4 = i - jj * D4;
+    const int cs = first + jj;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cs < count_limit) {
+      const int64_t row = idx_list ? (int64_t)idx_list[cs] : (int64_t)(base_row + cs);
+      v = *reinterpret_cast<const float4*>(embs + row * D + 4 * d4);
+    }
+    *reinterpret_cast<float4*>(tile + jj * Dp + 4 * d4) = v;
+  }
+}
+
 // ---- generic cross pass -------------------------------------------------------------------------------------------
 // rows r in row list, columns k in col list:  e = cc_k * [not excluded] * exp(<e_r, e_k>/tau)
 //   sum_out[r] += sum_k e                        (if sum_out)
@@ -115,8 +147,8 @@ scl_cross_kernel(const float* __restrict__ embs, int D, int T2, float inv_tau_di
                  const int* __restrict__ row_cnt, const int* __restrict__ col_idx, const int* __restrict__ col_cnt,
                  const float* __restrict__ rc_arr, float rc_const, const float* __restrict__ cc_arr, float cc_const,
                  int excl_same_video, float* __restrict__ sum_out, float* __restrict__ vec_out) {
-  extern __shared__ float sm[];
-  const int Dp = D + 1;
+  extern __shared__ __align__(16) float sm[];
+  const int Dp = D + 4;
   float* tile = sm;                 // [32][Dp]
   float* er = tile + 32 * Dp;       // [8][D]
   float* ccs = er + 8 * D;          // [32]
@@ -133,13 +165,10 @@ scl_cross_kernel(const float* __restrict__ embs, int D, int T2, float inv_tau_di
 #pragma unroll
   for (int k = 0; k < SCL_MAXD / 32; ++k) acc[k] = 0.f;
   float rsum = 0.f;
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
+  // columns are split over blockIdx.y (outputs are accumulated with atomics)
+  for (int c0 = blockIdx.y * 32; c0 < ncols; c0 += 32 * gridDim.y) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 32 * D; idx += blockDim.x) {
-      const int jj = idx / D, d = idx % D;
-      const int cs = c0 + jj;
-      tile[jj * Dp + d] = cs < ncols ? embs[(int64_t)col_idx[cs] * D + d] : 0.f;
-    }
+    load_tile(tile, Dp, embs, D, col_idx, c0, ncols, 0);
     if (threadIdx.x < 32) {
       const int cs = c0 + threadIdx.x;
       if (cs < ncols) {
@@ -152,8 +181,7 @@ scl_cross_kernel(const float* __restrict__ embs, int D, int T2, float inv_tau_di
       }
     }
     __syncthreads();
-    float dot = 0.f;
-    for (int d = 0; d < D; ++d) dot = fmaf(er[warp * D + d], tile[lane * Dp + d], dot);
+    const float dot = dot4(er + warp * D, tile + lane * Dp, D);
     float wgt = ccs[lane];
     if (excl_same_video && cvid[lane] == rvid) wgt = 0.f;
     const float ex = (wgt != 0.f && ractive) ? wgt * expf(__fdiv_rn(dot, inv_tau_div)) : 0.f;
@@ -173,13 +201,13 @@ scl_cross_kernel(const float* __restrict__ embs, int D, int T2, float inv_tau_di
   }
   rsum = warp_sum(rsum);
   if (!ractive) return;
-  if (sum_out && lane == 0) sum_out[r] += rsum;
+  if (sum_out && lane == 0 && rsum != 0.f) atomicAdd(sum_out + r, rsum);
   if (vec_out) {
     const float rc = rc_const * (rc_arr ? rc_arr[r] : 1.f);
 #pragma unroll
     for (int k = 0; k < SCL_MAXD / 32; ++k) {
       const int d = lane + 32 * k;
-      if (d < D) vec_out[(int64_t)r * D + d] += __fdiv_rn(rc * acc[k], inv_tau_div);
+      if (d < D && acc[k] != 0.f) atomicAdd(vec_out + (int64_t)r * D + d, __fdiv_rn(rc * acc[k], inv_tau_div));
     }
   }
 }
@@ -196,8 +224,8 @@ __global__ void __launch_bounds__(256)
 scl_pair_kernel(const float* __restrict__ embs, const int64_t* __restrict__ seq_lens, const int64_t* __restrict__ steps,
                 const float* __restrict__ masks, int T, int D, float tau, float two_var, SclWs w,
                 float* __restrict__ loss_out, float* __restrict__ d_embs) {
-  extern __shared__ float sm[];
-  const int Dp = D + 1;
+  extern __shared__ __align__(16) float sm[];
+  const int Dp = D + 4;
   float* tile = sm;            // [32][Dp] partner embeddings of the current column chunk
   float* er = tile + 32 * Dp;  // [8][D]   row embeddings
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -223,15 +251,10 @@ scl_pair_kernel(const float* __restrict__ embs, const int64_t* __restrict__ seq_
     pw[k] = 0.f;
     if (k < nch) {
       __syncthreads();
-      for (int idx = threadIdx.x; idx < 32 * D; idx += blockDim.x) {
-        const int jj = idx / D, d = idx % D;
-        const int j = k * 32 + jj;
-        tile[jj * Dp + d] = j < T ? embs[(int64_t)(pbase + j) * D + d] : 0.f;
-      }
+      load_tile(tile, Dp, embs, D, nullptr, k * 32, T, pbase);
       __syncthreads();
       const int j = k * 32 + lane;
-      float dot = 0.f;
-      for (int d = 0; d < D; ++d) dot = fmaf(er[warp * D + d], tile[lane * Dp + d], dot);
+      const float dot = dot4(er + warp * D, tile + lane * Dp, D);
       if (j < T) {
         l[k] = __fdiv_rn(dot, tau);
         const float mj = masks[pbase + j];
@@ -324,11 +347,7 @@ scl_pair_kernel(const float* __restrict__ embs, const int64_t* __restrict__ seq_
       }
       // reload the partner chunk and accumulate coef * e_j over lanes' d-slices
       __syncthreads();
-      for (int idx = threadIdx.x; idx < 32 * D; idx += blockDim.x) {
-        const int jj = idx / D, d = idx % D;
-        const int j2 = k * 32 + jj;
-        tile[jj * Dp + d] = j2 < T ? embs[(int64_t)(pbase + j2) * D + d] : 0.f;
-      }
+      load_tile(tile, Dp, embs, D, nullptr, k * 32, T, pbase);
       __syncthreads();
       for (int jj = 0; jj < 32; ++jj) {
         const float cf = __shfl_sync(0xffffffffu, coef, jj);
@@ -356,7 +375,9 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
                 float* d_embs, void* ws, size_t ws_bytes, cudaStream_t st) {
   MVF_REQUIRE(embs && seq_lens && steps && masks && loss_out && ws, MVF_ERR_BAD_ARG, "scl: null pointer");
   MVF_REQUIRE(Bv > 0 && T > 0 && D > 0, MVF_ERR_BAD_ARG, "scl: bad shape Bv=%d T=%d D=%d", Bv, T, D);
-  MVF_REQUIRE(D <= SCL_MAXD, MVF_ERR_UNSUPPORTED, "scl: embedding size %d > %d", D, SCL_MAXD);
+  MVF_REQUIRE(D <= SCL_MAXD && D % 4 == 0, MVF_ERR_UNSUPPORTED, "scl: embedding size %d must be a multiple of 4 and <= %d", D,
+              SCL_MAXD);
+  MVF_REQUIRE((((uintptr_t)embs) & 15) == 0, MVF_ERR_ALIGN, "scl: embeddings must be 16-byte aligned");
   MVF_REQUIRE(T <= 32 * SCL_MAXTC, MVF_ERR_UNSUPPORTED, "scl: %d frames > %d", T, 32 * SCL_MAXTC);
   MVF_REQUIRE(negative_type == MVF_NEG_SINGLE_NOSELF || negative_type == MVF_NEG_BATCH_NOSELF, MVF_ERR_UNSUPPORTED,
               "scl: negative_type %d", negative_type);
@@ -370,8 +391,11 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
   scl_prep_kernel<<<1, 1024, 0, st>>>(masks, N, w, loss_out);
   MVF_CHECK_LAUNCH();
 
-  const size_t smem = ((size_t)32 * (D + 1) + 8 * D + 64) * sizeof(float);
-  const int cross_grid = cdiv(N, 8);
+  const size_t smem = ((size_t)32 * (D + 4) + 8 * D + 64) * sizeof(float);
+  int cy = N / 512;  // split the column list over blockIdx.y so that small batches still fill the machine
+  cy = cy < 1 ? 1 : (cy > 8 ? 8 : cy);
+  if (cdiv(N, 8) * cy < 296) cy = cy < 4 ? 4 : cy;
+  const dim3 cross_grid(cdiv(N, 8), cy);
   const int T2 = 2 * T;
   const bool batch = negative_type == MVF_NEG_BATCH_NOSELF;
   // Z extras
