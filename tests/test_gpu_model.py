@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 CASES = ["tiny_penn", "tiny_fg_avg", "tiny_max_nohot", "tiny_lin", "tiny_batch_noself", "tiny_e1"]
 # parameters whose gradient is analytically zero (bias in front of a train-mode BatchNorm / key bias under softmax):
 # the reference's values are rounding noise, so they are compared with an absolute floor
-ZERO_GRAD = ("linear_K2d.bias", "linear_V2d.bias", "fc_layers.1.bias", "fc_layers.5.bias", "embedding_layer.bias",
+ZERO_GRAD = ("linear_K2d.bias", "cross_att.linear_V2d.bias", "fc_layers.1.bias", "fc_layers.5.bias", "embedding_layer.bias",
              "lin_final.bias", "ssl_projection.net.0.bias")
 
 

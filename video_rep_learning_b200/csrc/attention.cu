@@ -17,8 +17,8 @@ template <typename T, int DK>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict__ keymask, T* __restrict__ ctx,
                 float* __restrict__ lse) {
-  __shared__ float Ks[ATT_TILE][DK];
-  __shared__ float Vs[ATT_TILE][DK];
+  __shared__ __align__(16) float Ks[ATT_TILE][DK];
+  __shared__ __align__(16) float Vs[ATT_TILE][DK];
   __shared__ float Ms[ATT_TILE];
   const int b = blockIdx.z, h = blockIdx.y, heads = gridDim.y;
   const int i = blockIdx.x * ATT_THREADS + threadIdx.x;
@@ -57,9 +57,16 @@ attn_fwd_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict
     float tmax = -INFINITY;
 #pragma unroll
     for (int jj = 0; jj < ATT_TILE; ++jj) {
-      float acc = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four independent chains hide the FMA latency
 #pragma unroll
-      for (int d = 0; d < DK; ++d) acc = fmaf(q[d], Ks[jj][d], acc);
+      for (int d = 0; d < DK; d += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&Ks[jj][d]);
+        a0 = fmaf(q[d], kk.x, a0);
+        a1 = fmaf(q[d + 1], kk.y, a1);
+        a2 = fmaf(q[d + 2], kk.z, a2);
+        a3 = fmaf(q[d + 3], kk.w, a3);
+      }
+      float acc = (a0 + a1) + (a2 + a3);
       acc = Ms[jj] != 0.f ? acc * scale : -INFINITY;
       s[jj] = acc;
       tmax = fmaxf(tmax, acc);
@@ -75,7 +82,13 @@ attn_fwd_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict
       const float p = expf(s[jj] - m_new);  // exp(-inf) = 0 for masked keys
       l += p;
 #pragma unroll
-      for (int d = 0; d < DK; ++d) o[d] = fmaf(p, Vs[jj][d], o[d]);
+      for (int d = 0; d < DK; d += 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&Vs[jj][d]);
+        o[d] = fmaf(p, vv.x, o[d]);
+        o[d + 1] = fmaf(p, vv.y, o[d + 1]);
+        o[d + 2] = fmaf(p, vv.z, o[d + 2]);
+        o[d + 3] = fmaf(p, vv.w, o[d + 3]);
+      }
     }
     m = m_new;
   }
@@ -94,8 +107,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict__ keymask,
                    const T* __restrict__ ctx, const float* __restrict__ lse, const T* __restrict__ d_ctx,
                    T* __restrict__ d_qkv, float* __restrict__ delta) {
-  __shared__ float Ks[ATT_TILE][DK];
-  __shared__ float Vs[ATT_TILE][DK];
+  __shared__ __align__(16) float Ks[ATT_TILE][DK];
+  __shared__ __align__(16) float Vs[ATT_TILE][DK];
   __shared__ float Ms[ATT_TILE];
   const int b = blockIdx.z, h = blockIdx.y, heads = gridDim.y;
   const int i = blockIdx.x * ATT_THREADS + threadIdx.x;
@@ -138,16 +151,30 @@ attn_bwd_dq_kernel(int S, int H, const T* __restrict__ qkv, const float* __restr
 #pragma unroll 4
     for (int jj = 0; jj < ATT_TILE; ++jj) {
       if (Ms[jj] == 0.f) continue;  // block-uniform
-      float s = 0.f, dp = 0.f;
+      float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
 #pragma unroll
-      for (int d = 0; d < DK; ++d) {
-        s = fmaf(q[d], Ks[jj][d], s);
-        dp = fmaf(go[d], Vs[jj][d], dp);
+      for (int d = 0; d < DK; d += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&Ks[jj][d]);
+        const float4 vv = *reinterpret_cast<const float4*>(&Vs[jj][d]);
+        s0 = fmaf(q[d], kk.x, s0);
+        s1 = fmaf(q[d + 1], kk.y, s1);
+        s0 = fmaf(q[d + 2], kk.z, s0);
+        s1 = fmaf(q[d + 3], kk.w, s1);
+        p0 = fmaf(go[d], vv.x, p0);
+        p1 = fmaf(go[d + 1], vv.y, p1);
+        p0 = fmaf(go[d + 2], vv.z, p0);
+        p1 = fmaf(go[d + 3], vv.w, p1);
       }
-      const float p = expf(s * scale - lse_i);
-      const float ds = p * (dp - dl) * scale;
+      const float p = expf((s0 + s1) * scale - lse_i);
+      const float ds = p * ((p0 + p1) - dl) * scale;
 #pragma unroll
-      for (int d = 0; d < DK; ++d) dq[d] = fmaf(ds, Ks[jj][d], dq[d]);
+      for (int d = 0; d < DK; d += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&Ks[jj][d]);
+        dq[d] = fmaf(ds, kk.x, dq[d]);
+        dq[d + 1] = fmaf(ds, kk.y, dq[d + 1]);
+        dq[d + 2] = fmaf(ds, kk.z, dq[d + 2]);
+        dq[d + 3] = fmaf(ds, kk.w, dq[d + 3]);
+      }
     }
   }
   if (active) {
@@ -163,8 +190,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict__ keymask,
                     const float* __restrict__ lse, const T* __restrict__ d_ctx, const float* __restrict__ delta,
                     T* __restrict__ d_qkv) {
-  __shared__ float Qs[ATT_TILE][DK];
-  __shared__ float Gs[ATT_TILE][DK];
+  __shared__ __align__(16) float Qs[ATT_TILE][DK];
+  __shared__ __align__(16) float Gs[ATT_TILE][DK];
   __shared__ float Ls[ATT_TILE];
   __shared__ float Ds[ATT_TILE];
   const int b = blockIdx.z, h = blockIdx.y, heads = gridDim.y;
@@ -204,18 +231,34 @@ attn_bwd_dkv_kernel(int S, int H, const T* __restrict__ qkv, const float* __rest
     if (!active) continue;
 #pragma unroll 4
     for (int ii = 0; ii < ATT_TILE; ++ii) {
-      float s = 0.f, dp = 0.f;
+      float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
 #pragma unroll
-      for (int d = 0; d < DK; ++d) {
-        s = fmaf(Qs[ii][d], k[d], s);
-        dp = fmaf(Gs[ii][d], v[d], dp);
+      for (int d = 0; d < DK; d += 4) {
+        const float4 qq = *reinterpret_cast<const float4*>(&Qs[ii][d]);
+        const float4 gg = *reinterpret_cast<const float4*>(&Gs[ii][d]);
+        s0 = fmaf(qq.x, k[d], s0);
+        s1 = fmaf(qq.y, k[d + 1], s1);
+        s0 = fmaf(qq.z, k[d + 2], s0);
+        s1 = fmaf(qq.w, k[d + 3], s1);
+        p0 = fmaf(gg.x, v[d], p0);
+        p1 = fmaf(gg.y, v[d + 1], p1);
+        p0 = fmaf(gg.z, v[d + 2], p0);
+        p1 = fmaf(gg.w, v[d + 3], p1);
       }
-      const float p = expf(s * scale - Ls[ii]);
-      const float ds = p * (dp - Ds[ii]) * scale;
+      const float p = expf((s0 + s1) * scale - Ls[ii]);
+      const float ds = p * ((p0 + p1) - Ds[ii]) * scale;
 #pragma unroll
-      for (int d = 0; d < DK; ++d) {
-        dv[d] = fmaf(p, Gs[ii][d], dv[d]);
-        dk[d] = fmaf(ds, Qs[ii][d], dk[d]);
+      for (int d = 0; d < DK; d += 4) {
+        const float4 qq = *reinterpret_cast<const float4*>(&Qs[ii][d]);
+        const float4 gg = *reinterpret_cast<const float4*>(&Gs[ii][d]);
+        dv[d] = fmaf(p, gg.x, dv[d]);
+        dv[d + 1] = fmaf(p, gg.y, dv[d + 1]);
+        dv[d + 2] = fmaf(p, gg.z, dv[d + 2]);
+        dv[d + 3] = fmaf(p, gg.w, dv[d + 3]);
+        dk[d] = fmaf(ds, qq.x, dk[d]);
+        dk[d + 1] = fmaf(ds, qq.y, dk[d + 1]);
+        dk[d + 2] = fmaf(ds, qq.z, dk[d + 2]);
+        dk[d + 3] = fmaf(ds, qq.w, dk[d + 3]);
       }
     }
   }

@@ -16,6 +16,7 @@
 // Split-K (work item = tile x K-slice, fp32 atomics) fills the machine when M*N is small and K huge
 // (the weight gradient of the K/V projection: 768 x 2304 outputs, K = frames*196).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -449,7 +450,12 @@ int gemm_tc(int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64
     const int kb_est = cdiv(K, BLOCK_K);
     int sk_est = split_k > 0 ? split_k : ((dtype_c == MVF_F32 && !(flags & (MVF_GEMM_RELU | MVF_GEMM_RELUMASK)) && kb_est >= 16) ? kb_est / 8 : 1);
     if (sk_est < 1) sk_est = 1;
-    while (bn > 64 && (int64_t)cdiv(M, BLOCK_M) * cdiv(N, bn) * sk_est < g_num_sms) bn >>= 1;
+    static int fill_target = -1;  // tuning knob (CTAs wanted before tiles stop shrinking); default = number of SMs
+    if (fill_target < 0) {
+      const char* e = getenv("MVF_GEMM_FILL");
+      fill_target = e ? atoi(e) : g_num_sms;
+    }
+    while (bn > 64 && (int64_t)cdiv(M, BLOCK_M) * cdiv(N, bn) * sk_est < fill_target) bn >>= 1;
   }
   Params p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;

@@ -2,8 +2,10 @@
 // No device memory is allocated here: every buffer is a named region of the caller's `save`, `ws` or `gpack`
 // allocations, laid out deterministically from the descriptor.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -55,6 +57,43 @@ struct ProfScope {
     g_prof_n[tag] = slot + 1;
   }
 };
+
+// ------------------------------------------------------------------------------------------------------------
+// side stream: weight-gradient GEMMs and bias column-sums only feed the gradient buffer, so in backward they are
+// forked onto a second stream and overlap the dX chain on the caller's stream (joined before every return)
+// ------------------------------------------------------------------------------------------------------------
+struct SideCtl {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[64];
+  int n_ev = 0, next = 0;
+  std::mutex mu;
+};
+static SideCtl g_side;
+static int side_acquire(cudaStream_t* s) {
+  static int enabled = -1;  // MVF_SIDE_STREAM=0 keeps everything on the caller's stream (debugging / A-B timing)
+  if (enabled < 0) {
+    const char* e = getenv("MVF_SIDE_STREAM");
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!enabled) {
+    *s = nullptr;
+    return MVF_OK;
+  }
+  std::lock_guard<std::mutex> lk(g_side.mu);
+  if (g_side.stream == nullptr) {
+    MVF_CHECK_CUDA(cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 64; ++i) MVF_CHECK_CUDA(cudaEventCreateWithFlags(&g_side.ev[i], cudaEventDisableTiming));
+    g_side.n_ev = 64;
+  }
+  *s = g_side.stream;
+  return MVF_OK;
+}
+static cudaEvent_t side_event() {
+  std::lock_guard<std::mutex> lk(g_side.mu);
+  cudaEvent_t e = g_side.ev[g_side.next];
+  g_side.next = (g_side.next + 1) % g_side.n_ev;
+  return e;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // parameter table (canonical order == reference state_dict order of embed.* then ssl_projection.*)
@@ -279,15 +318,19 @@ static void head_ws_layout(const Model& m, Layout& L) {
   }
   L.add("dzA", m.rows, d.H, RT_F32);
   L.add("dzB", m.rows, d.H, RT_F32);
-  L.add("dg", m.rows, d.H, A);
-  L.add("df", m.rows, d.DFF, A);
+  // gradients that a forked weight-gradient GEMM reads get one region per use (no reuse before the join)
+  for (int l = 0; l < d.L; ++l) {
+    L.add(lname(l, "dgF"), m.rows, d.H, A);
+    L.add(lname(l, "dgA"), m.rows, d.H, A);
+    L.add(lname(l, "df"), m.rows, d.DFF, A);
+    L.add(lname(l, "dqkv"), m.rows, 3 * d.H, A);
+  }
   L.add("dr", m.rows, d.H, RT_F32);
   L.add("dctx", m.rows, d.H, A);
-  L.add("dqkv", m.rows, 3 * d.H, A);
   L.add("delta", (int64_t)d.BV * d.heads, m.S, RT_F32);
   L.add("dh3", m.R, m.Hin, A);
   L.add("da", m.R, maxfc, RT_F32);
-  L.add("dx", m.R, maxfc, A);
+  for (int i = 0; i < d.n_fc; ++i) L.add(fname(i, "dx"), m.R, d.fc[i], A);
   L.add("dh0", m.R, m.W0, A, m.ld0);
   L.add("dkv", m.F * d.P, 2 * d.SPC, A);
 }
@@ -381,13 +424,31 @@ struct Ctx {
   Buf S, W, G;
   const float* const* P;
   cudaStream_t st;
+  cudaStream_t side = nullptr;  // non-null: weight-gradient work is forked onto it
+  bool forked = false;
   int backend;
   float p;  // effective dropout rate
   int gemm(int dtype_c, int akm, int bkm, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
            int64_t ldb, void* C, int64_t ldc, const float* bias, const void* relu_src = nullptr, int64_t ld_relu = 0,
-           int flags = 0, int split_k = 1) const {
+           int flags = 0, int split_k = 1, cudaStream_t on = nullptr) const {
     return gemm_dispatch(backend, m.act, dtype_c, akm, bkm, M, N, K, A, lda, B, ldb, C, ldc, bias, relu_src, ld_relu,
-                         flags, split_k, st);
+                         flags, split_k, on ? on : st);
+  }
+  int fork() {
+    if (!side) return MVF_OK;
+    cudaEvent_t e = side_event();
+    MVF_CHECK_CUDA(cudaEventRecord(e, st));
+    MVF_CHECK_CUDA(cudaStreamWaitEvent(side, e, 0));
+    forked = true;
+    return MVF_OK;
+  }
+  int join() {
+    if (!side || !forked) return MVF_OK;
+    cudaEvent_t e = side_event();
+    MVF_CHECK_CUDA(cudaEventRecord(e, side));
+    MVF_CHECK_CUDA(cudaStreamWaitEvent(st, e, 0));
+    forked = false;
+    return MVF_OK;
   }
   // y = x W^T + b
   int linear(int dtype_c, int64_t M, int64_t N, int64_t K, const void* x, int64_t ldx, const void* Wp, int64_t ldw,
@@ -401,10 +462,13 @@ struct Ctx {
                 relu_src ? MVF_GEMM_RELUMASK : 0);
   }
   // dW += dY^T X ; db += colsum(dY)
+  // (dY and X must stay untouched until join(): callers give every dY its own scratch region)
   int linear_dw(int64_t M, int64_t Nout, int64_t Kin, const void* dY, int64_t lddy, const void* X, int64_t ldx,
-                float* dWp, int64_t lddw, float* db, int split_k = 0) const {
-    MVF_TRY(gemm(MVF_F32, 0, 0, Nout, Kin, M, dY, lddy, X, ldx, dWp, lddw, nullptr, nullptr, 0, MVF_GEMM_ACCUM, split_k));
-    if (db) MVF_TRY(colsum(m.act, dY, M, (int)Nout, lddy, db, st));
+                float* dWp, int64_t lddw, float* db, int split_k = 0) {
+    MVF_TRY(fork());
+    cudaStream_t on = side ? side : st;
+    MVF_TRY(gemm(MVF_F32, 0, 0, Nout, Kin, M, dY, lddy, X, ldx, dWp, lddw, nullptr, nullptr, 0, MVF_GEMM_ACCUM, split_k, on));
+    if (db) MVF_TRY(colsum(m.act, dY, M, (int)Nout, lddy, db, on));
     return MVF_OK;
   }
 };
@@ -643,28 +707,32 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         const int b = m.iLayer[l];
         const std::string g = "g." + std::string("l") + std::to_string(l) + ".";
         // FFN branch: z[2l+2] = z[2l+1] + drop(W2 f + b2)
-        MVF_TRY(dropout_cast(A, dz, c.W.p("dg"), m.rows, d.H, d.H, c.p, d.seed, SITE_ENC0 + 2 * l + 1, st));
-        MVF_TRY(c.linear_dw(m.rows, d.H, d.DFF, c.W.p("dg"), d.H, c.S.p(lname(l, "f")), d.DFF, c.G.f(g + "w.2"), d.DFF,
+        void* dgF = c.W.p(lname(l, "dgF"));
+        void* dgA = c.W.p(lname(l, "dgA"));
+        void* df = c.W.p(lname(l, "df"));
+        void* dqkv = c.W.p(lname(l, "dqkv"));
+        MVF_TRY(dropout_cast(A, dz, dgF, m.rows, d.H, d.H, c.p, d.seed, SITE_ENC0 + 2 * l + 1, st));
+        MVF_TRY(c.linear_dw(m.rows, d.H, d.DFF, dgF, d.H, c.S.p(lname(l, "f")), d.DFF, c.G.f(g + "w.2"), d.DFF,
                             c.G.f(g + "b.2")));
-        MVF_TRY(c.linear_dx(A, m.rows, d.H, d.DFF, c.W.p("dg"), d.H, c.S.p(lname(l, "w.2")), d.DFF, c.W.p("df"), d.DFF,
+        MVF_TRY(c.linear_dx(A, m.rows, d.H, d.DFF, dgF, d.H, c.S.p(lname(l, "w.2")), d.DFF, df, d.DFF,
                             c.S.p(lname(l, "f")), d.DFF));
-        MVF_TRY(c.linear_dw(m.rows, d.DFF, d.H, c.W.p("df"), d.DFF, c.S.p(lname(l, "r1")), d.H, c.G.f(g + "w.1"), d.H,
+        MVF_TRY(c.linear_dw(m.rows, d.DFF, d.H, df, d.DFF, c.S.p(lname(l, "r1")), d.H, c.G.f(g + "w.1"), d.H,
                             c.G.f(g + "b.1")));
-        MVF_TRY(c.linear_dx(MVF_F32, m.rows, d.DFF, d.H, c.W.p("df"), d.DFF, c.S.p(lname(l, "w.1")), d.H, c.W.p("dr"), d.H));
+        MVF_TRY(c.linear_dx(MVF_F32, m.rows, d.DFF, d.H, df, d.DFF, c.S.p(lname(l, "w.1")), d.H, c.W.p("dr"), d.H));
         const float* ln1 = c.S.f(lname(l, "ln1"));
         MVF_TRY(ln_bwd(c.W.f("dr"), c.S.f("z" + std::to_string(2 * l + 1)), ln1, ln1 + m.rows, c.P[b + L_LN1W], dz,
                        dz_other, c.G.f(g + "ln1w"), c.G.f(g + "ln1b"), m.rows, d.H, st));
         std::swap(dz, dz_other);
         // attention branch: z[2l+1] = z[2l] + drop(Wo ctx + bo)
-        MVF_TRY(dropout_cast(A, dz, c.W.p("dg"), m.rows, d.H, d.H, c.p, d.seed, SITE_ENC0 + 2 * l, st));
-        MVF_TRY(c.linear_dw(m.rows, d.H, d.H, c.W.p("dg"), d.H, c.S.p(lname(l, "ctx")), d.H, c.G.f(g + "w.o"), d.H,
+        MVF_TRY(dropout_cast(A, dz, dgA, m.rows, d.H, d.H, c.p, d.seed, SITE_ENC0 + 2 * l, st));
+        MVF_TRY(c.linear_dw(m.rows, d.H, d.H, dgA, d.H, c.S.p(lname(l, "ctx")), d.H, c.G.f(g + "w.o"), d.H,
                             c.G.f(g + "b.o")));
-        MVF_TRY(c.linear_dx(A, m.rows, d.H, d.H, c.W.p("dg"), d.H, c.S.p(lname(l, "w.o")), d.H, c.W.p("dctx"), d.H));
+        MVF_TRY(c.linear_dx(A, m.rows, d.H, d.H, dgA, d.H, c.S.p(lname(l, "w.o")), d.H, c.W.p("dctx"), d.H));
         MVF_TRY(attention_bwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
-                              c.S.f(lname(l, "lse")), c.W.p("dctx"), c.W.p("dqkv"), c.W.f("delta"), st));
-        MVF_TRY(c.linear_dw(m.rows, 3 * d.H, d.H, c.W.p("dqkv"), 3 * d.H, c.S.p(lname(l, "r0")), d.H, c.G.f(g + "w.qkv"),
+                              c.S.f(lname(l, "lse")), c.W.p("dctx"), dqkv, c.W.f("delta"), st));
+        MVF_TRY(c.linear_dw(m.rows, 3 * d.H, d.H, dqkv, 3 * d.H, c.S.p(lname(l, "r0")), d.H, c.G.f(g + "w.qkv"),
                             d.H, c.G.f(g + "b.qkv")));
-        MVF_TRY(c.linear_dx(MVF_F32, m.rows, 3 * d.H, d.H, c.W.p("dqkv"), 3 * d.H, c.S.p(lname(l, "w.qkv")), d.H,
+        MVF_TRY(c.linear_dx(MVF_F32, m.rows, 3 * d.H, d.H, dqkv, 3 * d.H, c.S.p(lname(l, "w.qkv")), d.H,
                             c.W.p("dr"), d.H));
         const float* ln0 = c.S.f(lname(l, "ln0"));
         MVF_TRY(ln_bwd(c.W.f("dr"), c.S.f("z" + std::to_string(2 * l)), ln0, ln0 + m.rows, c.P[b + L_LN0W], dz, dz_other,
@@ -694,8 +762,8 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
       const float pn = (i + 1 < d.n_fc) ? c.p : 0.f;  // dropout that followed this activation
       MVF_TRY(bn_bwd_apply(A, c.W.f("da"), C, c.S.f(fname(i, "x")), m.R, C, c.S.f(fname(i, "mi")), c.P[m.iFcG[i]],
                            c.P[m.iFcBeta[i]], 1, pn, d.seed, SITE_FC0 + i + 1, c.S.dbl(fname(i, "bsum")),
-                           bn_n_global(m, m.R), c.W.p("dx"), C, st));
-      d_in = c.W.p("dx");
+                           bn_n_global(m, m.R), c.W.p(fname(i, "dx")), C, st));
+      d_in = c.W.p(fname(i, "dx"));
       ld_din = C;
       const void* xin = i > 0 ? c.S.p(fname(i - 1, "a")) : c.S.p("h0");
       const int64_t ldin = i > 0 ? d.fc[i - 1] : m.ld0;
@@ -732,7 +800,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
       }
     }
   }
-  return MVF_OK;
+  return c.join();
 }
 
 // bn_bwd_stats with dropout: the dropout that follows activation i belongs to site SITE_FC0+i+1.
@@ -815,7 +883,7 @@ static int proj_backward_impl(Ctx& c, const float* d_out, int project, float* d_
       MVF_TRY(c.linear_dx(MVF_F32, m.N, d.PS, d.D, c.W.p("du1"), d.PS, c.S.p("w.p1"), d.D, d_emb, d.D));
     }
   }
-  return MVF_OK;
+  return c.join();
 }
 
 static int unpack_impl(const Model& m, const Layout& Lg, const float* gpack, float* const* grads, float scale,
@@ -1021,7 +1089,10 @@ int mvf_head_backward(const mvf_head_desc* d, const float* const* params, const 
   Ctx c;
   MVF_TRY(make_ctx(d, c, false, save, save_bytes, ws, ws_bytes, gpack, params, (cudaStream_t)stream));
   MVF_REQUIRE(tokens != nullptr && d_emb != nullptr && gpack != nullptr, MVF_ERR_BAD_ARG, "null tokens / d_emb / gpack");
-  return head_backward_impl(c, tokens, mask, d_emb, phase_begin, phase_end);
+  MVF_TRY(side_acquire(&c.side));
+  int rc = head_backward_impl(c, tokens, mask, d_emb, phase_begin, phase_end);
+  if (rc != MVF_OK) c.join();  // never leave forked work un-joined, even on an error path
+  return rc;
 }
 
 int mvf_proj_forward(const mvf_head_desc* d, const float* const* params, float* const* bn_running,
@@ -1041,7 +1112,10 @@ int mvf_proj_backward(const mvf_head_desc* d, const float* const* params, const 
   MVF_REQUIRE(d_out != nullptr && d_emb != nullptr, MVF_ERR_BAD_ARG, "null d_out / d_emb");
   MVF_REQUIRE(!project || gpack != nullptr, MVF_ERR_BAD_ARG, "null gpack");
   // the forward stores the normalised rows in `ehat` for both modes
-  return proj_backward_impl(c, d_out, project, d_emb, c.S.f("ehat"), phase_begin, phase_end);
+  MVF_TRY(side_acquire(&c.side));
+  int rc = proj_backward_impl(c, d_out, project, d_emb, c.S.f("ehat"), phase_begin, phase_end);
+  if (rc != MVF_OK) c.join();
+  return rc;
 }
 
 int mvf_unpack_grads(const mvf_head_desc* d, const float* gpack, float* const* grads, float scale, mvf_stream_t stream) {

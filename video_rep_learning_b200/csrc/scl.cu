@@ -392,9 +392,11 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
   MVF_CHECK_LAUNCH();
 
   const size_t smem = ((size_t)32 * (D + 4) + 8 * D + 64) * sizeof(float);
-  int cy = N / 512;  // split the column list over blockIdx.y so that small batches still fill the machine
-  cy = cy < 1 ? 1 : (cy > 8 ? 8 : cy);
-  if (cdiv(N, 8) * cy < 296) cy = cy < 4 ? 4 : cy;
+  // the column list is split over blockIdx.y: the row/column counts live on the device (valid vs masked frames), so the
+  // grid is sized for the worst case and short lists simply leave CTAs idle; 8-way split keeps every pass to a few
+  // tiles per CTA at training batch sizes
+  int cy = 8;
+  if ((int64_t)cdiv(N, 8) * cy > 65535 * 4) cy = 2;
   const dim3 cross_grid(cdiv(N, 8), cy);
   const int T2 = 2 * T;
   const bool batch = negative_type == MVF_NEG_BATCH_NOSELF;
