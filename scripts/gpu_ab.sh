@@ -2,7 +2,7 @@
 # A/B timing of tuning knobs on the bench step (no e2e / cpu legs)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-for cfg in "MVF_SIDE_STREAM=1 MVF_GEMM_FILL=148" "MVF_SIDE_STREAM=0 MVF_GEMM_FILL=148" "MVF_SIDE_STREAM=1 MVF_GEMM_FILL=74" "MVF_SIDE_STREAM=1 MVF_GEMM_FILL=40" "MVF_SIDE_STREAM=0 MVF_GEMM_FILL=296"; do
+for cfg in "MVF_SIDE_STREAM=1 MVF_GEMM_FILL=1" "MVF_SIDE_STREAM=1 MVF_GEMM_FILL=20" "MVF_SIDE_STREAM=1 MVF_GEMM_FILL=60" "MVF_SIDE_STREAM=0 MVF_GEMM_FILL=40" "MVF_SIDE_STREAM=0 MVF_GEMM_FILL=600"; do
   echo "== $cfg"
   env $cfg timeout 300 python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu 2>&1 | python -c "
 import sys, json
