@@ -450,10 +450,10 @@ int gemm_tc(int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64
     const int kb_est = cdiv(K, BLOCK_K);
     int sk_est = split_k > 0 ? split_k : ((dtype_c == MVF_F32 && !(flags & (MVF_GEMM_RELU | MVF_GEMM_RELUMASK)) && kb_est >= 16) ? kb_est / 8 : 1);
     if (sk_est < 1) sk_est = 1;
-    static int fill_target = -1;  // tuning knob (CTAs wanted before tiles stop shrinking); default = number of SMs
+    static int fill_target = -1;  // tuning knob: CTAs wanted before tiles stop shrinking
     if (fill_target < 0) {
       const char* e = getenv("MVF_GEMM_FILL");
-      fill_target = e ? atoi(e) : g_num_sms;
+      fill_target = e ? atoi(e) : 60;  // measured best with the side stream (profiles/r01_ab_knobs.txt)
     }
     while (bn > 64 && (int64_t)cdiv(M, BLOCK_M) * cdiv(N, bn) * sk_est < fill_target) bn >>= 1;
   }
