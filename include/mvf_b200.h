@@ -64,10 +64,12 @@ typedef struct mvf_head_desc {
   int32_t one_hot;      /* mvf_onehot                                                              */
   int32_t final_mode;   /* mvf_final                                                               */
   int32_t train_frames; /* TRAIN.NUM_FRAMES: pos-enc uses linspace positions when T differs        */
-  int32_t dtype;        /* mvf_dtype of tokens and of every GEMM operand (fp32 accumulate always)  */
+  int32_t dtype;        /* mvf_dtype of tokens, K|V and their gradients (the 96 % of the FLOPs);   */
+                        /* activations behind the pooling are fp32 (tf32 MMAs on the TC backend)   */
   int32_t training;     /* 1: BatchNorm batch statistics + dropout; 0: running statistics          */
   int32_t has_mask;     /* 1: video_masks given ([BV,T] float, 0 = padded frame)                   */
-  int32_t gemm_backend; /* mvf_gemm_backend; AUTO = tcgen05 for bf16, SIMT for fp32                */
+  int32_t gemm_backend; /* mvf_gemm_backend; AUTO = tcgen05 (bf16 + tf32) for bf16 tokens, exact   */
+                        /* fp32 FMA (SIMT) for fp32 tokens                                         */
   int32_t world_size;   /* ranks sharing BatchNorm statistics (1 = local statistics)               */
   float drop_p;         /* FC_DROPOUT_RATE (applied only when training)                            */
   float ln_eps, bn_eps, bn_momentum;
@@ -166,6 +168,7 @@ int mvf_scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* s
 /* ---- building blocks, exported for unit parity tests and micro-benchmarks --------------------------- */
 /* C[M,N] (+)= opA(A) * opB(B) + bias.  a_kmajor: A stored [M,K] row-major (else [K,M]);
  * b_kmajor: B stored [N,K] row-major like nn.Linear.weight (else [K,N]).  dtype_ab / dtype_c: mvf_dtype.
+ * Backend TCGEN05: bf16 operands -> tcgen05 kind::f16, fp32 operands -> kind::tf32 (fp32 output only).
  * flags: bit0 ReLU, bit1 accumulate into C (fp32 C only), bit2 multiply by (relu_src > 0). */
 #define MVF_GEMM_RELU 1
 #define MVF_GEMM_ACCUM 2
@@ -175,7 +178,8 @@ int mvf_gemm(int backend, int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor,
              const void* relu_src, int64_t ld_relu, int flags, int split_k, mvf_stream_t stream);
 
 /* a3-a5 alone (mvformer.py:243-266, 352-414; utils.py:11-44): kv [F*P, 2*SPC] (K | V), q_s [E,SPC],
- * q_b [SPC] -> attn [F,E,P] fp32, ent [F*E, ld_ent] (dtype), one-hot columns appended when one_hot = 1.
+ * q_b [SPC] -> attn [F,E,P] fp32, ent [F*E, ld_ent] fp32 (dropout applied), one-hot columns appended when
+ * one_hot = 1; d_ent is fp32 as well.  dtype is the element type of kv / d_kv.
  * ent_f32 (optional, [F*E, SPC] fp32): pooled entities before dropout; when given for bf16 and E <= 4 the
  * single-pass kernels run (each K|V row read once); backward needs the same buffer back. */
 int mvf_xattn_pool_fwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t SPC, const void* kv, const float* q_s,

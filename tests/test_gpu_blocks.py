@@ -39,13 +39,13 @@ def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype, single_pass):
     dev = "cuda"
     kv_d, qs_d, qb_d = kv.to(dev), q_s.to(dev), q_b.to(dev)      # keep references: raw pointers cross the C ABI
     attn = torch.empty(F, E, P, device=dev)
-    out = torch.full((F * E, ld), float("nan"), dtype=dtype, device=dev)
+    out = torch.full((F * E, ld), float("nan"), dtype=torch.float32, device=dev)   # pooled entities are always fp32
     ent32 = torch.full((F * E, SPC), float("nan"), device=dev) if single_pass else None
     md = L.MVF_BF16 if dtype == torch.bfloat16 else L.MVF_F32
     L.check(L.lib().mvf_xattn_pool_fwd(md, F, P, E, SPC, L.ptr(kv_d), L.ptr(qs_d), L.ptr(qb_d), L.ptr(attn),
                                        L.ptr(out), ld, L.ptr(ent32), one_hot, 0.0, 0, _stream()))
     torch.cuda.synchronize()
-    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    tol = 1e-5
     assert float((attn.cpu().double() - A.detach()).abs().max()) < 1e-5
     got = out.float().cpu().view(F, E, ld)
     assert float((got[..., :SPC].double() - ent.detach()).abs().max()) < tol
@@ -55,8 +55,8 @@ def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype, single_pass):
     if single_pass and dtype == torch.bfloat16 and E <= 4:
         assert float((ent32.cpu().double().view(F, E, SPC) - ent.detach()).abs().max()) < 1e-5
 
-    d_in = torch.zeros(F * E, ld, dtype=dtype)
-    d_in[:, :SPC] = d_ent.view(F * E, SPC).to(dtype)
+    d_in = torch.zeros(F * E, ld, dtype=torch.float32)
+    d_in[:, :SPC] = d_ent.view(F * E, SPC).float()
     d_in_d = d_in.to(dev)
     d_kv = torch.empty_like(kv_d)
     dqs, dqb = torch.zeros(E, SPC, device=dev), torch.zeros(SPC, device=dev)
@@ -65,12 +65,6 @@ def test_xattn_pool_fwd_bwd(F, P, E, SPC, one_hot, dtype, single_pass):
                                        L.ptr(d_in_d), ld, L.ptr(ent32), one_hot, 0.0, 0, L.ptr(d_kv), L.ptr(dqs), L.ptr(dqb),
                                        L.ptr(dbk), L.ptr(dbv), _stream()))
     torch.cuda.synchronize()
-    # with bf16 the incoming gradient was rounded too: compare against the reference of the rounded d_ent
-    if dtype == torch.bfloat16:
-        kvd.grad = None; qs.grad = None; qb.grad = None
-        A2 = torch.softmax(torch.einsum("fpc,ec->fep", kvd[..., :SPC], qs + qb) / np.sqrt(SPC), -1)
-        ent2 = torch.einsum("fep,fpc->fec", A2, kvd[..., SPC:])
-        (ent2 * d_ent.to(dtype).double()).sum().backward()
     rt = 2e-5 if dtype == torch.float32 else 2e-2
     assert H.rel_l2(d_kv.float().cpu().view(F, P, 2 * SPC), kvd.grad) < rt
     assert H.rel_l2(dqs.cpu(), qs.grad) < rt and H.rel_l2(dqb.cpu(), qb.grad) < rt

@@ -80,6 +80,35 @@ def test_tcgen05_bf16(a_k, b_k, M, N, K):
     assert float((C - Cs).abs().max() / ref.abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("a_k,b_k", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (256, 256, 128), (200, 72, 100), (3840, 512, 392), (130, 392, 516), (512, 1024, 3840)])
+def test_tcgen05_tf32(a_k, b_k, M, N, K):
+    """fp32 operands on the tensor cores (kind::tf32): compared with the exact product of the tf32-truncated operands
+    (tight) and with the exact fp32 product (tf32-level tolerance)."""
+    padA = (-(K if a_k else M)) % 4
+    padB = (-(K if b_k else N)) % 4
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + K)
+    A = torch.randn((M, K + padA) if a_k else (K, M + padA), generator=g, device="cuda")
+    B = torch.randn((N, K + padB) if b_k else (K, N + padB), generator=g, device="cuda")
+    Am = A[:, :K].double() if a_k else A[:, :M].double().t()
+    Bm = B[:, :K].double().t() if b_k else B[:, :N].double()
+    ref = Am @ Bm
+    bias = torch.randn(N, device="cuda")
+    C = _gemm(L.GEMM_TCGEN05, A, B, a_k, b_k, M, N, K, torch.float32, bias=bias)
+    err = float((C.double() - (ref + bias.double())).abs().max() / ref.abs().max())
+    assert err < 2e-3, f"tf32 error {err}"
+    trunc = lambda t: (t.float().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+    ref_t = trunc(Am) @ trunc(Bm)
+    err_t = float((C.double() - (ref_t + bias.double())).abs().max() / ref.abs().max())
+    assert err_t < 1e-3      # the hardware may round instead of truncate: only a loose bound is portable
+    base = torch.randn(M, N, device="cuda")
+    C2 = _gemm(L.GEMM_TCGEN05, A, B, a_k, b_k, M, N, K, torch.float32, flags=L.GEMM_ACCUM, split_k=0, C=base.clone())
+    assert float((C2.double() - (ref + base.double())).abs().max() / ref.abs().max()) < 2e-3
+    src = torch.randn(M, N, device="cuda")
+    C3 = _gemm(L.GEMM_TCGEN05, A, B, a_k, b_k, M, N, K, torch.float32, relu_src=src, flags=L.GEMM_RELUMASK)
+    assert float((C3.double() - ref * (src > 0)).abs().max() / ref.abs().max()) < 2e-3
+
+
 @pytest.mark.parametrize("split", [0, 2, 7])
 def test_tcgen05_split_k_weight_gradient_shape(split):
     """dW = dY^T X with a long contraction and few output tiles: both operands MN-major, fp32 atomics."""
@@ -106,5 +135,5 @@ def test_tcgen05_relumask_and_alignment_errors():
     A2 = torch.randn(M, K + 4, device="cuda").to(torch.bfloat16)      # row stride 136 B: not a multiple of 16
     with pytest.raises(RuntimeError, match="multiple of 8"):
         _gemm(L.GEMM_TCGEN05, A2, B, 1, 1, M, N, K, torch.float32)
-    with pytest.raises(RuntimeError, match="bf16"):
-        _gemm(L.GEMM_TCGEN05, A.float(), B.float(), 1, 1, M, N, K, torch.float32)
+    with pytest.raises(RuntimeError, match="fp32 output"):
+        _gemm(L.GEMM_TCGEN05, A.float(), B.float(), 1, 1, M, N, K, torch.bfloat16)

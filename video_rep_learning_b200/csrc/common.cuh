@@ -91,9 +91,9 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 int gemm_simt(int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A,
               int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias, const void* relu_src,
               int64_t ld_relu, int flags, cudaStream_t st);
-int gemm_tc(int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
-            const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias, const void* relu_src, int64_t ld_relu,
-            int flags, int split_k, cudaStream_t st);
+int gemm_tc(int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A,
+            int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias, const void* relu_src,
+            int64_t ld_relu, int flags, int split_k, cudaStream_t st);
 bool tc_available();
 
 int gemm_dispatch(int backend, int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K,

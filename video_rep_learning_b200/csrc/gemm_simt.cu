@@ -125,14 +125,16 @@ int gemm_simt(int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, 
 int gemm_dispatch(int backend, int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K,
                   const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
                   const void* relu_src, int64_t ld_relu, int flags, int split_k, cudaStream_t st) {
+  // AUTO: bf16 operands -> tcgen05 kind::f16; fp32 operands -> exact fp32 FMA (SIMT).  TCGEN05 with fp32 operands
+  // runs them as tf32 on the tensor cores.
   bool use_tc;
   if (backend == MVF_GEMM_SIMT) use_tc = false;
   else if (backend == MVF_GEMM_TCGEN05) use_tc = true;
   else use_tc = (dtype_ab == MVF_BF16);
   if (use_tc) {
-    MVF_REQUIRE(dtype_ab == MVF_BF16, MVF_ERR_UNSUPPORTED, "tcgen05 GEMM needs bf16 operands");
-    return gemm_tc(dtype_c, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc, bias, relu_src, ld_relu, flags, split_k,
-                   st);
+    MVF_REQUIRE(dtype_c == MVF_F32 || dtype_ab == MVF_BF16, MVF_ERR_UNSUPPORTED, "tf32 GEMM writes fp32 output only");
+    return gemm_tc(dtype_ab, dtype_c, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc, bias, relu_src, ld_relu, flags,
+                   split_k, st);
   }
   return gemm_simt(dtype_ab, dtype_c, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc, bias, relu_src, ld_relu,
                    flags, st);

@@ -1,5 +1,7 @@
-// bf16 x bf16 -> fp32 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands
-// staged by TMA (cp.async.bulk.tensor, 128B swizzle) through an mbarrier ring.  sm_100a only.
+// bf16 x bf16 -> fp32 (kind::f16) and tf32 x tf32 -> fp32 (kind::tf32, fp32 operands in memory) GEMM on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands staged by TMA (cp.async.bulk.tensor,
+// 128B swizzle) through an mbarrier ring.  sm_100a only.  The two element types share one kernel: a stage row is
+// always 128 bytes of K (64 bf16 or 32 fp32) and one MMA consumes 32 bytes of K (UMMA_K = 16 or 8).
 //
 //   C[M,N] (+)= opA(A)[M,K] * opB(B)[K,N] (+ bias)           fp32 accumulate in TMEM
 //
@@ -25,8 +27,7 @@ namespace mvf {
 namespace tc {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int UMMA_K = 16;
+constexpr int ROW_BYTES = 128;  // one swizzle row of K per stage: 64 bf16 or 32 fp32 (tf32)
 constexpr int NUM_THREADS = 256;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
@@ -79,14 +80,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <int EB>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if constexpr (EB == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane quadrant base + t).
@@ -105,13 +116,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
-//   K-major : rows of 128 B (64 bf16 along K); 8-row groups 1024 B apart (SBO); LBO unused.
-//   MN-major: k-rows of 128 B (64 bf16 along M/N); 8-k groups 1024 B apart (SBO); successive 64-element
-//             M/N chunks are separate TMA boxes of BLOCK_K*128 B = 8192 B (LBO).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool kmajor) {
+//   K-major : rows of 128 B along K; 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major: k-rows of 128 B along M/N (64 bf16 / 32 fp32); 8-k groups 1024 B apart (SBO); successive 128-byte
+//             M/N chunks are separate TMA boxes of block_k_rows*128 B (LBO): 8192 B for bf16, 4096 B for tf32.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool kmajor, int block_k_rows) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  uint32_t lbo = kmajor ? 1u : (uint32_t)((BLOCK_K * 128) >> 4);
+  uint32_t lbo = kmajor ? 1u : (uint32_t)((block_k_rows * 128) >> 4);
   uint32_t sbo = 1024u >> 4;
   d |= (uint64_t)(lbo & 0x3FFF) << 16;
   d |= (uint64_t)(sbo & 0x3FFF) << 32;
@@ -120,11 +131,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool kmajor) 
   return d;
 }
 
-// Instruction descriptor for kind::f16: D fp32, A/B bf16, M=128, N=n.
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_kmajor, bool b_kmajor) {
+// Instruction descriptor: D fp32, A/B bf16 (format 1, kind::f16) or tf32 (format 2, kind::tf32), M=128, N=n.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_kmajor, bool b_kmajor, int eb) {
   return (1u << 4)                        // c_format = F32
-         | (1u << 7)                      // a_format = BF16
-         | (1u << 10)                     // b_format = BF16
+         | ((eb == 2 ? 1u : 2u) << 7)     // a_format
+         | ((eb == 2 ? 1u : 2u) << 10)    // b_format
          | ((a_kmajor ? 0u : 1u) << 15)   // a_major (1 = MN-major)
          | ((b_kmajor ? 0u : 1u) << 16)   // b_major
          | ((uint32_t)(n >> 3) << 17)     // n_dim
@@ -140,15 +151,18 @@ struct Params {
   void* C;
   int64_t ldc;
   const float* bias;
-  const bf16* relu_src;
+  const void* relu_src;  // same element type as the operands
   int64_t ld_relu;
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int EB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
-  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int BLOCK_K = ROW_BYTES / EB;   // elements of K per stage (64 bf16 / 32 tf32)
+  constexpr int UMMA_K = 32 / EB;           // elements of K per tcgen05.mma (16 / 8)
+  constexpr int CHUNK = ROW_BYTES / EB;     // M/N elements per 128-byte row of an MN-major operand
+  constexpr int A_BYTES = BLOCK_M * ROW_BYTES;
+  constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                             : (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -206,15 +220,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_load_2d(&map_a, &full_bar[stage], sa, k, tm * BLOCK_M);
           } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c)
-              tma_load_2d(&map_a, &full_bar[stage], sa + c * (BLOCK_K * 128), tm * BLOCK_M + c * 64, k);
+            for (int c = 0; c < BLOCK_M / CHUNK; ++c)
+              tma_load_2d(&map_a, &full_bar[stage], sa + c * (BLOCK_K * 128), tm * BLOCK_M + c * CHUNK, k);
           }
           if (p.b_kmajor) {
             tma_load_2d(&map_b, &full_bar[stage], sb, k, tn * BLOCK_N);
           } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 64; ++c)
-              tma_load_2d(&map_b, &full_bar[stage], sb + c * (BLOCK_K * 128), tn * BLOCK_N + c * 64, k);
+            for (int c = 0; c < BLOCK_N / CHUNK; ++c)
+              tma_load_2d(&map_b, &full_bar[stage], sb + c * (BLOCK_K * 128), tn * BLOCK_N + c * CHUNK, k);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -223,10 +237,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_N, p.a_kmajor != 0, p.b_kmajor != 0);
-      // start-address advance (in 16 B units) per UMMA_K step inside a stage
-      const uint32_t adv_a = p.a_kmajor ? (UMMA_K * 2) >> 4 : (UMMA_K * 128) >> 4;
-      const uint32_t adv_b = p.b_kmajor ? (UMMA_K * 2) >> 4 : (UMMA_K * 128) >> 4;
+      const uint32_t idesc = make_idesc(BLOCK_N, p.a_kmajor != 0, p.b_kmajor != 0, EB);
+      // start-address advance (in 16 B units) per UMMA_K step inside a stage: 32 B along a K-major row,
+      // UMMA_K rows of 128 B for an MN-major operand
+      const uint32_t adv_a = p.a_kmajor ? (UMMA_K * EB) >> 4 : (UMMA_K * 128) >> 4;
+      const uint32_t adv_b = p.b_kmajor ? (UMMA_K * EB) >> 4 : (UMMA_K * 128) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -243,12 +258,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&full_bar[stage], phase, 3);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t da = make_smem_desc(sa, p.a_kmajor != 0);
-          const uint64_t db = make_smem_desc(sa + A_BYTES, p.b_kmajor != 0);
+          const uint64_t da = make_smem_desc(sa, p.a_kmajor != 0, BLOCK_K);
+          const uint64_t db = make_smem_desc(sa + A_BYTES, p.b_kmajor != 0, BLOCK_K);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_bf16(tmem_d, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc,
-                      (kb > kb0 || k > 0) ? 1u : 0u);
+            umma<EB>(tmem_d, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc,
+                     (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -295,10 +310,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (p.flags & MVF_GEMM_RELUMASK) {
-            const bf16* rs = p.relu_src + (int64_t)row * p.ld_relu + col0;
+            if constexpr (EB == 2) {
+              const bf16* rs = (const bf16*)p.relu_src + (int64_t)row * p.ld_relu + col0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] = (__bfloat162float(rs[j]) > 0.f) ? v[j] : 0.f;
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] = (__bfloat162float(rs[j]) > 0.f) ? v[j] : 0.f;
+            } else {
+              const float* rs = (const float*)p.relu_src + (int64_t)row * p.ld_relu + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] = (rs[j] > 0.f) ? v[j] : 0.f;
+            }
           }
           const bool full = col0 + 32 <= p.N;
           if (p.c_bf16) {
@@ -378,19 +400,21 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// rows x cols row-major bf16 matrix with leading dimension ld (elements); box = box_cols x box_rows.
+// rows x cols row-major matrix (bf16 when eb == 2, fp32 when eb == 4) with leading dimension ld (elements);
+// box = box_cols x box_rows.
 static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
-                    int box_rows) {
+                    int box_rows, int eb) {
   EncodeTiledFn fn = get_encode_fn();
   MVF_REQUIRE(fn != nullptr, MVF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   MVF_REQUIRE((((uintptr_t)ptr) & 15) == 0, MVF_ERR_ALIGN, "gemm_tc: operand base %p not 16-byte aligned", ptr);
-  MVF_REQUIRE((ld * 2) % 16 == 0, MVF_ERR_ALIGN, "gemm_tc: leading dimension %lld not a multiple of 8 elements",
-              (long long)ld);
+  MVF_REQUIRE((ld * eb) % 16 == 0, MVF_ERR_ALIGN, "gemm_tc: leading dimension %lld not a multiple of %d elements",
+              (long long)ld, 16 / eb);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * eb};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(map, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MVF_REQUIRE(r == CUDA_SUCCESS, MVF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
@@ -398,18 +422,18 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
   return MVF_OK;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int EB>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int num_sms, cudaStream_t st) {
-  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (BLOCK_M * ROW_BYTES + BLOCK_N * ROW_BYTES) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    MVF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MVF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         smem));
     configured = true;
   }
   int work = p.tiles_m * p.tiles_n * p.split_k;
   int grid = work < num_sms ? work : num_sms;
-  gemm_tc_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p);
+  gemm_tc_kernel<BLOCK_N, STAGES, EB><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -436,10 +460,13 @@ bool tc_available() {
   return g_cc_major == 10 && tc::get_encode_fn() != nullptr;
 }
 
-int gemm_tc(int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
-            const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias, const void* relu_src, int64_t ld_relu,
-            int flags, int split_k, cudaStream_t st) {
+int gemm_tc(int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A,
+            int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias, const void* relu_src,
+            int64_t ld_relu, int flags, int split_k, cudaStream_t st) {
   using namespace tc;
+  const int eb = dtype_ab == MVF_BF16 ? 2 : 4;   // fp32 operands run as tf32 (10-bit mantissa) on the tensor cores
+  const int BLOCK_K = ROW_BYTES / eb;
+  const int CHUNK = ROW_BYTES / eb;
   if (M <= 0 || N <= 0) return MVF_OK;
   MVF_REQUIRE(tc_available(), MVF_ERR_UNSUPPORTED, "tcgen05 GEMM requested but the device is not sm_100");
   MVF_REQUIRE(K > 0, MVF_ERR_BAD_ARG, "gemm_tc: K must be positive");
@@ -487,17 +514,22 @@ int gemm_tc(int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64
   p.c_bf16 = dtype_c == MVF_BF16;
   p.flags = flags;
   p.C = C; p.ldc = ldc; p.bias = bias;
-  p.relu_src = (const bf16*)relu_src; p.ld_relu = ld_relu;
+  p.relu_src = relu_src; p.ld_relu = ld_relu;
 
   CUtensorMap ma, mb;
-  if (a_kmajor) MVF_TRY(make_map(&ma, A, M, K, lda, BLOCK_K, BLOCK_M));
-  else MVF_TRY(make_map(&ma, A, K, M, lda, 64, BLOCK_K));
-  if (b_kmajor) MVF_TRY(make_map(&mb, B, N, K, ldb, BLOCK_K, bn));
-  else MVF_TRY(make_map(&mb, B, K, N, ldb, 64, BLOCK_K));
+  if (a_kmajor) MVF_TRY(make_map(&ma, A, M, K, lda, BLOCK_K, BLOCK_M, eb));
+  else MVF_TRY(make_map(&ma, A, K, M, lda, CHUNK, BLOCK_K, eb));
+  if (b_kmajor) MVF_TRY(make_map(&mb, B, N, K, ldb, BLOCK_K, bn, eb));
+  else MVF_TRY(make_map(&mb, B, K, N, ldb, CHUNK, BLOCK_K, eb));
 
-  if (bn == 256) return launch<256, 4>(ma, mb, p, g_num_sms, st);
-  if (bn == 128) return launch<128, 6>(ma, mb, p, g_num_sms, st);
-  return launch<64, 8>(ma, mb, p, g_num_sms, st);
+  if (eb == 2) {
+    if (bn == 256) return launch<256, 4, 2>(ma, mb, p, g_num_sms, st);
+    if (bn == 128) return launch<128, 6, 2>(ma, mb, p, g_num_sms, st);
+    return launch<64, 8, 2>(ma, mb, p, g_num_sms, st);
+  }
+  if (bn == 256) return launch<256, 4, 4>(ma, mb, p, g_num_sms, st);
+  if (bn == 128) return launch<128, 6, 4>(ma, mb, p, g_num_sms, st);
+  return launch<64, 8, 4>(ma, mb, p, g_num_sms, st);
 }
 
 }  // namespace mvf

@@ -110,7 +110,10 @@ struct Model {
   int ld0;     // padded
   int Hin;     // video_emb output width (== H unless one_hot == enc)
   int64_t F, R, S, rows, N;  // frames, entity rows, tokens per view, encoder rows, frame rows
-  int act;     // activation dtype
+  int act;     // dtype of every activation downstream of the pooling: always fp32 (exact FMA on the SIMT backend,
+               // tf32 tensor-core GEMMs on the tcgen05 backend -- bf16 there costs ~10 % on the gradient through the 1/tau
+               // amplification of SCL, tf32 ~2 %)
+  int kvt;     // dtype of tokens, W_k|W_v, K|V and dK|dV (the 96 % of the FLOPs): d.dtype
   std::vector<ParamInfo> params;
   // indices into params
   int iQs, iQb, iWk, ibk, iWv, ibv;
@@ -148,10 +151,12 @@ static int build_model(const mvf_head_desc* dp, Model& m) {
   MVF_REQUIRE(d.final_mode >= MVF_FINAL_MAX && d.final_mode <= MVF_FINAL_LIN, MVF_ERR_BAD_ARG, "final_mode %d",
               d.final_mode);
   MVF_REQUIRE(d.drop_p >= 0.f && d.drop_p < 1.f, MVF_ERR_BAD_ARG, "drop_p %f", d.drop_p);
-  if (d.dtype == MVF_BF16) {
-    bool ok = d.C_in % 8 == 0 && d.SPC % 8 == 0 && d.H % 8 == 0 && d.DFF % 8 == 0 && d.D % 8 == 0 && d.PS % 8 == 0;
-    for (int i = 0; i < d.n_fc; ++i) ok = ok && d.fc[i] % 8 == 0;
-    MVF_REQUIRE(ok, MVF_ERR_ALIGN, "bf16 mode needs every channel width to be a multiple of 8 (TMA 16-byte rows)");
+  if (d.dtype == MVF_BF16 || d.gemm_backend == MVF_GEMM_TCGEN05) {
+    bool ok = d.C_in % 8 == 0 && d.SPC % 8 == 0 && d.H % 4 == 0 && d.DFF % 4 == 0 && d.D % 4 == 0 && d.PS % 4 == 0;
+    for (int i = 0; i < d.n_fc; ++i) ok = ok && d.fc[i] % 4 == 0;
+    MVF_REQUIRE(ok, MVF_ERR_ALIGN,
+                "the tensor-core path needs C_in and SMART_POOL_CHANNELS to be multiples of 8 and every other channel "
+                "width a multiple of 4 (TMA 16-byte rows)");
   }
   m.E_oh = d.one_hot == MVF_ONEHOT_POOL ? d.E : 0;
   m.W0 = d.SPC + m.E_oh;
@@ -162,7 +167,8 @@ static int build_model(const mvf_head_desc* dp, Model& m) {
   m.S = (int64_t)d.E * d.T;
   m.rows = (int64_t)d.BV * m.S;
   m.N = m.F;
-  m.act = d.dtype;
+  m.act = MVF_F32;
+  m.kvt = d.dtype;
   m.params.clear();
   const std::string ca = "embed.pooling.cross_att.";
   m.iQs = add_param(m, ca + "Q_s", d.E, d.SPC);
@@ -253,7 +259,7 @@ static std::string fname(int i, const char* s) { return "fc" + std::to_string(i)
 static void head_save_layout(const Model& m, Layout& L) {
   const mvf_head_desc& d = m.d;
   const int A = m.act;
-  L.add("w.kv", 2 * d.SPC, d.C_in, A, round_up(d.C_in, 8));
+  L.add("w.kv", 2 * d.SPC, d.C_in, m.kvt, round_up(d.C_in, 8));
   L.add("b.kv", 1, 2 * d.SPC, RT_F32);
   int cin_ld = m.ld0;
   for (int i = 0; i < d.n_fc; ++i) {
@@ -270,7 +276,7 @@ static void head_save_layout(const Model& m, Layout& L) {
   }
   L.add("w.emb", d.D, d.H, A);
   if (d.final_mode == MVF_FINAL_LIN) L.add("w.lin", d.H, (int64_t)d.E * d.H, A);
-  L.add("kv", m.F * d.P, 2 * d.SPC, A);
+  L.add("kv", m.F * d.P, 2 * d.SPC, m.kvt);
   L.add("attn", m.F * d.E, d.P, RT_F32);
   L.add("h0", m.R, m.W0, A, m.ld0);
   L.add("ent32", m.R, d.SPC, RT_F32);
@@ -332,7 +338,7 @@ static void head_ws_layout(const Model& m, Layout& L) {
   L.add("da", m.R, maxfc, RT_F32);
   for (int i = 0; i < d.n_fc; ++i) L.add(fname(i, "dx"), m.R, d.fc[i], A);
   L.add("dh0", m.R, m.W0, A, m.ld0);
-  L.add("dkv", m.F * d.P, 2 * d.SPC, A);
+  L.add("dkv", m.F * d.P, 2 * d.SPC, m.kvt);
 }
 
 static void proj_save_layout(const Model& m, Layout& L) {
@@ -434,6 +440,12 @@ struct Ctx {
     return gemm_dispatch(backend, m.act, dtype_c, akm, bkm, M, N, K, A, lda, B, ldb, C, ldc, bias, relu_src, ld_relu,
                          flags, split_k, on ? on : st);
   }
+  // the two K|V contractions: operands in the token dtype
+  int gemm_kv(int dtype_c, int akm, int bkm, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+              int64_t ldb, void* C, int64_t ldc, const float* bias, int flags, int split_k) const {
+    return gemm_dispatch(backend, m.kvt, dtype_c, akm, bkm, M, N, K, A, lda, B, ldb, C, ldc, bias, nullptr, 0, flags,
+                         split_k, st);
+  }
   int fork() {
     if (!side) return MVF_OK;
     cudaEvent_t e = side_event();
@@ -492,9 +504,9 @@ static int make_ctx(const mvf_head_desc* d, Ctx& c, bool proj, void* save, size_
   c.P = params;
   c.st = st;
   c.backend = d->gemm_backend;
+  // AUTO: bf16 tokens -> tensor cores everywhere (bf16 K|V contractions, tf32 for the fp32 activations behind the
+  // pooling); fp32 tokens -> exact fp32 FMA everywhere (the 1e-5 parity mode).  TCGEN05 with fp32 tokens = all tf32.
   if (c.backend == MVF_GEMM_AUTO) c.backend = d->dtype == MVF_BF16 ? MVF_GEMM_TCGEN05 : MVF_GEMM_SIMT;
-  if (c.backend == MVF_GEMM_TCGEN05)
-    MVF_REQUIRE(d->dtype == MVF_BF16, MVF_ERR_UNSUPPORTED, "the tcgen05 GEMM needs dtype = bf16");
   c.p = d->training ? d->drop_p : 0.f;
   // the head needs embed.*; the projection needs ssl_projection.* (entries of the other part may be null)
   for (int i = 0; i < (int)c.m.params.size(); ++i) {
@@ -563,13 +575,13 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       // a4: K|V projection of every patch token -- the dominant contraction
       {
         ProfScope ps(0, st);
-        MVF_TRY(c.linear(A, m.F * d.P, 2 * d.SPC, d.C_in, tokens, d.C_in, c.S.p("w.kv"), c.S.ld("w.kv"), c.S.f("b.kv"),
-                         c.S.p("kv"), 2 * d.SPC));
+        MVF_TRY(c.gemm_kv(m.kvt, 1, 1, m.F * d.P, 2 * d.SPC, d.C_in, tokens, d.C_in, c.S.p("w.kv"), c.S.ld("w.kv"),
+                          c.S.p("kv"), 2 * d.SPC, c.S.f("b.kv"), 0, 1));
       }
       float* attn = c.S.f("attn");
       {
         ProfScope ps(2, st);
-        MVF_TRY(xattn_pool_fwd(A, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], attn, c.S.p("h0"), m.ld0,
+        MVF_TRY(xattn_pool_fwd(m.kvt, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], attn, c.S.p("h0"), m.ld0,
                                c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, st));
       }
       if (attn_out)
@@ -788,15 +800,15 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
       float* gbkv = c.G.f("g.b.kv");
       {
         ProfScope ps(3, st);
-        MVF_TRY(xattn_pool_bwd(A, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], c.S.f("attn"),
+        MVF_TRY(xattn_pool_bwd(m.kvt, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], c.S.f("attn"),
                                c.W.p("dh0"), m.ld0, c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, c.W.p("dkv"),
                                c.G.f("g.Qs"), c.G.f("g.Qb"), gbkv, gbkv + o_spc, st));
       }
       // dW_kv = dKV^T X : 2*SPC x C_in outputs, K = frames*tokens -> split-K across the machine
       {
         ProfScope ps(1, st);
-        MVF_TRY(c.gemm(MVF_F32, 0, 0, 2 * d.SPC, d.C_in, m.F * d.P, c.W.p("dkv"), 2 * d.SPC, tokens, d.C_in,
-                       c.G.f("g.w.kv"), c.Lg.find("g.w.kv")->ld, nullptr, nullptr, 0, MVF_GEMM_ACCUM, 0));
+        MVF_TRY(c.gemm_kv(MVF_F32, 0, 0, 2 * d.SPC, d.C_in, m.F * d.P, c.W.p("dkv"), 2 * d.SPC, tokens, d.C_in,
+                          c.G.f("g.w.kv"), c.Lg.find("g.w.kv")->ld, nullptr, MVF_GEMM_ACCUM, 0));
       }
     }
   }

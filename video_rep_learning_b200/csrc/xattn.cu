@@ -12,8 +12,8 @@ namespace mvf {
 template <typename T, int EMAX>
 __global__ void __launch_bounds__(256)
 xattn_fwd_kernel(int P, int E, int SPC, const T* __restrict__ kv, const float* __restrict__ q_s,
-                 const float* __restrict__ q_b, float* __restrict__ attn, T* __restrict__ ent, int64_t ld_ent, int one_hot,
-                 float p_drop, float inv_keep, uint64_t seed) {
+                 const float* __restrict__ q_b, float* __restrict__ attn, float* __restrict__ ent, int64_t ld_ent,
+                 int one_hot, float p_drop, float inv_keep, uint64_t seed) {
   extern __shared__ float sm[];
   float* Q = sm;                   // [E][SPC]
   float* A = sm + (size_t)E * SPC; // [E][P]
@@ -89,7 +89,7 @@ xattn_fwd_kernel(int P, int E, int SPC, const T* __restrict__ kv, const float* _
         const int64_t row = (int64_t)f * E + e;
         float v = acc[e];
         if (p_drop > 0.f) v *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + c), p_drop, inv_keep);
-        ent[row * ld_ent + c] = from_f<T>(v);
+        ent[row * ld_ent + c] = v;
       }
     }
   }
@@ -99,14 +99,14 @@ xattn_fwd_kernel(int P, int E, int SPC, const T* __restrict__ kv, const float* _
     const int64_t row = (int64_t)f * E + e;
     float v = (one_hot && j == e) ? 1.f : 0.f;
     if (v != 0.f && p_drop > 0.f) v *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + SPC + j), p_drop, inv_keep);
-    ent[row * ld_ent + SPC + j] = from_f<T>(v);
+    ent[row * ld_ent + SPC + j] = v;
   }
 }
 
 template <typename T, int EMAX>
 __global__ void __launch_bounds__(256)
 xattn_bwd_kernel(int P, int E, int SPC, const T* __restrict__ kv, const float* __restrict__ q_s,
-                 const float* __restrict__ q_b, const float* __restrict__ attn, const T* __restrict__ d_ent,
+                 const float* __restrict__ q_b, const float* __restrict__ attn, const float* __restrict__ d_ent,
                  int64_t ld_ent, int one_hot, float p_drop, float inv_keep, uint64_t seed, T* __restrict__ d_kv,
                  float* __restrict__ d_q_s, float* __restrict__ d_q_b, float* __restrict__ d_bk,
                  float* __restrict__ d_bv) {
@@ -127,7 +127,7 @@ xattn_bwd_kernel(int P, int E, int SPC, const T* __restrict__ kv, const float* _
     const int e = i / SPC, c = i % SPC;
     Q[i] = q_s[i] + q_b[c];
     const int64_t row = (int64_t)f * E + e;
-    float g = to_f<T>(d_ent[row * ld_ent + c]);
+    float g = d_ent[row * ld_ent + c];
     if (p_drop > 0.f) g *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + c), p_drop, inv_keep);
     dEnt[i] = g;
   }
@@ -235,7 +235,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 template <int EMAX, int CPL>
 __global__ void __launch_bounds__(256, 2)
 xattn_fwd_v2_kernel(int P, int E, int SPC, const bf16* __restrict__ kv, const float* __restrict__ q_s,
-                    const float* __restrict__ q_b, float* __restrict__ attn, bf16* __restrict__ ent, int64_t ld_ent,
+                    const float* __restrict__ q_b, float* __restrict__ attn, float* __restrict__ ent, int64_t ld_ent,
                     float* __restrict__ ent32, int one_hot, float p_drop, float inv_keep, uint64_t seed) {
   extern __shared__ __align__(16) float sm[];
   float* Q = sm;                         // [E][SPC]
@@ -351,21 +351,21 @@ xattn_fwd_v2_kernel(int P, int E, int SPC, const bf16* __restrict__ kv, const fl
     const int64_t row = (int64_t)f * E + e;
     if (ent32) ent32[row * SPC + c] = v;
     if (p_drop > 0.f) v *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + c), p_drop, inv_keep);
-    ent[row * ld_ent + c] = __float2bfloat16_rn(v);
+    ent[row * ld_ent + c] = v;
   }
   for (int i = tid; i < E * ((int)ld_ent - SPC); i += blockDim.x) {
     const int e = i / ((int)ld_ent - SPC), j = i % ((int)ld_ent - SPC);
     const int64_t row = (int64_t)f * E + e;
     float v = (one_hot && j == e) ? 1.f : 0.f;
     if (v != 0.f && p_drop > 0.f) v *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + SPC + j), p_drop, inv_keep);
-    ent[row * ld_ent + SPC + j] = __float2bfloat16_rn(v);
+    ent[row * ld_ent + SPC + j] = v;
   }
 }
 
 template <int EMAX, int CPL>
 __global__ void __launch_bounds__(256, 1)
 xattn_bwd_v2_kernel(int P, int E, int SPC, const bf16* __restrict__ kv, const float* __restrict__ q_s,
-                    const float* __restrict__ q_b, const float* __restrict__ attn, const bf16* __restrict__ d_ent,
+                    const float* __restrict__ q_b, const float* __restrict__ attn, const float* __restrict__ d_ent,
                     int64_t ld_ent, const float* __restrict__ ent32, int one_hot, float p_drop, float inv_keep,
                     uint64_t seed, bf16* __restrict__ d_kv, float* __restrict__ d_q_s, float* __restrict__ d_q_b,
                     float* __restrict__ d_bk, float* __restrict__ d_bv) {
@@ -385,7 +385,7 @@ xattn_bwd_v2_kernel(int P, int E, int SPC, const bf16* __restrict__ kv, const fl
     const int e = i / SPC, c = i - e * SPC;
     QG[(size_t)e * 2 * SPC + c] = q_s[i] + q_b[c];
     const int64_t row = (int64_t)f * E + e;
-    float g = __bfloat162float(d_ent[row * ld_ent + c]);
+    float g = d_ent[row * ld_ent + c];
     if (p_drop > 0.f) g *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + c), p_drop, inv_keep);
     QG[(size_t)e * 2 * SPC + SPC + c] = g;
   }
@@ -532,7 +532,7 @@ static int fwd_v2_launch(int F, int P, int E, int SPC, const void* kv, const flo
     cfgd = true;
   }
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  xattn_fwd_v2_kernel<EM, CPL><<<F, 256, smem, st>>>(P, E, SPC, (const bf16*)kv, q_s, q_b, attn, (bf16*)ent, ld_ent, ent32,
+  xattn_fwd_v2_kernel<EM, CPL><<<F, 256, smem, st>>>(P, E, SPC, (const bf16*)kv, q_s, q_b, attn, (float*)ent, ld_ent, ent32,
                                                      one_hot, drop_p, ik, seed);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
@@ -550,7 +550,7 @@ static int bwd_v2_launch(int F, int P, int E, int SPC, const void* kv, const flo
     cfgd = true;
   }
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  xattn_bwd_v2_kernel<EM, CPL><<<F, 256, smem, st>>>(P, E, SPC, (const bf16*)kv, q_s, q_b, attn, (const bf16*)d_ent, ld_ent,
+  xattn_bwd_v2_kernel<EM, CPL><<<F, 256, smem, st>>>(P, E, SPC, (const bf16*)kv, q_s, q_b, attn, (const float*)d_ent, ld_ent,
                                                      ent32, one_hot, drop_p, ik, seed, (bf16*)d_kv, d_q_s, d_q_b, d_bk, d_bv);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
@@ -566,7 +566,7 @@ static int fwd_t(int F, int P, int E, int SPC, const void* kv, const float* q_s,
     if (smem > 48 * 1024)                                                                                         \
       MVF_CHECK_CUDA(cudaFuncSetAttribute(xattn_fwd_kernel<T, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                           (int)smem));                                                            \
-    xattn_fwd_kernel<T, EM><<<F, 256, smem, st>>>(P, E, SPC, (const T*)kv, q_s, q_b, attn, (T*)ent, ld_ent, one_hot, \
+    xattn_fwd_kernel<T, EM><<<F, 256, smem, st>>>(P, E, SPC, (const T*)kv, q_s, q_b, attn, (float*)ent, ld_ent, one_hot, \
                                                   drop_p, ik, seed);                                              \
   } while (0)
   if (E <= 4) LAUNCH_F(4);
@@ -609,7 +609,7 @@ static int bwd_t(int F, int P, int E, int SPC, const void* kv, const float* q_s,
     if (smem > 48 * 1024)                                                                                         \
       MVF_CHECK_CUDA(cudaFuncSetAttribute(xattn_bwd_kernel<T, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                           (int)smem));                                                            \
-    xattn_bwd_kernel<T, EM><<<F, 256, smem, st>>>(P, E, SPC, (const T*)kv, q_s, q_b, attn, (const T*)d_ent, ld_ent, \
+    xattn_bwd_kernel<T, EM><<<F, 256, smem, st>>>(P, E, SPC, (const T*)kv, q_s, q_b, attn, (const float*)d_ent, ld_ent, \
                                                   one_hot, drop_p, ik, seed, (T*)d_kv, d_q_s, d_q_b, d_bk, d_bv); \
   } while (0)
   if (E <= 4) LAUNCH_B(4);
