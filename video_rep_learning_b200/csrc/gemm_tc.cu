@@ -119,15 +119,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major : rows of 128 B along K; 8-row groups 1024 B apart (SBO); LBO unused.
 //   MN-major: k-rows of 128 B along M/N (64 bf16 / 32 fp32); 8-k groups 1024 B apart (SBO); successive 128-byte
 //             M/N chunks are separate TMA boxes of block_k_rows*128 B (LBO): 8192 B for bf16, 4096 B for tf32.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool kmajor, int block_k_rows) {
+//   MN-major tf32 is special: the only legal layout is SWIZZLE_128B with a 32-byte swizzle atom ("128B_BASE32B",
+//   TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): k-rows of 128 B, swizzle period 4 rows, so 4-k groups are 512 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool kmajor, int block_k_rows, int eb) {
   uint64_t d = 0;
+  const bool base32 = !kmajor && eb == 4;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   uint32_t lbo = kmajor ? 1u : (uint32_t)((block_k_rows * 128) >> 4);
-  uint32_t sbo = 1024u >> 4;
+  uint32_t sbo = (base32 ? 512u : 1024u) >> 4;
   d |= (uint64_t)(lbo & 0x3FFF) << 16;
   d |= (uint64_t)(sbo & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)(base32 ? 1 : 2) << 61;   // SWIZZLE_128B_BASE32B : SWIZZLE_128B
   return d;
 }
 
@@ -258,8 +261,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&full_bar[stage], phase, 3);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t da = make_smem_desc(sa, p.a_kmajor != 0, BLOCK_K);
-          const uint64_t db = make_smem_desc(sa + A_BYTES, p.b_kmajor != 0, BLOCK_K);
+          const uint64_t da = make_smem_desc(sa, p.a_kmajor != 0, BLOCK_K, EB);
+          const uint64_t db = make_smem_desc(sa + A_BYTES, p.b_kmajor != 0, BLOCK_K, EB);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             umma<EB>(tmem_d, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc,
@@ -403,7 +406,7 @@ static EncodeTiledFn get_encode_fn() {
 // rows x cols row-major matrix (bf16 when eb == 2, fp32 when eb == 4) with leading dimension ld (elements);
 // box = box_cols x box_rows.
 static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
-                    int box_rows, int eb) {
+                    int box_rows, int eb, bool mn_major) {
   EncodeTiledFn fn = get_encode_fn();
   MVF_REQUIRE(fn != nullptr, MVF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   MVF_REQUIRE((((uintptr_t)ptr) & 15) == 0, MVF_ERR_ALIGN, "gemm_tc: operand base %p not 16-byte aligned", ptr);
@@ -414,8 +417,9 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                  const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  (mn_major && eb == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MVF_REQUIRE(r == CUDA_SUCCESS, MVF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
               (long long)rows, (long long)cols, (long long)ld);
@@ -517,10 +521,10 @@ int gemm_tc(int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, in
   p.relu_src = relu_src; p.ld_relu = ld_relu;
 
   CUtensorMap ma, mb;
-  if (a_kmajor) MVF_TRY(make_map(&ma, A, M, K, lda, BLOCK_K, BLOCK_M, eb));
-  else MVF_TRY(make_map(&ma, A, K, M, lda, CHUNK, BLOCK_K, eb));
-  if (b_kmajor) MVF_TRY(make_map(&mb, B, N, K, ldb, BLOCK_K, bn, eb));
-  else MVF_TRY(make_map(&mb, B, K, N, ldb, CHUNK, BLOCK_K, eb));
+  if (a_kmajor) MVF_TRY(make_map(&ma, A, M, K, lda, BLOCK_K, BLOCK_M, eb, false));
+  else MVF_TRY(make_map(&ma, A, K, M, lda, CHUNK, BLOCK_K, eb, true));
+  if (b_kmajor) MVF_TRY(make_map(&mb, B, N, K, ldb, BLOCK_K, bn, eb, false));
+  else MVF_TRY(make_map(&mb, B, K, N, ldb, CHUNK, BLOCK_K, eb, true));
 
   if (eb == 2) {
     if (bn == 256) return launch<256, 4, 2>(ma, mb, p, g_num_sms, st);
