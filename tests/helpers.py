@@ -103,3 +103,35 @@ def run_oracle(hc: O.HeadCfg, P, buf, tokens, masks, seq_lens, steps, *, dtype=t
     loss.backward()
     return dict(emb=emb.detach(), e=e.detach(), loss=loss.detach(), grads={k: v.grad for k, v in Pr.items()}, bufs=nb,
                 aux={k: v.detach() for k, v in aux.items()})
+
+
+def run_oracle_quantized(hc, P, tokens, masks, seq_lens, steps, negative_type="single_noself"):
+    """The reference algorithm in fp64 on the SAME quantised operands the bf16 path consumes: bf16 tokens, bf16 W_k|W_v,
+    and K|V rounded to bf16 (straight-through).  Separates the error of the implementation from the error that "bf16
+    operands" makes inevitable (which the 1/tau of SCL amplifies ~40x from embeddings to gradients)."""
+    import torch.nn.functional as F
+
+    def bf(x):
+        return x.float().bfloat16().double()
+
+    Pq = dict(P)
+    for k in ("embed.pooling.cross_att.linear_K2d.weight", "embed.pooling.cross_att.linear_V2d.weight"):
+        Pq[k] = P[k].bfloat16().float()
+    orig = O.xattn_pool
+
+    def xattn_q(Pd, tok, cfg):
+        pre = "embed.pooling.cross_att."
+        K = F.linear(tok, Pd[pre + "linear_K2d.weight"], Pd[pre + "linear_K2d.bias"])
+        V = F.linear(tok, Pd[pre + "linear_V2d.weight"], Pd[pre + "linear_V2d.bias"])
+        K = K + (bf(K.detach()) - K.detach())
+        V = V + (bf(V.detach()) - V.detach())
+        Q = Pd[pre + "Q_s"][0] + Pd[pre + "Q_s_b"]
+        A = torch.softmax(torch.einsum("btpc,ec->btep", K, Q) / np.sqrt(cfg.pool_channels), -1)
+        return torch.einsum("btep,btpc->btec", A, V), A
+
+    O.xattn_pool = xattn_q
+    try:
+        return run_oracle(hc, Pq, None, tokens.bfloat16().float(), masks, seq_lens, steps, dtype=torch.float64,
+                          negative_type=negative_type)
+    finally:
+        O.xattn_pool = orig

@@ -78,20 +78,29 @@ def test_every_stage_against_the_oracle(name):
 
 
 def test_bf16_step_within_north_star_tolerance():
-    """bf16 operands / fp32 accumulate through the tcgen05 GEMMs vs the fp32 reference golden: 2e-2 relative."""
+    """bf16 tokens / K|V on tcgen05 kind::f16, tf32 tensor-core GEMMs behind the pooling.
+    (1) against the reference evaluated on the same quantised operands: 2e-2 on embeddings, loss AND gradients;
+    (2) against the fp32 reference golden (fp32 tokens): 2e-2 on embeddings and loss; the gradient carries the
+        quantisation floor of bf16 tokens + bf16 W_k|W_v, amplified ~40x by SCL's 1/tau ("bf16 error budget")."""
     m, hc, z, P, G, B = H.load_case("tiny_fg_avg")
     tokens, masks, seq_lens, steps = _inputs(z)
     r = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16)
-    assert H.rel_l2(r["e"], torch.from_numpy(z["ref_e"])) < 2e-2
-    assert abs(float(r["loss"]) - float(z["ref_loss"])) / float(z["ref_loss"]) < 2e-2
     keys = list(P.keys())
-    err = H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(G, keys))
-    print("bf16 concatenated-gradient rel err", err)
-    assert err < 6e-2        # the reference's own bf16-autocast run is 1.7e-1 off its fp32 run (SURVEY.md 7.2-9)
-    # same bf16 inputs through the SIMT engine: isolates tensor-core GEMM error from bf16 rounding of operands
+    q = H.run_oracle_quantized(hc, P, tokens, masks, seq_lens, steps)
+    eq = H.rel_l2(r["e"], q["e"])
+    lq = abs(float(r["loss"]) - float(q["loss"])) / float(q["loss"])
+    gq = H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(q["grads"], keys))
+    print(f"bf16 vs same-operand oracle: embeddings {eq:.2e} loss {lq:.2e} gradient {gq:.2e}")
+    assert eq < 2e-2 and lq < 2e-2 and gq < 2e-2
+    e32 = H.rel_l2(r["e"], torch.from_numpy(z["ref_e"]))
+    l32 = abs(float(r["loss"]) - float(z["ref_loss"])) / float(z["ref_loss"])
+    g32 = H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(G, keys))
+    print(f"bf16 vs fp32 reference golden: embeddings {e32:.2e} loss {l32:.2e} gradient {g32:.2e}")
+    assert e32 < 2e-2 and l32 < 2e-2 and g32 < 8e-2
+    # same inputs through the exact-fp32 SIMT engine: isolates the tensor-core GEMMs from the operand quantisation
     r2 = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16, backend=L.GEMM_SIMT)
-    assert H.rel_l2(r["e"], r2["e"]) < 1e-2        # bf16 re-rounding of intermediates amplifies 1-ulp differences
-    assert H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(r2["grads"], keys)) < 3e-2
+    assert H.rel_l2(r["e"], r2["e"]) < 5e-3
+    assert H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(r2["grads"], keys)) < 2e-2
 
 
 def test_penn_cfg1_shape_fp32_digest():
@@ -119,14 +128,21 @@ def test_penn_cfg1_shape_fp32_digest():
         head = torch.tensor(dg["head"], dtype=torch.float64)
         assert float((g[:6] - head).abs().max()) < 1e-5 * dg["absmax"] + 1e-9, k
         tot += float(g.norm()) ** 2
-    # bf16 / tcgen05 at the same shape against the fp32 reference
+    # bf16 / tcgen05 at the same shape: (1) vs the fp32 reference golden, (2) vs the reference on the same quantised operands
     rb = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16)
     assert H.rel_l2(rb["e"], torch.from_numpy(z["ref_e"])) < 2e-2
     assert abs(float(rb["loss"]) - float(z["ref_loss"])) / float(z["ref_loss"]) < 2e-2
     keys = list(r["grads"].keys())
     eb = H.rel_l2(H.grad_vector(rb["grads"], keys), H.grad_vector(r["grads"], keys))
     print("cfg1 bf16-vs-fp32 concatenated gradient rel err", eb)
-    assert eb < 6e-2
+    assert eb < 8e-2       # quantisation floor measured with the fp64 oracle: 6.6e-2 ("bf16 error budget")
+    torch.set_num_threads(os.cpu_count() or 1)
+    q = H.run_oracle_quantized(hc, P, tokens, masks, seq_lens, steps)
+    eq = H.rel_l2(rb["e"], q["e"])
+    lq = abs(float(rb["loss"]) - float(q["loss"])) / float(q["loss"])
+    gq = H.rel_l2(H.grad_vector(rb["grads"], keys), H.grad_vector(q["grads"], keys))
+    print(f"cfg1 bf16 vs same-operand oracle: embeddings {eq:.2e} loss {lq:.2e} gradient {gq:.2e}")
+    assert eq < 2e-2 and lq < 2e-2 and gq < 2e-2
 
 
 def test_eval_forward_golden():
