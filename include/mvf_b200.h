@@ -169,10 +169,14 @@ int mvf_scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* s
 /* C[M,N] (+)= opA(A) * opB(B) + bias.  a_kmajor: A stored [M,K] row-major (else [K,M]);
  * b_kmajor: B stored [N,K] row-major like nn.Linear.weight (else [K,N]).  dtype_ab / dtype_c: mvf_dtype.
  * Backend TCGEN05: bf16 operands -> tcgen05 kind::f16, fp32 operands -> kind::tf32 (fp32 output only).
- * flags: bit0 ReLU, bit1 accumulate into C (fp32 C only), bit2 multiply by (relu_src > 0). */
+ * flags: bit0 ReLU, bit1 accumulate into C (fp32 C only), bit2 multiply by (relu_src > 0), bit3 (TCGEN05 backend,
+ * fp32 operands, both K-major; ignored otherwise) "bf16x3": each fp32 operand is split in shared memory into
+ * bf16 hi + lo and A_lo*B_hi + A_hi*B_lo + A_hi*B_hi is accumulated on kind::f16 -- 16 mantissa bits per operand
+ * instead of tf32's truncated 10.  The head uses it for every forward GEMM behind the pooling. */
 #define MVF_GEMM_RELU 1
 #define MVF_GEMM_ACCUM 2
 #define MVF_GEMM_RELUMASK 4
+#define MVF_GEMM_SPLIT3 8
 int mvf_gemm(int backend, int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K,
              const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
              const void* relu_src, int64_t ld_relu, int flags, int split_k, mvf_stream_t stream);

@@ -78,7 +78,7 @@ def test_errors_are_reported_not_swallowed():
     assert lib.mvf_num_params(C.byref(d)) == -1
     assert "bad input shape" in L.last_error()
     hc = O.HeadCfg(c_in=50)      # not a multiple of 8 -> illegal for bf16/TMA
-    with pytest.raises(RuntimeError, match="multiple of 8"):
+    with pytest.raises(RuntimeError, match="multiples of 8"):
         engine.Plan(H.spec_from_headcfg(hc), 2, 4, 9, L.MVF_BF16, True, False, 1, 0)
     with pytest.raises(NotImplementedError):
         engine.Plan(H.spec_from_headcfg(O.HeadCfg(c_in=48, fc_channels=(8, 8, 8, 8, 8))), 2, 4, 9, 0, True, False, 1, 0)

@@ -109,6 +109,35 @@ def test_tcgen05_tf32(a_k, b_k, M, N, K):
     assert float((C3.double() - ref * (src > 0)).abs().max() / ref.abs().max()) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (256, 256, 128), (200, 72, 100), (3840, 512, 392), (130, 392, 516),
+                                   (3840, 1024, 256), (1280, 128, 1024), (77, 1536, 388)])
+def test_tcgen05_bf16x3_split(M, N, K):
+    """MVF_GEMM_SPLIT3: fp32 operands split in shared memory into bf16 hi + lo, three kind::f16 MMAs per K slice.
+    Error bound: the dropped lo*lo term and the 16-bit mantissa of hi+lo, ~2^-16 relative per product."""
+    padK = (-K) % 4
+    g = torch.Generator(device="cuda").manual_seed(M + 5 * N + K)
+    A = torch.randn(M, K + padK, generator=g, device="cuda")
+    B = torch.randn(N, K + padK, generator=g, device="cuda")
+    ref = A[:, :K].double() @ B[:, :K].double().t()
+    bias = torch.randn(N, device="cuda")
+    C = _gemm(L.GEMM_TCGEN05, A, B, 1, 1, M, N, K, torch.float32, bias=bias, flags=L.GEMM_SPLIT3)
+    err = float((C.double() - (ref + bias.double())).abs().max() / ref.abs().max())
+    assert err < 2e-5, f"bf16x3 error {err}"
+    # exact model: product of the (hi + lo) operands minus the lo*lo term, fp32 accumulation
+    def split(t):
+        hi = t.bfloat16().float()
+        lo = (t - hi).bfloat16().float()
+        return hi.double(), lo.double()
+    ah, al = split(A[:, :K]); bh, bl = split(B[:, :K])
+    model = ah @ bh.t() + ah @ bl.t() + al @ bh.t()
+    assert float((C.double() - (model + bias.double())).abs().max() / ref.abs().max()) < 3e-6
+    Ct = _gemm(L.GEMM_TCGEN05, A, B, 1, 1, M, N, K, torch.float32, bias=bias)
+    err_t = float((Ct.double() - (ref + bias.double())).abs().max() / ref.abs().max())
+    assert err < err_t / 8, (err, err_t)          # and it really is far tighter than plain tf32
+    C2 = _gemm(L.GEMM_TCGEN05, A, B, 1, 1, M, N, K, torch.float32, bias=bias, flags=L.GEMM_SPLIT3 | L.GEMM_RELU)
+    assert float((C2.double() - (ref + bias.double()).clamp_min(0)).abs().max() / ref.abs().max()) < 2e-5
+
+
 @pytest.mark.parametrize("split", [0, 2, 7])
 def test_tcgen05_split_k_weight_gradient_shape(split):
     """dW = dY^T X with a long contraction and few output tiles: both operands MN-major, fp32 atomics."""

@@ -18,7 +18,7 @@ ONEHOT = {"none": 0, "pool": 1, "enc": 2}
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 NEG = {"single_noself": 0, "batch_noself": 1}
 PHASE_ALL = 255
-GEMM_RELU, GEMM_ACCUM, GEMM_RELUMASK = 1, 2, 4
+GEMM_RELU, GEMM_ACCUM, GEMM_RELUMASK, GEMM_SPLIT3 = 1, 2, 4, 8
 MAX_FC = 4
 SITE_FC0, SITE_POS, SITE_ENC0 = 0, 8, 16
 

@@ -17,6 +17,12 @@
 // Two TMEM accumulators (2*BLOCK_N columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 // Split-K (work item = tile x K-slice, fp32 atomics) fills the machine when M*N is small and K huge
 // (the weight gradient of the K/V projection: 768 x 2304 outputs, K = frames*196).
+//
+// SPLIT3 ("bf16x3") mode for fp32 operands, both K-major: kind::tf32 truncates the operands to 10 mantissa bits,
+// which the 1/temperature of SCL amplifies to a few 1e-2 on the gradients.  In this mode four extra warps (8..11)
+// rewrite every landed fp32 stage IN PLACE as bf16 pairs -- a 128-byte row of 32 fp32 becomes [hi(32) | lo(32)] bf16
+// with hi = bf16(x), lo = bf16(x - hi), same swizzle -- and the MMA warp issues A_lo*B_hi + A_hi*B_lo + A_hi*B_hi on
+// kind::f16 (6 MMAs of K=16 per stage).  16 mantissa bits per operand at 1.5x the tensor time of tf32.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -29,6 +35,7 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int ROW_BYTES = 128;  // one swizzle row of K per stage: 64 bf16 or 32 fp32 (tf32)
 constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS_SPLIT = 384;  // + 4 converter warps
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,6 +86,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int EB>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -158,8 +167,8 @@ struct Params {
   int64_t ld_relu;
 };
 
-template <int BLOCK_N, int STAGES, int EB>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BLOCK_N, int STAGES, int EB, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
   constexpr int BLOCK_K = ROW_BYTES / EB;   // elements of K per stage (64 bf16 / 32 tf32)
   constexpr int UMMA_K = 32 / EB;           // elements of K per tcgen05.mma (16 / 8)
@@ -177,7 +186,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint64_t* conv_bar = tmem_empty + 2;  // SPLIT: stage rewritten as bf16 hi|lo, ready for the MMA warp
+  uint32_t* tmem_slot = (uint32_t*)(conv_bar + STAGES);
+  static_assert(!SPLIT || EB == 4, "SPLIT3 applies to fp32 operands");
+  static_assert((3 * STAGES + 4) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
+  float* epi_stage = (float*)(smem + STAGES * STAGE_BYTES + 256);  // 4 warps x [32][33] fp32 transpose tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_work = p.tiles_m * p.tiles_n * p.split_k;
@@ -187,7 +200,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], NUM_THREADS_SPLIT - NUM_THREADS);
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -240,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_N, p.a_kmajor != 0, p.b_kmajor != 0, EB);
+      const uint32_t idesc = SPLIT ? make_idesc(BLOCK_N, true, true, 2) : make_idesc(BLOCK_N, p.a_kmajor != 0, p.b_kmajor != 0, EB);
       // start-address advance (in 16 B units) per UMMA_K step inside a stage: 32 B along a K-major row,
       // UMMA_K rows of 128 B for an MN-major operand
       const uint32_t adv_a = p.a_kmajor ? (UMMA_K * EB) >> 4 : (UMMA_K * 128) >> 4;
@@ -258,15 +275,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase, 3);
+          mbar_wait(SPLIT ? &conv_bar[stage] : &full_bar[stage], phase, 3);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t da = make_smem_desc(sa, p.a_kmajor != 0, BLOCK_K, EB);
-          const uint64_t db = make_smem_desc(sa + A_BYTES, p.b_kmajor != 0, BLOCK_K, EB);
+          if constexpr (SPLIT) {
+            // row = [hi k0..15 | hi k16..31 | lo k0..15 | lo k16..31] bf16, 32 bytes each: +2 descriptor units per slot
+            const uint64_t da = make_smem_desc(sa, true, BLOCK_K, 2);
+            const uint64_t db = make_smem_desc(sa + A_BYTES, true, BLOCK_K, 2);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma<EB>(tmem_d, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t hi = (uint64_t)(2 * j), lo = (uint64_t)(4 + 2 * j);
+              umma<2>(tmem_d, da + lo, db + hi, idesc, (kb > kb0 || j > 0) ? 1u : 0u);   // small terms first
+              umma<2>(tmem_d, da + hi, db + lo, idesc, 1u);
+              umma<2>(tmem_d, da + hi, db + hi, idesc, 1u);
+            }
+          } else {
+            const uint64_t da = make_smem_desc(sa, p.a_kmajor != 0, BLOCK_K, EB);
+            const uint64_t db = make_smem_desc(sa + A_BYTES, p.b_kmajor != 0, BLOCK_K, EB);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              umma<EB>(tmem_d, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc,
+                       (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -274,7 +304,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
       }
     }
-  } else if (warp >= 4) {
+  } else if (SPLIT && warp >= 8) {
+    // ===================== fp32 -> bf16 hi|lo converter (SPLIT3) =====================
+    // Thread t owns rows t, t+128, ... of the stage (A rows then B rows; both tiles are K-major, 128-byte rows,
+    // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r & 7)).  It reads its whole row and writes it back,
+    // so the rewrite is race-free in place; fence.proxy.async makes it visible to the tensor core's async proxy.
+    const int ct = threadIdx.x - NUM_THREADS;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int split = w / (p.tiles_m * p.tiles_n);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 5);
+        uint8_t* tile = smem + stage * STAGE_BYTES;
+#pragma unroll 1
+        for (int r = ct; r < BLOCK_M + BLOCK_N; r += NUM_THREADS_SPLIT - NUM_THREADS) {
+          uint4* rowp = reinterpret_cast<uint4*>(tile + r * ROW_BYTES);
+          const int sw = r & 7;
+          float4 v[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(rowp + (c ^ sw));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float x[8] = {v[2 * c].x, v[2 * c].y, v[2 * c].z, v[2 * c].w,
+                                v[2 * c + 1].x, v[2 * c + 1].y, v[2 * c + 1].z, v[2 * c + 1].w};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+              const float2 hf = __bfloat1622float2(h);
+              const __nv_bfloat162 l = __floats2bfloat162_rn(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
+              hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            rowp[c ^ sw] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            rowp[(4 + c) ^ sw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&conv_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     int it = 0;
@@ -292,6 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && split == 0;
       const bool atomic = p.split_k > 1;
+      float* ts = epi_stage + (warp - 4) * (32 * 33);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         const int col0 = tn * BLOCK_N + c0;
@@ -299,6 +374,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
         tmem_ld_wait();
+        if (!p.c_bf16) {
+          // fp32 output: transpose the 32x32 chunk through shared memory so that every global access of the warp is
+          // one coalesced 128-byte row segment (thread = row in TMEM, thread = column in memory)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ts[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          const int col = col0 + lane;
+          const bool col_ok = col < p.N;
+          const float bv = (add_bias && col_ok) ? __ldg(p.bias + col) : 0.f;
+          const int row_base = tm * BLOCK_M + q * 32;
+          if (has_k) {
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              const int row = row_base + rr;
+              if (row >= p.M) break;  // warp-uniform
+              float v = ts[rr * 33 + lane] + bv;
+              if (p.flags & MVF_GEMM_RELU) v = fmaxf(v, 0.f);
+              if (col_ok) {
+                if (p.flags & MVF_GEMM_RELUMASK) {
+                  float src;
+                  if constexpr (EB == 2) src = __bfloat162float(((const bf16*)p.relu_src)[(int64_t)row * p.ld_relu + col]);
+                  else src = ((const float*)p.relu_src)[(int64_t)row * p.ld_relu + col];
+                  v = src > 0.f ? v : 0.f;
+                }
+                float* cp = (float*)p.C + (int64_t)row * p.ldc + col;
+                if (atomic) atomicAdd(cp, v);
+                else if (p.flags & MVF_GEMM_ACCUM) *cp += v;
+                else *cp = v;
+              }
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         if (row_ok && has_k) {
           float v[32];
 #pragma unroll
@@ -326,7 +435,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           const bool full = col0 + 32 <= p.N;
-          if (p.c_bf16) {
+          {
             bf16* cp = (bf16*)p.C + (int64_t)row * p.ldc + col0;
             if (full && ((p.ldc & 7) == 0) && ((((uintptr_t)p.C) & 15) == 0)) {
 #pragma unroll
@@ -346,25 +455,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
-            }
-          } else {
-            float* cp = (float*)p.C + (int64_t)row * p.ldc + col0;
-            if (atomic) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) atomicAdd(cp + j, v[j]);
-            } else if (p.flags & MVF_GEMM_ACCUM) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) cp[j] += v[j];
-            } else if (full && ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) cp[j] = v[j];
             }
           }
         }
@@ -426,18 +516,18 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
   return MVF_OK;
 }
 
-template <int BLOCK_N, int STAGES, int EB>
+template <int BLOCK_N, int STAGES, int EB, bool SPLIT = false>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int num_sms, cudaStream_t st) {
-  constexpr int smem = STAGES * (BLOCK_M * ROW_BYTES + BLOCK_N * ROW_BYTES) + 1024 + 256;
+  constexpr int smem = STAGES * (BLOCK_M * ROW_BYTES + BLOCK_N * ROW_BYTES) + 1024 + 256 + 4 * 32 * 33 * 4;
   static bool configured = false;
   if (!configured) {
-    MVF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MVF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, EB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         smem));
     configured = true;
   }
   int work = p.tiles_m * p.tiles_n * p.split_k;
   int grid = work < num_sms ? work : num_sms;
-  gemm_tc_kernel<BLOCK_N, STAGES, EB><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p);
+  gemm_tc_kernel<BLOCK_N, STAGES, EB, SPLIT><<<grid, SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS, smem, st>>>(ma, mb, p);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -530,6 +620,11 @@ int gemm_tc(int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, in
     if (bn == 256) return launch<256, 4, 2>(ma, mb, p, g_num_sms, st);
     if (bn == 128) return launch<128, 6, 2>(ma, mb, p, g_num_sms, st);
     return launch<64, 8, 2>(ma, mb, p, g_num_sms, st);
+  }
+  if ((flags & MVF_GEMM_SPLIT3) && a_kmajor && b_kmajor) {
+    if (bn == 256) return launch<256, 4, 4, true>(ma, mb, p, g_num_sms, st);
+    if (bn == 128) return launch<128, 6, 4, true>(ma, mb, p, g_num_sms, st);
+    return launch<64, 8, 4, true>(ma, mb, p, g_num_sms, st);
   }
   if (bn == 256) return launch<256, 4, 4>(ma, mb, p, g_num_sms, st);
   if (bn == 128) return launch<128, 6, 4>(ma, mb, p, g_num_sms, st);

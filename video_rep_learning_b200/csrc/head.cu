@@ -465,7 +465,8 @@ struct Ctx {
   // y = x W^T + b
   int linear(int dtype_c, int64_t M, int64_t N, int64_t K, const void* x, int64_t ldx, const void* Wp, int64_t ldw,
              const float* bias, void* y, int64_t ldy, int flags = 0) const {
-    return gemm(dtype_c, 1, 1, M, N, K, x, ldx, Wp, ldw, y, ldy, bias, nullptr, 0, flags);
+    // forward GEMMs feed the softmax/temperature non-linearities of SCL: bf16x3 operands on the tensor-core backend
+    return gemm(dtype_c, 1, 1, M, N, K, x, ldx, Wp, ldw, y, ldy, bias, nullptr, 0, flags | MVF_GEMM_SPLIT3);
   }
   // dX = dY W (optionally masked by relu_src > 0)
   int linear_dx(int dtype_c, int64_t M, int64_t Nout, int64_t Kin, const void* dY, int64_t lddy, const void* Wp,
