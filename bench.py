@@ -12,9 +12,12 @@ across ranks and the flat head-gradient buffer is all-reduced once per step over
 
 One JSON line on stdout (rank 0).  `value` = videos/s with tokens already resident in HBM; `e2e` = videos/s
 through the public Python API (model + algos.SCL) with the step's tokens copied from pinned host memory inside
-the timed region and the loss read back; `roofline` = the K|V projection GEMM (tcgen05) timed with CUDA events on
-its launching stream inside the timed steps, against the measured cuBLAS bf16 peak; `cpu_baseline` = the CPU
-oracle port of the reference algorithm on this host's cores on a bounded sample.
+the timed region and the loss read back; `roofline` = the dominant kernel timed with CUDA events on its launching
+stream inside the timed steps: with the default folded entity pooling that is the streaming pooling pass over the
+tokens (HBM-bound, against the measured copy bandwidth); `dense_path` = the same step with the pooling evaluated as
+written in the reference (K|V projection GEMM on tcgen05 + attention over K|V), with the GEMM's fraction of the
+measured cuBLAS bf16 peak; `cpu_baseline` = the CPU oracle port of the reference algorithm on this host's cores on
+a bounded sample.
 """
 from __future__ import annotations
 
@@ -220,39 +223,50 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     lib = L.lib()
-    for _ in range(max(args.warmup, 3)):
-        step(tokens_dev)
-    sync_all()
+    head_opts = model.run_options
 
-    # ---- timed region 1: tokens resident in HBM -------------------------------------------------------------
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    lib.mvf_profile_enable(1)
-    n0 = lib.mvf_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    ev0.record()
-    for _ in range(args.steps):
-        loss = step(tokens_dev)
-    ev1.record()
-    sync_all()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = int(lib.mvf_launch_count() - n0)
-    buf = (ctypes.c_float * 512)()
-    n = ctypes.c_int(0)
-    prof = {}
-    for tag, name in ((0, "kv_proj_fwd"), (1, "kv_proj_dw"), (2, "xattn_fwd"), (3, "xattn_bwd")):
-        lib.mvf_profile_read(tag, buf, 512, ctypes.byref(n))
-        prof[name] = [buf[i] for i in range(n.value)]
-    lib.mvf_profile_enable(0)
-    clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    def timed_region(pool_mode, steps, warmup, sample_clocks):
+        """W untimed + K timed steps with the tokens resident in HBM; CUDA events; max over ranks."""
+        head_opts.pool_mode = pool_mode
+        for _ in range(warmup):
+            step(tokens_dev)
+        sync_all()
+        clocks = ClockSampler(local_rank)
+        if sample_clocks and rank == 0:
+            clocks.start()
+        lib.mvf_profile_enable(1)
+        n0 = lib.mvf_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        for _ in range(steps):
+            loss = step(tokens_dev)
+        ev1.record()
+        sync_all()
+        ms_total = ev0.elapsed_time(ev1)
+        launches = int(lib.mvf_launch_count() - n0)
+        buf = (ctypes.c_float * 512)()
+        n = ctypes.c_int(0)
+        prof = {}
+        for tag in range(6):
+            lib.mvf_profile_read(tag, buf, 512, ctypes.byref(n))
+            prof[tag] = [buf[i] for i in range(n.value)]
+        lib.mvf_profile_enable(0)
+        clk = clocks.stop() if (sample_clocks and rank == 0) else None
+        t = torch.tensor([ms_total], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dict(ms_step=float(t.item()) / steps, launches=launches, prof=prof, clocks=clk, loss=float(loss.item()))
+
+    pool_default = L.POOL_DENSE if args.pool == "dense" else L.POOL_FOLDED
+    main_run = timed_region(pool_default, args.steps, max(args.warmup, 3), True)
+    ms_step, launches, prof, clk, final_loss = (main_run["ms_step"], main_run["launches"], main_run["prof"],
+                                                main_run["clocks"], main_run["loss"])
     value = world * Bv / (ms_step / 1e3)
-    final_loss = float(loss.item())
+    dense_run = None
+    if args.pool == "folded" and not args.no_dense and world == 1:
+        dense_run = timed_region(L.POOL_DENSE, max(3, min(args.steps, 10)), 3, False)
+        head_opts.pool_mode = pool_default
 
     e2e_value = e2e_ms = None
     h2d = d2h = 0
@@ -316,28 +330,71 @@ def run_ours(args):
     if rank == 0:
         fl = flops_per_video()
         peaks = measured_peaks()
-        kv_ms = statistics.mean(prof["kv_proj_fwd"]) if prof["kv_proj_fwd"] else None
-        kv_flops = fl["kv_fwd"] * Bv
-        roof = None
-        if kv_ms:
+        mean = lambda xs: statistics.mean(xs) if xs else None
+        F_frames = BV * T
+
+        def dense_roofline(pr, ms):
+            kv_ms = mean(pr[0])
+            if not kv_ms:
+                return None
+            kv_flops = fl["kv_fwd"] * Bv
             achieved = kv_flops / (kv_ms * 1e-3) / 1e12
             traffic = None
             tp = os.path.join(ROOT, "profiles", "kv_proj_fwd_traffic.json")
             if os.path.exists(tp):
                 with open(tp) as f:
                     traffic = json.load(f).get("dram_bytes_per_launch")
-            roof = dict(bound="tensor", kernel="gemm_tc_kernel<256,4> (K|V projection, forward)", achieved=achieved,
-                        peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], traffic=traffic,
-                        peak_source=f"{peaks['source']} bf16_tflops_sustained", frac_of_nominal_2250=achieved / 2250.0,
-                        ms_per_launch=kv_ms, launches_timed=len(prof["kv_proj_fwd"]), flops_per_launch=kv_flops)
-            if prof["kv_proj_dw"]:
-                dw_ms = statistics.mean(prof["kv_proj_dw"])
-                roof["weight_grad_gemm"] = dict(ms_per_launch=dw_ms, achieved=kv_flops / (dw_ms * 1e-3) / 1e12,
-                                                frac=kv_flops / (dw_ms * 1e-3) / 1e12 / peaks["tflops"])
-            roof["share_of_step"] = dict(kv_proj_fwd=kv_ms / ms_step,
-                                         kv_proj_dw=(statistics.mean(prof["kv_proj_dw"]) / ms_step) if prof["kv_proj_dw"] else None,
-                                         xattn_fwd=(statistics.mean(prof["xattn_fwd"]) / ms_step) if prof["xattn_fwd"] else None,
-                                         xattn_bwd=(statistics.mean(prof["xattn_bwd"]) / ms_step) if prof["xattn_bwd"] else None)
+            r = dict(bound="tensor", kernel="gemm_tc_kernel<256,4,2> (K|V projection, forward)", achieved=achieved,
+                     peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], traffic=traffic,
+                     peak_source=f"{peaks['source']} bf16_tflops_sustained", frac_of_nominal_2250=achieved / 2250.0,
+                     ms_per_launch=kv_ms, launches_timed=len(pr[0]), flops_per_launch=kv_flops)
+            if pr[1]:
+                dw_ms = mean(pr[1])
+                r["weight_grad_gemm"] = dict(ms_per_launch=dw_ms, achieved=kv_flops / (dw_ms * 1e-3) / 1e12,
+                                             frac=kv_flops / (dw_ms * 1e-3) / 1e12 / peaks["tflops"])
+            r["share_of_step"] = dict(kv_proj_fwd=kv_ms / ms, kv_proj_dw=(mean(pr[1]) / ms) if pr[1] else None,
+                                      xattn_fwd=(mean(pr[2]) / ms) if pr[2] else None,
+                                      xattn_bwd=(mean(pr[3]) / ms) if pr[3] else None)
+            return r
+
+        def folded_roofline(pr, ms):
+            f_ms = mean(pr[0])
+            if not f_ms:
+                return None
+            # algorithmic bytes of one launch: every token read once (bf16) + the pooled rows and the
+            # attention maps written (fp32) + the folded query matrix read
+            E = WORKLOAD["entities"]
+            tok_bytes = F_frames * P * C_in * 2
+            fwd_bytes = tok_bytes + F_frames * E * C_in * 4 + F_frames * E * P * 4 + E * C_in * 4
+            achieved = fwd_bytes / (f_ms * 1e-3) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "pool_fold_fwd_traffic.json")
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            r = dict(bound="hbm", kernel="pool_fold_fwd_kernel<bf16,3,320> (entity pooling, streaming pass over the tokens)",
+                     achieved=achieved, peak=peaks["hbm"], unit="GB/s", frac=achieved / peaks["hbm"], traffic=traffic,
+                     peak_source=f"{peaks['source']} hbm_gbs (copy, read+write)", frac_of_nominal_8000=achieved / 8000.0,
+                     ms_per_launch=f_ms, launches_timed=len(pr[0]), bytes_per_launch=fwd_bytes)
+            if pr[1]:
+                b_ms = mean(pr[1])
+                bwd_bytes = tok_bytes + 2 * F_frames * E * C_in * 4 + F_frames * E * P * 4
+                r["backward_pass"] = dict(kernel="pool_fold_bwd_kernel<bf16,3,320>", ms_per_launch=b_ms, bytes_per_launch=bwd_bytes,
+                                          achieved=bwd_bytes / (b_ms * 1e-3) / 1e9,
+                                          frac=bwd_bytes / (b_ms * 1e-3) / 1e9 / peaks["hbm"])
+            r["share_of_step"] = dict(pool_stream_fwd=f_ms / ms, pool_stream_bwd=(mean(pr[1]) / ms) if pr[1] else None,
+                                      pool_rest_fwd=((mean(pr[2]) or 0) + (mean(pr[4]) or 0)) / ms if pr[4] else None,
+                                      pool_rest_bwd=((mean(pr[3]) or 0) + (mean(pr[5]) or 0)) / ms if pr[3] else None)
+            return r
+
+        roof = dense_roofline(prof, ms_step) if args.pool == "dense" else folded_roofline(prof, ms_step)
+        dense = None
+        if dense_run is not None:
+            dms = dense_run["ms_step"]
+            dense = dict(value=world * Bv / (dms / 1e3), unit=UNIT, ms_per_step=dms, gpu_launches=dense_run["launches"],
+                         whole_step_tflops=fl["total"] * Bv * world / (dms * 1e-3) / 1e12,
+                         note="same step, entity pooling evaluated as written (K|V GEMM on tcgen05 + attention over K|V)",
+                         roofline=dense_roofline(dense_run["prof"], dms))
         whole = fl["total"] * Bv * world / (ms_step * 1e-3) / 1e12
         cpu = None
         if not args.no_cpu:
@@ -354,9 +411,8 @@ def run_ours(args):
                                patch_tokens=P, token_channels=C_in, entities=3, dropout=0.1,
                                l2="inputs (1.16 GB of tokens per step) larger than L2; no flush needed",
                                parallelism=f"dp{world} (video shards; BN statistics + one flat gradient all-reduce)"),
-                   whole_step_tflops=whole, whole_step_frac_of_peak=whole / peaks["tflops"],
-                   gflop_per_video=fl["total"] / 1e9, loss=final_loss,
-                   roofline=roof, cpu_baseline=cpu,
+                   as_written_tflops=whole, gflop_per_video_as_written=fl["total"] / 1e9, loss=final_loss,
+                   pooling=args.pool, roofline=roof, dense_path=dense, cpu_baseline=cpu,
                    e2e=None if args.no_e2e else dict(
                        value=e2e_value, unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=k2,
                        note="pinned host tokens -> HBM on a copy stream (double buffered) + loss.item() per step"),
@@ -374,6 +430,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-to-device leg")
     ap.add_argument("--no-cpu", action="store_true", help="profiling runs: skip the CPU baseline sample")
+    ap.add_argument("--pool", default="folded", choices=["folded", "dense"],
+                    help="entity pooling: folded (default product path) or dense (as written: K|V GEMM + attention)")
+    ap.add_argument("--no-dense", action="store_true", help="skip the short as-written (dense pooling) comparison leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MVF_ABI_VERSION 1
+#define MVF_ABI_VERSION 2
 
 typedef void* mvf_stream_t; /* cudaStream_t */
 
@@ -39,6 +39,11 @@ enum mvf_final { MVF_FINAL_MAX = 0, MVF_FINAL_ONE = 1, MVF_FINAL_AVG = 2, MVF_FI
 enum mvf_onehot { MVF_ONEHOT_NONE = 0, MVF_ONEHOT_POOL = 1, MVF_ONEHOT_ENC = 2 };
 enum mvf_gemm_backend { MVF_GEMM_AUTO = 0, MVF_GEMM_SIMT = 1, MVF_GEMM_TCGEN05 = 2 };
 enum mvf_negative { MVF_NEG_SINGLE_NOSELF = 0, MVF_NEG_BATCH_NOSELF = 1 };
+/* How the entity cross-attention pooling (a3-a5) is evaluated.  FOLDED: the E static queries are folded into the key
+ * projection (Wq = Q Wk / sqrt(SPC), [E, C_in]) and the value projection is applied after the pooling, so K and V are
+ * never formed: one HBM-bound streaming pass over the tokens per direction, identical results up to fp32
+ * re-association.  DENSE: as written in the reference (K|V projection GEMM on tcgen05, then attention over K|V). */
+enum mvf_pool_mode { MVF_POOL_AUTO = 0, MVF_POOL_DENSE = 1, MVF_POOL_FOLDED = 2 };
 
 #define MVF_MAX_FC 4
 #define MVF_MAX_ENTITIES 16
@@ -71,6 +76,8 @@ typedef struct mvf_head_desc {
   int32_t gemm_backend; /* mvf_gemm_backend; AUTO = tcgen05 (bf16 + tf32) for bf16 tokens, exact   */
                         /* fp32 FMA (SIMT) for fp32 tokens                                         */
   int32_t world_size;   /* ranks sharing BatchNorm statistics (1 = local statistics)               */
+  int32_t pool_mode;    /* mvf_pool_mode; AUTO = FOLDED whenever C_in % 8 == 0 (env MVF_POOL_MODE   */
+                        /* = dense|folded overrides AUTO for A/B measurements)                      */
   float drop_p;         /* FC_DROPOUT_RATE (applied only when training)                            */
   float ln_eps, bn_eps, bn_momentum;
   uint64_t seed;        /* dropout stream of this step (counter-based, same in fwd and bwd)        */
@@ -83,8 +90,10 @@ const char* mvf_last_error(void);
 int mvf_has_tcgen05(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t mvf_launch_count(void);
-/* Measurement aid: when enabled, CUDA events are recorded on the launching stream around the dominant kernels
- * (tag 0: K|V projection GEMM, 1: its weight-gradient GEMM, 2: cross-attention pooling fwd, 3: its bwd).
+/* Measurement aid: when enabled, CUDA events are recorded on the launching stream around the dominant kernels.
+ * DENSE pooling: tag 0 K|V projection GEMM, 1 its weight-gradient GEMM, 2 cross-attention pooling fwd, 3 its bwd.
+ * FOLDED pooling: tag 0 streaming pooling pass fwd, 1 streaming pass bwd, 2 the rest of the forward pooling block
+ * (Wq fold, px Wv^T GEMM, dropout/one-hot), 3 the rest of its backward (dEnt, G and dWv GEMMs, dWk/dQ finish).
  * mvf_profile_read synchronises on the recorded events and returns the durations in milliseconds. */
 int mvf_profile_enable(int on);
 int mvf_profile_read(int tag, float* ms, int cap, int* n);
@@ -193,6 +202,19 @@ int mvf_xattn_pool_bwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t SPC, 
                        const float* q_b, const float* attn, const void* d_ent, int64_t ld_ent, const float* ent_f32,
                        int one_hot, float drop_p, uint64_t seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk,
                        float* d_bv, mvf_stream_t stream);
+
+/* a3-a5 folded (see mvf_pool_mode): the four pieces around the two small GEMMs (ent = px Wv^T + bv forward;
+ * G = dEnt Wv and dWv = dEnt^T px backward, done with mvf_gemm).  tokens [F*P, C_in] token-major (dtype), everything
+ * else fp32: wq [E, C_in]; attn [F, E, P]; px [F*E, C_in] (attention-pooled tokens); g [F*E, C_in];
+ * d_wq [E, C_in] (accumulated: zero it first); d_wk [SPC, ld_dwk], d_q_s [E, SPC], d_q_b [SPC] (accumulated). */
+int mvf_pool_fold_prep(const float* q_s, const float* q_b, const float* w_k, int32_t E, int32_t SPC, int32_t C_in,
+                       float* wq, mvf_stream_t stream);
+int mvf_pool_fold_fwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t C_in, const void* tokens, const float* wq,
+                      float* attn, float* px, mvf_stream_t stream);
+int mvf_pool_fold_bwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t C_in, const void* tokens, const float* g,
+                      const float* px, const float* attn, float* d_wq, mvf_stream_t stream);
+int mvf_pool_fold_finish(const float* d_wq, const float* q_s, const float* q_b, const float* w_k, int32_t E, int32_t SPC,
+                         int32_t C_in, float* d_wk, int64_t ld_dwk, float* d_q_s, float* d_q_b, mvf_stream_t stream);
 
 /* a5/a8 temporal self-attention core (utils.py:11-44 with the [B,1,1,S] key mask): qkv [B*S, 3*H]
  * (Q | K | V, head h at columns h*dk), keymask [B,S] fp32 or NULL -> ctx [B*S, H], lse [B,heads,S] fp32. */

@@ -50,7 +50,7 @@ def grad_vector(g: Dict[str, torch.Tensor], keys):
 
 def run_cuda(hc: O.HeadCfg, P: Dict[str, torch.Tensor], buf: Optional[Dict[str, torch.Tensor]], tokens, masks, seq_lens,
              steps, *, dtype=torch.float32, negative_type="single_noself", training=True, drop_p=0.0, seed=0,
-             backend=0, quirk=True, project=True, device="cuda"):
+             backend=0, quirk=True, project=True, device="cuda", pool_mode=0):
     """One step of the CUDA path through engine.ModelFn + engine.SCLFn.  Returns a dict with emb (head output),
     e (normalised projection), loss, grads (by reference state_dict name), new BN buffers, the CallState."""
     from video_rep_learning_b200 import engine
@@ -64,7 +64,7 @@ def run_cuda(hc: O.HeadCfg, P: Dict[str, torch.Tensor], buf: Optional[Dict[str, 
     for pre in bn_names:
         running += [buf[pre + ".running_mean"].to(dev).float().clone(), buf[pre + ".running_var"].to(dev).float().clone()]
         tracked.append(buf[pre + ".num_batches_tracked"].to(dev).clone())
-    opts = engine.RunOptions(gemm_backend=backend, scl_quirk=quirk)
+    opts = engine.RunOptions(gemm_backend=backend, scl_quirk=quirk, pool_mode=pool_mode)
     cs = engine.CallState(spec=spec, opts=opts, training=training, bn_running=running, bn_tracked=tracked,
                           project=1 if project else 0, seed=seed)
     tok = tokens.to(dev).to(dtype)
@@ -105,11 +105,17 @@ def run_oracle(hc: O.HeadCfg, P, buf, tokens, masks, seq_lens, steps, *, dtype=t
                 aux={k: v.detach() for k, v in aux.items()})
 
 
-def run_oracle_quantized(hc, P, tokens, masks, seq_lens, steps, negative_type="single_noself"):
-    """The reference algorithm in fp64 on the SAME quantised operands the bf16 path consumes: bf16 tokens, bf16 W_k|W_v,
-    and K|V rounded to bf16 (straight-through).  Separates the error of the implementation from the error that "bf16
-    operands" makes inevitable (which the 1/tau of SCL amplifies ~40x from embeddings to gradients)."""
+def run_oracle_quantized(hc, P, tokens, masks, seq_lens, steps, negative_type="single_noself", kv_bf16=True):
+    """The reference algorithm in fp64 on the SAME quantised operands the bf16 path consumes.  Dense pooling
+    (kv_bf16=True): bf16 tokens, bf16 W_k|W_v, and K|V rounded to bf16 (straight-through).  Folded pooling
+    (kv_bf16=False): only the tokens are bf16 -- K|V never exist and the weights stay fp32.  Separates the error of the
+    implementation from the error that "bf16 operands" makes inevitable (which the 1/tau of SCL amplifies ~40x from
+    embeddings to gradients)."""
     import torch.nn.functional as F
+
+    if not kv_bf16:
+        return run_oracle(hc, P, None, tokens.bfloat16().float(), masks, seq_lens, steps, dtype=torch.float64,
+                          negative_type=negative_type)
 
     def bf(x):
         return x.float().bfloat16().double()

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/mvf_b200.h but not exported"
     assert set(declared) == set(L.EXPORTED_SYMBOLS), set(declared) ^ set(L.EXPORTED_SYMBOLS)
-    assert lib.mvf_version() == 1
+    assert lib.mvf_version() == 2
 
 
 def test_struct_layout_matches_header():
@@ -58,9 +58,15 @@ def test_param_table_is_reference_state_dict_order(kw):
 
 def test_layout_lookup_and_bn_stat_regions():
     hc = O.HeadCfg(c_in=2304)
-    plan = engine.Plan.get(H.spec_from_headcfg(hc), 64, 20, 196, L.MVF_BF16, True, True, 1, 0)
+    plan = engine.Plan.get(H.spec_from_headcfg(hc), 64, 20, 196, L.MVF_BF16, True, True, 1, 0, L.POOL_DENSE)
     off, rows, cols, ld, dt = plan.lookup("kv")
     assert (rows, cols, ld, dt) == (64 * 20 * 196, 768, 768, 1)
+    folded = engine.Plan.get(H.spec_from_headcfg(hc), 64, 20, 196, L.MVF_BF16, True, True, 1, 0)      # AUTO -> folded
+    with pytest.raises(RuntimeError, match="no region"):
+        folded.lookup("kv")                    # K|V are never materialised
+    off, rows, cols, ld, dt = folded.lookup("px")
+    assert (rows, cols, dt) == (64 * 20 * 3, 2304, 0)
+    assert folded.save_bytes < plan.save_bytes - 64 * 20 * 196 * 768 * 2 + 64 * 20 * 3 * 2304 * 4 + (1 << 20)
     off, rows, cols, ld, dt = plan.lookup("h0")
     assert (cols, ld) == (387, 392)          # one-hot columns, padded to a 16-byte row for TMA
     off, rows, cols, ld, dt = plan.lookup("g.w.kv")

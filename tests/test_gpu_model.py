@@ -39,11 +39,13 @@ def _check_grads(got, ref, keys, tol, floor_scale):
     return worst
 
 
+@pytest.mark.parametrize("pool_mode", [L.POOL_FOLDED, L.POOL_DENSE], ids=["folded", "dense"])
 @pytest.mark.parametrize("name", CASES)
-def test_fp32_step_matches_reference_golden(name):
+def test_fp32_step_matches_reference_golden(name, pool_mode):
     m, hc, z, P, G, B = H.load_case(name)
     tokens, masks, seq_lens, steps = _inputs(z)
-    r = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.float32, negative_type=m["negative_type"])
+    r = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.float32, negative_type=m["negative_type"],
+                   pool_mode=pool_mode)
     assert float((r["emb"] - torch.from_numpy(z["ref_emb"])).abs().max()) < 2e-5
     assert float((r["e"] - torch.from_numpy(z["ref_e"])).abs().max()) < 1e-5
     assert abs(float(r["loss"]) - float(z["ref_loss"])) / float(z["ref_loss"]) < 1e-5
@@ -77,16 +79,19 @@ def test_every_stage_against_the_oracle(name):
     assert float((r["e"].double() - o["e"]).abs().max()) < 1e-5
 
 
-def test_bf16_step_within_north_star_tolerance():
-    """bf16 tokens / K|V on tcgen05 kind::f16, tf32 tensor-core GEMMs behind the pooling.
+@pytest.mark.parametrize("pool_mode", [L.POOL_FOLDED, L.POOL_DENSE], ids=["folded", "dense"])
+def test_bf16_step_within_north_star_tolerance(pool_mode):
+    """bf16 tokens; forward GEMMs behind the pooling as bf16x3, backward GEMMs tf32, on tcgen05.  Dense pooling adds
+    bf16 W_k|W_v and bf16 K|V (kind::f16); folded pooling keeps everything but the tokens in fp32.
     (1) against the reference evaluated on the same quantised operands: 2e-2 on embeddings, loss AND gradients;
     (2) against the fp32 reference golden (fp32 tokens): 2e-2 on embeddings and loss; the gradient carries the
-        quantisation floor of bf16 tokens + bf16 W_k|W_v, amplified ~40x by SCL's 1/tau ("bf16 error budget")."""
+        quantisation floor of bf16 tokens (+ bf16 W_k|W_v when dense), amplified ~40x by SCL's 1/tau (DESIGN.md,
+        "bf16 error budget")."""
     m, hc, z, P, G, B = H.load_case("tiny_fg_avg")
     tokens, masks, seq_lens, steps = _inputs(z)
-    r = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16)
+    r = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16, pool_mode=pool_mode)
     keys = list(P.keys())
-    q = H.run_oracle_quantized(hc, P, tokens, masks, seq_lens, steps)
+    q = H.run_oracle_quantized(hc, P, tokens, masks, seq_lens, steps, kv_bf16=pool_mode == L.POOL_DENSE)
     eq = H.rel_l2(r["e"], q["e"])
     lq = abs(float(r["loss"]) - float(q["loss"])) / float(q["loss"])
     gq = H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(q["grads"], keys))
@@ -98,7 +103,8 @@ def test_bf16_step_within_north_star_tolerance():
     print(f"bf16 vs fp32 reference golden: embeddings {e32:.2e} loss {l32:.2e} gradient {g32:.2e}")
     assert e32 < 2e-2 and l32 < 2e-2 and g32 < 8e-2
     # same inputs through the exact-fp32 SIMT engine: isolates the tensor-core GEMMs from the operand quantisation
-    r2 = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16, backend=L.GEMM_SIMT)
+    r2 = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16, backend=L.GEMM_SIMT,
+                    pool_mode=pool_mode)
     assert H.rel_l2(r["e"], r2["e"]) < 5e-3
     assert H.rel_l2(H.grad_vector(r["grads"], keys), H.grad_vector(r2["grads"], keys)) < 2e-2
 
@@ -137,12 +143,16 @@ def test_penn_cfg1_shape_fp32_digest():
     print("cfg1 bf16-vs-fp32 concatenated gradient rel err", eb)
     assert eb < 8e-2       # quantisation floor measured with the fp64 oracle: 6.6e-2 ("bf16 error budget")
     torch.set_num_threads(os.cpu_count() or 1)
-    q = H.run_oracle_quantized(hc, P, tokens, masks, seq_lens, steps)
+    q = H.run_oracle_quantized(hc, P, tokens, masks, seq_lens, steps, kv_bf16=False)   # default pooling is folded
     eq = H.rel_l2(rb["e"], q["e"])
     lq = abs(float(rb["loss"]) - float(q["loss"])) / float(q["loss"])
     gq = H.rel_l2(H.grad_vector(rb["grads"], keys), H.grad_vector(q["grads"], keys))
     print(f"cfg1 bf16 vs same-operand oracle: embeddings {eq:.2e} loss {lq:.2e} gradient {gq:.2e}")
     assert eq < 2e-2 and lq < 2e-2 and gq < 2e-2
+    # the as-written (dense tcgen05 K|V) evaluation of the same step agrees with the folded one
+    rd = H.run_cuda(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.float32, pool_mode=L.POOL_DENSE)
+    assert H.rel_l2(rd["e"], r["e"]) < 1e-5
+    assert H.rel_l2(H.grad_vector(rd["grads"], keys), H.grad_vector(r["grads"], keys)) < 1e-5
 
 
 def test_eval_forward_golden():

@@ -17,6 +17,7 @@ FINAL = {"max": 0, "one": 1, "avg": 2, "lin": 3}
 ONEHOT = {"none": 0, "pool": 1, "enc": 2}
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 NEG = {"single_noself": 0, "batch_noself": 1}
+POOL_AUTO, POOL_DENSE, POOL_FOLDED = 0, 1, 2
 PHASE_ALL = 255
 GEMM_RELU, GEMM_ACCUM, GEMM_RELUMASK, GEMM_SPLIT3 = 1, 2, 4, 8
 MAX_FC = 4
@@ -31,7 +32,7 @@ class HeadDesc(C.Structure):
         ("H", C.c_int32), ("DFF", C.c_int32), ("heads", C.c_int32), ("L", C.c_int32),
         ("D", C.c_int32), ("PS", C.c_int32), ("one_hot", C.c_int32), ("final_mode", C.c_int32),
         ("train_frames", C.c_int32), ("dtype", C.c_int32), ("training", C.c_int32), ("has_mask", C.c_int32),
-        ("gemm_backend", C.c_int32), ("world_size", C.c_int32),
+        ("gemm_backend", C.c_int32), ("world_size", C.c_int32), ("pool_mode", C.c_int32),
         ("drop_p", C.c_float), ("ln_eps", C.c_float), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
         ("seed", C.c_uint64),
     ]
@@ -74,6 +75,10 @@ _PROTOS = {
     "mvf_xattn_pool_fwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_int, _f32, _u64, _vp]),
     "mvf_xattn_pool_bwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_int, _f32, _u64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvf_pool_fold_prep": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "mvf_pool_fold_fwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mvf_pool_fold_bwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvf_pool_fold_finish": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "mvf_attention_fwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mvf_attention_bwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvf_dropout_mask": (C.c_int, [_u64, _i32, _i64, _i64, _f32, _vp, _vp]),

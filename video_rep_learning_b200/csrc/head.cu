@@ -114,6 +114,7 @@ struct Model {
                // tf32 tensor-core GEMMs on the tcgen05 backend -- bf16 there costs ~10 % on the gradient through the 1/tau
                // amplification of SCL, tf32 ~2 %)
   int kvt;     // dtype of tokens, W_k|W_v, K|V and dK|dV (the 96 % of the FLOPs): d.dtype
+  bool fold;   // rank-E folded pooling (pool_fold.cu): no K|V tensors, one streaming pass over the tokens per direction
   std::vector<ParamInfo> params;
   // indices into params
   int iQs, iQb, iWk, ibk, iWv, ibv;
@@ -169,6 +170,19 @@ static int build_model(const mvf_head_desc* dp, Model& m) {
   m.N = m.F;
   m.act = MVF_F32;
   m.kvt = d.dtype;
+  {
+    int pm = d.pool_mode;
+    MVF_REQUIRE(pm >= MVF_POOL_AUTO && pm <= MVF_POOL_FOLDED, MVF_ERR_BAD_ARG, "pool_mode %d", pm);
+    if (pm == MVF_POOL_AUTO) {
+      const char* e = getenv("MVF_POOL_MODE");   // A/B measurements only
+      if (e && strcmp(e, "dense") == 0) pm = MVF_POOL_DENSE;
+      else if (e && strcmp(e, "folded") == 0) pm = MVF_POOL_FOLDED;
+    }
+    const bool ok = pool_fold_supported(d.dtype, d.C_in, d.E, d.P);
+    MVF_REQUIRE(pm != MVF_POOL_FOLDED || ok, MVF_ERR_UNSUPPORTED,
+                "folded pooling needs C_in (%d) to be a multiple of 8 and at most 5120", d.C_in);
+    m.fold = pm == MVF_POOL_FOLDED || (pm == MVF_POOL_AUTO && ok);
+  }
   m.params.clear();
   const std::string ca = "embed.pooling.cross_att.";
   m.iQs = add_param(m, ca + "Q_s", d.E, d.SPC);
@@ -259,8 +273,12 @@ static std::string fname(int i, const char* s) { return "fc" + std::to_string(i)
 static void head_save_layout(const Model& m, Layout& L) {
   const mvf_head_desc& d = m.d;
   const int A = m.act;
-  L.add("w.kv", 2 * d.SPC, d.C_in, m.kvt, round_up(d.C_in, 8));
-  L.add("b.kv", 1, 2 * d.SPC, RT_F32);
+  if (m.fold) {
+    L.add("wq", d.E, d.C_in, RT_F32);
+  } else {
+    L.add("w.kv", 2 * d.SPC, d.C_in, m.kvt, round_up(d.C_in, 8));
+    L.add("b.kv", 1, 2 * d.SPC, RT_F32);
+  }
   int cin_ld = m.ld0;
   for (int i = 0; i < d.n_fc; ++i) {
     L.add(fname(i, "w"), d.fc[i], i == 0 ? m.W0 : d.fc[i - 1], A, cin_ld);
@@ -276,7 +294,8 @@ static void head_save_layout(const Model& m, Layout& L) {
   }
   L.add("w.emb", d.D, d.H, A);
   if (d.final_mode == MVF_FINAL_LIN) L.add("w.lin", d.H, (int64_t)d.E * d.H, A);
-  L.add("kv", m.F * d.P, 2 * d.SPC, m.kvt);
+  if (m.fold) L.add("px", m.R, d.C_in, RT_F32);      // attention-pooled tokens: the only C_in-wide activation kept
+  else L.add("kv", m.F * d.P, 2 * d.SPC, m.kvt);
   L.add("attn", m.F * d.E, d.P, RT_F32);
   L.add("h0", m.R, m.W0, A, m.ld0);
   L.add("ent32", m.R, d.SPC, RT_F32);
@@ -338,7 +357,13 @@ static void head_ws_layout(const Model& m, Layout& L) {
   L.add("da", m.R, maxfc, RT_F32);
   for (int i = 0; i < d.n_fc; ++i) L.add(fname(i, "dx"), m.R, d.fc[i], A);
   L.add("dh0", m.R, m.W0, A, m.ld0);
-  L.add("dkv", m.F * d.P, 2 * d.SPC, m.kvt);
+  if (m.fold) {
+    L.add("dent", m.R, d.SPC, RT_F32);
+    L.add("G", m.R, d.C_in, RT_F32);
+    L.add("dwq", d.E, d.C_in, RT_F32);
+  } else {
+    L.add("dkv", m.F * d.P, 2 * d.SPC, m.kvt);
+  }
 }
 
 static void proj_save_layout(const Model& m, Layout& L) {
@@ -535,10 +560,12 @@ static int pack_head_weights(Ctx& c) {
     e.push_back(PackEntry{c.P[pidx], c.S.base + r->off + (size_t)col0 * 4, 1, (int)pi.cols, (int)pi.cols, 0});
   };
   (void)bf;
-  mat("w.kv", m.iWk, 0);
-  mat("w.kv", m.iWv, d.SPC);
-  vec("b.kv", m.ibk, 0);
-  vec("b.kv", m.ibv, d.SPC);
+  if (!m.fold) {
+    mat("w.kv", m.iWk, 0);
+    mat("w.kv", m.iWv, d.SPC);
+    vec("b.kv", m.ibk, 0);
+    vec("b.kv", m.ibv, d.SPC);
+  }
   for (int i = 0; i < d.n_fc; ++i) mat(fname(i, "w"), m.iFcW[i]);
   mat("w.e", m.iWe);
   for (int l = 0; l < d.L; ++l) {
@@ -573,17 +600,37 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
   for (int ph = ph0; ph < ph1; ++ph) {
     if (ph == 0) {
       MVF_TRY(pack_head_weights(c));
-      // a4: K|V projection of every patch token -- the dominant contraction
-      {
-        ProfScope ps(0, st);
-        MVF_TRY(c.gemm_kv(m.kvt, 1, 1, m.F * d.P, 2 * d.SPC, d.C_in, tokens, d.C_in, c.S.p("w.kv"), c.S.ld("w.kv"),
-                          c.S.p("kv"), 2 * d.SPC, c.S.f("b.kv"), 0, 1));
-      }
       float* attn = c.S.f("attn");
-      {
-        ProfScope ps(2, st);
-        MVF_TRY(xattn_pool_fwd(m.kvt, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], attn, c.S.p("h0"), m.ld0,
-                               c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, st));
+      if (m.fold) {
+        // a3-a5 folded: Wq = Q Wk / sqrt(SPC); one streaming pass over the tokens (online softmax + pooling of X);
+        // the value projection is applied to the E pooled rows per frame instead of the P token rows
+        {
+          ProfScope ps(2, st);
+          MVF_TRY(fold_prep(c.P[m.iQs], c.P[m.iQb], c.P[m.iWk], d.E, d.SPC, d.C_in, c.S.f("wq"), st));
+        }
+        {
+          ProfScope ps(0, st);
+          MVF_TRY(pool_fold_fwd(m.kvt, (int)m.F, d.P, d.E, d.C_in, tokens, c.S.f("wq"), attn, c.S.f("px"), st));
+        }
+        {
+          ProfScope ps(4, st);
+          MVF_TRY(c.linear(MVF_F32, m.R, d.SPC, d.C_in, c.S.p("px"), d.C_in, c.P[m.iWv], d.C_in, c.P[m.ibv], c.S.p("ent32"),
+                           d.SPC));
+          MVF_TRY(ent_finish_fwd(c.S.f("ent32"), c.S.f("h0"), m.ld0, m.R, d.SPC, d.E, d.one_hot == MVF_ONEHOT_POOL, c.p,
+                                 d.seed, st));
+        }
+      } else {
+        // a4 as written: K|V projection of every patch token -- the dominant contraction
+        {
+          ProfScope ps(0, st);
+          MVF_TRY(c.gemm_kv(m.kvt, 1, 1, m.F * d.P, 2 * d.SPC, d.C_in, tokens, d.C_in, c.S.p("w.kv"), c.S.ld("w.kv"),
+                            c.S.p("kv"), 2 * d.SPC, c.S.f("b.kv"), 0, 1));
+        }
+        {
+          ProfScope ps(2, st);
+          MVF_TRY(xattn_pool_fwd(m.kvt, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], attn, c.S.p("h0"),
+                                 m.ld0, c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, st));
+        }
       }
       if (attn_out)
         MVF_CHECK_CUDA(cudaMemcpyAsync(attn_out, attn, (size_t)m.F * d.E * d.P * 4, cudaMemcpyDeviceToDevice, st));
@@ -799,6 +846,31 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
       // ---- entity cross-attention pooling and the K|V projection weight gradient ----
       const int o_spc = d.SPC;
       float* gbkv = c.G.f("g.b.kv");
+      if (m.fold) {
+        const int64_t ldg = c.Lg.find("g.w.kv")->ld;
+        float* gwk = c.G.f("g.w.kv");
+        float* gwv = gwk + (size_t)d.SPC * ldg;
+        {
+          ProfScope ps(3, st);
+          MVF_TRY(ent_finish_bwd(c.W.f("dh0"), m.ld0, c.W.f("dent"), m.R, d.SPC, m.W0, c.p, d.seed, st));
+          // dWv = dEnt^T px, dbv = colsum(dEnt) (forked); d(bk) is analytically zero (a per-entity constant under softmax)
+          MVF_TRY(c.linear_dw(m.R, d.SPC, d.C_in, c.W.p("dent"), d.SPC, c.S.p("px"), d.C_in, gwv, ldg, gbkv + o_spc));
+          // G = dEnt Wv
+          MVF_TRY(c.linear_dx(MVF_F32, m.R, d.SPC, d.C_in, c.W.p("dent"), d.SPC, c.P[m.iWv], d.C_in, c.W.p("G"), d.C_in));
+          MVF_CHECK_CUDA(cudaMemsetAsync(c.W.p("dwq"), 0, (size_t)d.E * d.C_in * 4, st));
+        }
+        {
+          ProfScope ps(1, st);
+          MVF_TRY(pool_fold_bwd(m.kvt, (int)m.F, d.P, d.E, d.C_in, tokens, c.W.f("G"), c.S.f("px"), c.S.f("attn"),
+                                c.W.f("dwq"), st));
+        }
+        {
+          ProfScope ps(5, st);
+          MVF_TRY(fold_finish(c.W.f("dwq"), c.P[m.iQs], c.P[m.iQb], c.P[m.iWk], d.E, d.SPC, d.C_in, gwk, ldg, c.G.f("g.Qs"),
+                              c.G.f("g.Qb"), st));
+        }
+        continue;
+      }
       {
         ProfScope ps(3, st);
         MVF_TRY(xattn_pool_bwd(m.kvt, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], c.S.f("attn"),
@@ -1171,6 +1243,30 @@ int mvf_xattn_pool_bwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t SPC, 
               "xattn bwd: null pointer");
   return xattn_pool_bwd(dtype, F, P, E, SPC, kv, q_s, q_b, attn, d_ent, ld_ent, ent_f32, one_hot, drop_p, seed, d_kv, d_q_s,
                         d_q_b, d_bk, d_bv, (cudaStream_t)stream);
+}
+
+int mvf_pool_fold_prep(const float* q_s, const float* q_b, const float* w_k, int32_t E, int32_t SPC, int32_t C_in, float* wq,
+                       mvf_stream_t stream) {
+  MVF_REQUIRE(q_s && q_b && w_k && wq, MVF_ERR_BAD_ARG, "pool_fold_prep: null pointer");
+  MVF_REQUIRE(E >= 1 && E <= MVF_MAX_ENTITIES && SPC > 0 && C_in > 0, MVF_ERR_BAD_ARG, "pool_fold_prep: bad shape");
+  return fold_prep(q_s, q_b, w_k, E, SPC, C_in, wq, (cudaStream_t)stream);
+}
+int mvf_pool_fold_fwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t C_in, const void* tokens, const float* wq,
+                      float* attn, float* px, mvf_stream_t stream) {
+  MVF_REQUIRE(tokens && wq && attn && px, MVF_ERR_BAD_ARG, "pool_fold_fwd: null pointer");
+  return pool_fold_fwd(dtype, F, P, E, C_in, tokens, wq, attn, px, (cudaStream_t)stream);
+}
+int mvf_pool_fold_bwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t C_in, const void* tokens, const float* g,
+                      const float* px, const float* attn, float* d_wq, mvf_stream_t stream) {
+  MVF_REQUIRE(tokens && g && px && attn && d_wq, MVF_ERR_BAD_ARG, "pool_fold_bwd: null pointer");
+  return pool_fold_bwd(dtype, F, P, E, C_in, tokens, g, px, attn, d_wq, (cudaStream_t)stream);
+}
+int mvf_pool_fold_finish(const float* d_wq, const float* q_s, const float* q_b, const float* w_k, int32_t E, int32_t SPC,
+                         int32_t C_in, float* d_wk, int64_t ld_dwk, float* d_q_s, float* d_q_b, mvf_stream_t stream) {
+  MVF_REQUIRE(d_wq && q_s && q_b && w_k && d_wk && d_q_s && d_q_b, MVF_ERR_BAD_ARG, "pool_fold_finish: null pointer");
+  MVF_REQUIRE(E >= 1 && E <= MVF_MAX_ENTITIES && SPC > 0 && C_in > 0 && ld_dwk >= C_in, MVF_ERR_BAD_ARG,
+              "pool_fold_finish: bad shape");
+  return fold_finish(d_wq, q_s, q_b, w_k, E, SPC, C_in, d_wk, ld_dwk, d_q_s, d_q_b, (cudaStream_t)stream);
 }
 
 int mvf_attention_fwd(int dtype, int32_t B, int32_t S, int32_t heads, int32_t dk, const void* qkv, const float* keymask,

@@ -87,6 +87,25 @@ int xattn_pool_bwd(int dtype, int F, int P, int E, int SPC, const void* kv, cons
                    const float* attn, const void* d_ent, int64_t ld_ent, const float* ent32, int one_hot, float drop_p,
                    uint64_t seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv, cudaStream_t st);
 
+// ---- pool_fold.cu: rank-E folded entity pooling (no K|V tensors; one streaming pass over the tokens per direction) ------
+bool pool_fold_supported(int dtype, int C, int E, int P);
+// Wq[E,C] = (Q_s + Q_b) Wk / sqrt(SPC)
+int fold_prep(const float* q_s, const float* q_b, const float* Wk, int E, int SPC, int C, float* Wq, cudaStream_t st);
+// attn[F,E,P] = softmax_p(Wq X^T), px[F*E,C] = attn X        (X: [F*P, C] token-major, dtype bf16 / fp32)
+int pool_fold_fwd(int dtype, int F, int P, int E, int C, const void* X, const float* Wq, float* attn, float* px,
+                  cudaStream_t st);
+// dWq[E,C] += sum_f (attn * (G X^T - <G, px>)) X              (G = dEnt Wv, [F*E, C] fp32)
+int pool_fold_bwd(int dtype, int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,
+                  float* dWq, cudaStream_t st);
+// dWk += Q^T dWq / sqrt(SPC); dQ_s += dWq Wk^T / sqrt(SPC); dQ_b += column sums of dQ_s
+int fold_finish(const float* dWq, const float* q_s, const float* q_b, const float* Wk, int E, int SPC, int C, float* dWk,
+                int64_t ld_dwk, float* dQs, float* dQb, cudaStream_t st);
+// h0 = [drop(ent) | drop(one-hot) | 0]  and its backward
+int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, int E, int one_hot, float p, uint64_t seed,
+                   cudaStream_t st);
+int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SPC, int W, float p, uint64_t seed,
+                   cudaStream_t st);
+
 // ---- attention.cu --------------------------------------------------------------------------------------------
 int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, void* ctx,
                   float* lse, cudaStream_t st);

@@ -1,0 +1,727 @@
+// Rank-E folded entity pooling: the cross-attention of LSTPCrossAtt (mvformer.py:352-414) has only E (3..16) static
+// queries and one head, so K = X Wk^T + bk and V = X Wv^T + bv never need to exist:
+//
+//   scores[e,p] = (Q_s[e]+Q_b) . K[p] / sqrt(SPC) = Wq[e,:] . X[p,:] + const(e)      Wq = (Q_s+Q_b) Wk / sqrt(SPC)  [E, C_in]
+//   A[e,:]      = softmax_p(scores[e,:])                                             (the constant cancels)
+//   ent[e,:]    = sum_p A[e,p] V[p,:] = (sum_p A[e,p] X[p,:]) Wv^T + bv = px[e,:] Wv^T + bv       (rows of A sum to 1)
+//
+// which turns 2*2*P*C_in*SPC FLOPs per frame (96 % of the whole step at the BASELINE shapes) into ONE streaming pass
+// over the patch tokens: 4*E*P*C_in FLOPs on CUDA cores, bound by the HBM read of X.  Backward is the same kind of pass:
+//
+//   G[e,:]   = dEnt[e,:] Wv                     (small GEMM)          delta[e] = G[e,:] . px[e,:] = sum_p A[e,p] dA[e,p]
+//   dA[e,p]  = G[e,:] . X[p,:]                                        dS[e,p]  = A[e,p] (dA[e,p] - delta[e])
+//   dWq[e,:] = sum_{frames,p} dS[e,p] X[p,:]    -> dWk = Q^T dWq / sqrt(SPC), dQ = dWq Wk^T / sqrt(SPC);  dWv = dEnt^T px
+//
+// Kernel shape (both directions): persistent CTAs, one frame at a time; the token rows of a frame are contiguous in
+// the ViT-native token-major layout, so groups of 8 tokens (8*C_in*sizeof(T) bytes) are streamed into a shared-memory
+// ring by bulk async copies (cp.async.bulk + mbarrier complete_tx).  Thread t owns channels [8t, 8t+8) for the whole
+// kernel: its slice of Wq (or G) and of the running accumulators lives in registers, every 16-byte shared-memory read
+// is conflict-free, and the only cross-thread traffic is the reduction of the 8*E partial dot products of a group
+// (recursive-halving warp shuffles, then one shared-memory hop across warps).  Forward keeps an online softmax
+// (running max / sum per entity, accumulators rescaled when the max moves), so X is read exactly once.
+#include "kernels.cuh"
+
+namespace mvf {
+namespace fold {
+
+constexpr int TG = 8;         // tokens per group (one pipeline stage)
+constexpr int MAX_STAGES = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {  // a protocol bug must trap, never hang the GPU
+      printf("mvf pool_fold: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- the 8 channels a thread owns in one token row ------------------------------------------------------------------
+template <typename T> struct XV;
+template <> struct XV<bf16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const uint8_t* row, int cv) { u = *reinterpret_cast<const uint4*>(row + cv * 16); }
+  __device__ __forceinline__ void zero() { u = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void get(float* f) const {
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+  }
+};
+template <> struct XV<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const uint8_t* row, int cv) {
+    a = *reinterpret_cast<const float4*>(row + cv * 32);
+    b = *reinterpret_cast<const float4*>(row + cv * 32 + 16);
+  }
+  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+  __device__ __forceinline__ void get(float* f) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+
+// ---- recursive-halving warp reduction of N per-lane values: lane L ends with the full sum of value red_index(L) ------
+// (N + ~5 shuffles instead of 5 N).  Odd sizes are padded with a zero; lanes that end on padding get index -1.
+template <int N, int BIT>
+struct Red {
+  static __device__ __forceinline__ void run(float* v, int lane) {
+    if constexpr (BIT > 0) {
+      if constexpr (N == 1) {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], BIT);
+        Red<1, BIT / 2>::run(v, lane);
+      } else {
+        constexpr int NP = (N + 1) & ~1, H = NP / 2;
+        if constexpr (NP != N) v[N] = 0.f;
+        const bool up = (lane & BIT) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          const float send = up ? v[i] : v[i + H];
+          const float keep = up ? v[i + H] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
+        }
+        Red<H, BIT / 2>::run(v, lane);
+      }
+    }
+  }
+  static __device__ __forceinline__ int index(int lane) {
+    if constexpr (BIT == 0) return 0;
+    else if constexpr (N == 1) return 0;
+    else {
+      constexpr int NP = (N + 1) & ~1, H = NP / 2;
+      const int sub = Red<H, BIT / 2>::index(lane);
+      const int pos = ((lane & BIT) ? H : 0) + sub;
+      return (sub < 0 || pos >= N) ? -1 : pos;
+    }
+  }
+};
+
+struct Geom {
+  int F, P, C;        // frames, tokens per frame, channels
+  int Etot, e0;       // entities in the model, first entity of this pass
+  int stages;
+  int row_bytes;      // C * sizeof(T)
+};
+
+// shared-memory carve-up (bytes), identical for both directions
+struct Carve {
+  size_t ring, bars, partial, wbuf, table, misc, total;
+};
+static Carve carve(int stages, int row_bytes, int nwarps, int E, int P) {
+  Carve c;
+  c.ring = (size_t)stages * TG * row_bytes;
+  c.bars = 8 * MAX_STAGES;
+  c.partial = (size_t)2 * nwarps * 32 * 4;
+  c.wbuf = (size_t)nwarps * 40 * 4;
+  c.table = ((size_t)E * P * 4 + 15) / 16 * 16;   // raw scores (fwd) / probabilities (bwd) of the current frame
+  c.misc = ((size_t)(2 * E + nwarps * E) * 4 + 15) / 16 * 16;
+  c.total = c.ring + c.bars + c.partial + c.wbuf + c.table + c.misc;
+  return c;
+}
+
+#define MVF_FOLD_SMEM_SETUP()                                                                         \
+  extern __shared__ __align__(128) uint8_t smraw[];                                                   \
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = blockDim.x >> 5;                 \
+  uint8_t* ring = smraw;                                                                              \
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)g.stages * TG * g.row_bytes);           \
+  float* partial = reinterpret_cast<float*>(full + MAX_STAGES);                                       \
+  float* wbuf = partial + 2 * NW * 32;                                                                \
+  float* table = wbuf + NW * 40;                                                                      \
+  float* misc = table + (((size_t)E * g.P + 3) / 4) * 4;                                              \
+  const int cv = tid;                                                                                 \
+  const bool act = cv < (g.C >> 3);                                                                   \
+  const int nG = (g.P + TG - 1) / TG;                                                                 \
+  const int nF = blockIdx.x < g.F ? (g.F - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;               \
+  const int total = nF * nG;                                                                          \
+  if (tid == 0) {                                                                                     \
+    for (int s = 0; s < g.stages; ++s) mbar_init(&full[s], 1);                                        \
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                                \
+  }                                                                                                   \
+  __syncthreads();                                                                                    \
+  auto issue = [&](int n2) {                                                                          \
+    const int fi2 = n2 / nG, g2 = n2 - fi2 * nG;                                                      \
+    const int64_t f2 = blockIdx.x + (int64_t)fi2 * gridDim.x;                                         \
+    const int nt2 = min(TG, g.P - g2 * TG);                                                           \
+    const uint32_t bytes = (uint32_t)nt2 * (uint32_t)g.row_bytes;                                     \
+    const int s2 = n2 % g.stages;                                                                     \
+    mbar_expect_tx(&full[s2], bytes);                                                                 \
+    bulk_g2s(ring + (size_t)s2 * TG * g.row_bytes,                                                    \
+             reinterpret_cast<const uint8_t*>(X) + (f2 * g.P + (int64_t)g2 * TG) * g.row_bytes, bytes, &full[s2]); \
+  };                                                                                                  \
+  if (tid == 0)                                                                                       \
+    for (int n2 = 0; n2 < g.stages && n2 < total; ++n2) issue(n2);
+
+// =====================================================================================================================
+// forward:  A = softmax_p(Wq X^T) (online), px = A X
+// =====================================================================================================================
+template <typename T, int E, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1)
+pool_fold_fwd_kernel(const T* __restrict__ X, const float* __restrict__ Wq, float* __restrict__ attn,
+                     float* __restrict__ px, const Geom g) {
+  constexpr int NV = TG * E;
+  MVF_FOLD_SMEM_SETUP();
+  float* fin = misc;  // [2][E]: final max, 1/sum
+
+  float wq[E][8];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (act) {
+      const float4 a = *reinterpret_cast<const float4*>(Wq + (size_t)(g.e0 + e) * g.C + cv * 8);
+      const float4 b = *reinterpret_cast<const float4*>(Wq + (size_t)(g.e0 + e) * g.C + cv * 8 + 4);
+      wq[e][0] = a.x; wq[e][1] = a.y; wq[e][2] = a.z; wq[e][3] = a.w;
+      wq[e][4] = b.x; wq[e][5] = b.y; wq[e][6] = b.z; wq[e][7] = b.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) wq[e][c] = 0.f;
+    }
+  }
+  const int ridx = Red<NV, 16>::index(lane);
+  const int le = lane >> 3, lp = lane & 7;   // the (entity, token-in-group) pair this lane finishes the softmax for
+
+  int n = 0, slot = 0;
+  uint32_t phase = 0;
+  for (int fi = 0; fi < nF; ++fi) {
+    const int64_t f = blockIdx.x + (int64_t)fi * gridDim.x;
+    float acc[E][8];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[e][c] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int gi = 0; gi < nG; ++gi, ++n) {
+      const int ntok = min(TG, g.P - gi * TG);
+      mbar_wait(&full[slot], phase);
+      const uint8_t* st = ring + (size_t)slot * TG * g.row_bytes;
+      XV<T> xv[TG];
+#pragma unroll
+      for (int p = 0; p < TG; ++p) {
+        if (act && p < ntok) xv[p].load(st + (size_t)p * g.row_bytes, cv);
+        else xv[p].zero();
+      }
+      // partial scores of this thread's 8 channels
+      float part[NV];
+#pragma unroll
+      for (int p = 0; p < TG; ++p) {
+        float xf[8];
+        xv[p].get(xf);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) s = fmaf(wq[e][c], xf[c], s);
+          part[e * TG + p] = s;
+        }
+      }
+      Red<NV, 16>::run(part, lane);
+      if (ridx >= 0) partial[((n & 1) * NW + warp) * 32 + ridx] = part[0];
+      __syncthreads();   // every thread holds its slice of the stage in registers: the slot can be refilled
+      if (tid == 0 && n + g.stages < total) issue(n + g.stages);
+      if (++slot == g.stages) { slot = 0; phase ^= 1; }
+
+      // softmax bookkeeping, redundantly per warp (lane = (entity, token))
+      float s = 0.f;
+      if (lane < NV)
+        for (int w = 0; w < NW; ++w) s += partial[((n & 1) * NW + w) * 32 + lane];
+      const bool valid = lane < NV && lp < ntok;
+      if (warp == 0 && valid) table[le * g.P + gi * TG + lp] = s;
+      float mx = valid ? s : -INFINITY;
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      const float m_new = fmaxf(m_run, mx);
+      const float w_ = valid ? expf(s - m_new) : 0.f;
+      const float fac = (lane < NV) ? expf(m_run - m_new) : 0.f;   // first group: exp(-inf) = 0
+      float ls = w_;
+      ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+      ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+      ls += __shfl_xor_sync(0xffffffffu, ls, 4);
+      l_run = l_run * fac + ls;
+      m_run = m_new;
+      float* wb = wbuf + warp * 40;
+      wb[lane] = w_;
+      if (lane < NV && lp == 0) wb[32 + le] = fac;
+      __syncwarp();
+      // px accumulators
+      float wreg[E][TG], fr[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + e * TG);
+        const float4 w1 = *reinterpret_cast<const float4*>(wb + e * TG + 4);
+        wreg[e][0] = w0.x; wreg[e][1] = w0.y; wreg[e][2] = w0.z; wreg[e][3] = w0.w;
+        wreg[e][4] = w1.x; wreg[e][5] = w1.y; wreg[e][6] = w1.z; wreg[e][7] = w1.w;
+        fr[e] = wb[32 + e];
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[e][c] *= fr[e];
+#pragma unroll
+      for (int p = 0; p < TG; ++p) {
+        float xf[8];
+        xv[p].get(xf);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[e][c] = fmaf(wreg[e][p], xf[c], acc[e][c]);
+      }
+    }
+
+    // ---- end of frame: normalise, write px and the attention map ----
+    if (warp == 0 && lane < NV && lp == 0) { fin[le] = m_run; fin[E + le] = 1.f / l_run; }
+    __syncthreads();
+    if (act) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float inv = fin[E + e];
+        float* dst = px + ((size_t)f * g.Etot + g.e0 + e) * g.C + cv * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[e][0] * inv, acc[e][1] * inv, acc[e][2] * inv, acc[e][3] * inv);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[e][4] * inv, acc[e][5] * inv, acc[e][6] * inv, acc[e][7] * inv);
+      }
+    }
+    for (int i = tid; i < E * g.P; i += blockDim.x) {
+      const int e = i / g.P, p = i - e * g.P;
+      attn[((size_t)f * g.Etot + g.e0 + e) * g.P + p] = expf(table[i] - fin[e]) * fin[E + e];
+    }
+    // (the next frame's first write to table / fin happens after that frame's first __syncthreads)
+  }
+}
+
+// =====================================================================================================================
+// backward:  dS = A * (G X^T - delta),  dWq += dS X   (accumulated over every frame of the CTA, one atomic flush)
+// =====================================================================================================================
+template <typename T, int E, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1)
+pool_fold_bwd_kernel(const T* __restrict__ X, const float* __restrict__ G, const float* __restrict__ px,
+                     const float* __restrict__ attn, float* __restrict__ dWq, const Geom g) {
+  constexpr int NV = TG * E;
+  MVF_FOLD_SMEM_SETUP();
+  float* red = misc;  // [NW][E] partial delta
+
+  const int ridx = Red<NV, 16>::index(lane);
+  const int le = lane >> 3, lp = lane & 7;
+  float acc[E][8];
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[e][c] = 0.f;
+
+  int n = 0, slot = 0;
+  uint32_t phase = 0;
+  for (int fi = 0; fi < nF; ++fi) {
+    const int64_t f = blockIdx.x + (int64_t)fi * gridDim.x;
+    __syncthreads();   // the previous frame's readers of table / red are done
+    float gv[E][8], dpart[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      dpart[e] = 0.f;
+      if (act) {
+        const size_t off = ((size_t)f * g.Etot + g.e0 + e) * g.C + cv * 8;
+        const float4 a = *reinterpret_cast<const float4*>(G + off), b = *reinterpret_cast<const float4*>(G + off + 4);
+        const float4 pa = *reinterpret_cast<const float4*>(px + off), pb = *reinterpret_cast<const float4*>(px + off + 4);
+        gv[e][0] = a.x; gv[e][1] = a.y; gv[e][2] = a.z; gv[e][3] = a.w;
+        gv[e][4] = b.x; gv[e][5] = b.y; gv[e][6] = b.z; gv[e][7] = b.w;
+        dpart[e] = a.x * pa.x + a.y * pa.y + a.z * pa.z + a.w * pa.w + b.x * pb.x + b.y * pb.y + b.z * pb.z + b.w * pb.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) gv[e][c] = 0.f;
+      }
+    }
+    for (int i = tid; i < E * g.P; i += blockDim.x) {
+      const int e = i / g.P, p = i - e * g.P;
+      table[i] = attn[((size_t)f * g.Etot + g.e0 + e) * g.P + p];
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float s = warp_sum(dpart[e]);
+      if (lane == 0) red[warp * E + e] = s;
+    }
+    __syncthreads();
+    float delta = 0.f;
+    if (lane < NV)
+      for (int w = 0; w < NW; ++w) delta += red[w * E + le];
+
+    for (int gi = 0; gi < nG; ++gi, ++n) {
+      const int ntok = min(TG, g.P - gi * TG);
+      mbar_wait(&full[slot], phase);
+      const uint8_t* st = ring + (size_t)slot * TG * g.row_bytes;
+      XV<T> xv[TG];
+#pragma unroll
+      for (int p = 0; p < TG; ++p) {
+        if (act && p < ntok) xv[p].load(st + (size_t)p * g.row_bytes, cv);
+        else xv[p].zero();
+      }
+      float part[NV];
+#pragma unroll
+      for (int p = 0; p < TG; ++p) {
+        float xf[8];
+        xv[p].get(xf);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) s = fmaf(gv[e][c], xf[c], s);
+          part[e * TG + p] = s;
+        }
+      }
+      Red<NV, 16>::run(part, lane);
+      if (ridx >= 0) partial[((n & 1) * NW + warp) * 32 + ridx] = part[0];
+      __syncthreads();
+      if (tid == 0 && n + g.stages < total) issue(n + g.stages);
+      if (++slot == g.stages) { slot = 0; phase ^= 1; }
+
+      float dA = 0.f;
+      if (lane < NV)
+        for (int w = 0; w < NW; ++w) dA += partial[((n & 1) * NW + w) * 32 + lane];
+      const bool valid = lane < NV && lp < ntok;
+      const float dS = valid ? table[le * g.P + gi * TG + lp] * (dA - delta) : 0.f;
+      float* wb = wbuf + warp * 40;
+      wb[lane] = dS;
+      __syncwarp();
+      float wreg[E][TG];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + e * TG);
+        const float4 w1 = *reinterpret_cast<const float4*>(wb + e * TG + 4);
+        wreg[e][0] = w0.x; wreg[e][1] = w0.y; wreg[e][2] = w0.z; wreg[e][3] = w0.w;
+        wreg[e][4] = w1.x; wreg[e][5] = w1.y; wreg[e][6] = w1.z; wreg[e][7] = w1.w;
+      }
+#pragma unroll
+      for (int p = 0; p < TG; ++p) {
+        float xf[8];
+        xv[p].get(xf);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[e][c] = fmaf(wreg[e][p], xf[c], acc[e][c]);
+      }
+    }
+  }
+  if (act && nF > 0) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) atomicAdd(dWq + (size_t)(g.e0 + e) * g.C + cv * 8 + c, acc[e][c]);
+  }
+}
+
+// =====================================================================================================================
+// small helpers around the streaming passes
+// =====================================================================================================================
+// Wq[e,c] = scale * sum_j (Q_s[e,j] + Q_b[j]) Wk[j,c];  block = 32 channels x 8 slices of j, deterministic reduction
+__global__ void __launch_bounds__(256)
+fold_prep_kernel(const float* __restrict__ q_s, const float* __restrict__ q_b, const float* __restrict__ Wk, int E, int SPC,
+                 int C, float scale, float* __restrict__ Wq) {
+  extern __shared__ float sm[];
+  float* Qf = sm;                       // [E][SPC]
+  float* red = sm + (size_t)E * SPC;    // [8][E][32]
+  const int tid = threadIdx.x, cl = tid & 31, js = tid >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  for (int i = tid; i < E * SPC; i += blockDim.x) Qf[i] = q_s[i] + q_b[i % SPC];
+  __syncthreads();
+  float acc[MVF_MAX_ENTITIES];
+#pragma unroll
+  for (int e = 0; e < MVF_MAX_ENTITIES; ++e) acc[e] = 0.f;
+  if (c < C) {
+    for (int j = js; j < SPC; j += 8) {
+      const float wk = Wk[(size_t)j * C + c];
+#pragma unroll
+      for (int e = 0; e < MVF_MAX_ENTITIES; ++e)
+        if (e < E) acc[e] = fmaf(Qf[e * SPC + j], wk, acc[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < MVF_MAX_ENTITIES; ++e)
+    if (e < E) red[(js * E + e) * 32 + cl] = acc[e];
+  __syncthreads();
+  for (int i = tid; i < E * 32; i += blockDim.x) {
+    const int e = i >> 5, l = i & 31;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[(k * E + e) * 32 + l];
+    if (blockIdx.x * 32 + l < C) Wq[(size_t)e * C + blockIdx.x * 32 + l] = s * scale;
+  }
+}
+
+// dWk[j,:] += scale * sum_e Qf[e,j] dWq[e,:];  dQ_s[e,j] += scale * dWq[e,:] . Wk[j,:];  dQ_b[j] += sum_e of that
+__global__ void __launch_bounds__(256)
+fold_finish_kernel(const float* __restrict__ dWq, const float* __restrict__ q_s, const float* __restrict__ q_b,
+                   const float* __restrict__ Wk, int E, int SPC, int C, float scale, float* __restrict__ dWk, int64_t ld_dwk,
+                   float* __restrict__ dQs, float* __restrict__ dQb) {
+  __shared__ float red[8][MVF_MAX_ENTITIES];
+  const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float qf[MVF_MAX_ENTITIES], dot[MVF_MAX_ENTITIES];
+#pragma unroll
+  for (int e = 0; e < MVF_MAX_ENTITIES; ++e) {
+    qf[e] = e < E ? (q_s[e * SPC + j] + q_b[j]) * scale : 0.f;
+    dot[e] = 0.f;
+  }
+  for (int c = tid; c < C; c += blockDim.x) {
+    const float wk = Wk[(size_t)j * C + c];
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < MVF_MAX_ENTITIES; ++e) {
+      if (e < E) {
+        const float d = dWq[(size_t)e * C + c];
+        s = fmaf(qf[e], d, s);
+        dot[e] = fmaf(d, wk, dot[e]);
+      }
+    }
+    dWk[(size_t)j * ld_dwk + c] += s;
+  }
+#pragma unroll
+  for (int e = 0; e < MVF_MAX_ENTITIES; ++e) {
+    if (e < E) {
+      const float s = warp_sum(dot[e]);
+      if (lane == 0) red[warp][e] = s;
+    }
+  }
+  __syncthreads();
+  if (tid < E) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][tid];
+    red[0][tid] = s * scale;
+  }
+  __syncthreads();
+  if (tid < E) dQs[tid * SPC + j] += red[0][tid];
+  if (tid == 0) {
+    float s = 0.f;
+    for (int e = 0; e < E; ++e) s += red[0][e];
+    dQb[j] += s;
+  }
+}
+
+// h0[row, :] = [drop(ent[row, :SPC]) | drop(one-hot entity id) | 0 padding]   (mvformer.py:144-151)
+__global__ void ent_finish_fwd_kernel(const float* __restrict__ ent, float* __restrict__ h0, int64_t ld, int64_t R, int SPC,
+                                      int E, int one_hot, float p, float inv_keep, uint64_t seed) {
+  const int W = SPC + (one_hot ? E : 0);
+  const int64_t total = R * ld;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / ld;
+    const int c = (int)(i - row * ld);
+    float v = 0.f;
+    if (c < SPC) v = ent[row * SPC + c];
+    else if (one_hot && c - SPC == (int)(row % E)) v = 1.f;
+    if (v != 0.f && p > 0.f && c < W) v *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + c), p, inv_keep);
+    h0[i] = v;
+  }
+}
+// dEnt[row, c] = drop'(d_h0[row, c]) for c < SPC
+__global__ void ent_finish_bwd_kernel(const float* __restrict__ d_h0, int64_t ld, float* __restrict__ dEnt, int64_t R, int SPC,
+                                      int W, float p, float inv_keep, uint64_t seed) {
+  const int64_t total = R * SPC;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / SPC;
+    const int c = (int)(i - row * SPC);
+    float v = d_h0[row * ld + c];
+    if (p > 0.f) v *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + c), p, inv_keep);
+    dEnt[i] = v;
+  }
+}
+
+// ---- launch plumbing ---------------------------------------------------------------------------------------------------
+static int g_sms = -1;
+static int num_sms() {
+  if (g_sms < 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    g_sms = (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ? prop.multiProcessorCount : 1;
+  }
+  return g_sms;
+}
+
+struct LaunchCfg {
+  int nt, stages, grid;
+  size_t smem;
+};
+
+template <typename KernelT>
+static int plan_launch(KernelT kernel, int F, int P, int C, int E, int elem, LaunchCfg& L) {
+  L.nt = (int)round_up(C / 8, 32);
+  const int row_bytes = C * elem, nw = L.nt / 32;
+  int stages = 4;
+  static int env_stages = -1;
+  if (env_stages < 0) {
+    const char* e = getenv("MVF_FOLD_STAGES");
+    env_stages = e ? atoi(e) : 0;
+  }
+  if (env_stages >= 2 && env_stages <= MAX_STAGES) stages = env_stages;
+  while (stages > 2 && carve(stages, row_bytes, nw, E, P).total > 200 * 1024) --stages;
+  Carve cv = carve(stages, row_bytes, nw, E, P);
+  MVF_REQUIRE(cv.total <= 227 * 1024, MVF_ERR_UNSUPPORTED, "pool_fold: %d channels x %d B need %zu B of shared memory", C,
+              elem, cv.total);
+  L.stages = stages;
+  L.smem = cv.total;
+  MVF_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  int occ = 0;
+  MVF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, L.nt, L.smem));
+  if (occ < 1) occ = 1;
+  static int env_occ = -1;
+  if (env_occ < 0) {
+    const char* e = getenv("MVF_FOLD_CTAS_PER_SM");
+    env_occ = e ? atoi(e) : 0;
+  }
+  if (env_occ > 0 && env_occ < occ) occ = env_occ;
+  const int64_t slots = (int64_t)occ * num_sms();
+  L.grid = (int)(F < slots ? F : slots);
+  return MVF_OK;
+}
+
+template <typename T, int E, int NTMAX>
+static int fwd_launch(const Geom& g, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st) {
+  LaunchCfg L;
+  MVF_TRY(plan_launch(pool_fold_fwd_kernel<T, E, NTMAX>, g.F, g.P, g.C, E, (int)sizeof(T), L));
+  Geom gg = g;
+  gg.stages = L.stages;
+  pool_fold_fwd_kernel<T, E, NTMAX><<<L.grid, L.nt, L.smem, st>>>((const T*)X, Wq, attn, px, gg);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+template <typename T, int E, int NTMAX>
+static int bwd_launch(const Geom& g, const void* X, const float* G, const float* px, const float* attn, float* dWq,
+                      cudaStream_t st) {
+  LaunchCfg L;
+  MVF_TRY(plan_launch(pool_fold_bwd_kernel<T, E, NTMAX>, g.F, g.P, g.C, E, (int)sizeof(T), L));
+  Geom gg = g;
+  gg.stages = L.stages;
+  pool_fold_bwd_kernel<T, E, NTMAX><<<L.grid, L.nt, L.smem, st>>>((const T*)X, G, px, attn, dWq, gg);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+template <typename T, int E>
+static int fwd_nt(const Geom& g, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st) {
+  const int nt = g.C / 8;
+  if (nt <= 128) return fwd_launch<T, E, 128>(g, X, Wq, attn, px, st);
+  if (nt <= 320) return fwd_launch<T, E, 320>(g, X, Wq, attn, px, st);
+  return fwd_launch<T, E, 640>(g, X, Wq, attn, px, st);
+}
+template <typename T, int E>
+static int bwd_nt(const Geom& g, const void* X, const float* G, const float* px, const float* attn, float* dWq, cudaStream_t st) {
+  const int nt = g.C / 8;
+  if (nt <= 128) return bwd_launch<T, E, 128>(g, X, G, px, attn, dWq, st);
+  if (nt <= 320) return bwd_launch<T, E, 320>(g, X, G, px, attn, dWq, st);
+  return bwd_launch<T, E, 640>(g, X, G, px, attn, dWq, st);
+}
+template <typename T>
+static int fwd_e(int e, const Geom& g, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st) {
+  switch (e) {
+    case 1: return fwd_nt<T, 1>(g, X, Wq, attn, px, st);
+    case 2: return fwd_nt<T, 2>(g, X, Wq, attn, px, st);
+    case 3: return fwd_nt<T, 3>(g, X, Wq, attn, px, st);
+    default: return fwd_nt<T, 4>(g, X, Wq, attn, px, st);
+  }
+}
+template <typename T>
+static int bwd_e(int e, const Geom& g, const void* X, const float* G, const float* px, const float* attn, float* dWq,
+                 cudaStream_t st) {
+  switch (e) {
+    case 1: return bwd_nt<T, 1>(g, X, G, px, attn, dWq, st);
+    case 2: return bwd_nt<T, 2>(g, X, G, px, attn, dWq, st);
+    case 3: return bwd_nt<T, 3>(g, X, G, px, attn, dWq, st);
+    default: return bwd_nt<T, 4>(g, X, G, px, attn, dWq, st);
+  }
+}
+
+}  // namespace fold
+
+bool pool_fold_supported(int dtype, int C, int E, int P) {
+  (void)dtype;
+  return C > 0 && C % 8 == 0 && C / 8 <= 640 && E >= 1 && E <= MVF_MAX_ENTITIES && P >= 1;
+}
+
+static int fold_check(int dtype, int F, int P, int E, int C, const void* X) {
+  MVF_REQUIRE(pool_fold_supported(dtype, C, E, P), MVF_ERR_UNSUPPORTED,
+              "pool_fold: needs C_in (%d) a multiple of 8 and at most 5120, 1 <= E (%d) <= %d", C, E, MVF_MAX_ENTITIES);
+  MVF_REQUIRE(F >= 0 && X != nullptr && (((uintptr_t)X) & 15) == 0, MVF_ERR_ALIGN, "pool_fold: tokens must be 16-byte aligned");
+  return MVF_OK;
+}
+
+int pool_fold_fwd(int dtype, int F, int P, int E, int C, const void* X, const float* Wq, float* attn, float* px,
+                  cudaStream_t st) {
+  MVF_TRY(fold_check(dtype, F, P, E, C, X));
+  if (F == 0) return MVF_OK;
+  for (int e0 = 0; e0 < E; e0 += 4) {   // entity passes of <= 4 (X is re-streamed per pass; E = 3 in every penn config)
+    fold::Geom g{F, P, C, E, e0, 0, C * (dtype == MVF_BF16 ? 2 : 4)};
+    const int ne = E - e0 < 4 ? E - e0 : 4;
+    if (dtype == MVF_BF16) MVF_TRY(fold::fwd_e<bf16>(ne, g, X, Wq, attn, px, st));
+    else MVF_TRY(fold::fwd_e<float>(ne, g, X, Wq, attn, px, st));
+  }
+  return MVF_OK;
+}
+
+int pool_fold_bwd(int dtype, int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,
+                  float* dWq, cudaStream_t st) {
+  MVF_TRY(fold_check(dtype, F, P, E, C, X));
+  if (F == 0) return MVF_OK;
+  for (int e0 = 0; e0 < E; e0 += 4) {
+    fold::Geom g{F, P, C, E, e0, 0, C * (dtype == MVF_BF16 ? 2 : 4)};
+    const int ne = E - e0 < 4 ? E - e0 : 4;
+    if (dtype == MVF_BF16) MVF_TRY(fold::bwd_e<bf16>(ne, g, X, G, px, attn, dWq, st));
+    else MVF_TRY(fold::bwd_e<float>(ne, g, X, G, px, attn, dWq, st));
+  }
+  return MVF_OK;
+}
+
+int fold_prep(const float* q_s, const float* q_b, const float* Wk, int E, int SPC, int C, float* Wq, cudaStream_t st) {
+  const size_t smem = ((size_t)E * SPC + (size_t)8 * E * 32) * sizeof(float);
+  MVF_REQUIRE(smem <= 200 * 1024, MVF_ERR_UNSUPPORTED, "fold_prep: E*SPC too large");
+  if (smem > 48 * 1024)
+    MVF_CHECK_CUDA(cudaFuncSetAttribute(fold::fold_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fold::fold_prep_kernel<<<cdiv(C, 32), 256, smem, st>>>(q_s, q_b, Wk, E, SPC, C, 1.f / sqrtf((float)SPC), Wq);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+int fold_finish(const float* dWq, const float* q_s, const float* q_b, const float* Wk, int E, int SPC, int C, float* dWk,
+                int64_t ld_dwk, float* dQs, float* dQb, cudaStream_t st) {
+  fold::fold_finish_kernel<<<SPC, 256, 0, st>>>(dWq, q_s, q_b, Wk, E, SPC, C, 1.f / sqrtf((float)SPC), dWk, ld_dwk, dQs, dQb);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, int E, int one_hot, float p, uint64_t seed,
+                   cudaStream_t st) {
+  if (R <= 0) return MVF_OK;
+  const int64_t total = R * ld;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  fold::ent_finish_fwd_kernel<<<blocks, 256, 0, st>>>(ent, h0, ld, R, SPC, E, one_hot, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SPC, int W, float p, uint64_t seed,
+                   cudaStream_t st) {
+  if (R <= 0) return MVF_OK;
+  const int64_t total = R * SPC;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  fold::ent_finish_bwd_kernel<<<blocks, 256, 0, st>>>(d_h0, ld, dEnt, R, SPC, W, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
+}  // namespace mvf

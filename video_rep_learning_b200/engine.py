@@ -56,6 +56,7 @@ class RunOptions:
     allreduce_grads: bool = True    # all-reduce the flat gradient buffer inside backward (reference: DDP)
     process_group: Optional[object] = None
     scl_quirk: bool = True          # keep the 1e-6 weight on masked columns (algos/scl.py:80)
+    pool_mode: int = L.POOL_AUTO    # entity pooling: AUTO -> folded (no K|V tensors); POOL_DENSE = as written in the reference
 
 
 def _world(opts: RunOptions) -> int:
@@ -70,7 +71,7 @@ class Plan:
     _cache: Dict[tuple, "Plan"] = {}
 
     def __init__(self, spec: HeadSpec, BV: int, T: int, P: int, dtype: int, training: bool, has_mask: bool,
-                 world: int, backend: int):
+                 world: int, backend: int, pool_mode: int = L.POOL_AUTO):
         lib = L.lib()
         d = L.HeadDesc()
         d.BV, d.T, d.P, d.C_in = BV, T, P, spec.c_in
@@ -90,6 +91,7 @@ class Plan:
         d.has_mask = 1 if has_mask else 0
         d.gemm_backend = backend
         d.world_size = world
+        d.pool_mode = pool_mode
         d.drop_p = spec.drop_p
         d.ln_eps, d.bn_eps, d.bn_momentum = spec.ln_eps, spec.bn_eps, spec.bn_momentum
         d.seed = 0
@@ -121,11 +123,11 @@ class Plan:
 
     @classmethod
     def get(cls, spec: HeadSpec, BV: int, T: int, P: int, dtype: int, training: bool, has_mask: bool, world: int,
-            backend: int) -> "Plan":
-        key = (spec, BV, T, P, dtype, training, has_mask, world, backend)
+            backend: int, pool_mode: int = L.POOL_AUTO) -> "Plan":
+        key = (spec, BV, T, P, dtype, training, has_mask, world, backend, pool_mode)
         p = cls._cache.get(key)
         if p is None:
-            p = cls(spec, BV, T, P, dtype, training, has_mask, world, backend)
+            p = cls(spec, BV, T, P, dtype, training, has_mask, world, backend, pool_mode)
             cls._cache[key] = p
         return p
 
@@ -318,7 +320,7 @@ class HeadFn(torch.autograd.Function):
         mask = _prep_mask(mask, BV, T, tokens.device)
         with torch.cuda.device(tokens.device):
             plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _world(cs.opts),
-                            cs.opts.gemm_backend)
+                            cs.opts.gemm_backend, cs.opts.pool_mode)
             d = plan.desc_with_seed(cs.seed)
             save = torch.empty(plan.save_bytes, dtype=torch.uint8, device=tokens.device)
             ws = _scratch(tokens.device, plan.ws_bytes, "head")
@@ -359,7 +361,7 @@ class ProjFn(torch.autograd.Function):
         embc = emb.contiguous().float()
         with torch.cuda.device(emb.device):
             plan = Plan.get(cs.spec, BV, T, 1, L.MVF_F32 if cs.opts.gemm_backend != L.GEMM_TCGEN05 else L.MVF_BF16,
-                            cs.training, False, _world(cs.opts), cs.opts.gemm_backend)
+                            cs.training, False, _world(cs.opts), cs.opts.gemm_backend, cs.opts.pool_mode)
             d = plan.desc_with_seed(0)
             save = torch.empty(plan.proj_save_bytes, dtype=torch.uint8, device=emb.device)
             ws = _scratch(emb.device, plan.proj_ws_bytes, "proj")
@@ -403,7 +405,7 @@ class ModelFn(torch.autograd.Function):
         dev = tokens.device
         with torch.cuda.device(dev):
             plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _world(cs.opts),
-                            cs.opts.gemm_backend)
+                            cs.opts.gemm_backend, cs.opts.pool_mode)
             d = plan.desc_with_seed(cs.seed)
             save = torch.empty(plan.save_bytes, dtype=torch.uint8, device=dev)
             psave = torch.empty(plan.proj_save_bytes, dtype=torch.uint8, device=dev)
