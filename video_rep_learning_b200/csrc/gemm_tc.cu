@@ -190,7 +190,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = (uint32_t*)(conv_bar + STAGES);
   static_assert(!SPLIT || EB == 4, "SPLIT3 applies to fp32 operands");
   static_assert((3 * STAGES + 4) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
-  float* epi_stage = (float*)(smem + STAGES * STAGE_BYTES + 256);  // 4 warps x [32][33] fp32 transpose tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_work = p.tiles_m * p.tiles_n * p.split_k;
@@ -366,7 +365,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && split == 0;
       const bool atomic = p.split_k > 1;
-      float* ts = epi_stage + (warp - 4) * (32 * 33);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         const int col0 = tn * BLOCK_N + c0;
@@ -374,40 +372,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
         tmem_ld_wait();
-        if (!p.c_bf16) {
-          // fp32 output: transpose the 32x32 chunk through shared memory so that every global access of the warp is
-          // one coalesced 128-byte row segment (thread = row in TMEM, thread = column in memory)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) ts[lane * 33 + j] = __uint_as_float(r[j]);
-          __syncwarp();
-          const int col = col0 + lane;
-          const bool col_ok = col < p.N;
-          const float bv = (add_bias && col_ok) ? __ldg(p.bias + col) : 0.f;
-          const int row_base = tm * BLOCK_M + q * 32;
-          if (has_k) {
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-              const int row = row_base + rr;
-              if (row >= p.M) break;  // warp-uniform
-              float v = ts[rr * 33 + lane] + bv;
-              if (p.flags & MVF_GEMM_RELU) v = fmaxf(v, 0.f);
-              if (col_ok) {
-                if (p.flags & MVF_GEMM_RELUMASK) {
-                  float src;
-                  if constexpr (EB == 2) src = __bfloat162float(((const bf16*)p.relu_src)[(int64_t)row * p.ld_relu + col]);
-                  else src = ((const float*)p.relu_src)[(int64_t)row * p.ld_relu + col];
-                  v = src > 0.f ? v : 0.f;
-                }
-                float* cp = (float*)p.C + (int64_t)row * p.ldc + col;
-                if (atomic) atomicAdd(cp, v);
-                else if (p.flags & MVF_GEMM_ACCUM) *cp += v;
-                else *cp = v;
-              }
-            }
-          }
-          __syncwarp();
-          continue;
-        }
         if (row_ok && has_k) {
           float v[32];
 #pragma unroll
@@ -435,7 +399,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           const bool full = col0 + 32 <= p.N;
-          {
+          if (p.c_bf16) {
             bf16* cp = (bf16*)p.C + (int64_t)row * p.ldc + col0;
             if (full && ((p.ldc & 7) == 0) && ((((uintptr_t)p.C) & 15) == 0)) {
 #pragma unroll
@@ -455,6 +419,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+            }
+          } else {
+            // fp32 output: each thread owns 128 contiguous bytes of its row (8 x 16-byte stores; measured 25x fewer
+            // instructions than a shared-memory transpose to row-coalesced 4-byte stores, profiles/r01_gemm_small.txt)
+            float* cp = (float*)p.C + (int64_t)row * p.ldc + col0;
+            if (atomic) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(cp + j, v[j]);
+            } else if (p.flags & MVF_GEMM_ACCUM) {
+              if (full && ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 o = *reinterpret_cast<float4*>(cp + j);
+                  o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
+                  *reinterpret_cast<float4*>(cp + j) = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) cp[j] += v[j];
+              }
+            } else if (full && ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) cp[j] = v[j];
             }
           }
         }
@@ -518,7 +512,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
 
 template <int BLOCK_N, int STAGES, int EB, bool SPLIT = false>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int num_sms, cudaStream_t st) {
-  constexpr int smem = STAGES * (BLOCK_M * ROW_BYTES + BLOCK_N * ROW_BYTES) + 1024 + 256 + 4 * 32 * 33 * 4;
+  constexpr int smem = STAGES * (BLOCK_M * ROW_BYTES + BLOCK_N * ROW_BYTES) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     MVF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, EB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
