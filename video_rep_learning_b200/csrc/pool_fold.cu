@@ -19,6 +19,9 @@
 // is conflict-free, and the only cross-thread traffic is the reduction of the 8*E partial dot products of a group
 // (recursive-halving warp shuffles, then one shared-memory hop across warps).  Forward keeps an online softmax
 // (running max / sum per entity, accumulators rescaled when the max moves), so X is read exactly once.
+#include <math.h>
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace mvf {
@@ -60,30 +63,102 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-// ---- the 8 channels a thread owns in one token row ------------------------------------------------------------------
+// ---- packed fp32 pairs: Blackwell issues fma.rn.f32x2 (FFMA2) at the rate of a scalar FFMA, and the FMA pipe is what
+// bounds these kernels (3 warps per scheduler x ~400 FFMA per 8-token group otherwise) ---------------------------------
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float a, float b) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 up2(f2_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f2_t ffma2(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2_t fmul2(f2_t a, f2_t b) {
+  f2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// ---- the 8 channels a thread owns in one token row, as 4 fp32 pairs ------------------------------------------------------
 template <typename T> struct XV;
 template <> struct XV<bf16> {
-  uint4 u;
-  __device__ __forceinline__ void load(const uint8_t* row, int cv) { u = *reinterpret_cast<const uint4*>(row + cv * 16); }
-  __device__ __forceinline__ void zero() { u = make_uint4(0u, 0u, 0u, 0u); }
-  __device__ __forceinline__ void get(float* f) const {
-    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
-    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
-    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
-    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+  static __device__ __forceinline__ void load(const uint8_t* row, int cv, f2_t* x2) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + cv * 16);
+    x2[0] = pk2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+    x2[1] = pk2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    x2[2] = pk2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u));
+    x2[3] = pk2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
   }
 };
 template <> struct XV<float> {
-  float4 a, b;
-  __device__ __forceinline__ void load(const uint8_t* row, int cv) {
-    a = *reinterpret_cast<const float4*>(row + cv * 32);
-    b = *reinterpret_cast<const float4*>(row + cv * 32 + 16);
-  }
-  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
-  __device__ __forceinline__ void get(float* f) const {
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  static __device__ __forceinline__ void load(const uint8_t* row, int cv, f2_t* x2) {
+    const float4 a = *reinterpret_cast<const float4*>(row + cv * 32);
+    const float4 b = *reinterpret_cast<const float4*>(row + cv * 32 + 16);
+    x2[0] = pk2(a.x, a.y); x2[1] = pk2(a.z, a.w); x2[2] = pk2(b.x, b.y); x2[3] = pk2(b.z, b.w);
   }
 };
+
+// x2[p][k]: token p of the group, channel pair k of this thread (zero for tokens past the end of the frame)
+template <typename T>
+__device__ __forceinline__ void load_group(const uint8_t* st, int row_bytes, int cv, bool act, int ntok, f2_t (&x2)[8][4]) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    if (act && p < ntok) XV<T>::load(st + (size_t)p * row_bytes, cv, x2[p]);
+    else x2[p][0] = x2[p][1] = x2[p][2] = x2[p][3] = 0ull;
+  }
+}
+// part[e*8+p] = sum over this thread's 8 channels of v[e][c] * x[p][c]
+template <int E>
+__device__ __forceinline__ void dot_group(const f2_t (&v2)[E][4], const f2_t (&x2)[8][4], float* part) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      f2_t s2 = fmul2(v2[e][0], x2[p][0]);
+#pragma unroll
+      for (int k = 1; k < 4; ++k) s2 = ffma2(v2[e][k], x2[p][k], s2);
+      const float2 s = up2(s2);
+      part[e * 8 + p] = s.x + s.y;
+    }
+  }
+}
+// acc[e][c] += w[e][p] * x[p][c]   (w: E*8 floats in shared memory, broadcast reads)
+template <int E>
+__device__ __forceinline__ void axpy_group(const float* wb, const f2_t (&x2)[8][4], f2_t (&acc2)[E][4]) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const float4 w0 = *reinterpret_cast<const float4*>(wb + e * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(wb + e * 8 + 4);
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const f2_t ww = pk2(w[p], w[p]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc2[e][k] = ffma2(ww, x2[p][k], acc2[e][k]);
+    }
+  }
+}
+template <int E>
+__device__ __forceinline__ void load_vec(const float* src, bool act, f2_t (&v2)[E][4], size_t stride) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (act) {
+      const float4 a = *reinterpret_cast<const float4*>(src + e * stride);
+      const float4 b = *reinterpret_cast<const float4*>(src + e * stride + 4);
+      v2[e][0] = pk2(a.x, a.y); v2[e][1] = pk2(a.z, a.w); v2[e][2] = pk2(b.x, b.y); v2[e][3] = pk2(b.z, b.w);
+    } else {
+      v2[e][0] = v2[e][1] = v2[e][2] = v2[e][3] = 0ull;
+    }
+  }
+}
 
 // ---- recursive-halving warp reduction of N per-lane values: lane L ends with the full sum of value red_index(L) ------
 // (N + ~5 shuffles instead of 5 N).  Odd sizes are padded with a zero; lanes that end on padding get index -1.
@@ -186,19 +261,8 @@ pool_fold_fwd_kernel(const T* __restrict__ X, const float* __restrict__ Wq, floa
   MVF_FOLD_SMEM_SETUP();
   float* fin = misc;  // [2][E]: final max, 1/sum
 
-  float wq[E][8];
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    if (act) {
-      const float4 a = *reinterpret_cast<const float4*>(Wq + (size_t)(g.e0 + e) * g.C + cv * 8);
-      const float4 b = *reinterpret_cast<const float4*>(Wq + (size_t)(g.e0 + e) * g.C + cv * 8 + 4);
-      wq[e][0] = a.x; wq[e][1] = a.y; wq[e][2] = a.z; wq[e][3] = a.w;
-      wq[e][4] = b.x; wq[e][5] = b.y; wq[e][6] = b.z; wq[e][7] = b.w;
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) wq[e][c] = 0.f;
-    }
-  }
+  f2_t wq2[E][4];
+  load_vec<E>(Wq + (size_t)g.e0 * g.C + cv * 8, act, wq2, (size_t)g.C);
   const int ridx = Red<NV, 16>::index(lane);
   const int le = lane >> 3, lp = lane & 7;   // the (entity, token-in-group) pair this lane finishes the softmax for
 
@@ -206,37 +270,19 @@ pool_fold_fwd_kernel(const T* __restrict__ X, const float* __restrict__ Wq, floa
   uint32_t phase = 0;
   for (int fi = 0; fi < nF; ++fi) {
     const int64_t f = blockIdx.x + (int64_t)fi * gridDim.x;
-    float acc[E][8];
+    f2_t acc2[E][4];
 #pragma unroll
-    for (int e = 0; e < E; ++e)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[e][c] = 0.f;
+    for (int e = 0; e < E; ++e) acc2[e][0] = acc2[e][1] = acc2[e][2] = acc2[e][3] = 0ull;
     float m_run = -INFINITY, l_run = 0.f;
 
     for (int gi = 0; gi < nG; ++gi, ++n) {
       const int ntok = min(TG, g.P - gi * TG);
       mbar_wait(&full[slot], phase);
       const uint8_t* st = ring + (size_t)slot * TG * g.row_bytes;
-      XV<T> xv[TG];
-#pragma unroll
-      for (int p = 0; p < TG; ++p) {
-        if (act && p < ntok) xv[p].load(st + (size_t)p * g.row_bytes, cv);
-        else xv[p].zero();
-      }
-      // partial scores of this thread's 8 channels
+      f2_t x2[TG][4];
+      load_group<T>(st, g.row_bytes, cv, act, ntok, x2);
       float part[NV];
-#pragma unroll
-      for (int p = 0; p < TG; ++p) {
-        float xf[8];
-        xv[p].get(xf);
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          float s = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) s = fmaf(wq[e][c], xf[c], s);
-          part[e * TG + p] = s;
-        }
-      }
+      dot_group<E>(wq2, x2, part);   // partial scores of this thread's 8 channels
       Red<NV, 16>::run(part, lane);
       if (ridx >= 0) partial[((n & 1) * NW + warp) * 32 + ridx] = part[0];
       __syncthreads();   // every thread holds its slice of the stage in registers: the slot can be refilled
@@ -266,29 +312,15 @@ pool_fold_fwd_kernel(const T* __restrict__ X, const float* __restrict__ Wq, floa
       wb[lane] = w_;
       if (lane < NV && lp == 0) wb[32 + le] = fac;
       __syncwarp();
-      // px accumulators
-      float wreg[E][TG], fr[E];
+      // px accumulators: rescale by exp(m_old - m_new), then add this group's weighted tokens
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        const float4 w0 = *reinterpret_cast<const float4*>(wb + e * TG);
-        const float4 w1 = *reinterpret_cast<const float4*>(wb + e * TG + 4);
-        wreg[e][0] = w0.x; wreg[e][1] = w0.y; wreg[e][2] = w0.z; wreg[e][3] = w0.w;
-        wreg[e][4] = w1.x; wreg[e][5] = w1.y; wreg[e][6] = w1.z; wreg[e][7] = w1.w;
-        fr[e] = wb[32 + e];
+        const float fr = wb[32 + e];
+        const f2_t f2 = pk2(fr, fr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc2[e][k] = fmul2(acc2[e][k], f2);
       }
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[e][c] *= fr[e];
-#pragma unroll
-      for (int p = 0; p < TG; ++p) {
-        float xf[8];
-        xv[p].get(xf);
-#pragma unroll
-        for (int e = 0; e < E; ++e)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[e][c] = fmaf(wreg[e][p], xf[c], acc[e][c]);
-      }
+      axpy_group<E>(wb, x2, acc2);
     }
 
     // ---- end of frame: normalise, write px and the attention map ----
@@ -299,8 +331,9 @@ pool_fold_fwd_kernel(const T* __restrict__ X, const float* __restrict__ Wq, floa
       for (int e = 0; e < E; ++e) {
         const float inv = fin[E + e];
         float* dst = px + ((size_t)f * g.Etot + g.e0 + e) * g.C + cv * 8;
-        *reinterpret_cast<float4*>(dst) = make_float4(acc[e][0] * inv, acc[e][1] * inv, acc[e][2] * inv, acc[e][3] * inv);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[e][4] * inv, acc[e][5] * inv, acc[e][6] * inv, acc[e][7] * inv);
+        const float2 a0 = up2(acc2[e][0]), a1 = up2(acc2[e][1]), a2 = up2(acc2[e][2]), a3 = up2(acc2[e][3]);
+        *reinterpret_cast<float4*>(dst) = make_float4(a0.x * inv, a0.y * inv, a1.x * inv, a1.y * inv);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(a2.x * inv, a2.y * inv, a3.x * inv, a3.y * inv);
       }
     }
     for (int i = tid; i < E * g.P; i += blockDim.x) {
@@ -432,26 +465,28 @@ pool_fold_bwd_kernel(const T* __restrict__ X, const float* __restrict__ G, const
 // =====================================================================================================================
 // small helpers around the streaming passes
 // =====================================================================================================================
-// Wq[e,c] = scale * sum_j (Q_s[e,j] + Q_b[j]) Wk[j,c];  block = 32 channels x 8 slices of j, deterministic reduction
+// Wq[e,c] = scale * sum_j (Q_s[e,j] + Q_b[j]) Wk[j,c];  block = 32 channels x 8 slices of j, deterministic reduction.
+// Accumulated in fp64 and rounded once: Wq is shared by every token of every frame, so its rounding error acts like a
+// coherent perturbation of W_k (measured: fp32 accumulation costs 1.5e-5 on the gradients at C_in = 1152, fp64 none).
 __global__ void __launch_bounds__(256)
 fold_prep_kernel(const float* __restrict__ q_s, const float* __restrict__ q_b, const float* __restrict__ Wk, int E, int SPC,
                  int C, float scale, float* __restrict__ Wq) {
-  extern __shared__ float sm[];
-  float* Qf = sm;                       // [E][SPC]
-  float* red = sm + (size_t)E * SPC;    // [8][E][32]
+  extern __shared__ double smd[];
+  float* Qf = reinterpret_cast<float*>(smd + (size_t)8 * E * 32);   // [E][SPC] (fp32 sum, like mvformer.py:383)
+  double* red = smd;                                                // [8][E][32]
   const int tid = threadIdx.x, cl = tid & 31, js = tid >> 5;
   const int c = blockIdx.x * 32 + cl;
   for (int i = tid; i < E * SPC; i += blockDim.x) Qf[i] = q_s[i] + q_b[i % SPC];
   __syncthreads();
-  float acc[MVF_MAX_ENTITIES];
+  double acc[MVF_MAX_ENTITIES];
 #pragma unroll
-  for (int e = 0; e < MVF_MAX_ENTITIES; ++e) acc[e] = 0.f;
+  for (int e = 0; e < MVF_MAX_ENTITIES; ++e) acc[e] = 0.0;
   if (c < C) {
     for (int j = js; j < SPC; j += 8) {
-      const float wk = Wk[(size_t)j * C + c];
+      const double wk = (double)Wk[(size_t)j * C + c];
 #pragma unroll
       for (int e = 0; e < MVF_MAX_ENTITIES; ++e)
-        if (e < E) acc[e] = fmaf(Qf[e * SPC + j], wk, acc[e]);
+        if (e < E) acc[e] = fma((double)Qf[e * SPC + j], wk, acc[e]);
     }
   }
 #pragma unroll
@@ -460,10 +495,10 @@ fold_prep_kernel(const float* __restrict__ q_s, const float* __restrict__ q_b, c
   __syncthreads();
   for (int i = tid; i < E * 32; i += blockDim.x) {
     const int e = i >> 5, l = i & 31;
-    float s = 0.f;
+    double s = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += red[(k * E + e) * 32 + l];
-    if (blockIdx.x * 32 + l < C) Wq[(size_t)e * C + blockIdx.x * 32 + l] = s * scale;
+    if (blockIdx.x * 32 + l < C) Wq[(size_t)e * C + blockIdx.x * 32 + l] = (float)(s * (double)scale);
   }
 }
 
@@ -559,17 +594,24 @@ struct LaunchCfg {
   size_t smem;
 };
 
+// Planned once per (kernel instantiation, shape): cudaFuncSetAttribute / the occupancy query are host-side calls that
+// must not sit on the per-step launch path.
+struct PlanKey {
+  int F, P, C;
+  bool valid = false;
+  LaunchCfg cfg;
+};
 template <typename KernelT>
-static int plan_launch(KernelT kernel, int F, int P, int C, int E, int elem, LaunchCfg& L) {
+static int plan_launch(KernelT kernel, PlanKey& cache, int F, int P, int C, int E, int elem, LaunchCfg& L) {
+  if (cache.valid && cache.F == F && cache.P == P && cache.C == C) {
+    L = cache.cfg;
+    return MVF_OK;
+  }
   L.nt = (int)round_up(C / 8, 32);
   const int row_bytes = C * elem, nw = L.nt / 32;
   int stages = 4;
-  static int env_stages = -1;
-  if (env_stages < 0) {
-    const char* e = getenv("MVF_FOLD_STAGES");
-    env_stages = e ? atoi(e) : 0;
-  }
-  if (env_stages >= 2 && env_stages <= MAX_STAGES) stages = env_stages;
+  const char* es = getenv("MVF_FOLD_STAGES");
+  if (es && atoi(es) >= 2 && atoi(es) <= MAX_STAGES) stages = atoi(es);
   while (stages > 2 && carve(stages, row_bytes, nw, E, P).total > 200 * 1024) --stages;
   Carve cv = carve(stages, row_bytes, nw, E, P);
   MVF_REQUIRE(cv.total <= 227 * 1024, MVF_ERR_UNSUPPORTED, "pool_fold: %d channels x %d B need %zu B of shared memory", C,
@@ -580,21 +622,19 @@ static int plan_launch(KernelT kernel, int F, int P, int C, int E, int elem, Lau
   int occ = 0;
   MVF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, L.nt, L.smem));
   if (occ < 1) occ = 1;
-  static int env_occ = -1;
-  if (env_occ < 0) {
-    const char* e = getenv("MVF_FOLD_CTAS_PER_SM");
-    env_occ = e ? atoi(e) : 0;
-  }
-  if (env_occ > 0 && env_occ < occ) occ = env_occ;
+  const char* eo = getenv("MVF_FOLD_CTAS_PER_SM");
+  if (eo && atoi(eo) > 0 && atoi(eo) < occ) occ = atoi(eo);
   const int64_t slots = (int64_t)occ * num_sms();
   L.grid = (int)(F < slots ? F : slots);
+  cache.F = F; cache.P = P; cache.C = C; cache.cfg = L; cache.valid = true;
   return MVF_OK;
 }
 
 template <typename T, int E, int NTMAX>
 static int fwd_launch(const Geom& g, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st) {
   LaunchCfg L;
-  MVF_TRY(plan_launch(pool_fold_fwd_kernel<T, E, NTMAX>, g.F, g.P, g.C, E, (int)sizeof(T), L));
+  static thread_local PlanKey cache;
+  MVF_TRY(plan_launch(pool_fold_fwd_kernel<T, E, NTMAX>, cache, g.F, g.P, g.C, E, (int)sizeof(T), L));
   Geom gg = g;
   gg.stages = L.stages;
   pool_fold_fwd_kernel<T, E, NTMAX><<<L.grid, L.nt, L.smem, st>>>((const T*)X, Wq, attn, px, gg);
@@ -605,7 +645,8 @@ template <typename T, int E, int NTMAX>
 static int bwd_launch(const Geom& g, const void* X, const float* G, const float* px, const float* attn, float* dWq,
                       cudaStream_t st) {
   LaunchCfg L;
-  MVF_TRY(plan_launch(pool_fold_bwd_kernel<T, E, NTMAX>, g.F, g.P, g.C, E, (int)sizeof(T), L));
+  static thread_local PlanKey cache;
+  MVF_TRY(plan_launch(pool_fold_bwd_kernel<T, E, NTMAX>, cache, g.F, g.P, g.C, E, (int)sizeof(T), L));
   Geom gg = g;
   gg.stages = L.stages;
   pool_fold_bwd_kernel<T, E, NTMAX><<<L.grid, L.nt, L.smem, st>>>((const T*)X, G, px, attn, dWq, gg);
@@ -688,11 +729,11 @@ int pool_fold_bwd(int dtype, int F, int P, int E, int C, const void* X, const fl
 }
 
 int fold_prep(const float* q_s, const float* q_b, const float* Wk, int E, int SPC, int C, float* Wq, cudaStream_t st) {
-  const size_t smem = ((size_t)E * SPC + (size_t)8 * E * 32) * sizeof(float);
+  const size_t smem = (size_t)E * SPC * sizeof(float) + (size_t)8 * E * 32 * sizeof(double);
   MVF_REQUIRE(smem <= 200 * 1024, MVF_ERR_UNSUPPORTED, "fold_prep: E*SPC too large");
   if (smem > 48 * 1024)
     MVF_CHECK_CUDA(cudaFuncSetAttribute(fold::fold_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fold::fold_prep_kernel<<<cdiv(C, 32), 256, smem, st>>>(q_s, q_b, Wk, E, SPC, C, 1.f / sqrtf((float)SPC), Wq);
+  fold::fold_prep_kernel<<<cdiv(C, 32), 256, smem, st>>>(q_s, q_b, Wk, E, SPC, C, (float)(1.0 / sqrt((double)SPC)), Wq);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
