@@ -40,3 +40,11 @@ for M, N, K in SHAPES:
     b = run(M, N, K, L.MVF_BF16, 0)
     bb = run(M, N, K, L.MVF_BF16, 0, torch.bfloat16)
     print(f"{M:6d} {N:5d} {K:5d} | {t:8.2f} {s:9.2f} {b:8.2f} {bb:10.2f} | {2e-9 * M * N * K:.2f}")
+
+print("\nK sweep at 3840 x 512 (fp32 out): fixed cost vs per-k-block cost")
+for K in (32, 64, 128, 256, 512, 1024, 2048):
+    print(f"  K={K:5d}  tf32 {run(3840, 512, K, L.MVF_F32, 0):7.2f} us   bf16x3 {run(3840, 512, K, L.MVF_F32, L.GEMM_SPLIT3):7.2f} us   "
+          f"bf16 {run(3840, 512, K, L.MVF_BF16, 0):7.2f} us")
+print("N sweep at 3840 x N x 256 tf32")
+for N in (64, 128, 256, 512, 1024):
+    print(f"  N={N:5d}  tf32 {run(3840, N, 256, L.MVF_F32, 0):7.2f} us")

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 
 # (F, P, E, C_in, SPC, dtype): bench shape slice, ragged token groups (P % 8 != 0), E > 4 (two entity passes), E = 16,
 # more frames than resident CTAs (several frames per CTA), tiny channels (partially filled warps)
-SHAPES = [(6, 196, 3, 2304, 384, torch.bfloat16), (5, 196, 3, 1152, 384, torch.float32), (7, 50, 6, 384, 64, torch.bfloat16),
+SHAPES = [(6, 196, 3, 2304, 384, torch.bfloat16), (3, 196, 3, 1152, 384, torch.bfloat16), (5, 30, 8, 768, 64, torch.bfloat16),
+          (4, 16, 11, 256, 32, torch.bfloat16), (300, 40, 3, 2304, 384, torch.bfloat16), (5, 196, 3, 1152, 384, torch.float32), (7, 50, 6, 384, 64, torch.bfloat16),
           (3, 17, 16, 64, 32, torch.float32), (400, 33, 3, 2304, 384, torch.bfloat16), (9, 9, 1, 48, 32, torch.float32),
           (4, 8, 2, 200, 40, torch.bfloat16), (310, 196, 4, 768, 384, torch.float32)]
 
@@ -104,6 +105,17 @@ def test_fold_backward_equals_autograd_of_dense_formulation(F, P, E, C, SPC, dty
     assert rel(dEnt.view(F * E, SPC).double().t() @ px.double(), d_Wv) < tol
     assert rel(dEnt.view(F * E, SPC).double().sum(0), d_bv) < 1e-12
     assert float(d_bk.abs().max()) < 1e-9 * float(d_bv.abs().max())
+
+
+def test_fold_mma_and_cuda_core_paths_agree(monkeypatch):
+    """bf16 tokens with C_in % 16 == 0 run on mma.sync (pool_fold_mma.cu); MVF_FOLD_MMA=0 forces the CUDA-core kernels."""
+    F, P, E, C, SPC = 9, 196, 3, 2304, 384
+    X, qs, qb, Wk, Wv, bk, bv = _mk(F, P, E, C, SPC, torch.bfloat16, seed=3)
+    _, attn_m, px_m = _fold_forward(X, qs, qb, Wk)
+    monkeypatch.setenv("MVF_FOLD_MMA", "0")
+    _, attn_c, px_c = _fold_forward(X, qs, qb, Wk)
+    assert float((attn_m - attn_c).abs().max()) < 2e-6
+    assert float((px_m - px_c).abs().max() / px_c.abs().max()) < 5e-6
 
 
 def test_fold_rejects_unsupported_shapes():

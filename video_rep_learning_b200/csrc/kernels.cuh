@@ -100,6 +100,11 @@ int pool_fold_bwd(int dtype, int F, int P, int E, int C, const void* X, const fl
 // dWk += Q^T dWq / sqrt(SPC); dQ_s += dWq Wk^T / sqrt(SPC); dQ_b += column sums of dQ_s
 int fold_finish(const float* dWq, const float* q_s, const float* q_b, const float* Wk, int E, int SPC, int C, float* dWk,
                 int64_t ld_dwk, float* dQs, float* dQb, cudaStream_t st);
+// bf16 tokens, C % 16 == 0: the same two passes on mma.sync tensor cores (pool_fold_mma.cu); called by the two above
+bool pool_fold_mma_supported(int dtype, int C, int P);
+int pool_fold_mma_fwd(int F, int P, int E, int C, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st);
+int pool_fold_mma_bwd(int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,
+                      float* dWq, cudaStream_t st);
 // h0 = [drop(ent) | drop(one-hot) | 0]  and its backward
 int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, int E, int one_hot, float p, uint64_t seed,
                    cudaStream_t st);

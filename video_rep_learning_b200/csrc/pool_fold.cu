@@ -357,41 +357,34 @@ pool_fold_bwd_kernel(const T* __restrict__ X, const float* __restrict__ G, const
 
   const int ridx = Red<NV, 16>::index(lane);
   const int le = lane >> 3, lp = lane & 7;
-  float acc[E][8];
+  f2_t acc2[E][4];
 #pragma unroll
-  for (int e = 0; e < E; ++e)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[e][c] = 0.f;
+  for (int e = 0; e < E; ++e) acc2[e][0] = acc2[e][1] = acc2[e][2] = acc2[e][3] = 0ull;
 
   int n = 0, slot = 0;
   uint32_t phase = 0;
   for (int fi = 0; fi < nF; ++fi) {
     const int64_t f = blockIdx.x + (int64_t)fi * gridDim.x;
     __syncthreads();   // the previous frame's readers of table / red are done
-    float gv[E][8], dpart[E];
+    const size_t off = ((size_t)f * g.Etot + g.e0) * g.C + cv * 8;
+    f2_t gv2[E][4];
+    load_vec<E>(G + off, act, gv2, (size_t)g.C);
+    {
+      f2_t pv2[E][4];
+      load_vec<E>(px + off, act, pv2, (size_t)g.C);
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      dpart[e] = 0.f;
-      if (act) {
-        const size_t off = ((size_t)f * g.Etot + g.e0 + e) * g.C + cv * 8;
-        const float4 a = *reinterpret_cast<const float4*>(G + off), b = *reinterpret_cast<const float4*>(G + off + 4);
-        const float4 pa = *reinterpret_cast<const float4*>(px + off), pb = *reinterpret_cast<const float4*>(px + off + 4);
-        gv[e][0] = a.x; gv[e][1] = a.y; gv[e][2] = a.z; gv[e][3] = a.w;
-        gv[e][4] = b.x; gv[e][5] = b.y; gv[e][6] = b.z; gv[e][7] = b.w;
-        dpart[e] = a.x * pa.x + a.y * pa.y + a.z * pa.z + a.w * pa.w + b.x * pb.x + b.y * pb.y + b.z * pb.z + b.w * pb.w;
-      } else {
+      for (int e = 0; e < E; ++e) {
+        f2_t d2 = fmul2(gv2[e][0], pv2[e][0]);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) gv[e][c] = 0.f;
+        for (int k = 1; k < 4; ++k) d2 = ffma2(gv2[e][k], pv2[e][k], d2);
+        const float2 d = up2(d2);
+        const float s = warp_sum(d.x + d.y);
+        if (lane == 0) red[warp * E + e] = s;
       }
     }
     for (int i = tid; i < E * g.P; i += blockDim.x) {
       const int e = i / g.P, p = i - e * g.P;
       table[i] = attn[((size_t)f * g.Etot + g.e0 + e) * g.P + p];
-    }
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const float s = warp_sum(dpart[e]);
-      if (lane == 0) red[warp * E + e] = s;
     }
     __syncthreads();
     float delta = 0.f;
@@ -402,25 +395,10 @@ pool_fold_bwd_kernel(const T* __restrict__ X, const float* __restrict__ G, const
       const int ntok = min(TG, g.P - gi * TG);
       mbar_wait(&full[slot], phase);
       const uint8_t* st = ring + (size_t)slot * TG * g.row_bytes;
-      XV<T> xv[TG];
-#pragma unroll
-      for (int p = 0; p < TG; ++p) {
-        if (act && p < ntok) xv[p].load(st + (size_t)p * g.row_bytes, cv);
-        else xv[p].zero();
-      }
+      f2_t x2[TG][4];
+      load_group<T>(st, g.row_bytes, cv, act, ntok, x2);
       float part[NV];
-#pragma unroll
-      for (int p = 0; p < TG; ++p) {
-        float xf[8];
-        xv[p].get(xf);
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          float s = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) s = fmaf(gv[e][c], xf[c], s);
-          part[e * TG + p] = s;
-        }
-      }
+      dot_group<E>(gv2, x2, part);
       Red<NV, 16>::run(part, lane);
       if (ridx >= 0) partial[((n & 1) * NW + warp) * 32 + ridx] = part[0];
       __syncthreads();
@@ -435,30 +413,18 @@ pool_fold_bwd_kernel(const T* __restrict__ X, const float* __restrict__ G, const
       float* wb = wbuf + warp * 40;
       wb[lane] = dS;
       __syncwarp();
-      float wreg[E][TG];
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const float4 w0 = *reinterpret_cast<const float4*>(wb + e * TG);
-        const float4 w1 = *reinterpret_cast<const float4*>(wb + e * TG + 4);
-        wreg[e][0] = w0.x; wreg[e][1] = w0.y; wreg[e][2] = w0.z; wreg[e][3] = w0.w;
-        wreg[e][4] = w1.x; wreg[e][5] = w1.y; wreg[e][6] = w1.z; wreg[e][7] = w1.w;
-      }
-#pragma unroll
-      for (int p = 0; p < TG; ++p) {
-        float xf[8];
-        xv[p].get(xf);
-#pragma unroll
-        for (int e = 0; e < E; ++e)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[e][c] = fmaf(wreg[e][p], xf[c], acc[e][c]);
-      }
+      axpy_group<E>(wb, x2, acc2);
     }
   }
   if (act && nF > 0) {
 #pragma unroll
     for (int e = 0; e < E; ++e)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) atomicAdd(dWq + (size_t)(g.e0 + e) * g.C + cv * 8 + c, acc[e][c]);
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = up2(acc2[e][k]);
+        atomicAdd(dWq + (size_t)(g.e0 + e) * g.C + cv * 8 + 2 * k, a.x);
+        atomicAdd(dWq + (size_t)(g.e0 + e) * g.C + cv * 8 + 2 * k + 1, a.y);
+      }
   }
 }
 
@@ -695,6 +661,14 @@ bool pool_fold_supported(int dtype, int C, int E, int P) {
   return C > 0 && C % 8 == 0 && C / 8 <= 640 && E >= 1 && E <= MVF_MAX_ENTITIES && P >= 1;
 }
 
+// bf16 tokens with C_in % 16 == 0 run on the warp-level tensor cores (pool_fold_mma.cu); MVF_FOLD_MMA=0 forces the
+// CUDA-core kernels of this file (A/B measurements, and the path fp32 tokens always take)
+static bool use_mma(int dtype, int C, int P) {
+  const char* e = getenv("MVF_FOLD_MMA");
+  if (e && atoi(e) == 0) return false;
+  return pool_fold_mma_supported(dtype, C, P);
+}
+
 static int fold_check(int dtype, int F, int P, int E, int C, const void* X) {
   MVF_REQUIRE(pool_fold_supported(dtype, C, E, P), MVF_ERR_UNSUPPORTED,
               "pool_fold: needs C_in (%d) a multiple of 8 and at most 5120, 1 <= E (%d) <= %d", C, E, MVF_MAX_ENTITIES);
@@ -706,6 +680,7 @@ int pool_fold_fwd(int dtype, int F, int P, int E, int C, const void* X, const fl
                   cudaStream_t st) {
   MVF_TRY(fold_check(dtype, F, P, E, C, X));
   if (F == 0) return MVF_OK;
+  if (use_mma(dtype, C, P)) return pool_fold_mma_fwd(F, P, E, C, X, Wq, attn, px, st);
   for (int e0 = 0; e0 < E; e0 += 4) {   // entity passes of <= 4 (X is re-streamed per pass; E = 3 in every penn config)
     fold::Geom g{F, P, C, E, e0, 0, C * (dtype == MVF_BF16 ? 2 : 4)};
     const int ne = E - e0 < 4 ? E - e0 : 4;
@@ -719,6 +694,7 @@ int pool_fold_bwd(int dtype, int F, int P, int E, int C, const void* X, const fl
                   float* dWq, cudaStream_t st) {
   MVF_TRY(fold_check(dtype, F, P, E, C, X));
   if (F == 0) return MVF_OK;
+  if (use_mma(dtype, C, P)) return pool_fold_mma_bwd(F, P, E, C, X, G, px, attn, dWq, st);
   for (int e0 = 0; e0 < E; e0 += 4) {
     fold::Geom g{F, P, C, E, e0, 0, C * (dtype == MVF_BF16 ? 2 : 4)};
     const int ne = E - e0 < 4 ? E - e0 : 4;
