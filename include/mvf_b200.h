@@ -186,6 +186,10 @@ int mvf_scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* s
 #define MVF_GEMM_ACCUM 2
 #define MVF_GEMM_RELUMASK 4
 #define MVF_GEMM_SPLIT3 8
+/* with SPLIT3: B ([N, K] K-major) is already stored "pre-split": each 32-float block of a row holds 32 bf16 hi values
+ * followed by 32 bf16 lo values (rows padded with zeros to a multiple of 32 floats; ldb counts floats).  Weights are
+ * packed this way once per step, which removes two thirds of the in-kernel conversion work. */
+#define MVF_GEMM_B_PRESPLIT 16
 int mvf_gemm(int backend, int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K,
              const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
              const void* relu_src, int64_t ld_relu, int flags, int split_k, mvf_stream_t stream);

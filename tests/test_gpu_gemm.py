@@ -138,6 +138,39 @@ def test_tcgen05_bf16x3_split(M, N, K):
     assert float((C2.double() - (ref + bias.double()).clamp_min(0)).abs().max() / ref.abs().max()) < 2e-5
 
 
+def _presplit(W, K):
+    """[N, K] fp32 -> container [N, round_up(K, 32)] 'floats' whose 32-float blocks hold [hi(32) | lo(32)] bf16."""
+    N = W.shape[0]
+    Kp = (K + 31) // 32 * 32
+    Wp = torch.zeros(N, Kp, device=W.device)
+    Wp[:, :K] = W[:, :K]
+    hi = Wp.bfloat16()
+    lo = (Wp - hi.float()).bfloat16()
+    cont = torch.stack([hi.view(N, Kp // 32, 32), lo.view(N, Kp // 32, 32)], dim=2).reshape(N, Kp * 2).contiguous()
+    return cont.view(torch.float32).view(N, Kp)
+
+
+@pytest.mark.parametrize("split_k", [1, 0])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (200, 72, 100), (3840, 512, 392), (3840, 256, 1024), (3840, 384, 2304)])
+def test_tcgen05_bf16x3_presplit_weights(M, N, K, split_k):
+    """MVF_GEMM_B_PRESPLIT: the weight operand arrives already split (packed once per step); split_k = 0 lets long
+    contractions be split along K with the TMA reduce-add epilogue."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + 7 * K)
+    padK = (-K) % 4
+    A = torch.randn(M, K + padK, generator=g, device="cuda")
+    W = torch.randn(N, K, generator=g, device="cuda")
+    ref = A[:, :K].double() @ W.double().t()
+    bias = torch.randn(N, device="cuda")
+    Wc = _presplit(W, K)
+    C = _gemm(L.GEMM_TCGEN05, A, Wc, 1, 1, M, N, K, torch.float32, bias=bias, flags=L.GEMM_SPLIT3 | L.GEMM_B_PRESPLIT,
+              split_k=split_k)
+    err = float((C.double() - (ref + bias.double())).abs().max() / ref.abs().max())
+    assert err < 2e-5, err
+    C1 = _gemm(L.GEMM_TCGEN05, A, W, 1, 1, M, N, K, torch.float32, bias=bias, flags=L.GEMM_SPLIT3) if K % 4 == 0 else None
+    if C1 is not None:
+        assert float((C - C1).abs().max() / ref.abs().max()) < 2e-5      # same operands, different staging (and K split)
+
+
 @pytest.mark.parametrize("split", [0, 2, 7])
 def test_tcgen05_split_k_weight_gradient_shape(split):
     """dW = dY^T X with a long contraction and few output tiles: both operands MN-major, fp32 atomics."""

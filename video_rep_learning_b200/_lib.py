@@ -19,7 +19,7 @@ GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 NEG = {"single_noself": 0, "batch_noself": 1}
 POOL_AUTO, POOL_DENSE, POOL_FOLDED = 0, 1, 2
 PHASE_ALL = 255
-GEMM_RELU, GEMM_ACCUM, GEMM_RELUMASK, GEMM_SPLIT3 = 1, 2, 4, 8
+GEMM_RELU, GEMM_ACCUM, GEMM_RELUMASK, GEMM_SPLIT3, GEMM_B_PRESPLIT = 1, 2, 4, 8, 16
 MAX_FC = 4
 SITE_FC0, SITE_POS, SITE_ENC0 = 0, 8, 16
 

@@ -23,7 +23,14 @@ __global__ void pack_kernel(const PackTable tab) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int r = (int)(i / en.ld_dst), c = (int)(i - (int64_t)r * en.ld_dst);
     float v = c < en.cols ? en.src[(int64_t)r * en.cols + c] : 0.f;
-    if (en.dst_bf16) ((bf16*)en.dst)[i] = __float2bfloat16_rn(v);
+    if (en.dst_bf16 == 2) {
+      // "pre-split" container for the bf16x3 GEMM: every 32-float block of a row holds [hi(32) | lo(32)] bf16
+      const bf16 hi = __float2bfloat16_rn(v);
+      const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      bf16* row = (bf16*)en.dst + (int64_t)r * en.ld_dst * 2;
+      row[(c >> 5) * 64 + (c & 31)] = hi;
+      row[(c >> 5) * 64 + 32 + (c & 31)] = lo;
+    } else if (en.dst_bf16) ((bf16*)en.dst)[i] = __float2bfloat16_rn(v);
     else ((float*)en.dst)[i] = v;
   }
 }

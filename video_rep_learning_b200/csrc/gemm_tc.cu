@@ -79,6 +79,21 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// TMA store / reduce-add of a 32 x 32 fp32 box (SWIZZLE_128B staging tile in shared memory) + bulk-group bookkeeping
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -159,17 +174,28 @@ struct Params {
   int tiles_m, tiles_n, split_k, kb_per_split, num_kb;
   int a_kmajor, b_kmajor;
   int c_bf16;
+  int b_presplit;  // SPLIT3: the B tile lands already converted (MVF_GEMM_B_PRESPLIT): only the A rows are rewritten
+  int c_tma;   // fp32 C written by TMA (store, or reduce-add for ACCUM / split-K) from a swizzled shared-memory staging tile
   int flags;
   void* C;
   int64_t ldc;
   const float* bias;
   const void* relu_src;  // same element type as the operands
   int64_t ld_relu;
+  unsigned long long* dbg;  // MVF_GEMM_DBG=1: %globaltimer stamps of CTA 0 (debug aid, null otherwise)
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define MVF_STAMP(i) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[i] = gtimer(); } while (0)
 
 template <int BLOCK_N, int STAGES, int EB, bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const Params p) {
   constexpr int BLOCK_K = ROW_BYTES / EB;   // elements of K per stage (64 bf16 / 32 tf32)
   constexpr int UMMA_K = 32 / EB;           // elements of K per tcgen05.mma (16 / 8)
   constexpr int CHUNK = ROW_BYTES / EB;     // M/N elements per 128-byte row of an MN-major operand
@@ -188,15 +214,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* conv_bar = tmem_empty + 2;  // SPLIT: stage rewritten as bf16 hi|lo, ready for the MMA warp
   uint32_t* tmem_slot = (uint32_t*)(conv_bar + STAGES);
+  // epilogue staging for the TMA store path: 4 warps x 2 buffers x [32 rows x 128 B], 1024-byte aligned
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES + 1024;
   static_assert(!SPLIT || EB == 4, "SPLIT3 applies to fp32 operands");
   static_assert((3 * STAGES + 4) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_work = p.tiles_m * p.tiles_n * p.split_k;
+  if (threadIdx.x == 0) MVF_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (p.c_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -217,6 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) MVF_STAMP(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -276,6 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(SPLIT ? &conv_bar[stage] : &full_bar[stage], phase, 3);
           tcgen05_fence_after();
+          if (it == 0 && kb == kb0) MVF_STAMP(2);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           if constexpr (SPLIT) {
             // row = [hi k0..15 | hi k16..31 | lo k0..15 | lo k16..31] bf16, 32 bytes each: +2 descriptor units per slot
@@ -301,6 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (it == 0) MVF_STAMP(3);
       }
     }
   } else if (SPLIT && warp >= 8) {
@@ -318,8 +351,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase, 5);
         uint8_t* tile = smem + stage * STAGE_BYTES;
+        const int conv_rows = p.b_presplit ? BLOCK_M : BLOCK_M + BLOCK_N;
 #pragma unroll 1
-        for (int r = ct; r < BLOCK_M + BLOCK_N; r += NUM_THREADS_SPLIT - NUM_THREADS) {
+        for (int r = ct; r < conv_rows; r += NUM_THREADS_SPLIT - NUM_THREADS) {
           uint4* rowp = reinterpret_cast<uint4*>(tile + r * ROW_BYTES);
           const int sw = r & 7;
           float4 v[8];
@@ -351,6 +385,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     int it = 0;
+    uint32_t n_chunks = 0;   // TMA path: chunks issued by this warp (staging buffer = n_chunks & 1)
+    uint8_t* my_stage = epi_stage + (warp - 4) * 8192;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -359,12 +395,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int tm = rem / p.tiles_n, tn = rem - tm * p.tiles_n;
       const int kb0 = split * p.kb_per_split;
       const bool has_k = kb0 < p.num_kb;
-      mbar_wait(&tmem_full[acc], acc_phase, 4);
-      tcgen05_fence_after();
       const int row = tm * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && split == 0;
       const bool atomic = p.split_k > 1;
+      if (p.c_tma) {
+        // ---- fp32 output through TMA: registers -> swizzled staging tile -> cp.async.bulk.tensor store / reduce-add ----
+        const int row0 = tm * BLOCK_M + q * 32;
+        const bool reduce = atomic || (p.flags & MVF_GEMM_ACCUM);
+        // the bias of the first chunk is fetched before the accumulator is waited for (overlaps the main loop)
+        float bnext = 0.f;
+        {
+          const int c = tn * BLOCK_N + lane;
+          if (add_bias && c < p.N) bnext = __ldg(p.bias + c);
+        }
+        mbar_wait(&tmem_full[acc], acc_phase, 4);
+        tcgen05_fence_after();
+        if (it == 0 && warp == 4 && lane == 0) MVF_STAMP(4);
+        if (has_k && row0 < p.M) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            const int col0 = tn * BLOCK_N + c0;
+            if (col0 >= p.N) break;  // warp-uniform
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
+            const float bcur = bnext;
+            {
+              const int c = col0 + 32 + lane;
+              bnext = (add_bias && c0 + 32 < BLOCK_N && c < p.N) ? __ldg(p.bias + c) : 0.f;
+            }
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (add_bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bcur, j);
+            }
+            if (p.flags & MVF_GEMM_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if ((p.flags & MVF_GEMM_RELUMASK) && row_ok) {
+              if constexpr (EB == 2) {
+                const bf16* rs = (const bf16*)p.relu_src + (int64_t)row * p.ld_relu + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) v[j] = (__bfloat162float(rs[j]) > 0.f) ? v[j] : 0.f;
+              } else {
+                const float* rs = (const float*)p.relu_src + (int64_t)row * p.ld_relu + col0;
+                if (col0 + 32 <= p.N && (p.ld_relu & 3) == 0 && ((((uintptr_t)p.relu_src) & 15) == 0)) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    const float4 m = *reinterpret_cast<const float4*>(rs + j);
+                    v[j] = m.x > 0.f ? v[j] : 0.f; v[j + 1] = m.y > 0.f ? v[j + 1] : 0.f;
+                    v[j + 2] = m.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = m.w > 0.f ? v[j + 3] : 0.f;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (col0 + j < p.N) v[j] = (rs[j] > 0.f) ? v[j] : 0.f;
+                }
+              }
+            }
+            uint8_t* sb = my_stage + (n_chunks & 1) * 4096;
+            if (n_chunks >= 2) {   // the store that last read this buffer (two chunks ago) must have drained it
+              if (lane == 0) bulk_wait_read_1();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (reduce) tma_reduce_add_2d(&map_c, sb, col0, row0);
+              else tma_store_2d(&map_c, sb, col0, row0);
+              bulk_commit();
+            }
+            ++n_chunks;
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (it == 0 && warp == 4 && lane == 0) MVF_STAMP(5);
+        continue;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase, 4);
+      tcgen05_fence_after();
+      if (it == 0 && warp == 4 && lane == 0) MVF_STAMP(4);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         const int col0 = tn * BLOCK_N + c0;
@@ -456,11 +577,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (it == 0 && warp == 4 && lane == 0) MVF_STAMP(5);
     }
+    if (p.c_tma && lane == 0) bulk_wait_all();   // every TMA store of this warp has completed before the CTA exits
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) MVF_STAMP(6);
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
@@ -511,8 +635,11 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
 }
 
 template <int BLOCK_N, int STAGES, int EB, bool SPLIT = false>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int num_sms, cudaStream_t st) {
-  constexpr int smem = STAGES * (BLOCK_M * ROW_BYTES + BLOCK_N * ROW_BYTES) + 1024 + 256;
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const Params& p, int num_sms,
+                  cudaStream_t st) {
+  // stages | 1 KB (barriers + TMEM slot) | 32 KB epilogue staging | 1 KB alignment slack
+  constexpr int smem = STAGES * (BLOCK_M * ROW_BYTES + BLOCK_N * ROW_BYTES) + 1024 + 4 * 8192 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     MVF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, EB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -521,7 +648,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
   }
   int work = p.tiles_m * p.tiles_n * p.split_k;
   int grid = work < num_sms ? work : num_sms;
-  gemm_tc_kernel<BLOCK_N, STAGES, EB, SPLIT><<<grid, SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS, smem, st>>>(ma, mb, p);
+  gemm_tc_kernel<BLOCK_N, STAGES, EB, SPLIT><<<grid, SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS, smem, st>>>(ma, mb, mc, p);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -600,29 +727,67 @@ int gemm_tc(int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, in
   p.split_k = cdiv(p.num_kb, p.kb_per_split);
   p.a_kmajor = a_kmajor; p.b_kmajor = b_kmajor;
   p.c_bf16 = dtype_c == MVF_BF16;
+  const bool split3 = eb == 4 && (flags & MVF_GEMM_SPLIT3) && a_kmajor && b_kmajor;
+  p.b_presplit = (split3 && (flags & MVF_GEMM_B_PRESPLIT)) ? 1 : 0;
+  MVF_REQUIRE(!(flags & MVF_GEMM_B_PRESPLIT) || split3, MVF_ERR_BAD_ARG,
+              "gemm_tc: a pre-split B operand needs SPLIT3 with fp32, K-major operands");
+  MVF_REQUIRE(!p.b_presplit || ldb % 32 == 0, MVF_ERR_ALIGN, "gemm_tc: pre-split B needs ldb (%lld) to be a multiple of 32",
+              (long long)ldb);
   p.flags = flags;
   p.C = C; p.ldc = ldc; p.bias = bias;
   p.relu_src = relu_src; p.ld_relu = ld_relu;
+  p.dbg = nullptr;
+  static int dbg_on = -1;
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg_on < 0) {
+    const char* e = getenv("MVF_GEMM_DBG");
+    dbg_on = (e && atoi(e) != 0) ? 1 : 0;
+    if (dbg_on && cudaMalloc(&dbg_buf, 8 * sizeof(unsigned long long)) != cudaSuccess) dbg_on = 0;   // debug aid only
+  }
+  if (dbg_on) {
+    cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(unsigned long long), st);
+    p.dbg = dbg_buf;
+  }
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mc;
+  memset(&mc, 0, sizeof(mc));
+  // fp32 C goes out through TMA whenever its rows are 16-byte aligned (MVF_GEMM_TMA_STORE=0 keeps the register path)
+  static int tma_store_on = -1;
+  if (tma_store_on < 0) {
+    const char* e = getenv("MVF_GEMM_TMA_STORE");
+    tma_store_on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  p.c_tma = (tma_store_on && dtype_c == MVF_F32 && (ldc % 4) == 0 && ((((uintptr_t)C) & 15) == 0)) ? 1 : 0;
+  if (p.c_tma) MVF_TRY(make_map(&mc, C, M, N, ldc, 32, 32, 4, false));
   if (a_kmajor) MVF_TRY(make_map(&ma, A, M, K, lda, BLOCK_K, BLOCK_M, eb, false));
   else MVF_TRY(make_map(&ma, A, K, M, lda, CHUNK, BLOCK_K, eb, true));
-  if (b_kmajor) MVF_TRY(make_map(&mb, B, N, K, ldb, BLOCK_K, bn, eb, false));
+  if (b_kmajor) MVF_TRY(make_map(&mb, B, N, p.b_presplit ? round_up(K, 32) : K, ldb, BLOCK_K, bn, eb, false));
   else MVF_TRY(make_map(&mb, B, K, N, ldb, CHUNK, BLOCK_K, eb, true));
 
+  int rc;
   if (eb == 2) {
-    if (bn == 256) return launch<256, 4, 2>(ma, mb, p, g_num_sms, st);
-    if (bn == 128) return launch<128, 6, 2>(ma, mb, p, g_num_sms, st);
-    return launch<64, 8, 2>(ma, mb, p, g_num_sms, st);
+    if (bn == 256) rc = launch<256, 4, 2>(ma, mb, mc, p, g_num_sms, st);
+    else if (bn == 128) rc = launch<128, 6, 2>(ma, mb, mc, p, g_num_sms, st);
+    else rc = launch<64, 8, 2>(ma, mb, mc, p, g_num_sms, st);
+  } else if ((flags & MVF_GEMM_SPLIT3) && a_kmajor && b_kmajor) {
+    if (bn == 256) rc = launch<256, 4, 4, true>(ma, mb, mc, p, g_num_sms, st);
+    else if (bn == 128) rc = launch<128, 6, 4, true>(ma, mb, mc, p, g_num_sms, st);
+    else rc = launch<64, 8, 4, true>(ma, mb, mc, p, g_num_sms, st);
+  } else {
+    if (bn == 256) rc = launch<256, 4, 4>(ma, mb, mc, p, g_num_sms, st);
+    else if (bn == 128) rc = launch<128, 6, 4>(ma, mb, mc, p, g_num_sms, st);
+    else rc = launch<64, 8, 4>(ma, mb, mc, p, g_num_sms, st);
   }
-  if ((flags & MVF_GEMM_SPLIT3) && a_kmajor && b_kmajor) {
-    if (bn == 256) return launch<256, 4, 4, true>(ma, mb, p, g_num_sms, st);
-    if (bn == 128) return launch<128, 6, 4, true>(ma, mb, p, g_num_sms, st);
-    return launch<64, 8, 4, true>(ma, mb, p, g_num_sms, st);
+  if (rc == MVF_OK && dbg_on) {
+    unsigned long long h[8];
+    if (cudaStreamSynchronize(st) == cudaSuccess && cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      auto d = [&](int i) { return h[i] >= h[0] ? (double)(h[i] - h[0]) * 1e-3 : -1.0; };
+      fprintf(stderr, "gemm_tc dbg M=%lld N=%lld K=%lld bn=%d split=%d eb=%d: setup %.2f | first stage ready %.2f | mma issued %.2f | "
+              "acc ready %.2f | epilogue done %.2f | exit %.2f us\n", (long long)M, (long long)N, (long long)K, bn, p.split_k, eb,
+              d(1), d(2), d(3), d(4), d(5), d(6));
+    }
   }
-  if (bn == 256) return launch<256, 4, 4>(ma, mb, p, g_num_sms, st);
-  if (bn == 128) return launch<128, 6, 4>(ma, mb, p, g_num_sms, st);
-  return launch<64, 8, 4>(ma, mb, p, g_num_sms, st);
+  return rc;
 }
 
 }  // namespace mvf

@@ -114,6 +114,7 @@ struct Model {
                // tf32 tensor-core GEMMs on the tcgen05 backend -- bf16 there costs ~10 % on the gradient through the 1/tau
                // amplification of SCL, tf32 ~2 %)
   int kvt;     // dtype of tokens, W_k|W_v, K|V and dK|dV (the 96 % of the FLOPs): d.dtype
+  bool tc;     // chain GEMMs on tcgen05 (bf16 tokens or an explicit TCGEN05 backend): forward weights are also packed pre-split
   bool fold;   // rank-E folded pooling (pool_fold.cu): no K|V tensors, one streaming pass over the tokens per direction
   std::vector<ParamInfo> params;
   // indices into params
@@ -170,6 +171,7 @@ static int build_model(const mvf_head_desc* dp, Model& m) {
   m.N = m.F;
   m.act = MVF_F32;
   m.kvt = d.dtype;
+  m.tc = d.gemm_backend == MVF_GEMM_TCGEN05 || (d.gemm_backend == MVF_GEMM_AUTO && d.dtype == MVF_BF16);
   {
     int pm = d.pool_mode;
     MVF_REQUIRE(pm >= MVF_POOL_AUTO && pm <= MVF_POOL_FOLDED, MVF_ERR_BAD_ARG, "pool_mode %d", pm);
@@ -266,6 +268,11 @@ struct Layout {
   }
 };
 
+// pre-split (bf16 hi|lo blocks) copy of a forward weight [rows, cols]: container of round_up(cols, 32) floats per row
+static void add_split(Layout& L, const std::string& name, int64_t rows, int64_t cols) {
+  L.add(name + ".s", rows, round_up(cols, 32), RT_F32);
+}
+
 static std::string lname(int l, const char* s) { return "l" + std::to_string(l) + "." + s; }
 static std::string fname(int i, const char* s) { return "fc" + std::to_string(i) + "." + s; }
 
@@ -275,6 +282,7 @@ static void head_save_layout(const Model& m, Layout& L) {
   const int A = m.act;
   if (m.fold) {
     L.add("wq", d.E, d.C_in, RT_F32);
+    if (m.tc) add_split(L, "w.v", d.SPC, d.C_in);
   } else {
     L.add("w.kv", 2 * d.SPC, d.C_in, m.kvt, round_up(d.C_in, 8));
     L.add("b.kv", 1, 2 * d.SPC, RT_F32);
@@ -282,18 +290,30 @@ static void head_save_layout(const Model& m, Layout& L) {
   int cin_ld = m.ld0;
   for (int i = 0; i < d.n_fc; ++i) {
     L.add(fname(i, "w"), d.fc[i], i == 0 ? m.W0 : d.fc[i - 1], A, cin_ld);
+    if (m.tc) add_split(L, fname(i, "w"), d.fc[i], cin_ld);
     cin_ld = d.fc[i];
   }
   L.add("w.e", m.Hin, d.n_fc ? d.fc[d.n_fc - 1] : m.W0, A, cin_ld);
+  if (m.tc) add_split(L, "w.e", m.Hin, cin_ld);
   for (int l = 0; l < d.L; ++l) {
     L.add(lname(l, "w.qkv"), 3 * d.H, d.H, A);
     L.add(lname(l, "b.qkv"), 1, 3 * d.H, RT_F32);
     L.add(lname(l, "w.o"), d.H, d.H, A);
     L.add(lname(l, "w.1"), d.DFF, d.H, A);
     L.add(lname(l, "w.2"), d.H, d.DFF, A);
+    if (m.tc) {
+      add_split(L, lname(l, "w.qkv"), 3 * d.H, d.H);
+      add_split(L, lname(l, "w.o"), d.H, d.H);
+      add_split(L, lname(l, "w.1"), d.DFF, d.H);
+      add_split(L, lname(l, "w.2"), d.H, d.DFF);
+    }
   }
   L.add("w.emb", d.D, d.H, A);
-  if (d.final_mode == MVF_FINAL_LIN) L.add("w.lin", d.H, (int64_t)d.E * d.H, A);
+  if (m.tc) add_split(L, "w.emb", d.D, d.H);
+  if (d.final_mode == MVF_FINAL_LIN) {
+    L.add("w.lin", d.H, (int64_t)d.E * d.H, A);
+    if (m.tc) add_split(L, "w.lin", d.H, (int64_t)d.E * d.H);
+  }
   if (m.fold) L.add("px", m.R, d.C_in, RT_F32);      // attention-pooled tokens: the only C_in-wide activation kept
   else L.add("kv", m.F * d.P, 2 * d.SPC, m.kvt);
   L.add("attn", m.F * d.E, d.P, RT_F32);
@@ -371,6 +391,10 @@ static void proj_save_layout(const Model& m, Layout& L) {
   const int A = m.act;
   L.add("w.p1", d.PS, d.D, A);
   L.add("w.p2", d.D, d.PS, A);
+  if (m.tc) {
+    add_split(L, "w.p1", d.PS, d.D);
+    add_split(L, "w.p2", d.D, d.PS);
+  }
   L.add("emb", m.N, d.D, A);
   L.add("u1", m.N, d.PS, RT_F32);
   L.add("p.sum", 1, 2 * d.PS, RT_F64);
@@ -487,11 +511,19 @@ struct Ctx {
     forked = false;
     return MVF_OK;
   }
-  // y = x W^T + b
+  // y = x W^T + b.  Forward GEMMs feed the softmax/temperature non-linearities of SCL: on the tensor-core backend they
+  // run as bf16x3, with the weight taken from its pre-split copy `wsplit` (region "<name>.s") when there is one, and
+  // K >= 512 contractions that cannot fill the machine are split along K (TMA reduce-add epilogue).
   int linear(int dtype_c, int64_t M, int64_t N, int64_t K, const void* x, int64_t ldx, const void* Wp, int64_t ldw,
-             const float* bias, void* y, int64_t ldy, int flags = 0) const {
-    // forward GEMMs feed the softmax/temperature non-linearities of SCL: bf16x3 operands on the tensor-core backend
-    return gemm(dtype_c, 1, 1, M, N, K, x, ldx, Wp, ldw, y, ldy, bias, nullptr, 0, flags | MVF_GEMM_SPLIT3);
+             const float* bias, void* y, int64_t ldy, int flags = 0, const char* wsplit = nullptr) const {
+    const int sk = (m.tc && !(flags & MVF_GEMM_RELU) && dtype_c == MVF_F32) ? 0 : 1;
+    if (m.tc && wsplit != nullptr) {
+      const Region* r = Ls.find(std::string(wsplit) + ".s");
+      if (r != nullptr)
+        return gemm(dtype_c, 1, 1, M, N, K, x, ldx, S.base + r->off, r->ld, y, ldy, bias, nullptr, 0,
+                    flags | MVF_GEMM_SPLIT3 | MVF_GEMM_B_PRESPLIT, sk);
+    }
+    return gemm(dtype_c, 1, 1, M, N, K, x, ldx, Wp, ldw, y, ldy, bias, nullptr, 0, flags | MVF_GEMM_SPLIT3, sk);
   }
   // dX = dY W (optionally masked by relu_src > 0)
   int linear_dx(int dtype_c, int64_t M, int64_t Nout, int64_t Kin, const void* dY, int64_t lddy, const void* Wp,
@@ -560,19 +592,35 @@ static int pack_head_weights(Ctx& c) {
     e.push_back(PackEntry{c.P[pidx], c.S.base + r->off + (size_t)col0 * 4, 1, (int)pi.cols, (int)pi.cols, 0});
   };
   (void)bf;
+  auto split = [&](const std::string& reg, int pidx, int row0 = 0) {   // pre-split copy for the forward bf16x3 GEMMs
+    if (!m.tc) return;
+    const Region* r = c.Ls.find(reg + ".s");
+    if (r == nullptr) return;
+    const ParamInfo& pi = m.params[pidx];
+    char* dst = c.S.base + r->off + (size_t)row0 * r->ld * 4;
+    e.push_back(PackEntry{c.P[pidx], dst, (int)pi.rows, (int)pi.cols, (int)r->ld, 2});
+  };
+  if (m.fold) split("w.v", m.iWv);
   if (!m.fold) {
     mat("w.kv", m.iWk, 0);
     mat("w.kv", m.iWv, d.SPC);
     vec("b.kv", m.ibk, 0);
     vec("b.kv", m.ibv, d.SPC);
   }
-  for (int i = 0; i < d.n_fc; ++i) mat(fname(i, "w"), m.iFcW[i]);
+  for (int i = 0; i < d.n_fc; ++i) { mat(fname(i, "w"), m.iFcW[i]); split(fname(i, "w"), m.iFcW[i]); }
   mat("w.e", m.iWe);
+  split("w.e", m.iWe);
   for (int l = 0; l < d.L; ++l) {
     const int b = m.iLayer[l];
     mat(lname(l, "w.qkv"), b + L_WQ, 0);
     mat(lname(l, "w.qkv"), b + L_WK, d.H);
     mat(lname(l, "w.qkv"), b + L_WV, 2 * d.H);
+    split(lname(l, "w.qkv"), b + L_WQ, 0);
+    split(lname(l, "w.qkv"), b + L_WK, d.H);
+    split(lname(l, "w.qkv"), b + L_WV, 2 * d.H);
+    split(lname(l, "w.o"), b + L_WO);
+    split(lname(l, "w.1"), b + L_W1);
+    split(lname(l, "w.2"), b + L_W2);
     vec(lname(l, "b.qkv"), b + L_BQ, 0);
     vec(lname(l, "b.qkv"), b + L_BK, d.H);
     vec(lname(l, "b.qkv"), b + L_BV, 2 * d.H);
@@ -581,7 +629,8 @@ static int pack_head_weights(Ctx& c) {
     mat(lname(l, "w.2"), b + L_W2);
   }
   mat("w.emb", m.iWemb);
-  if (d.final_mode == MVF_FINAL_LIN) mat("w.lin", m.iWlin);
+  split("w.emb", m.iWemb);
+  if (d.final_mode == MVF_FINAL_LIN) { mat("w.lin", m.iWlin); split("w.lin", m.iWlin); }
   return pack_params(e.data(), (int)e.size(), c.st);
 }
 
@@ -615,7 +664,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
         {
           ProfScope ps(4, st);
           MVF_TRY(c.linear(MVF_F32, m.R, d.SPC, d.C_in, c.S.p("px"), d.C_in, c.P[m.iWv], d.C_in, c.P[m.ibv], c.S.p("ent32"),
-                           d.SPC));
+                           d.SPC, 0, "w.v"));
           MVF_TRY(ent_finish_fwd(c.S.f("ent32"), c.S.f("h0"), m.ld0, m.R, d.SPC, d.E, d.one_hot == MVF_ONEHOT_POOL, c.p,
                                  d.seed, st));
         }
@@ -656,7 +705,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
     if (ph < d.n_fc) {
       const int C = d.fc[ph];
       MVF_TRY(c.linear(MVF_F32, m.R, C, kin, xin, ldin, c.S.p(fname(ph, "w")), c.S.ld(fname(ph, "w")), c.P[m.iFcB[ph]],
-                       c.S.p(fname(ph, "x")), C));
+                       c.S.p(fname(ph, "x")), C, 0, fname(ph, "w").c_str()));
       if (d.training) {
         MVF_CHECK_CUDA(cudaMemsetAsync(c.S.p(fname(ph, "sum")), 0, (size_t)2 * C * 8, st));
         MVF_TRY(bn_stats(c.S.f(fname(ph, "x")), m.R, C, c.S.dbl(fname(ph, "sum")), st));
@@ -664,7 +713,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       continue;
     }
     // ---- last phase: video_emb, positional encoding, temporal encoder, entity reduction, embedding ----
-    MVF_TRY(c.linear(MVF_F32, m.R, m.Hin, kin, xin, ldin, c.S.p("w.e"), c.S.ld("w.e"), c.P[m.ibe], c.S.p("h3"), m.Hin));
+    MVF_TRY(c.linear(MVF_F32, m.R, m.Hin, kin, xin, ldin, c.S.p("w.e"), c.S.ld("w.e"), c.P[m.ibe], c.S.p("h3"), m.Hin, 0, "w.e"));
     MVF_TRY(posenc_table(c.S.f("pe"), d.T, d.H, d.train_frames, st));
     MVF_TRY(posenc_add(c.S.f("h3"), c.S.f("pe"), c.S.f("z0"), d.BV, d.T, d.E, d.H, c.p, d.seed, st));
     const float* keymask_src = d.has_mask ? mask : nullptr;
@@ -690,18 +739,18 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       MVF_TRY(ln_fwd(A, c.S.f(zin), pend_o, c.S.f(z0n), c.S.p(lname(l, "r0")), ln0, ln0 + m.rows, c.P[b + L_LN0W],
                      c.P[b + L_LN0B], m.rows, d.H, d.ln_eps, c.p, d.seed, pend_site, st));
       MVF_TRY(c.linear(A, m.rows, 3 * d.H, d.H, c.S.p(lname(l, "r0")), d.H, c.S.p(lname(l, "w.qkv")), d.H,
-                       c.S.f(lname(l, "b.qkv")), c.S.p(lname(l, "qkv")), 3 * d.H));
+                       c.S.f(lname(l, "b.qkv")), c.S.p(lname(l, "qkv")), 3 * d.H, 0, lname(l, "w.qkv").c_str()));
       MVF_TRY(attention_fwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
                             c.S.f(lname(l, "lse")), st));
       MVF_TRY(c.linear(MVF_F32, m.rows, d.H, d.H, c.S.p(lname(l, "ctx")), d.H, c.S.p(lname(l, "w.o")), d.H, c.P[b + L_BO],
-                       o, d.H));
+                       o, d.H, 0, lname(l, "w.o").c_str()));
       float* ln1 = c.S.f(lname(l, "ln1"));
       MVF_TRY(ln_fwd(A, c.S.f(z0n), o, c.S.f(zmid), c.S.p(lname(l, "r1")), ln1, ln1 + m.rows, c.P[b + L_LN1W],
                      c.P[b + L_LN1B], m.rows, d.H, d.ln_eps, c.p, d.seed, SITE_ENC0 + 2 * l, st));
       MVF_TRY(c.linear(A, m.rows, d.DFF, d.H, c.S.p(lname(l, "r1")), d.H, c.S.p(lname(l, "w.1")), d.H, c.P[b + L_B1],
-                       c.S.p(lname(l, "f")), d.DFF, MVF_GEMM_RELU));
+                       c.S.p(lname(l, "f")), d.DFF, MVF_GEMM_RELU, lname(l, "w.1").c_str()));
       MVF_TRY(c.linear(MVF_F32, m.rows, d.H, d.DFF, c.S.p(lname(l, "f")), d.DFF, c.S.p(lname(l, "w.2")), d.DFF,
-                       c.P[b + L_B2], o, d.H));
+                       c.P[b + L_B2], o, d.H, 0, lname(l, "w.2").c_str()));
       pend_o = o;
       pend_site = SITE_ENC0 + 2 * l + 1;
       zi = 2 * l + 1;
@@ -714,13 +763,13 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
     if (d.final_mode == MVF_FINAL_LIN) {
       MVF_TRY(entity_gather_lin(A, c.S.f(zlast), c.S.p("zl"), d.BV, d.T, d.E, d.H, st));
       MVF_TRY(c.linear(MVF_F32, m.N, d.H, (int64_t)d.E * d.H, c.S.p("zl"), (int64_t)d.E * d.H, c.S.p("w.lin"),
-                       (int64_t)d.E * d.H, c.P[m.iblin], c.S.p("ylin"), d.H));
+                       (int64_t)d.E * d.H, c.P[m.iblin], c.S.p("ylin"), d.H, 0, "w.lin"));
       MVF_TRY(cast_f32(A, c.S.f("ylin"), c.S.p("y"), m.N * d.H, st));
     } else {
       MVF_TRY(entity_reduce_fwd(A, c.S.f(zlast), c.S.p("y"), d.final_mode == MVF_FINAL_MAX ? (int32_t*)c.S.p("argmax") : nullptr,
                                 d.BV, d.T, d.E, d.H, d.final_mode, st));
     }
-    MVF_TRY(c.linear(MVF_F32, m.N, d.D, d.H, c.S.p("y"), d.H, c.S.p("w.emb"), d.H, c.P[m.ibemb], out_emb, d.D));
+    MVF_TRY(c.linear(MVF_F32, m.N, d.D, d.H, c.S.p("y"), d.H, c.S.p("w.emb"), d.H, c.P[m.ibemb], out_emb, d.D, 0, "w.emb"));
   }
   return MVF_OK;
 }
@@ -909,14 +958,21 @@ static int proj_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
   if (ph1 > 2) ph1 = 2;
   for (int ph = ph0; ph < ph1; ++ph) {
     if (ph == 0) {
-      PackEntry e[2];
+      PackEntry e[4];
+      int ne = 2;
       const Region* r1 = c.Ls.find("w.p1");
       const Region* r2 = c.Ls.find("w.p2");
       e[0] = PackEntry{c.P[m.iWp1], c.S.base + r1->off, d.PS, d.D, (int)r1->ld, r1->dtype == RT_BF16};
       e[1] = PackEntry{c.P[m.iWp2], c.S.base + r2->off, d.D, d.PS, (int)r2->ld, r2->dtype == RT_BF16};
-      MVF_TRY(pack_params(e, 2, st));
+      if (m.tc) {
+        const Region* s1 = c.Ls.find("w.p1.s");
+        const Region* s2 = c.Ls.find("w.p2.s");
+        e[ne++] = PackEntry{c.P[m.iWp1], c.S.base + s1->off, d.PS, d.D, (int)s1->ld, 2};
+        e[ne++] = PackEntry{c.P[m.iWp2], c.S.base + s2->off, d.D, d.PS, (int)s2->ld, 2};
+      }
+      MVF_TRY(pack_params(e, ne, st));
       MVF_TRY(cast_f32(A, emb, c.S.p("emb"), m.N * d.D, st));
-      MVF_TRY(c.linear(MVF_F32, m.N, d.PS, d.D, c.S.p("emb"), d.D, c.S.p("w.p1"), d.D, c.P[m.ibp1], c.S.p("u1"), d.PS));
+      MVF_TRY(c.linear(MVF_F32, m.N, d.PS, d.D, c.S.p("emb"), d.D, c.S.p("w.p1"), d.D, c.P[m.ibp1], c.S.p("u1"), d.PS, 0, "w.p1"));
       if (d.training) {
         MVF_CHECK_CUDA(cudaMemsetAsync(c.S.p("p.sum"), 0, (size_t)2 * d.PS * 8, st));
         MVF_TRY(bn_stats(c.S.f("u1"), m.N, d.PS, c.S.dbl("p.sum"), st));
@@ -928,7 +984,7 @@ static int proj_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       MVF_TRY(bn_finalize(c.S.dbl("p.sum"), d.PS, bn_n_global(m, m.N), d.bn_eps, d.training, d.bn_momentum, rm, rv,
                           bn_tracked ? bn_tracked[ibn] : nullptr, c.S.f("p.mi"), st));
       MVF_TRY(bn_apply(A, c.S.f("u1"), m.N, d.PS, c.S.f("p.mi"), c.P[m.iGp], c.P[m.iBp], 1, c.S.p("a3"), d.PS, 0.f, 0, 0, st));
-      MVF_TRY(c.linear(MVF_F32, m.N, d.D, d.PS, c.S.p("a3"), d.PS, c.S.p("w.p2"), d.PS, c.P[m.ibp2], c.S.p("u"), d.D));
+      MVF_TRY(c.linear(MVF_F32, m.N, d.D, d.PS, c.S.p("a3"), d.PS, c.S.p("w.p2"), d.PS, c.P[m.ibp2], c.S.p("u"), d.D, 0, "w.p2"));
       if (project == 2) {  // MLPHead.forward on its own (resnet_c2d.py:122-126): no normalisation
         MVF_CHECK_CUDA(cudaMemcpyAsync(out, c.S.p("u"), (size_t)m.N * d.D * 4, cudaMemcpyDeviceToDevice, st));
       } else {

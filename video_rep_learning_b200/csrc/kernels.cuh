@@ -8,7 +8,7 @@ namespace mvf {
 struct PackEntry {
   const float* src;  // fp32 [rows, cols] contiguous
   void* dst;         // [rows, ld_dst] in dst dtype, zero padded
-  int rows, cols, ld_dst, dst_bf16;
+  int rows, cols, ld_dst, dst_bf16;  // dst_bf16: 0 fp32, 1 bf16, 2 pre-split bf16 hi|lo blocks (ld_dst floats, multiple of 32)
 };
 int pack_params(const PackEntry* entries, int n, cudaStream_t st);
 struct UnpackEntry {

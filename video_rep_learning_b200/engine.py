@@ -204,9 +204,19 @@ class CallState:
     proj_save: Optional[torch.Tensor] = None
 
 
+_seed_pool: List[int] = []
+_seed_state = None
+
+
 def new_seed() -> int:
-    """Dropout seed of one step, drawn from torch's CPU generator (deterministic under torch.manual_seed)."""
-    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    """Dropout seed of one step, drawn from torch's CPU generator (deterministic under torch.manual_seed).
+    Seeds are drawn 64 at a time; re-seeding the generator (a different initial_seed) discards the pooled ones."""
+    global _seed_state
+    st = torch.initial_seed()
+    if not _seed_pool or _seed_state != st:
+        _seed_state = st
+        _seed_pool[:] = torch.randint(0, 2 ** 62, (64,), dtype=torch.int64).tolist()[::-1]
+    return _seed_pool.pop()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -287,10 +297,22 @@ def _run_proj_backward(cs: CallState, plan: Plan, d, params_arr, d_out, save, ws
 
 
 def _finish_grads(cs: CallState, plan: Plan, d, gpack: torch.Tensor, params: Sequence[Optional[torch.Tensor]]):
-    """One all-reduce of the flat gradient buffer (SUM), then scatter * 1/world into per-parameter tensors."""
+    """One all-reduce of the flat gradient buffer (SUM), then scatter * 1/world into per-parameter tensors.
+    The per-parameter gradients are views of ONE dense buffer (one allocation per step instead of one per parameter)."""
     scale = parallel.finish_flat_grads_(gpack, cs.opts.process_group) if (plan.world > 1 and cs.opts.allreduce_grads) else 1.0
-    grads = [None if p is None else torch.empty_like(p) for p in params]
-    L.check(L.lib().mvf_unpack_grads(C.byref(d), L.ptr(gpack), L.ptr_array(grads), scale, _stream()), "mvf_unpack_grads")
+    present = [p for p in params if p is not None]
+    if not present:
+        return [None] * len(params)
+    flat = torch.empty(sum(p.numel() for p in present), dtype=torch.float32, device=gpack.device)
+    views = iter(torch._utils._unflatten_dense_tensors(flat, present))
+    grads = [None if p is None else next(views) for p in params]
+    arr = (C.c_void_p * len(params))()
+    base, off = flat.data_ptr(), 0
+    for i, p in enumerate(params):
+        if p is not None:
+            arr[i] = base + 4 * off
+            off += p.numel()
+    L.check(L.lib().mvf_unpack_grads(C.byref(d), L.ptr(gpack), arr, scale, _stream()), "mvf_unpack_grads")
     return grads
 
 
@@ -418,15 +440,15 @@ class ModelFn(torch.autograd.Function):
             _run_proj_forward(cs, plan, d, arr, emb, psave, pws, out)
         cs.plan, cs.head_save, cs.proj_save = plan, save, psave
         ctx.cs, ctx.seed = cs, cs.seed
-        ctx.save_for_backward(tokens, mask if mask is not None else torch.empty(0, device=dev), *params)
-        ctx.has_mask = mask is not None
+        # the parameters are only read through raw pointers in backward (before any optimizer step), so they are kept as
+        # plain references: routing ~56 tensors through save_for_backward costs more host time than the SCL kernels
+        ctx.tokens, ctx.mask, ctx.params, ctx.param_ptrs = tokens, mask, params, arr
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         cs: CallState = ctx.cs
-        tokens, mask, *params = ctx.saved_tensors
-        mask = mask if ctx.has_mask else None
+        tokens, mask, params = ctx.tokens, ctx.mask, ctx.params
         plan = cs.plan
         dev = tokens.device
         with torch.cuda.device(dev):
@@ -435,7 +457,7 @@ class ModelFn(torch.autograd.Function):
             pws = _scratch(dev, plan.proj_ws_bytes, "proj")
             gpack = torch.zeros(plan.gpack_elems, dtype=torch.float32, device=dev)
             d_emb = torch.empty(d_out.shape, dtype=torch.float32, device=dev)
-            arr = L.ptr_array(list(params))
+            arr = ctx.param_ptrs
             _run_proj_backward(cs, plan, d, arr, d_out.contiguous().float(), cs.proj_save, pws, gpack, d_emb)
             _run_head_backward(cs, plan, d, arr, tokens, mask, d_emb, cs.head_save, ws, gpack)
             grads = _finish_grads(cs, plan, d, gpack, list(params))

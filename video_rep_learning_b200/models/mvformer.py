@@ -156,6 +156,7 @@ class MultiEntityTransformerEmbModel(nn.Module):
         self.spec = head_spec_from_cfg(cfg)
         self.run_options = engine.RunOptions()
         self._param_order: Optional[List[str]] = None
+        self._param_slots = None
         self.last_call: Optional[engine.CallState] = None
 
     # ---- reference API -------------------------------------------------------------------------------
@@ -172,7 +173,15 @@ class MultiEntityTransformerEmbModel(nn.Module):
         return self._param_order
 
     def head_params(self) -> List[torch.Tensor]:
-        return [self.get_parameter(n) for n in self.head_param_names()]
+        # (owning module, attribute) pairs are resolved once; the per-step cost is one dict lookup per parameter,
+        # and a re-assigned parameter (module.weight = nn.Parameter(...)) is still picked up
+        if self._param_slots is None:
+            slots = []
+            for n in self.head_param_names():
+                mod_path, _, attr = n.rpartition(".")
+                slots.append((self.get_submodule(mod_path)._parameters if mod_path else self._parameters, attr))
+            self._param_slots = slots
+        return [d[a] for d, a in self._param_slots]
 
     def bn_buffers(self):
         bns = [m for m in self.fc_layers if isinstance(m, nn.BatchNorm1d)] if isinstance(self.fc_layers, nn.Sequential) else []
