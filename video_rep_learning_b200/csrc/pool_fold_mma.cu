@@ -184,14 +184,24 @@ __device__ __forceinline__ void load_bfrag(const float* __restrict__ M, int64_t 
 template <int TPW>
 __device__ __forceinline__ void scores_phase(uint32_t slot_addr, uint32_t a_off, const uint32_t (&bh)[TPW][2],
                                              const uint32_t (&bl)[TPW][2], float* pw, int q, int r8) {
-  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  // four independent accumulation chains (lo / hi operand x even / odd tile): a single chain would serialise 2*TPW
+  // dependent MMAs per group (measured: "wait" + "short scoreboard" stalls dominate, tensor pipe 22 % busy)
+  float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int t = 0; t < TPW; ++t) {
     uint32_t a[4];
     ldsm_x4(slot_addr + a_off + t * 32, a);
-    mma16816(s, a, bl[t][0], bl[t][1]);
-    mma16816(s, a, bh[t][0], bh[t][1]);
+    if (t & 1) {
+      mma16816(sc, a, bl[t][0], bl[t][1]);
+      mma16816(sd, a, bh[t][0], bh[t][1]);
+    } else {
+      mma16816(sa, a, bl[t][0], bl[t][1]);
+      mma16816(sb, a, bh[t][0], bh[t][1]);
+    }
   }
+  float s[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s[i] = (sa[i] + sc[i]) + (sb[i] + sd[i]);
   pw[(2 * q) * TG + r8] = s[0];
   pw[(2 * q + 1) * TG + r8] = s[1];
   pw[(2 * q) * TG + r8 + 8] = s[2];

@@ -33,6 +33,7 @@ struct SclWs {
   int* counts;    // [2] n_valid, n_masked
   int* valid;     // [N]
   int* masked;    // [N]
+  int* chunk;     // [2 * (nchunks + 1)] valid / masked counts per 1024-row chunk, then their exclusive scans (large N only)
 };
 
 static size_t scl_ws_layout(int N, SclWs* w, char* base) {
@@ -51,6 +52,8 @@ static size_t scl_ws_layout(int N, SclWs* w, char* base) {
   int* counts = (int*)take(sizeof(int) * 4);
   int* valid = (int*)take(sizeof(int) * N);
   int* masked = (int*)take(sizeof(int) * N);
+  int* chunk = (int*)take(sizeof(int) * 2 * ((size_t)(N + 1023) / 1024 + 1));
+  if (w) { w->chunk = chunk; }
   if (w) { w->M = M; w->Z = Z; w->g = g; w->den = den; w->c = c; w->zext = zext; w->counts = counts; w->valid = valid; w->masked = masked; }
   return off;
 }
@@ -105,6 +108,77 @@ __global__ void scl_prep_kernel(const float* __restrict__ masks, int N, SclWs w,
   }
 }
 
+// ---- prep for large batches (N > 8192): the same outputs from three launches -----------------------------------------
+// (1) per-chunk counts, M (mask sum: integers, exact in fp32 whatever the order), zeroed accumulators;
+// (2) one CTA scans the chunk counts; (3) every chunk scans locally and writes its slice of the ordered lists.
+__global__ void __launch_bounds__(1024) scl_prep_count_kernel(const float* __restrict__ masks, int N, SclWs w, float* loss_out) {
+  __shared__ int cnt[32];
+  __shared__ float sum[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const float m = i < N ? masks[i] : 0.f;
+  if (i < N) { w.zext[i] = 0.f; w.c[i] = 0.f; }
+  const int v = __popc(__ballot_sync(0xffffffffu, i < N && m != 0.f));
+  const float ms = warp_sum(m);
+  if ((threadIdx.x & 31) == 0) { cnt[threadIdx.x >> 5] = v; sum[threadIdx.x >> 5] = ms; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    float t = 0.f;
+    for (int k = 0; k < 32; ++k) { c += cnt[k]; t += sum[k]; }
+    w.chunk[blockIdx.x] = c;
+    if (t != 0.f) atomicAdd(w.M, t);
+    if (blockIdx.x == 0) *loss_out = 0.f;
+  }
+}
+__global__ void __launch_bounds__(1024) scl_prep_scan_kernel(int N, int nchunks, SclWs w) {
+  // exclusive scan of chunk[0..nchunks) -> chunk[nchunks+1 ..] (valid bases); masked base = 1024*c - valid base
+  __shared__ int scan[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  int* base = w.chunk + nchunks + 1;
+  for (int c0 = 0; c0 < nchunks; c0 += 1024) {
+    const int c = c0 + threadIdx.x;
+    const int v = c < nchunks ? w.chunk[c] : 0;
+    scan[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = threadIdx.x >= o ? scan[threadIdx.x - o] : 0;
+      __syncthreads();
+      scan[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (c < nchunks) base[c] = carry + scan[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += scan[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    w.counts[0] = carry;
+    w.counts[1] = N - carry;
+  }
+}
+__global__ void __launch_bounds__(1024) scl_prep_write_kernel(const float* __restrict__ masks, int N, int nchunks, SclWs w) {
+  __shared__ int scan[1024];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int v = (i < N && masks[i] != 0.f) ? 1 : 0;
+  scan[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int t = threadIdx.x >= o ? scan[threadIdx.x - o] : 0;
+    __syncthreads();
+    scan[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (i < N) {
+    const int bv = w.chunk[nchunks + 1 + blockIdx.x];
+    const int bm = blockIdx.x * 1024 - bv;
+    const int incl = scan[threadIdx.x];
+    if (v) w.valid[bv + incl - 1] = i;
+    else w.masked[bm + (threadIdx.x + 1 - incl) - 1] = i;
+  }
+}
+
 // 4-way unrolled dot product of two shared-memory vectors (16-byte aligned, D % 4 == 0).  Row i vs row j and row j vs
 // row i go through the same sequence of operations, so l_ij == l_ji bit for bit.
 __device__ __forceinline__ float dot4(const float* __restrict__ a, const float* __restrict__ b, int D) {
@@ -155,59 +229,63 @@ scl_cross_kernel(const float* __restrict__ embs, int D, int T2, float inv_tau_di
   int* cvid = (int*)(ccs + 32);     // [32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nrows = *row_cnt, ncols = *col_cnt;
-  const int rslot = blockIdx.x * 8 + warp;
-  if (blockIdx.x * 8 >= nrows) return;  // whole CTA idle (uniform)
-  const bool ractive = rslot < nrows;
-  const int r = ractive ? row_idx[rslot] : 0;
-  const int rvid = r / T2;
-  for (int d = lane; d < D; d += 32) er[warp * D + d] = ractive ? embs[(int64_t)r * D + d] : 0.f;
-  float acc[SCL_MAXD / 32];
+  if (nrows == 0 || ncols == 0) return;   // nothing to couple (e.g. no masked frame in the batch): uniform exit
+  for (int rb = blockIdx.x; rb * 8 < nrows; rb += gridDim.x) {   // row blocks, grid-stride (the grid is sized for the SMs)
+    const int rslot = rb * 8 + warp;
+    const bool ractive = rslot < nrows;
+    const int r = ractive ? row_idx[rslot] : 0;
+    const int rvid = r / T2;
+    __syncthreads();   // the previous row block's readers of er are done
+    for (int d = lane; d < D; d += 32) er[warp * D + d] = ractive ? embs[(int64_t)r * D + d] : 0.f;
+    float acc[SCL_MAXD / 32];
 #pragma unroll
-  for (int k = 0; k < SCL_MAXD / 32; ++k) acc[k] = 0.f;
-  float rsum = 0.f;
-  // columns are split over blockIdx.y (outputs are accumulated with atomics)
-  for (int c0 = blockIdx.y * 32; c0 < ncols; c0 += 32 * gridDim.y) {
-    __syncthreads();
-    load_tile(tile, Dp, embs, D, col_idx, c0, ncols, 0);
-    if (threadIdx.x < 32) {
-      const int cs = c0 + threadIdx.x;
-      if (cs < ncols) {
-        const int k = col_idx[cs];
-        ccs[threadIdx.x] = cc_const * (cc_arr ? cc_arr[k] : 1.f);
-        cvid[threadIdx.x] = k / T2;
-      } else {
-        ccs[threadIdx.x] = 0.f;
-        cvid[threadIdx.x] = -1;
+    for (int k = 0; k < SCL_MAXD / 32; ++k) acc[k] = 0.f;
+    float rsum = 0.f;
+    // columns are split over blockIdx.y (outputs are accumulated with atomics)
+    for (int c0 = blockIdx.y * 32; c0 < ncols; c0 += 32 * gridDim.y) {
+      __syncthreads();
+      load_tile(tile, Dp, embs, D, col_idx, c0, ncols, 0);
+      if (threadIdx.x < 32) {
+        const int cs = c0 + threadIdx.x;
+        if (cs < ncols) {
+          const int k = col_idx[cs];
+          ccs[threadIdx.x] = cc_const * (cc_arr ? cc_arr[k] : 1.f);
+          cvid[threadIdx.x] = k / T2;
+        } else {
+          ccs[threadIdx.x] = 0.f;
+          cvid[threadIdx.x] = -1;
+        }
       }
-    }
-    __syncthreads();
-    const float dot = dot4(er + warp * D, tile + lane * Dp, D);
-    float wgt = ccs[lane];
-    if (excl_same_video && cvid[lane] == rvid) wgt = 0.f;
-    const float ex = (wgt != 0.f && ractive) ? wgt * expf(__fdiv_rn(dot, inv_tau_div)) : 0.f;
-    rsum += ex;
-    if (vec_out) {
-      for (int jj = 0; jj < 32; ++jj) {
-        const float gx = __shfl_sync(0xffffffffu, ex, jj);
-        if (gx != 0.f) {
+      __syncthreads();
+      const float dot = dot4(er + warp * D, tile + lane * Dp, D);
+      float wgt = ccs[lane];
+      if (excl_same_video && cvid[lane] == rvid) wgt = 0.f;
+      const float ex = (wgt != 0.f && ractive) ? wgt * expf(__fdiv_rn(dot, inv_tau_div)) : 0.f;
+      rsum += ex;
+      if (vec_out) {
+        for (int jj = 0; jj < 32; ++jj) {
+          const float gx = __shfl_sync(0xffffffffu, ex, jj);
+          if (gx != 0.f) {
 #pragma unroll
-          for (int k = 0; k < SCL_MAXD / 32; ++k) {
-            const int d = lane + 32 * k;
-            if (d < D) acc[k] = fmaf(gx, tile[jj * Dp + d], acc[k]);
+            for (int k = 0; k < SCL_MAXD / 32; ++k) {
+              const int d = lane + 32 * k;
+              if (d < D) acc[k] = fmaf(gx, tile[jj * Dp + d], acc[k]);
+            }
           }
         }
       }
     }
-  }
-  rsum = warp_sum(rsum);
-  if (!ractive) return;
-  if (sum_out && lane == 0 && rsum != 0.f) atomicAdd(sum_out + r, rsum);
-  if (vec_out) {
-    const float rc = rc_const * (rc_arr ? rc_arr[r] : 1.f);
+    rsum = warp_sum(rsum);
+    if (ractive) {
+      if (sum_out && lane == 0 && rsum != 0.f) atomicAdd(sum_out + r, rsum);
+      if (vec_out) {
+        const float rc = rc_const * (rc_arr ? rc_arr[r] : 1.f);
 #pragma unroll
-    for (int k = 0; k < SCL_MAXD / 32; ++k) {
-      const int d = lane + 32 * k;
-      if (d < D && acc[k] != 0.f) atomicAdd(vec_out + (int64_t)r * D + d, __fdiv_rn(rc * acc[k], inv_tau_div));
+        for (int k = 0; k < SCL_MAXD / 32; ++k) {
+          const int d = lane + 32 * k;
+          if (d < D && acc[k] != 0.f) atomicAdd(vec_out + (int64_t)r * D + d, __fdiv_rn(rc * acc[k], inv_tau_div));
+        }
+      }
     }
   }
 }
@@ -370,6 +448,195 @@ scl_pair_kernel(const float* __restrict__ embs, const int64_t* __restrict__ seq_
   }
 }
 
+// =====================================================================================================================
+// Fused per-pair kernel: ONE CTA per video pair does the whole own-pair part of the loss and of its gradient.
+//   stage E0, E1 [T, D] in shared memory (the only HBM reads: 2*T*D*4 B + steps/masks), ex = exp(E0 E1^T / tau) [T, T],
+//   row statistics of both view directions (warp per row, shuffle reductions), the coefficient matrix
+//   coef_ij = dloss/dl_ij of both directions, dE0 = coef E1 / tau, dE1 = coef^T E0 / tau (the only HBM writes).
+// The T x T block never leaves shared memory and every embedding row is read from HBM exactly once, so the kernel is
+// bound by 4*T*D*4 bytes per pair.  zext (masked-column / batch-negative extras of Z, produced by the cross pass before
+// this kernel) is read per row; c_i = g_i / (Z_i M) is written for the gradient cross passes that follow.
+// =====================================================================================================================
+constexpr int SCL_RG = 10;   // rows per register tile of the dE phase (RG float4 accumulators per thread)
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+scl_pair_fused_kernel(const float* __restrict__ embs, const int64_t* __restrict__ seq_lens, const int64_t* __restrict__ steps,
+                      const float* __restrict__ masks, int T, int D, float tau, float two_var, SclWs w,
+                      float* __restrict__ loss_out, float* __restrict__ d_embs) {
+  extern __shared__ __align__(16) float sm[];
+  const int Dp = D + 4, Tp = T + 1;
+  float* E = sm;                          // [2T][Dp]  rows 0..T-1 = view 0, T..2T-1 = view 1
+  float* EX = E + (size_t)2 * T * Dp;     // [T][Tp]   exp(l_ij), later coef_ij   (i: view 0, j: view 1)
+  float* st = EX + (size_t)T * Tp;        // [2T] steps as float
+  float* mk = st + 2 * T;                 // [2T] masks
+  float* Zs = mk + 2 * T;                 // [2T] partition sums
+  float* gs = Zs + 2 * T;                 // [2T] g
+  float* dn = gs + 2 * T;                 // [2T] label normalisers
+  __shared__ float red_loss[NT / 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int v = blockIdx.x;
+  const int64_t row0 = (int64_t)v * 2 * T;
+  const float M = *w.M;
+  const float L0 = (float)seq_lens[v * 2], L1 = (float)seq_lens[v * 2 + 1];
+
+  // ---- stage the pair ----
+  const int D4 = D >> 2;
+  for (int i = tid; i < 2 * T * D4; i += NT) {
+    const int r = i / D4, d4 = i - r * D4;
+    *reinterpret_cast<float4*>(E + r * Dp + 4 * d4) = *reinterpret_cast<const float4*>(embs + (row0 + r) * D + 4 * d4);
+  }
+  for (int i = tid; i < 2 * T; i += NT) {
+    st[i] = (float)steps[row0 + i];
+    mk[i] = masks[row0 + i];
+  }
+  __syncthreads();
+
+  // ---- ex_ij = exp(<e0_i, e1_j> / tau): 2 x 2 register tiles ----
+  const int T2h = (T + 1) >> 1;
+  for (int tix = tid; tix < T2h * T2h; tix += NT) {
+    const int ti = tix / T2h, tj = tix - ti * T2h;
+    const int i0 = 2 * ti, i1 = min(2 * ti + 1, T - 1), j0 = 2 * tj, j1 = min(2 * tj + 1, T - 1);
+    const float* a0 = E + i0 * Dp;
+    const float* a1 = E + i1 * Dp;
+    const float* b0 = E + (T + j0) * Dp;
+    const float* b1 = E + (T + j1) * Dp;
+    float s00[4] = {0.f, 0.f, 0.f, 0.f}, s01[4] = {0.f, 0.f, 0.f, 0.f}, s10[4] = {0.f, 0.f, 0.f, 0.f}, s11[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int d = 0; d < D; d += 4) {
+      const float4 x0 = *reinterpret_cast<const float4*>(a0 + d), x1 = *reinterpret_cast<const float4*>(a1 + d);
+      const float4 y0 = *reinterpret_cast<const float4*>(b0 + d), y1 = *reinterpret_cast<const float4*>(b1 + d);
+      s00[0] = fmaf(x0.x, y0.x, s00[0]); s00[1] = fmaf(x0.y, y0.y, s00[1]); s00[2] = fmaf(x0.z, y0.z, s00[2]); s00[3] = fmaf(x0.w, y0.w, s00[3]);
+      s01[0] = fmaf(x0.x, y1.x, s01[0]); s01[1] = fmaf(x0.y, y1.y, s01[1]); s01[2] = fmaf(x0.z, y1.z, s01[2]); s01[3] = fmaf(x0.w, y1.w, s01[3]);
+      s10[0] = fmaf(x1.x, y0.x, s10[0]); s10[1] = fmaf(x1.y, y0.y, s10[1]); s10[2] = fmaf(x1.z, y0.z, s10[2]); s10[3] = fmaf(x1.w, y0.w, s10[3]);
+      s11[0] = fmaf(x1.x, y1.x, s11[0]); s11[1] = fmaf(x1.y, y1.y, s11[1]); s11[2] = fmaf(x1.z, y1.z, s11[2]); s11[3] = fmaf(x1.w, y1.w, s11[3]);
+    }
+    // same summation tree as dot4() of the row-warp kernels
+    EX[i0 * Tp + j0] = expf(__fdiv_rn((s00[0] + s00[1]) + (s00[2] + s00[3]), tau));
+    EX[i0 * Tp + j1] = expf(__fdiv_rn((s01[0] + s01[1]) + (s01[2] + s01[3]), tau));
+    EX[i1 * Tp + j0] = expf(__fdiv_rn((s10[0] + s10[1]) + (s10[2] + s10[3]), tau));
+    EX[i1 * Tp + j1] = expf(__fdiv_rn((s11[0] + s11[1]) + (s11[2] + s11[3]), tau));
+  }
+  __syncthreads();
+
+  // ---- row statistics of both directions: warp per row r (r < T: view-0 row i over j; r >= T: view-1 row j over i) ----
+  float loss_acc = 0.f;
+  for (int r = warp; r < 2 * T; r += NT / 32) {
+    const bool dir1 = r >= T;
+    const int a = dir1 ? r - T : r;                 // index inside the own view
+    const float mi = mk[r], si = st[r];
+    const float Li = dir1 ? L1 : L0, Lj = dir1 ? L0 : L1;
+    const int pb = dir1 ? 0 : T;                    // partner block offset in st / mk
+    float den = 0.f, zp = 0.f;
+    for (int b = lane; b < T; b += 32) {
+      const bool mm = mi != 0.f && mk[pb + b] != 0.f;
+      if (mm) {
+        const float dd = ts_dist(si, Li, Lj, st[pb + b]);
+        den += expf(__fdiv_rn(-(dd * dd), two_var));
+        zp += dir1 ? EX[b * Tp + a] : EX[a * Tp + b];
+      }
+    }
+    den = warp_sum(den);
+    zp = warp_sum(zp);
+    const float Z = zp + w.zext[row0 + r];
+    float g = 0.f, loss = 0.f;
+    if (mi != 0.f && Z > 0.f) {
+      for (int b = lane; b < T; b += 32) {
+        if (mk[pb + b] != 0.f) {
+          const float dd = ts_dist(si, Li, Lj, st[pb + b]);
+          const float pw = expf(__fdiv_rn(-(dd * dd), two_var));
+          const float y = den > 0.f ? __fdiv_rn(pw, den) : 0.f;
+          const float p = __fdiv_rn(dir1 ? EX[b * Tp + a] : EX[a * Tp + b], Z);
+          const float q = p + 1e-6f;
+          if (y > 0.f) {
+            loss += y * (logf(y) - logf(q));
+            g += y * __fdiv_rn(p, q);
+          }
+        }
+      }
+    }
+    g = warp_sum(g);
+    loss = warp_sum(loss);
+    if (lane == 0) {
+      Zs[r] = Z;
+      gs[r] = g;
+      dn[r] = den;
+      w.c[row0 + r] = (mi != 0.f && Z > 0.f) ? g / (Z * M) : 0.f;
+      loss_acc += loss;
+    }
+  }
+  if (lane == 0) red_loss[warp] = loss_acc;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int k = 0; k < NT / 32; ++k) t += red_loss[k];
+    if (t != 0.f) atomicAdd(loss_out, t / M);
+  }
+  if (d_embs == nullptr) return;
+
+  // ---- coef_ij = ( [p g_i - y r]_dir0 + [p' g'_j - y' r']_dir1 ) / M, in place over ex ----
+  for (int ix = tid; ix < T * T; ix += NT) {
+    const int i = ix / T, j = ix - i * T;
+    float coef = 0.f;
+    if (mk[i] != 0.f && mk[T + j] != 0.f) {
+      const float ex = EX[i * Tp + j];
+      const float Zi = Zs[i], Zj = Zs[T + j];
+      if (Zi > 0.f) {
+        const float dd = ts_dist(st[i], L0, L1, st[T + j]);
+        const float pw = expf(__fdiv_rn(-(dd * dd), two_var));
+        const float y = dn[i] > 0.f ? __fdiv_rn(pw, dn[i]) : 0.f;
+        const float p = __fdiv_rn(ex, Zi);
+        coef += p * gs[i] - y * __fdiv_rn(p, p + 1e-6f);
+      }
+      if (Zj > 0.f) {
+        const float dd = ts_dist(st[T + j], L1, L0, st[i]);
+        const float pw = expf(__fdiv_rn(-(dd * dd), two_var));
+        const float y = dn[T + j] > 0.f ? __fdiv_rn(pw, dn[T + j]) : 0.f;
+        const float p = __fdiv_rn(ex, Zj);
+        coef += p * gs[T + j] - y * __fdiv_rn(p, p + 1e-6f);
+      }
+      coef = coef / M;
+    }
+    EX[i * Tp + j] = coef;
+  }
+  __syncthreads();
+
+  // ---- dE0_i = sum_j coef_ij e1_j / tau ; dE1_j = sum_i coef_ij e0_i / tau : register tiles of SCL_RG rows x 4 channels ----
+  const int ngroups = (T + SCL_RG - 1) / SCL_RG;
+  const int ntasks = 2 * ngroups * D4;               // (view, row group, 4-channel chunk)
+  for (int task = tid; task < ntasks; task += NT) {
+    const int d4 = task % D4;
+    const int gr = (task / D4) % ngroups;
+    const int view = task / (D4 * ngroups);
+    const int r0 = gr * SCL_RG;
+    const float* other = E + (view ? 0 : T) * Dp + 4 * d4;   // partner rows
+    float4 acc[SCL_RG];
+#pragma unroll
+    for (int k = 0; k < SCL_RG; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < T; ++b) {
+      const float4 x = *reinterpret_cast<const float4*>(other + b * Dp);
+#pragma unroll
+      for (int k = 0; k < SCL_RG; ++k) {
+        const int a = min(r0 + k, T - 1);
+        const float cf = view ? EX[b * Tp + a] : EX[a * Tp + b];
+        acc[k].x = fmaf(cf, x.x, acc[k].x); acc[k].y = fmaf(cf, x.y, acc[k].y);
+        acc[k].z = fmaf(cf, x.z, acc[k].z); acc[k].w = fmaf(cf, x.w, acc[k].w);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SCL_RG; ++k) {
+      const int a = r0 + k;
+      if (a < T)
+        *reinterpret_cast<float4*>(d_embs + (row0 + view * T + a) * D + 4 * d4) =
+            make_float4(__fdiv_rn(acc[k].x, tau), __fdiv_rn(acc[k].y, tau), __fdiv_rn(acc[k].z, tau), __fdiv_rn(acc[k].w, tau));
+    }
+  }
+}
+
+static size_t scl_fused_smem(int T, int D) {
+  return ((size_t)2 * T * (D + 4) + (size_t)T * (T + 1) + (size_t)10 * T) * sizeof(float);
+}
+
 int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps, const float* masks, int Bv, int T,
                 int D, float temperature, float label_variance, int negative_type, int quirk, float* loss_out,
                 float* d_embs, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -388,16 +655,33 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
   size_t need = scl_ws_layout(N, &w, (char*)ws);
   MVF_REQUIRE(ws_bytes >= need, MVF_ERR_WORKSPACE, "scl: workspace %zu < %zu bytes", ws_bytes, need);
 
-  scl_prep_kernel<<<1, 1024, 0, st>>>(masks, N, w, loss_out);
-  MVF_CHECK_LAUNCH();
+  if (N <= 8192) {
+    scl_prep_kernel<<<1, 1024, 0, st>>>(masks, N, w, loss_out);
+    MVF_CHECK_LAUNCH();
+  } else {
+    const int nchunks = cdiv(N, 1024);
+    MVF_CHECK_CUDA(cudaMemsetAsync(w.M, 0, sizeof(float), st));
+    scl_prep_count_kernel<<<nchunks, 1024, 0, st>>>(masks, N, w, loss_out);
+    MVF_CHECK_LAUNCH();
+    scl_prep_scan_kernel<<<1, 1024, 0, st>>>(N, nchunks, w);
+    MVF_CHECK_LAUNCH();
+    scl_prep_write_kernel<<<nchunks, 1024, 0, st>>>(masks, N, nchunks, w);
+    MVF_CHECK_LAUNCH();
+  }
 
   const size_t smem = ((size_t)32 * (D + 4) + 8 * D + 64) * sizeof(float);
-  // the column list is split over blockIdx.y: the row/column counts live on the device (valid vs masked frames), so the
-  // grid is sized for the worst case and short lists simply leave CTAs idle; 8-way split keeps every pass to a few
-  // tiles per CTA at training batch sizes
-  int cy = 8;
-  if ((int64_t)cdiv(N, 8) * cy > 65535 * 4) cy = 2;
-  const dim3 cross_grid(cdiv(N, 8), cy);
+  // cross passes: row blocks are visited grid-stride (row / column counts live on the device, so the grid is sized for the
+  // machine, not for the worst case) and the column list is split over blockIdx.y (outputs accumulate with atomics)
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    sms = (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ? prop.multiProcessorCount : 148;
+  }
+  const int cy = 8;
+  int cx = cdiv(N, 8);
+  if (cx > sms * 2) cx = sms * 2;
+  const dim3 cross_grid(cx, cy);
   const int T2 = 2 * T;
   const bool batch = negative_type == MVF_NEG_BATCH_NOSELF;
   // Z extras
@@ -412,14 +696,44 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
     MVF_CHECK_LAUNCH();
   }
 
-  const int pair_grid = Bv * 2 * cdiv(T, 8);
-  scl_pair_kernel<0><<<pair_grid, 256, smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature,
-                                                   2.f * label_variance, w, loss_out, nullptr);
-  MVF_CHECK_LAUNCH();
-  if (d_embs) {
-    scl_pair_kernel<1><<<pair_grid, 256, smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature,
-                                                     2.f * label_variance, w, loss_out, d_embs);
+  // own-pair part: one fused CTA per pair when the pair fits in shared memory, else the two row-warp passes
+  const size_t fsmem = scl_fused_smem(T, D);
+  static int fused_on = -1;
+  if (fused_on < 0) {
+    const char* e = getenv("MVF_SCL_FUSED");
+    fused_on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (fused_on && fsmem <= 200 * 1024) {
+    if (T * T >= 2048) {
+      static size_t configured = 0;
+      if (fsmem > configured) {
+        MVF_CHECK_CUDA(cudaFuncSetAttribute(scl_pair_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        configured = fsmem;
+      }
+      scl_pair_fused_kernel<256><<<Bv, 256, fsmem, st>>>(embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
+                                                         w, loss_out, d_embs);
+    } else {
+      static size_t configured = 0;
+      if (fsmem > configured) {
+        MVF_CHECK_CUDA(cudaFuncSetAttribute(scl_pair_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        configured = fsmem;
+      }
+      scl_pair_fused_kernel<128><<<Bv, 128, fsmem, st>>>(embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
+                                                         w, loss_out, d_embs);
+    }
     MVF_CHECK_LAUNCH();
+  } else {
+    const int pair_grid = Bv * 2 * cdiv(T, 8);
+    scl_pair_kernel<0><<<pair_grid, 256, smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature,
+                                                     2.f * label_variance, w, loss_out, nullptr);
+    MVF_CHECK_LAUNCH();
+    if (d_embs) {
+      scl_pair_kernel<1><<<pair_grid, 256, smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature,
+                                                       2.f * label_variance, w, loss_out, d_embs);
+      MVF_CHECK_LAUNCH();
+    }
+  }
+  if (d_embs) {
     if (quirk) {
       // rows valid i, columns masked k: dE_i += c_i 1e-6 e^{l_ik} e_k / tau
       scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.masked,
