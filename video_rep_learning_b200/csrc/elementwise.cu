@@ -475,6 +475,47 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TI* __restrict__ X, i
     atomicAdd(out + c, s);
   }
 }
+// Batched variant: every bias gradient of one backward call in ONE launch (blockIdx.z = matrix).  The dY buffers all stay
+// alive until the side stream is joined, so the column sums can be deferred to the end instead of costing one launch each.
+struct ColsumTable {
+  int n;
+  ColsumEntry e[COLSUM_MAX];
+};
+__global__ void __launch_bounds__(256) colsum_batched_kernel(const ColsumTable tab) {
+  const ColsumEntry& en = tab.e[blockIdx.z];
+  __shared__ float sh[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (blockIdx.x * 32 >= en.C) return;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < en.C)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < en.R; r += (int64_t)gridDim.y * 8) s += en.X[r * en.ld + c];
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < en.C) {
+    for (int j = 1; j < 8; ++j) s += sh[j][tx];
+    atomicAdd(en.out + c, s);
+  }
+}
+int colsum_batched(const ColsumEntry* entries, int n, cudaStream_t st) {
+  for (int base = 0; base < n; base += COLSUM_MAX) {
+    ColsumTable tab;
+    tab.n = n - base < COLSUM_MAX ? n - base : COLSUM_MAX;
+    int maxC = 1;
+    int64_t maxR = 1;
+    for (int i = 0; i < tab.n; ++i) {
+      tab.e[i] = entries[base + i];
+      if (tab.e[i].C > maxC) maxC = tab.e[i].C;
+      if (tab.e[i].R > maxR) maxR = tab.e[i].R;
+    }
+    int gy = cdiv(maxR, 8 * 32);
+    gy = gy > 32 ? 32 : (gy < 1 ? 1 : gy);
+    colsum_batched_kernel<<<dim3(cdiv(maxC, 32), gy, tab.n), 256, 0, st>>>(tab);
+    MVF_CHECK_LAUNCH();
+  }
+  return MVF_OK;
+}
+
 int colsum(int dtype_in, const void* X, int64_t R, int C, int64_t ld, float* out, cudaStream_t st) {
   int gy = cdiv(R, 8 * 32);
   if (gy > 128) gy = 128;

@@ -481,6 +481,7 @@ struct Ctx {
   cudaStream_t st;
   cudaStream_t side = nullptr;  // non-null: weight-gradient work is forked onto it
   bool forked = false;
+  std::vector<ColsumEntry> bias_sums;   // bias gradients (column sums of dY) deferred to one batched launch at the join
   int backend;
   float p;  // effective dropout rate
   int gemm(int dtype_c, int akm, int bkm, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
@@ -504,6 +505,10 @@ struct Ctx {
     return MVF_OK;
   }
   int join() {
+    if (!bias_sums.empty()) {   // every dY region is still intact here (callers give each its own scratch region)
+      MVF_TRY(colsum_batched(bias_sums.data(), (int)bias_sums.size(), side && forked ? side : st));
+      bias_sums.clear();
+    }
     if (!side || !forked) return MVF_OK;
     cudaEvent_t e = side_event();
     MVF_CHECK_CUDA(cudaEventRecord(e, side));
@@ -538,7 +543,7 @@ struct Ctx {
     MVF_TRY(fork());
     cudaStream_t on = side ? side : st;
     MVF_TRY(gemm(MVF_F32, 0, 0, Nout, Kin, M, dY, lddy, X, ldx, dWp, lddw, nullptr, nullptr, 0, MVF_GEMM_ACCUM, split_k, on));
-    if (db) MVF_TRY(colsum(m.act, dY, M, (int)Nout, lddy, db, on));
+    if (db) bias_sums.push_back(ColsumEntry{(const float*)dY, db, M, lddy, (int)Nout});   // m.act is fp32
     return MVF_OK;
   }
 };

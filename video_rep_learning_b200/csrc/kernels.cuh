@@ -57,6 +57,15 @@ int bn_bwd_apply(int dtype_out, const float* d_out, int64_t ld_d, const float* x
                  double n_global, void* dx, int64_t ld_dx, cudaStream_t st);
 
 // ---- misc ------------------------------------------------------------------------------------------------
+// out[c] += sum_r X[r,c] for a table of fp32 matrices in one launch
+struct ColsumEntry {
+  const float* X;
+  float* out;
+  int64_t R, ld;
+  int C;
+};
+constexpr int COLSUM_MAX = 32;
+int colsum_batched(const ColsumEntry* entries, int n, cudaStream_t st);
 // out[c] += sum_r X[r,c]
 int colsum(int dtype_in, const void* X, int64_t R, int C, int64_t ld, float* out, cudaStream_t st);
 // out = in * dropmask (site) cast to dtype_out; p = 0 -> plain cast
