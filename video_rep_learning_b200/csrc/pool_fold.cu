@@ -434,12 +434,13 @@ pool_fold_bwd_kernel(const T* __restrict__ X, const float* __restrict__ G, const
 // Wq[e,c] = scale * sum_j (Q_s[e,j] + Q_b[j]) Wk[j,c];  block = 32 channels x 8 slices of j, deterministic reduction.
 // Accumulated in fp64 and rounded once: Wq is shared by every token of every frame, so its rounding error acts like a
 // coherent perturbation of W_k (measured: fp32 accumulation costs 1.5e-5 on the gradients at C_in = 1152, fp64 none).
-__global__ void __launch_bounds__(256)
+constexpr int PREP_SLICES = 32;   // j-slices per CTA: 32 channels x 32 slices = 1024 threads
+__global__ void __launch_bounds__(1024)
 fold_prep_kernel(const float* __restrict__ q_s, const float* __restrict__ q_b, const float* __restrict__ Wk, int E, int SPC,
                  int C, float scale, float* __restrict__ Wq) {
   extern __shared__ double smd[];
-  float* Qf = reinterpret_cast<float*>(smd + (size_t)8 * E * 32);   // [E][SPC] (fp32 sum, like mvformer.py:383)
-  double* red = smd;                                                // [8][E][32]
+  float* Qf = reinterpret_cast<float*>(smd + (size_t)PREP_SLICES * E * 32);   // [E][SPC] (fp32 sum, like mvformer.py:383)
+  double* red = smd;                                                          // [PREP_SLICES][E][32]
   const int tid = threadIdx.x, cl = tid & 31, js = tid >> 5;
   const int c = blockIdx.x * 32 + cl;
   for (int i = tid; i < E * SPC; i += blockDim.x) Qf[i] = q_s[i] + q_b[i % SPC];
@@ -448,7 +449,7 @@ fold_prep_kernel(const float* __restrict__ q_s, const float* __restrict__ q_b, c
 #pragma unroll
   for (int e = 0; e < MVF_MAX_ENTITIES; ++e) acc[e] = 0.0;
   if (c < C) {
-    for (int j = js; j < SPC; j += 8) {
+    for (int j = js; j < SPC; j += PREP_SLICES) {
       const double wk = (double)Wk[(size_t)j * C + c];
 #pragma unroll
       for (int e = 0; e < MVF_MAX_ENTITIES; ++e)
@@ -462,8 +463,8 @@ fold_prep_kernel(const float* __restrict__ q_s, const float* __restrict__ q_b, c
   for (int i = tid; i < E * 32; i += blockDim.x) {
     const int e = i >> 5, l = i & 31;
     double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s += red[(k * E + e) * 32 + l];
+#pragma unroll 8
+    for (int k = 0; k < PREP_SLICES; ++k) s += red[(k * E + e) * 32 + l];   // fixed order: deterministic
     if (blockIdx.x * 32 + l < C) Wq[(size_t)e * C + blockIdx.x * 32 + l] = (float)(s * (double)scale);
   }
 }
@@ -705,11 +706,11 @@ int pool_fold_bwd(int dtype, int F, int P, int E, int C, const void* X, const fl
 }
 
 int fold_prep(const float* q_s, const float* q_b, const float* Wk, int E, int SPC, int C, float* Wq, cudaStream_t st) {
-  const size_t smem = (size_t)E * SPC * sizeof(float) + (size_t)8 * E * 32 * sizeof(double);
+  const size_t smem = (size_t)E * SPC * sizeof(float) + (size_t)fold::PREP_SLICES * E * 32 * sizeof(double);
   MVF_REQUIRE(smem <= 200 * 1024, MVF_ERR_UNSUPPORTED, "fold_prep: E*SPC too large");
   if (smem > 48 * 1024)
     MVF_CHECK_CUDA(cudaFuncSetAttribute(fold::fold_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fold::fold_prep_kernel<<<cdiv(C, 32), 256, smem, st>>>(q_s, q_b, Wk, E, SPC, C, (float)(1.0 / sqrt((double)SPC)), Wq);
+  fold::fold_prep_kernel<<<cdiv(C, 32), 1024, smem, st>>>(q_s, q_b, Wk, E, SPC, C, (float)(1.0 / sqrt((double)SPC)), Wq);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
