@@ -166,7 +166,7 @@ static Carve carve(int C, int NW, int P) {
 // bf16 hi/lo B fragments of a [8 ent, C] fp32 matrix (rows e >= ne are zero) for this warp's tiles
 template <int TPW>
 __device__ __forceinline__ void load_bfrag(const float* __restrict__ M, int64_t stride, int ne, int ch_base, int q, int r8,
-                                           uint32_t (&bh)[TPW][2], uint32_t (&bl)[TPW][2]) {
+                                           uint32_t (&bh)[TPW][2], uint32_t (&bl)[TPW][2], float mul) {
 #pragma unroll
   for (int t = 0; t < TPW; ++t) {
     float2 v0 = make_float2(0.f, 0.f), v1 = v0;
@@ -175,8 +175,8 @@ __device__ __forceinline__ void load_bfrag(const float* __restrict__ M, int64_t 
       v0 = *reinterpret_cast<const float2*>(p);
       v1 = *reinterpret_cast<const float2*>(p + 8);
     }
-    split2(v0.x, v0.y, bh[t][0], bl[t][0]);
-    split2(v1.x, v1.y, bh[t][1], bl[t][1]);
+    split2(v0.x * mul, v0.y * mul, bh[t][0], bl[t][0]);
+    split2(v1.x * mul, v1.y * mul, bh[t][1], bl[t][1]);
   }
 }
 
@@ -232,15 +232,17 @@ __device__ __forceinline__ void pool_phase(uint32_t slot_addr, uint32_t t_off, c
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
-template <int TPW>
+// NI = ceil(ne / 2): rounds of the softmax bookkeeping (each round serves two entities, one per half-warp)
+template <int TPW, int NI>
 __global__ void __launch_bounds__(max_threads(TPW), 1)
 pool_foldm_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, float* __restrict__ attn,
                       float* __restrict__ px, const Geom g) {
   MVF_FOLDM_SETUP();
   float* fin = misc + warp * 16;   // this warp's copy of [max(8) | 1/sum(8)] at the end of a frame
 
+  // the scores live in the log2 domain (log2 e folded into the Wq fragments): exp2f is one MUFU + fix-ups, expf ~4x that
   uint32_t bh[TPW][2], bl[TPW][2];
-  load_bfrag<TPW>(Wq + (int64_t)g.e0 * g.C, g.C, g.ne, warp * TPW * 16, q, r8, bh, bl);
+  load_bfrag<TPW>(Wq + (int64_t)g.e0 * g.C, g.C, g.ne, warp * TPW * 16, q, r8, bh, bl, 1.4426950408889634f);
 
   int n = 0;
   for (int fi = 0; fi < nF; ++fi) {
@@ -248,9 +250,9 @@ pool_foldm_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, 
     float acc[TPW][4];
 #pragma unroll
     for (int t = 0; t < TPW; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
-    float m_run[4], l_run[4];
+    float m_run[NI], l_run[NI];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { m_run[i] = -INFINITY; l_run[i] = 0.f; }
+    for (int i = 0; i < NI; ++i) { m_run[i] = -INFINITY; l_run[i] = 0.f; }
 
     for (int gi = 0; gi < nG; ++gi, ++n) {
       const int slot = n % SLOTS;
@@ -260,36 +262,52 @@ pool_foldm_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, 
       scores_phase<TPW>(slot_addr, a_off, bh, bl, partial + ((n & 1) * NW + warp) * (EN * TG), q, r8);
       compute_sync(nthr);
 
-      // softmax bookkeeping, redundantly per warp: lane = (token ltok, entities lh, lh+2, lh+4, lh+6)
+      // softmax bookkeeping, redundantly per warp: lane = (token ltok, entities lh, lh+2, ...).  The NI rounds are written
+      // as straight-line code over small arrays so that their shuffle / exp2 chains interleave (ILP), not as a loop.
       float* wb = wbuf + warp * (EN * TG + 16);
       const bool tvalid = ltok < ntok;
+      float sv[NI], mx[NI], wg[NI], fc[NI], ls[NI];
+      bool ev[NI];
+      const float* pbase = partial + (n & 1) * NW * (EN * TG) + ltok;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (2 * i >= g.ne) break;          // warp-uniform
-        const int e = lh + 2 * i;
-        const bool ev = e < g.ne;          // the upper half-warp may hold a padding entity: it still takes part in the shuffles
-        float s = 0.f;
-        if (ev)
-          for (int w = 0; w < NW; ++w) s += partial[((n & 1) * NW + w) * (EN * TG) + e * TG + ltok];
-        if (warp == 0 && tvalid && ev) table[e * g.P + gi * TG + ltok] = s;
-        float mx = (tvalid && ev) ? s : -INFINITY;
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-        const float m_new = fmaxf(m_run[i], mx);
-        const float wgt = (tvalid && ev) ? expf(s - m_new) : 0.f;
-        const float fac = ev ? expf(m_run[i] - m_new) : 1.f;   // first group: exp(-inf) = 0
-        float ls = wgt;
-        ls += __shfl_xor_sync(0xffffffffu, ls, 1);
-        ls += __shfl_xor_sync(0xffffffffu, ls, 2);
-        ls += __shfl_xor_sync(0xffffffffu, ls, 4);
-        ls += __shfl_xor_sync(0xffffffffu, ls, 8);
-        if (ev) {
-          l_run[i] = l_run[i] * fac + ls;
-          m_run[i] = m_new;
-          wb[e * TG + ltok] = wgt;
-          if (ltok == 0) wb[EN * TG + e] = fac;
+      for (int i = 0; i < NI; ++i) {
+        ev[i] = lh + 2 * i < g.ne;   // the upper half-warp may hold a padding entity: it still takes part in the shuffles
+        sv[i] = 0.f;
+      }
+      for (int w = 0; w < NW; ++w) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+          if (ev[i]) sv[i] += pbase[w * (EN * TG) + (lh + 2 * i) * TG];
+      }
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        if (warp == 0 && tvalid && ev[i]) table[(lh + 2 * i) * g.P + gi * TG + ltok] = sv[i];
+        mx[i] = (tvalid && ev[i]) ? sv[i] : -INFINITY;
+      }
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], o));
+      }
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const float m_new = fmaxf(m_run[i], mx[i]);
+        wg[i] = (tvalid && ev[i]) ? exp2f(sv[i] - m_new) : 0.f;
+        fc[i] = ev[i] ? exp2f(m_run[i] - m_new) : 1.f;   // first group: 2^-inf = 0
+        ls[i] = wg[i];
+        if (ev[i]) m_run[i] = m_new;
+      }
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) ls[i] += __shfl_xor_sync(0xffffffffu, ls[i], o);
+      }
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        if (ev[i]) {
+          l_run[i] = l_run[i] * fc[i] + ls[i];
+          wb[(lh + 2 * i) * TG + ltok] = wg[i];
+          if (ltok == 0) wb[EN * TG + lh + 2 * i] = fc[i];
         }
       }
       __syncwarp();
@@ -307,7 +325,7 @@ pool_foldm_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, 
 
     // ---- end of frame ----
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NI; ++i) {
       const int e = lh + 2 * i;
       if (e < g.ne && ltok == 0) { fin[e] = m_run[i]; fin[8 + e] = 1.f / l_run[i]; }
     }
@@ -326,7 +344,7 @@ pool_foldm_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, 
     compute_sync(nthr);   // warp 0's raw scores of the whole frame are visible
     for (int i = tid; i < g.ne * g.P; i += nthr) {
       const int e = i / g.P, p = i - e * g.P;
-      attn[((int64_t)f * g.Etot + g.e0 + e) * g.P + p] = expf(table[i] - fin[e]) * fin[8 + e];
+      attn[((int64_t)f * g.Etot + g.e0 + e) * g.P + p] = exp2f(table[i] - fin[e]) * fin[8 + e];
     }
     compute_sync(nthr);   // table / fin are free for the next frame
   }
@@ -471,13 +489,22 @@ static int plan(KernelT kernel, Plan& pl, int F, int P, int C, int NW) {
   return MVF_OK;
 }
 
-template <int TPW>
-static int fwd_launch(const Geom& g, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st) {
+template <int TPW, int NI>
+static int fwd_launch_ni(const Geom& g, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st) {
   static thread_local Plan pl;
-  MVF_TRY(plan(pool_foldm_fwd_kernel<TPW>, pl, g.F, g.P, g.C, g.NW));
-  pool_foldm_fwd_kernel<TPW><<<pl.grid, (g.NW + 1) * 32, pl.smem, st>>>((const bf16*)X, Wq, attn, px, g);
+  MVF_TRY(plan(pool_foldm_fwd_kernel<TPW, NI>, pl, g.F, g.P, g.C, g.NW));
+  pool_foldm_fwd_kernel<TPW, NI><<<pl.grid, (g.NW + 1) * 32, pl.smem, st>>>((const bf16*)X, Wq, attn, px, g);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
+}
+template <int TPW>
+static int fwd_launch(const Geom& g, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st) {
+  switch ((g.ne + 1) / 2) {
+    case 1: return fwd_launch_ni<TPW, 1>(g, X, Wq, attn, px, st);
+    case 2: return fwd_launch_ni<TPW, 2>(g, X, Wq, attn, px, st);
+    case 3: return fwd_launch_ni<TPW, 3>(g, X, Wq, attn, px, st);
+    default: return fwd_launch_ni<TPW, 4>(g, X, Wq, attn, px, st);
+  }
 }
 template <int TPW>
 static int bwd_launch(const Geom& g, const void* X, const float* G, const float* px, const float* attn, float* dWq,
