@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-for f in test_gpu_gemm test_gpu_fold test_gpu_blocks test_gpu_scl test_gpu_model test_gpu_dropin test_gpu_multi; do
+for f in test_gpu_gemm test_gpu_fold test_gpu_fullsize test_gpu_blocks test_gpu_scl test_gpu_model test_gpu_dropin test_gpu_multi; do
   echo "=== $f ===" | tee -a gpurun_out/pytest_summary.txt
   timeout 900 python -m pytest tests/$f.py -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/$f.log 2>&1
   echo "exit $?" | tee -a gpurun_out/pytest_summary.txt
