@@ -66,32 +66,38 @@ struct SideCtl {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[64];
   int n_ev = 0, next = 0;
-  std::mutex mu;
 };
-static SideCtl g_side;
-static int side_acquire(cudaStream_t* s) {
+constexpr int MAX_DEVICES = 64;
+static SideCtl g_side[MAX_DEVICES];   // one side stream + event ring per device (streams and events are device-bound)
+static std::mutex g_side_mu;
+static int side_acquire(cudaStream_t* s, int* dev_out) {
   static int enabled = -1;  // MVF_SIDE_STREAM=0 keeps everything on the caller's stream (debugging / A-B timing)
   if (enabled < 0) {
     const char* e = getenv("MVF_SIDE_STREAM");
     enabled = (e && atoi(e) == 0) ? 0 : 1;
   }
-  if (!enabled) {
-    *s = nullptr;
-    return MVF_OK;
+  *s = nullptr;
+  *dev_out = 0;
+  if (!enabled) return MVF_OK;
+  int dev = 0;
+  MVF_CHECK_CUDA(cudaGetDevice(&dev));
+  MVF_REQUIRE(dev >= 0 && dev < MAX_DEVICES, MVF_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  SideCtl& c = g_side[dev];
+  if (c.stream == nullptr) {
+    MVF_CHECK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 64; ++i) MVF_CHECK_CUDA(cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming));
+    c.n_ev = 64;
   }
-  std::lock_guard<std::mutex> lk(g_side.mu);
-  if (g_side.stream == nullptr) {
-    MVF_CHECK_CUDA(cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 64; ++i) MVF_CHECK_CUDA(cudaEventCreateWithFlags(&g_side.ev[i], cudaEventDisableTiming));
-    g_side.n_ev = 64;
-  }
-  *s = g_side.stream;
+  *s = c.stream;
+  *dev_out = dev;
   return MVF_OK;
 }
-static cudaEvent_t side_event() {
-  std::lock_guard<std::mutex> lk(g_side.mu);
-  cudaEvent_t e = g_side.ev[g_side.next];
-  g_side.next = (g_side.next + 1) % g_side.n_ev;
+static cudaEvent_t side_event(int dev) {
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  SideCtl& c = g_side[dev];
+  cudaEvent_t e = c.ev[c.next];
+  c.next = (c.next + 1) % c.n_ev;
   return e;
 }
 
@@ -480,6 +486,7 @@ struct Ctx {
   const float* const* P;
   cudaStream_t st;
   cudaStream_t side = nullptr;  // non-null: weight-gradient work is forked onto it
+  int side_dev = 0;             // device the side stream / its events belong to
   bool forked = false;
   std::vector<ColsumEntry> bias_sums;   // bias gradients (column sums of dY) deferred to one batched launch at the join
   int backend;
@@ -498,7 +505,7 @@ struct Ctx {
   }
   int fork() {
     if (!side) return MVF_OK;
-    cudaEvent_t e = side_event();
+    cudaEvent_t e = side_event(side_dev);
     MVF_CHECK_CUDA(cudaEventRecord(e, st));
     MVF_CHECK_CUDA(cudaStreamWaitEvent(side, e, 0));
     forked = true;
@@ -510,7 +517,7 @@ struct Ctx {
       bias_sums.clear();
     }
     if (!side || !forked) return MVF_OK;
-    cudaEvent_t e = side_event();
+    cudaEvent_t e = side_event(side_dev);
     MVF_CHECK_CUDA(cudaEventRecord(e, side));
     MVF_CHECK_CUDA(cudaStreamWaitEvent(st, e, 0));
     forked = false;
@@ -1235,7 +1242,7 @@ int mvf_head_backward(const mvf_head_desc* d, const float* const* params, const 
   Ctx c;
   MVF_TRY(make_ctx(d, c, false, save, save_bytes, ws, ws_bytes, gpack, params, (cudaStream_t)stream));
   MVF_REQUIRE(tokens != nullptr && d_emb != nullptr && gpack != nullptr, MVF_ERR_BAD_ARG, "null tokens / d_emb / gpack");
-  MVF_TRY(side_acquire(&c.side));
+  MVF_TRY(side_acquire(&c.side, &c.side_dev));
   int rc = head_backward_impl(c, tokens, mask, d_emb, phase_begin, phase_end);
   if (rc != MVF_OK) c.join();  // never leave forked work un-joined, even on an error path
   return rc;
@@ -1258,7 +1265,7 @@ int mvf_proj_backward(const mvf_head_desc* d, const float* const* params, const 
   MVF_REQUIRE(d_out != nullptr && d_emb != nullptr, MVF_ERR_BAD_ARG, "null d_out / d_emb");
   MVF_REQUIRE(!project || gpack != nullptr, MVF_ERR_BAD_ARG, "null gpack");
   // the forward stores the normalised rows in `ehat` for both modes
-  MVF_TRY(side_acquire(&c.side));
+  MVF_TRY(side_acquire(&c.side, &c.side_dev));
   int rc = proj_backward_impl(c, d_out, project, d_emb, c.S.f("ehat"), phase_begin, phase_end);
   if (rc != MVF_OK) c.join();
   return rc;
