@@ -9,11 +9,13 @@
 // row-major, needed by dX = dY*W and dW = dY^T*X) -- selected per operand through the shared-memory
 // descriptor + instruction descriptor, never by materialising a transpose.
 //
-// Kernel shape: persistent, one CTA per SM, 8 warps:
+// Kernel shape: persistent, one CTA per SM, 12 warps (16 in SPLIT3 mode):
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      MMA issuer   (one elected lane; tcgen05.mma cta_group::1, M=128, N=BLOCK_N, K=16)
 //   warp 2      TMEM allocator / deallocator
-//   warps 4..7  epilogue: tcgen05.ld (lane quadrant = warp%4) -> bias/ReLU/mask -> global (store or red.add)
+//   warps 4..7 + the last four warps   epilogue, two warps per TMEM lane quadrant (= warp%4), each taking half of the
+//               tile's columns: tcgen05.ld -> bias/ReLU/mask -> swizzled staging tile -> TMA store / reduce-add (fp32)
+//               or registers -> global (bf16)
 // Two TMEM accumulators (2*BLOCK_N columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 // Split-K (work item = tile x K-slice, fp32 atomics) fills the machine when M*N is small and K huge
 // (the weight gradient of the K/V projection: 768 x 2304 outputs, K = frames*196).
@@ -34,8 +36,10 @@ namespace tc {
 
 constexpr int BLOCK_M = 128;
 constexpr int ROW_BYTES = 128;  // one swizzle row of K per stage: 64 bf16 or 32 fp32 (tf32)
-constexpr int NUM_THREADS = 256;
-constexpr int NUM_THREADS_SPLIT = 384;  // + 4 converter warps
+constexpr int NUM_THREADS = 256;        // warps 0..7: TMA, MMA, TMEM alloc, (idle), 4 epilogue warps
+constexpr int NUM_THREADS_SPLIT = 384;  // + 4 converter warps (8..11)
+constexpr int EXTRA_EPI_THREADS = 128;  // + 4 more epilogue warps at the end of the CTA: the TMA-store epilogue of one
+                                        // 128 x BLOCK_N tile is split column-wise over two warps per TMEM lane quadrant
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,7 +95,7 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -193,7 +197,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define MVF_STAMP(i) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[i] = gtimer(); } while (0)
 
 template <int BLOCK_N, int STAGES, int EB, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS, 1)
+__global__ void __launch_bounds__((SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS) + EXTRA_EPI_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const Params p) {
   constexpr int BLOCK_K = ROW_BYTES / EB;   // elements of K per stage (64 bf16 / 32 tf32)
@@ -234,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&empty_bar[s], 1);
       mbar_init(&conv_bar[s], NUM_THREADS_SPLIT - NUM_THREADS);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -336,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (it == 0) MVF_STAMP(3);
       }
     }
-  } else if (SPLIT && warp >= 8) {
+  } else if (SPLIT && warp >= 8 && warp < 12) {
     // ===================== fp32 -> bf16 hi|lo converter (SPLIT3) =====================
     // Thread t owns rows t, t+128, ... of the stage (A rows then B rows; both tiles are K-major, 128-byte rows,
     // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r & 7)).  It reads its whole row and writes it back,
@@ -381,12 +385,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || warp >= (SPLIT ? 12 : 8)) {
     // ===================== epilogue =====================
+    // two warps per TMEM lane quadrant: `half` 0 (warps 4..7) takes the first BLOCK_N/2 columns of the tile, `half` 1
+    // (the last four warps of the CTA) the rest
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int half = warp >= 8 ? 1 : 0;
+    constexpr int C_BEGIN1 = (BLOCK_N / 2 + 31) / 32 * 32;   // first column chunk of half 1
+    const int c_begin = half ? C_BEGIN1 : 0, c_end = half ? BLOCK_N : C_BEGIN1;
     int it = 0;
-    uint32_t n_chunks = 0;   // TMA path: chunks issued by this warp (staging buffer = n_chunks & 1)
-    uint8_t* my_stage = epi_stage + (warp - 4) * 8192;
+    uint32_t n_chunks = 0;   // TMA path: chunks issued by this warp
+    uint8_t* my_stage = epi_stage + (half * 4 + q) * 4096;   // one 32 x 128 B staging tile per epilogue warp
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -406,7 +415,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // the bias of the first chunk is fetched before the accumulator is waited for (overlaps the main loop)
         float bnext = 0.f;
         {
-          const int c = tn * BLOCK_N + lane;
+          const int c = tn * BLOCK_N + c_begin + lane;
           if (add_bias && c < p.N) bnext = __ldg(p.bias + c);
         }
         mbar_wait(&tmem_full[acc], acc_phase, 4);
@@ -414,7 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (it == 0 && warp == 4 && lane == 0) MVF_STAMP(4);
         if (has_k && row0 < p.M) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             const int col0 = tn * BLOCK_N + c0;
             if (col0 >= p.N) break;  // warp-uniform
             uint32_t r[32];
@@ -422,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const float bcur = bnext;
             {
               const int c = col0 + 32 + lane;
-              bnext = (add_bias && c0 + 32 < BLOCK_N && c < p.N) ? __ldg(p.bias + c) : 0.f;
+              bnext = (add_bias && c0 + 32 < c_end && c < p.N) ? __ldg(p.bias + c) : 0.f;
             }
             tmem_ld_wait();
             float v[32];
@@ -458,9 +467,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
               }
             }
-            uint8_t* sb = my_stage + (n_chunks & 1) * 4096;
-            if (n_chunks >= 2) {   // the store that last read this buffer (two chunks ago) must have drained it
-              if (lane == 0) bulk_wait_read_1();
+            uint8_t* sb = my_stage;
+            if (n_chunks >= 1) {   // the previous store of this warp must have drained the staging tile
+              if (lane == 0) bulk_wait_read_0();
               __syncwarp();
             }
 #pragma unroll
@@ -487,7 +496,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tcgen05_fence_after();
       if (it == 0 && warp == 4 && lane == 0) MVF_STAMP(4);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         const int col0 = tn * BLOCK_N + c0;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
@@ -648,7 +657,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   }
   int work = p.tiles_m * p.tiles_n * p.split_k;
   int grid = work < num_sms ? work : num_sms;
-  gemm_tc_kernel<BLOCK_N, STAGES, EB, SPLIT><<<grid, SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS, smem, st>>>(ma, mb, mc, p);
+  gemm_tc_kernel<BLOCK_N, STAGES, EB, SPLIT><<<grid, (SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS) + EXTRA_EPI_THREADS, smem, st>>>(ma, mb, mc, p);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
