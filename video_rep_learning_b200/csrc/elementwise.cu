@@ -204,7 +204,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ dz_in,
                                                      float* __restrict__ dz_out, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int64_t rows, int H) {
+                                                     float* __restrict__ dbeta, int64_t rows, int H,
+                                                     float* __restrict__ drop_out, float p, float inv_keep, uint64_t seed,
+                                                     int site) {
   extern __shared__ float acc[];  // [8 warps][2][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float gam[VPL], ag[VPL], ab[VPL];
@@ -237,6 +239,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       float v = rs * (d[k] * gam[k] - s1 - xh[k] * s2);
       if (dz_in) v += dz_in[row * H + c];
       dz_out[row * H + c] = v;
+      // the gradient that enters the next residual branch is dz masked by that branch's dropout: written here instead of
+      // by a separate dropout_cast launch
+      if (drop_out) drop_out[row * H + c] = p > 0.f ? v * drop_scale(seed, site, (uint64_t)(row * H + c), p, inv_keep) : v;
     }
   }
 #pragma unroll
@@ -258,14 +263,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 }
 
 int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd, const float* gamma,
-           const float* dz_in, float* dz_out, float* dgamma, float* dbeta, int64_t rows, int H, cudaStream_t st) {
+           const float* dz_in, float* dz_out, float* dgamma, float* dbeta, int64_t rows, int H, cudaStream_t st,
+           float* drop_out, float p, uint64_t seed, int site) {
+  const float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
   int grid = cdiv(rows, 8 * 2);
   if (grid > 592) grid = 592;
   if (grid < 1) grid = 1;
   size_t smem = (size_t)8 * 2 * H * sizeof(float);
   MVF_REQUIRE(H % 32 == 0 && H <= 1024 && smem <= 48 * 1024, MVF_ERR_UNSUPPORTED,
               "ln_bwd: hidden size %d must be a multiple of 32 and <= 768", H);
-#define MVF_LNB(V) ln_bwd_kernel<V><<<grid, 256, smem, st>>>(dr, z, mean, rstd, gamma, dz_in, dz_out, dgamma, dbeta, rows, H)
+#define MVF_LNB(V) ln_bwd_kernel<V><<<grid, 256, smem, st>>>(dr, z, mean, rstd, gamma, dz_in, dz_out, dgamma, dbeta, rows, H, drop_out, p, ik, seed, site)
   switch (H / 32) {
     case 1: MVF_LNB(1); break;
     case 2: MVF_LNB(2); break;

@@ -832,7 +832,8 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         void* dgA = c.W.p(lname(l, "dgA"));
         void* df = c.W.p(lname(l, "df"));
         void* dqkv = c.W.p(lname(l, "dqkv"));
-        MVF_TRY(dropout_cast(A, dz, dgF, m.rows, d.H, d.H, c.p, d.seed, SITE_ENC0 + 2 * l + 1, st));
+        // dgF = drop'(dz): written by the ln_bwd of the layer above (fused), by a stand-alone launch for the top layer
+        if (l == d.L - 1) MVF_TRY(dropout_cast(A, dz, dgF, m.rows, d.H, d.H, c.p, d.seed, SITE_ENC0 + 2 * l + 1, st));
         MVF_TRY(c.linear_dw(m.rows, d.H, d.DFF, dgF, d.H, c.S.p(lname(l, "f")), d.DFF, c.G.f(g + "w.2"), d.DFF,
                             c.G.f(g + "b.2")));
         MVF_TRY(c.linear_dx(A, m.rows, d.H, d.DFF, dgF, d.H, c.S.p(lname(l, "w.2")), d.DFF, df, d.DFF,
@@ -841,11 +842,12 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
                             c.G.f(g + "b.1")));
         MVF_TRY(c.linear_dx(MVF_F32, m.rows, d.DFF, d.H, df, d.DFF, c.S.p(lname(l, "w.1")), d.H, c.W.p("dr"), d.H));
         const float* ln1 = c.S.f(lname(l, "ln1"));
+        // ... and the masked copy the attention branch consumes (dgA = drop'(dz_out), site 2l) comes out of the same launch
         MVF_TRY(ln_bwd(c.W.f("dr"), c.S.f("z" + std::to_string(2 * l + 1)), ln1, ln1 + m.rows, c.P[b + L_LN1W], dz,
-                       dz_other, c.G.f(g + "ln1w"), c.G.f(g + "ln1b"), m.rows, d.H, st));
+                       dz_other, c.G.f(g + "ln1w"), c.G.f(g + "ln1b"), m.rows, d.H, st, (float*)dgA, c.p, d.seed,
+                       SITE_ENC0 + 2 * l));
         std::swap(dz, dz_other);
         // attention branch: z[2l+1] = z[2l] + drop(Wo ctx + bo)
-        MVF_TRY(dropout_cast(A, dz, dgA, m.rows, d.H, d.H, c.p, d.seed, SITE_ENC0 + 2 * l, st));
         MVF_TRY(c.linear_dw(m.rows, d.H, d.H, dgA, d.H, c.S.p(lname(l, "ctx")), d.H, c.G.f(g + "w.o"), d.H,
                             c.G.f(g + "b.o")));
         MVF_TRY(c.linear_dx(A, m.rows, d.H, d.H, dgA, d.H, c.S.p(lname(l, "w.o")), d.H, c.W.p("dctx"), d.H));
@@ -856,8 +858,11 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         MVF_TRY(c.linear_dx(MVF_F32, m.rows, 3 * d.H, d.H, dqkv, 3 * d.H, c.S.p(lname(l, "w.qkv")), d.H,
                             c.W.p("dr"), d.H));
         const float* ln0 = c.S.f(lname(l, "ln0"));
+        // the layer below consumes drop'(dz_out) with the site of ITS FFN branch (2(l-1)+1)
+        float* next_dgF = l > 0 ? (float*)c.W.p(lname(l - 1, "dgF")) : nullptr;
         MVF_TRY(ln_bwd(c.W.f("dr"), c.S.f("z" + std::to_string(2 * l)), ln0, ln0 + m.rows, c.P[b + L_LN0W], dz, dz_other,
-                       c.G.f(g + "ln0w"), c.G.f(g + "ln0b"), m.rows, d.H, st));
+                       c.G.f(g + "ln0w"), c.G.f(g + "ln0b"), m.rows, d.H, st, next_dgF, c.p, d.seed,
+                       SITE_ENC0 + 2 * (l - 1) + 1));
         std::swap(dz, dz_other);
       }
       // ---- positional encoding (+dropout) and video_emb ----

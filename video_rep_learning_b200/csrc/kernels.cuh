@@ -33,8 +33,10 @@ int ln_fwd(int dtype_out, const float* z_in, const float* o, float* z_out, void*
            const float* gamma, const float* beta, int64_t rows, int H, float eps, float p, uint64_t seed, int site,
            cudaStream_t st);
 // dz_out = dz_in + LN'(dr); dgamma/dbeta accumulated (atomics). dz_in may be null (treated as 0).
+// drop_out (optional): also writes dz_out * dropmask(site) -- the masked gradient the next residual branch consumes.
 int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd, const float* gamma,
-           const float* dz_in, float* dz_out, float* dgamma, float* dbeta, int64_t rows, int H, cudaStream_t st);
+           const float* dz_in, float* dz_out, float* dgamma, float* dbeta, int64_t rows, int H, cudaStream_t st,
+           float* drop_out = nullptr, float p = 0.f, uint64_t seed = 0, int site = 0);
 
 // ---- BatchNorm1d (+ReLU +dropout) in training / eval mode ---------------------------------------------
 // The statistics are produced in three launches so that a multi-GPU caller can all-reduce `sums` in between:
