@@ -20,6 +20,13 @@ struct UnpackTable {
 __global__ void pack_kernel(const PackTable tab) {
   const PackEntry& en = tab.e[blockIdx.y];
   const int64_t total = (int64_t)en.rows * en.ld_dst;
+  if (en.dst_bf16 == 0 && en.ld_dst == en.cols && (total & 3) == 0 && ((((uintptr_t)en.src) | ((uintptr_t)en.dst)) & 15) == 0) {
+    // plain fp32 copy of a dense matrix: 16-byte vectors, no index arithmetic
+    const float4* s4 = reinterpret_cast<const float4*>(en.src);
+    float4* d4 = reinterpret_cast<float4*>(en.dst);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (total >> 2); i += (int64_t)gridDim.x * blockDim.x) d4[i] = s4[i];
+    return;
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int r = (int)(i / en.ld_dst), c = (int)(i - (int64_t)r * en.ld_dst);
     float v = c < en.cols ? en.src[(int64_t)r * en.cols + c] : 0.f;
@@ -49,6 +56,15 @@ int pack_params(const PackEntry* entries, int n, cudaStream_t st) {
 __global__ void unpack_kernel(const UnpackTable tab, float scale) {
   const UnpackEntry& en = tab.e[blockIdx.y];
   const int64_t total = (int64_t)en.rows * en.cols;
+  if (en.ld_src == en.cols && (total & 3) == 0 && ((((uintptr_t)en.src) | ((uintptr_t)en.dst)) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(en.src);
+    float4* d4 = reinterpret_cast<float4*>(en.dst);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (total >> 2); i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 v = s4[i];
+      d4[i] = make_float4(scale * v.x, scale * v.y, scale * v.z, scale * v.w);
+    }
+    return;
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int r = (int)(i / en.cols), c = (int)(i - (int64_t)r * en.cols);
     en.dst[i] = scale * en.src[(int64_t)r * en.ld_src + c];
