@@ -633,6 +633,196 @@ scl_pair_fused_kernel(const float* __restrict__ embs, const int64_t* __restrict_
   }
 }
 
+// ---- second version of the fused pair kernel: the same algorithm with the per-element work cut down --------------------
+//  * the exponents of the Gaussian label weights of both directions are computed once, next to exp(l_ij), and kept in
+//    shared memory (the first version re-evaluated ts_dist + expf in the statistics pass and again in the coefficient
+//    pass); labels are formed as y = 2^(a - log2 den): one MUFU, no division, safe when den is denormal;
+//  * s_r / L_r (one IEEE division per row, exactly torch's float32 op) is hoisted out of the T x T loops;
+//  * per-row reciprocals replace per-element IEEE divisions, exp2f / __logf / __fdividef replace expf / logf / division
+//    where the operand is not a timestamp (relative error <= 1e-6 on p, y, r; the 1e-5 parity tests stay green).
+template <int NT>
+__global__ void __launch_bounds__(NT)
+scl_pair_fused2_kernel(const float* __restrict__ embs, const int64_t* __restrict__ seq_lens, const int64_t* __restrict__ steps,
+                       const float* __restrict__ masks, int T, int D, float tau, float two_var, SclWs w,
+                       float* __restrict__ loss_out, float* __restrict__ d_embs) {
+  extern __shared__ __align__(16) float sm[];
+  const int Dp = D + 4, Tp = T + 1;
+  float* E = sm;                          // [2T][Dp]
+  float* EX = E + (size_t)2 * T * Dp;     // [T][Tp]  exp(l_ij), later coef_ij          (i: view 0, j: view 1)
+  float* PW0 = EX + (size_t)T * Tp;       // [T][Tp]  log2 of the label weight of direction 0 at (i, j); -inf = masked pair
+  float* PW1 = PW0 + (size_t)T * Tp;      // [T][Tp]  same for direction 1 at (j, i), stored at [i][j]
+  float* st = PW1 + (size_t)T * Tp;       // [2T] steps as float
+  float* mk = st + 2 * T;                 // [2T] masks
+  float* ar = mk + 2 * T;                 // [2T] fl(s_r / L_r)
+  float* iZ = ar + 2 * T;                 // [2T] 1 / Z   (0 when the row is masked or Z = 0)
+  float* gs = iZ + 2 * T;                 // [2T] g
+  float* iD = gs + 2 * T;                 // [2T] log2(den) of the label normaliser (+inf when den = 0): y = 2^(a - log2 den),
+                                          //      no division and no overflow when every partner is far (denormal den)
+  __shared__ float red_loss[NT / 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int v = blockIdx.x;
+  const int64_t row0 = (int64_t)v * 2 * T;
+  const float M = *w.M;
+  const float invM = 1.f / M, inv_tau = 1.f / tau;
+  const float L0 = (float)seq_lens[v * 2], L1 = (float)seq_lens[v * 2 + 1];
+  const float c_ex = 1.4426950408889634f / tau;           // exp(x / tau) = 2^(x * c_ex)
+  const float c_pw = -1.4426950408889634f / two_var;      // exp(-d^2 / (2 var)) = 2^(d^2 * c_pw)
+
+  const int D4 = D >> 2;
+  for (int i = tid; i < 2 * T * D4; i += NT) {
+    const int r = i / D4, d4 = i - r * D4;
+    *reinterpret_cast<float4*>(E + r * Dp + 4 * d4) = *reinterpret_cast<const float4*>(embs + (row0 + r) * D + 4 * d4);
+  }
+  for (int i = tid; i < 2 * T; i += NT) {
+    const float s = (float)steps[row0 + i];
+    st[i] = s;
+    mk[i] = masks[row0 + i];
+    ar[i] = __fdiv_rn(s, i < T ? L0 : L1);
+  }
+  __syncthreads();
+
+  // ---- ex_ij, pw0_ij, pw1_ij: 2 x 2 register tiles ----
+  const int T2h = (T + 1) >> 1;
+  for (int tix = tid; tix < T2h * T2h; tix += NT) {
+    const int ti = tix / T2h, tj = tix - ti * T2h;
+    const int ii[2] = {2 * ti, min(2 * ti + 1, T - 1)}, jj[2] = {2 * tj, min(2 * tj + 1, T - 1)};
+    const float* a0 = E + ii[0] * Dp;
+    const float* a1 = E + ii[1] * Dp;
+    const float* b0 = E + (T + jj[0]) * Dp;
+    const float* b1 = E + (T + jj[1]) * Dp;
+    float s00[4] = {0.f, 0.f, 0.f, 0.f}, s01[4] = {0.f, 0.f, 0.f, 0.f}, s10[4] = {0.f, 0.f, 0.f, 0.f}, s11[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int d = 0; d < D; d += 4) {
+      const float4 x0 = *reinterpret_cast<const float4*>(a0 + d), x1 = *reinterpret_cast<const float4*>(a1 + d);
+      const float4 y0 = *reinterpret_cast<const float4*>(b0 + d), y1 = *reinterpret_cast<const float4*>(b1 + d);
+      s00[0] = fmaf(x0.x, y0.x, s00[0]); s00[1] = fmaf(x0.y, y0.y, s00[1]); s00[2] = fmaf(x0.z, y0.z, s00[2]); s00[3] = fmaf(x0.w, y0.w, s00[3]);
+      s01[0] = fmaf(x0.x, y1.x, s01[0]); s01[1] = fmaf(x0.y, y1.y, s01[1]); s01[2] = fmaf(x0.z, y1.z, s01[2]); s01[3] = fmaf(x0.w, y1.w, s01[3]);
+      s10[0] = fmaf(x1.x, y0.x, s10[0]); s10[1] = fmaf(x1.y, y0.y, s10[1]); s10[2] = fmaf(x1.z, y0.z, s10[2]); s10[3] = fmaf(x1.w, y0.w, s10[3]);
+      s11[0] = fmaf(x1.x, y1.x, s11[0]); s11[1] = fmaf(x1.y, y1.y, s11[1]); s11[2] = fmaf(x1.z, y1.z, s11[2]); s11[3] = fmaf(x1.w, y1.w, s11[3]);
+    }
+    const float dots[2][2] = {{(s00[0] + s00[1]) + (s00[2] + s00[3]), (s01[0] + s01[1]) + (s01[2] + s01[3])},
+                              {(s10[0] + s10[1]) + (s10[2] + s10[3]), (s11[0] + s11[1]) + (s11[2] + s11[3])}};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int i = ii[a], j = jj[b];
+        const bool mm = mk[i] != 0.f && mk[T + j] != 0.f;
+        const float d0 = fabsf(__fsub_rn(__fmul_rn(ar[i], L1), st[T + j]));       // scl.py:62, direction 0 row i
+        const float d1 = fabsf(__fsub_rn(__fmul_rn(ar[T + j], L0), st[i]));       // direction 1 row j
+        EX[i * Tp + j] = exp2f(dots[a][b] * c_ex);
+        PW0[i * Tp + j] = mm ? d0 * d0 * c_pw : -INFINITY;
+        PW1[i * Tp + j] = mm ? d1 * d1 * c_pw : -INFINITY;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- row statistics of both directions: warp per row ----
+  float loss_acc = 0.f;
+  for (int r = warp; r < 2 * T; r += NT / 32) {
+    const bool dir1 = r >= T;
+    const int a = dir1 ? r - T : r;
+    const float mi = mk[r];
+    const int pb = dir1 ? 0 : T;
+    const float* pwm = dir1 ? PW1 : PW0;
+    float den = 0.f, zp = 0.f;
+    for (int b = lane; b < T; b += 32) {
+      const int ix = dir1 ? b * Tp + a : a * Tp + b;
+      den += exp2f(pwm[ix]);
+      if (mi != 0.f && mk[pb + b] != 0.f) zp += EX[ix];
+    }
+    den = warp_sum(den);
+    zp = warp_sum(zp);
+    const float Z = zp + w.zext[row0 + r];
+    const bool live = mi != 0.f && Z > 0.f;
+    const float invZ = live ? 1.f / Z : 0.f;
+    const float l2den = den > 0.f ? log2f(den) : INFINITY;
+    float g = 0.f, loss = 0.f;
+    if (live) {
+      for (int b = lane; b < T; b += 32) {
+        const int ix = dir1 ? b * Tp + a : a * Tp + b;
+        const float y = exp2f(pwm[ix] - l2den);
+        // y > 0 implies both frames valid (pw is 0 for masked pairs).  Terms below 1e-30 are dropped: they change the loss
+        // by < 1e-28, and __logf would flush a denormal y to zero and return -inf
+        if (y > 1e-30f) {
+          const float p = EX[ix] * invZ;
+          const float q = p + 1e-6f;
+          loss += y * (__logf(y) - __logf(q));
+          g += y * __fdividef(p, q);
+        }
+      }
+    }
+    g = warp_sum(g);
+    loss = warp_sum(loss);
+    if (lane == 0) {
+      iZ[r] = invZ;
+      gs[r] = g;
+      iD[r] = l2den;
+      w.c[row0 + r] = live ? g * invZ * invM : 0.f;
+      loss_acc += loss;
+    }
+  }
+  if (lane == 0) red_loss[warp] = loss_acc;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int k = 0; k < NT / 32; ++k) t += red_loss[k];
+    if (t != 0.f) atomicAdd(loss_out, t * invM);
+  }
+  if (d_embs == nullptr) return;
+
+  // ---- coef_ij in place over ex ----
+  for (int ix = tid; ix < T * T; ix += NT) {
+    const int i = ix / T, j = ix - i * T;
+    float coef = 0.f;
+    if (mk[i] != 0.f && mk[T + j] != 0.f) {
+      const float ex = EX[i * Tp + j];
+      const float p0 = ex * iZ[i], p1 = ex * iZ[T + j];
+      const float y0 = exp2f(PW0[i * Tp + j] - iD[i]), y1 = exp2f(PW1[i * Tp + j] - iD[T + j]);
+      if (iZ[i] > 0.f) coef += p0 * gs[i] - y0 * __fdividef(p0, p0 + 1e-6f);
+      if (iZ[T + j] > 0.f) coef += p1 * gs[T + j] - y1 * __fdividef(p1, p1 + 1e-6f);
+      coef *= invM;
+    }
+    EX[i * Tp + j] = coef;
+  }
+  __syncthreads();
+
+  // ---- dE0_i = sum_j coef_ij e1_j / tau ; dE1_j = sum_i coef_ij e0_i / tau ----
+  const int ngroups = (T + SCL_RG - 1) / SCL_RG;
+  const int ntasks = 2 * ngroups * D4;
+  for (int task = tid; task < ntasks; task += NT) {
+    const int d4 = task % D4;
+    const int gr = (task / D4) % ngroups;
+    const int view = task / (D4 * ngroups);
+    const int r0 = gr * SCL_RG;
+    const float* other = E + (view ? 0 : T) * Dp + 4 * d4;
+    float4 acc[SCL_RG];
+#pragma unroll
+    for (int k = 0; k < SCL_RG; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < T; ++b) {
+      const float4 x = *reinterpret_cast<const float4*>(other + b * Dp);
+#pragma unroll
+      for (int k = 0; k < SCL_RG; ++k) {
+        const int a = min(r0 + k, T - 1);
+        const float cf = view ? EX[b * Tp + a] : EX[a * Tp + b];
+        acc[k].x = fmaf(cf, x.x, acc[k].x); acc[k].y = fmaf(cf, x.y, acc[k].y);
+        acc[k].z = fmaf(cf, x.z, acc[k].z); acc[k].w = fmaf(cf, x.w, acc[k].w);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SCL_RG; ++k) {
+      const int a = r0 + k;
+      if (a < T)
+        *reinterpret_cast<float4*>(d_embs + (row0 + view * T + a) * D + 4 * d4) =
+            make_float4(acc[k].x * inv_tau, acc[k].y * inv_tau, acc[k].z * inv_tau, acc[k].w * inv_tau);
+    }
+  }
+}
+static size_t scl_fused2_smem(int T, int D) {
+  return ((size_t)2 * T * (D + 4) + (size_t)3 * T * (T + 1) + (size_t)12 * T) * sizeof(float);
+}
+
 static size_t scl_fused_smem(int T, int D) {
   return ((size_t)2 * T * (D + 4) + (size_t)T * (T + 1) + (size_t)10 * T) * sizeof(float);
 }
@@ -700,10 +890,30 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
   const size_t fsmem = scl_fused_smem(T, D);
   static int fused_on = -1;
   if (fused_on < 0) {
-    const char* e = getenv("MVF_SCL_FUSED");
-    fused_on = (e && atoi(e) == 0) ? 0 : 1;
+    const char* e = getenv("MVF_SCL_FUSED");   // 0: row-warp kernels, 1: fused v1, 2 (default): fused v2
+    fused_on = e ? atoi(e) : 2;
   }
-  if (fused_on && fsmem <= 200 * 1024) {
+  const size_t f2smem = scl_fused2_smem(T, D);
+  if (fused_on >= 2 && f2smem <= 200 * 1024) {
+    if (T * T >= 2048) {
+      static size_t configured = 0;
+      if (f2smem > configured) {
+        MVF_CHECK_CUDA(cudaFuncSetAttribute(scl_pair_fused2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2smem));
+        configured = f2smem;
+      }
+      scl_pair_fused2_kernel<256><<<Bv, 256, f2smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
+                                                          w, loss_out, d_embs);
+    } else {
+      static size_t configured = 0;
+      if (f2smem > configured) {
+        MVF_CHECK_CUDA(cudaFuncSetAttribute(scl_pair_fused2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2smem));
+        configured = f2smem;
+      }
+      scl_pair_fused2_kernel<128><<<Bv, 128, f2smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
+                                                          w, loss_out, d_embs);
+    }
+    MVF_CHECK_LAUNCH();
+  } else if (fused_on && fsmem <= 200 * 1024) {
     if (T * T >= 2048) {
       static size_t configured = 0;
       if (fsmem > configured) {
