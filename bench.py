@@ -258,8 +258,70 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return dict(ms_step=float(t.item()) / steps, launches=launches, prof=prof, clocks=clk, loss=float(loss.item()))
 
+    def read_prof():
+        buf = (ctypes.c_float * 512)()
+        n = ctypes.c_int(0)
+        prof = {}
+        for tag in range(6):
+            lib.mvf_profile_read(tag, buf, 512, ctypes.byref(n))
+            prof[tag] = [buf[i] for i in range(n.value)]
+        return prof
+
+    def graph_region(pool_mode, steps, warmup, sample_clocks):
+        """The same step captured once as a CUDA graph (video_rep_learning_b200.graph.GraphedTrainStep) and replayed:
+        W untimed + K timed replays, tokens resident in HBM, CUDA events, max over ranks.  The library's event brackets
+        around the dominant kernels are part of the graph (external event-record nodes); they are read after the timed
+        region from extra replays, one synchronisation per replay."""
+        from video_rep_learning_b200.graph import GraphedTrainStep
+        head_opts.pool_mode = pool_mode
+        gs = GraphedTrainStep(model, algo, Bv, T, P, C_in, dtype=torch.bfloat16, device=dev)
+        gs.adopt_tokens(tokens_dev)
+        gs.set_inputs(seq_lens=seq_lens_d, steps=steps_d, masks=masks_d)
+        gs.capture(profile=True)
+        for _ in range(warmup):
+            gs()
+        sync_all()
+        clocks = ClockSampler(local_rank)
+        if sample_clocks and rank == 0:
+            clocks.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        for _ in range(steps):
+            loss = gs()
+        ev1.record()
+        sync_all()
+        ms_total = ev0.elapsed_time(ev1)
+        clk = clocks.stop() if (sample_clocks and rank == 0) else None
+        prof = {tag: [] for tag in range(6)}
+        for _ in range(min(steps, 20)):
+            gs()
+            torch.cuda.synchronize()
+            for tag, vals in read_prof().items():
+                prof[tag] += vals
+        lib.mvf_profile_enable(0)
+        final = float(loss.item())
+        launches = gs.launches_per_step * steps
+        gs.release()
+        t = torch.tensor([ms_total], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dict(ms_step=float(t.item()) / steps, launches=launches, prof=prof, clocks=clk, loss=final)
+
     pool_default = L.POOL_DENSE if args.pool == "dense" else L.POOL_FOLDED
-    main_run = timed_region(pool_default, args.steps, max(args.warmup, 3), True)
+    graph_note = None
+    eager_run = None
+    if args.eager:
+        main_run = timed_region(pool_default, args.steps, max(args.warmup, 3), True)
+    else:
+        try:
+            main_run = graph_region(pool_default, args.steps, max(args.warmup, 3), True)
+            graph_note = "one cudaGraphLaunch per step (GraphedTrainStep)"
+            eager_run = timed_region(pool_default, max(3, min(args.steps, 20)), 3, False)
+        except Exception as e:  # capture refused (e.g. a collective that cannot be captured): fall back to eager launches
+            graph_note = f"capture failed, eager launches timed instead: {type(e).__name__}: {str(e)[:200]}"
+            torch.cuda.synchronize()
+            main_run = timed_region(pool_default, args.steps, max(args.warmup, 3), True)
     ms_step, launches, prof, clk, final_loss = (main_run["ms_step"], main_run["launches"], main_run["prof"],
                                                 main_run["clocks"], main_run["loss"])
     value = world * Bv / (ms_step / 1e3)
@@ -412,7 +474,11 @@ def run_ours(args):
                                l2="inputs (1.16 GB of tokens per step) larger than L2; no flush needed",
                                parallelism=f"dp{world} (video shards; BN statistics + one flat gradient all-reduce)"),
                    as_written_tflops=whole, gflop_per_video_as_written=fl["total"] / 1e9, loss=final_loss,
-                   pooling=args.pool, roofline=roof, dense_path=dense, cpu_baseline=cpu,
+                   pooling=args.pool, launch_mode=("eager" if args.eager else "cuda_graph"), launch_note=graph_note,
+                   eager=None if eager_run is None else dict(
+                       value=world * Bv / (eager_run["ms_step"] / 1e3), unit=UNIT, ms_per_step=eager_run["ms_step"],
+                       note="same step issued kernel by kernel through the drop-in Python API (no graph)"),
+                   roofline=roof, dense_path=dense, cpu_baseline=cpu,
                    e2e=None if args.no_e2e else dict(
                        value=e2e_value, unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=k2,
                        note="pinned host tokens -> HBM on a copy stream (double buffered) + loss.item() per step"),
@@ -432,6 +498,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="profiling runs: skip the CPU baseline sample")
     ap.add_argument("--pool", default="folded", choices=["folded", "dense"],
                     help="entity pooling: folded (default product path) or dense (as written: K|V GEMM + attention)")
+    ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-dense", action="store_true", help="skip the short as-written (dense pooling) comparison leg")
     args = ap.parse_args()
     if args.impl == "reference":

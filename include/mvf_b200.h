@@ -81,6 +81,9 @@ typedef struct mvf_head_desc {
   float drop_p;         /* FC_DROPOUT_RATE (applied only when training)                            */
   float ln_eps, bn_eps, bn_momentum;
   uint64_t seed;        /* dropout stream of this step (counter-based, same in fwd and bwd)        */
+  const uint64_t* seed_dev; /* optional DEVICE counter added to `seed` inside the kernels (NULL = none): */
+                        /* a CUDA-graph-captured step freezes `seed`, so the caller advances *seed_dev  */
+                        /* on the device once per replay to keep drawing fresh dropout masks            */
 } mvf_head_desc;
 
 /* ---- library / bookkeeping ------------------------------------------------------------------------ */

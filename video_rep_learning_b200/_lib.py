@@ -34,7 +34,7 @@ class HeadDesc(C.Structure):
         ("train_frames", C.c_int32), ("dtype", C.c_int32), ("training", C.c_int32), ("has_mask", C.c_int32),
         ("gemm_backend", C.c_int32), ("world_size", C.c_int32), ("pool_mode", C.c_int32),
         ("drop_p", C.c_float), ("ln_eps", C.c_float), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
-        ("seed", C.c_uint64),
+        ("seed", C.c_uint64), ("seed_dev", C.c_void_p),
     ]
 
 

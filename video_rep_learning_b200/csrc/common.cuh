@@ -81,6 +81,17 @@ __host__ __device__ __forceinline__ float drop_scale(uint64_t seed, int site, ui
   float u = (float)(h >> 8) * (1.0f / 16777216.0f);
   return u >= p ? inv_keep : 0.0f;
 }
+// Dropout stream of one step = host value + optional device-resident counter.  The device half exists for CUDA-graph
+// replay: kernel arguments are frozen at capture time, so a captured step advances `*dev` on the device (one tiny
+// launch per replay) and every replay still draws a fresh mask.  Forward and backward of one step read the same value.
+struct DropSeed {
+  uint64_t base;
+  const uint64_t* dev;
+  __host__ __device__ DropSeed(uint64_t b = 0, const uint64_t* d = nullptr) : base(b), dev(d) {}
+};
+__device__ __forceinline__ float drop_scale(DropSeed s, int site, uint64_t idx, float p, float inv_keep) {
+  return drop_scale(s.base + (s.dev ? __ldg(s.dev) : 0ull), site, idx, p, inv_keep);
+}
 
 enum DropSite { SITE_FC0 = 0, SITE_POS = 8, SITE_ENC0 = 16 };
 

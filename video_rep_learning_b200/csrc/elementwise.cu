@@ -106,7 +106,7 @@ int posenc_table(float* table, int T, int H, int train_frames, cudaStream_t st) 
 }
 
 __global__ void posenc_add_kernel(const float* __restrict__ h3, const float* __restrict__ table, float* __restrict__ z,
-                                  int BV, int T, int E, int H, float p, float inv_keep, uint64_t seed) {
+                                  int BV, int T, int E, int H, float p, float inv_keep, DropSeed seed) {
   int64_t total = (int64_t)BV * E * T * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % H);
@@ -119,7 +119,7 @@ __global__ void posenc_add_kernel(const float* __restrict__ h3, const float* __r
     z[i] = v;
   }
 }
-int posenc_add(const float* h3, const float* table, float* z, int BV, int T, int E, int H, float p, uint64_t seed,
+int posenc_add(const float* h3, const float* table, float* z, int BV, int T, int E, int H, float p, DropSeed seed,
                cudaStream_t st) {
   int64_t total = (int64_t)BV * E * T * H;
   int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
@@ -130,7 +130,7 @@ int posenc_add(const float* h3, const float* table, float* z, int BV, int T, int
 
 template <typename TO>
 __global__ void posenc_bwd_kernel(const float* __restrict__ dz, TO* __restrict__ dh3, int BV, int T, int E, int H,
-                                  float p, float inv_keep, uint64_t seed) {
+                                  float p, float inv_keep, DropSeed seed) {
   int64_t total = (int64_t)BV * E * T * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % H);
@@ -143,7 +143,7 @@ __global__ void posenc_bwd_kernel(const float* __restrict__ dz, TO* __restrict__
     dh3[(((int64_t)b * T + t) * E + e) * H + c] = from_f<TO>(v);
   }
 }
-int posenc_bwd(int dtype_out, const float* dz, void* dh3, int BV, int T, int E, int H, float p, uint64_t seed,
+int posenc_bwd(int dtype_out, const float* dz, void* dh3, int BV, int T, int E, int H, float p, DropSeed seed,
                cudaStream_t st) {
   int64_t total = (int64_t)BV * E * T * H;
   int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ z
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      int64_t rows, int H, float eps, float p, float inv_keep,
-                                                     uint64_t seed, int site) {
+                                                     DropSeed seed, int site) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ z
 }
 
 int ln_fwd(int dtype_out, const float* z_in, const float* o, float* z_out, void* r, float* mean, float* rstd,
-           const float* gamma, const float* beta, int64_t rows, int H, float eps, float p, uint64_t seed, int site,
+           const float* gamma, const float* beta, int64_t rows, int H, float eps, float p, DropSeed seed, int site,
            cudaStream_t st) {
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
   int grid = cdiv(rows, 8);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ gamma, const float* __restrict__ dz_in,
                                                      float* __restrict__ dz_out, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, int64_t rows, int H,
-                                                     float* __restrict__ drop_out, float p, float inv_keep, uint64_t seed,
+                                                     float* __restrict__ drop_out, float p, float inv_keep, DropSeed seed,
                                                      int site) {
   extern __shared__ float acc[];  // [8 warps][2][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 
 int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd, const float* gamma,
            const float* dz_in, float* dz_out, float* dgamma, float* dbeta, int64_t rows, int H, cudaStream_t st,
-           float* drop_out, float p, uint64_t seed, int site) {
+           float* drop_out, float p, DropSeed seed, int site) {
   const float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
   int grid = cdiv(rows, 8 * 2);
   if (grid > 592) grid = 592;
@@ -375,7 +375,7 @@ int bn_finalize(const double* sums, int C, double n_global, float eps, int train
 template <typename TO>
 __global__ void bn_apply_kernel(const float* __restrict__ x, int64_t R, int C, const float* __restrict__ mi,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                                TO* __restrict__ out, int64_t ld_out, float p, float inv_keep, uint64_t seed, int site) {
+                                TO* __restrict__ out, int64_t ld_out, float p, float inv_keep, DropSeed seed, int site) {
   int64_t total = R * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -387,7 +387,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, int64_t R, int C, c
   }
 }
 int bn_apply(int dtype_out, const float* x, int64_t R, int C, const float* mi, const float* gamma, const float* beta,
-             int relu, void* out, int64_t ld_out, float p, uint64_t seed, int site, cudaStream_t st) {
+             int relu, void* out, int64_t ld_out, float p, DropSeed seed, int site, cudaStream_t st) {
   int64_t total = R * C;
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
@@ -403,7 +403,7 @@ int bn_apply(int dtype_out, const float* x, int64_t R, int C, const float* mi, c
 __global__ void __launch_bounds__(256)
 bn_bwd_stats_kernel(const float* __restrict__ d_out, int64_t ld_d, const float* __restrict__ x, int64_t R, int C,
                     const float* __restrict__ mi, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    int relu, float p, float inv_keep, uint64_t seed, int site, double* __restrict__ bsums,
+                    int relu, float p, float inv_keep, DropSeed seed, int site, double* __restrict__ bsums,
                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ double sh[2][8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -432,7 +432,7 @@ bn_bwd_stats_kernel(const float* __restrict__ d_out, int64_t ld_d, const float* 
   }
 }
 int bn_bwd_stats(const float* d_out, int64_t ld_d, const float* x, int64_t R, int C, const float* mi,
-                 const float* gamma, const float* beta, int relu, float p, uint64_t seed, int site, double* bsums,
+                 const float* gamma, const float* beta, int relu, float p, DropSeed seed, int site, double* bsums,
                  float* dgamma, float* dbeta, cudaStream_t st) {
   int gy = cdiv(R, 8 * 16);
   if (gy > 64) gy = 64;
@@ -448,7 +448,7 @@ int bn_bwd_stats(const float* d_out, int64_t ld_d, const float* x, int64_t R, in
 template <typename TO>
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ d_out, int64_t ld_d, const float* __restrict__ x,
                                     int64_t R, int C, const float* __restrict__ mi, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, int relu, float p, float inv_keep, uint64_t seed,
+                                    const float* __restrict__ beta, int relu, float p, float inv_keep, DropSeed seed,
                                     int site, const double* __restrict__ bsums, double n, TO* __restrict__ dx,
                                     int64_t ld_dx) {
   int64_t total = R * C;
@@ -466,7 +466,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ d_out, int64_t ld_
   }
 }
 int bn_bwd_apply(int dtype_out, const float* d_out, int64_t ld_d, const float* x, int64_t R, int C, const float* mi,
-                 const float* gamma, const float* beta, int relu, float p, uint64_t seed, int site, const double* bsums,
+                 const float* gamma, const float* beta, int relu, float p, DropSeed seed, int site, const double* bsums,
                  double n_global, void* dx, int64_t ld_dx, cudaStream_t st) {
   int64_t total = R * C;
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
@@ -552,7 +552,7 @@ int colsum(int dtype_in, const void* X, int64_t R, int C, int64_t ld, float* out
 
 template <typename TO>
 __global__ void dropout_cast_kernel(const float* __restrict__ in, TO* __restrict__ out, int64_t rows, int cols,
-                                    int64_t ld_out, float p, float inv_keep, uint64_t seed, int site) {
+                                    int64_t ld_out, float p, float inv_keep, DropSeed seed, int site) {
   int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     float v = in[i];
@@ -561,7 +561,7 @@ __global__ void dropout_cast_kernel(const float* __restrict__ in, TO* __restrict
   }
 }
 int dropout_cast(int dtype_out, const float* in, void* out, int64_t rows, int cols, int64_t ld_out, float p,
-                 uint64_t seed, int site, cudaStream_t st) {
+                 DropSeed seed, int site, cudaStream_t st) {
   int64_t total = rows * cols;
   if (total == 0) return MVF_OK;
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
@@ -577,11 +577,11 @@ int cast_f32(int dtype_out, const float* in, void* out, int64_t n, cudaStream_t 
   return dropout_cast(dtype_out, in, out, 1, (int)n, n, 0.f, 0, 0, st);
 }
 
-__global__ void dropout_mask_kernel(uint64_t seed, int site, int64_t total, float p, float inv_keep, float* out) {
+__global__ void dropout_mask_kernel(DropSeed seed, int site, int64_t total, float p, float inv_keep, float* out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = p > 0.f ? drop_scale(seed, site, (uint64_t)i, p, inv_keep) : 1.f;
 }
-int dropout_mask_export(uint64_t seed, int site, int64_t rows, int64_t cols, float p, float* out, cudaStream_t st) {
+int dropout_mask_export(DropSeed seed, int site, int64_t rows, int64_t cols, float p, float* out, cudaStream_t st) {
   int64_t total = rows * cols;
   if (total == 0) return MVF_OK;
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);

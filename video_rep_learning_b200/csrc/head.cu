@@ -49,12 +49,21 @@ struct ProfScope {
       }
       g_prof_init[tag][slot] = true;
     }
-    cudaEventRecord(g_prof_ev[tag][slot][0], st);
+    record(g_prof_ev[tag][slot][0]);
   }
   ~ProfScope() {
     if (slot < 0) return;
-    cudaEventRecord(g_prof_ev[tag][slot][1], st);
+    record(g_prof_ev[tag][slot][1]);
     g_prof_n[tag] = slot + 1;
+  }
+  // inside a stream capture a plain record is only a dependency edge; an EXTERNAL record becomes an event-record node
+  // that fires on every replay, so the pair can be read back with cudaEventElapsedTime after a graph launch
+  void record(cudaEvent_t e) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive)
+      cudaEventRecordWithFlags(e, st, cudaEventRecordExternal);
+    else
+      cudaEventRecord(e, st);
   }
 };
 
@@ -678,7 +687,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
           MVF_TRY(c.linear(MVF_F32, m.R, d.SPC, d.C_in, c.S.p("px"), d.C_in, c.P[m.iWv], d.C_in, c.P[m.ibv], c.S.p("ent32"),
                            d.SPC, 0, "w.v"));
           MVF_TRY(ent_finish_fwd(c.S.f("ent32"), c.S.f("h0"), m.ld0, m.R, d.SPC, d.E, d.one_hot == MVF_ONEHOT_POOL, c.p,
-                                 d.seed, st));
+                                 DropSeed(d.seed, d.seed_dev), st));
         }
       } else {
         // a4 as written: K|V projection of every patch token -- the dominant contraction
@@ -690,7 +699,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
         {
           ProfScope ps(2, st);
           MVF_TRY(xattn_pool_fwd(m.kvt, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], attn, c.S.p("h0"),
-                                 m.ld0, c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, st));
+                                 m.ld0, c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, DropSeed(d.seed, d.seed_dev), st));
         }
       }
       if (attn_out)
@@ -711,7 +720,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       // dropout of the NEXT FC layer is applied to this activation (fc_layers.{4i}: Dropout before Linear)
       const float pn = (i + 1 < d.n_fc) ? c.p : 0.f;
       MVF_TRY(bn_apply(A, c.S.f(fname(i, "x")), m.R, C, c.S.f(fname(i, "mi")), c.P[m.iFcG[i]], c.P[m.iFcBeta[i]], 1,
-                       c.S.p(fname(i, "a")), C, pn, d.seed, SITE_FC0 + i + 1, st));
+                       c.S.p(fname(i, "a")), C, pn, DropSeed(d.seed, d.seed_dev), SITE_FC0 + i + 1, st));
       xin = c.S.p(fname(i, "a")); ldin = C; kin = C;
     }
     if (ph < d.n_fc) {
@@ -727,7 +736,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
     // ---- last phase: video_emb, positional encoding, temporal encoder, entity reduction, embedding ----
     MVF_TRY(c.linear(MVF_F32, m.R, m.Hin, kin, xin, ldin, c.S.p("w.e"), c.S.ld("w.e"), c.P[m.ibe], c.S.p("h3"), m.Hin, 0, "w.e"));
     MVF_TRY(posenc_table(c.S.f("pe"), d.T, d.H, d.train_frames, st));
-    MVF_TRY(posenc_add(c.S.f("h3"), c.S.f("pe"), c.S.f("z0"), d.BV, d.T, d.E, d.H, c.p, d.seed, st));
+    MVF_TRY(posenc_add(c.S.f("h3"), c.S.f("pe"), c.S.f("z0"), d.BV, d.T, d.E, d.H, c.p, DropSeed(d.seed, d.seed_dev), st));
     const float* keymask_src = d.has_mask ? mask : nullptr;
     // key mask over s = e*T + t replicates the frame mask per entity (mvformer.py:174-177)
     float* keymask = nullptr;
@@ -749,7 +758,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       float* ln0 = c.S.f(lname(l, "ln0"));
       // z[2l] = z_prev + drop(pending o); r0 = LN(z[2l])
       MVF_TRY(ln_fwd(A, c.S.f(zin), pend_o, c.S.f(z0n), c.S.p(lname(l, "r0")), ln0, ln0 + m.rows, c.P[b + L_LN0W],
-                     c.P[b + L_LN0B], m.rows, d.H, d.ln_eps, c.p, d.seed, pend_site, st));
+                     c.P[b + L_LN0B], m.rows, d.H, d.ln_eps, c.p, DropSeed(d.seed, d.seed_dev), pend_site, st));
       MVF_TRY(c.linear(A, m.rows, 3 * d.H, d.H, c.S.p(lname(l, "r0")), d.H, c.S.p(lname(l, "w.qkv")), d.H,
                        c.S.f(lname(l, "b.qkv")), c.S.p(lname(l, "qkv")), 3 * d.H, 0, lname(l, "w.qkv").c_str()));
       MVF_TRY(attention_fwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
@@ -758,7 +767,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
                        o, d.H, 0, lname(l, "w.o").c_str()));
       float* ln1 = c.S.f(lname(l, "ln1"));
       MVF_TRY(ln_fwd(A, c.S.f(z0n), o, c.S.f(zmid), c.S.p(lname(l, "r1")), ln1, ln1 + m.rows, c.P[b + L_LN1W],
-                     c.P[b + L_LN1B], m.rows, d.H, d.ln_eps, c.p, d.seed, SITE_ENC0 + 2 * l, st));
+                     c.P[b + L_LN1B], m.rows, d.H, d.ln_eps, c.p, DropSeed(d.seed, d.seed_dev), SITE_ENC0 + 2 * l, st));
       MVF_TRY(c.linear(A, m.rows, d.DFF, d.H, c.S.p(lname(l, "r1")), d.H, c.S.p(lname(l, "w.1")), d.H, c.P[b + L_B1],
                        c.S.p(lname(l, "f")), d.DFF, MVF_GEMM_RELU, lname(l, "w.1").c_str()));
       MVF_TRY(c.linear(MVF_F32, m.rows, d.H, d.DFF, c.S.p(lname(l, "f")), d.DFF, c.S.p(lname(l, "w.2")), d.DFF,
@@ -770,7 +779,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
     const std::string zlast = "z" + std::to_string(2 * d.L);
     if (d.L > 0)
       MVF_TRY(ln_fwd(A, c.S.f("z" + std::to_string(zi)), pend_o, c.S.f(zlast), nullptr, nullptr, nullptr, nullptr, nullptr,
-                     m.rows, d.H, d.ln_eps, c.p, d.seed, pend_site, st));
+                     m.rows, d.H, d.ln_eps, c.p, DropSeed(d.seed, d.seed_dev), pend_site, st));
     // a9: entity reduction + embedding layer
     if (d.final_mode == MVF_FINAL_LIN) {
       MVF_TRY(entity_gather_lin(A, c.S.f(zlast), c.S.p("zl"), d.BV, d.T, d.E, d.H, st));
@@ -833,7 +842,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         void* df = c.W.p(lname(l, "df"));
         void* dqkv = c.W.p(lname(l, "dqkv"));
         // dgF = drop'(dz): written by the ln_bwd of the layer above (fused), by a stand-alone launch for the top layer
-        if (l == d.L - 1) MVF_TRY(dropout_cast(A, dz, dgF, m.rows, d.H, d.H, c.p, d.seed, SITE_ENC0 + 2 * l + 1, st));
+        if (l == d.L - 1) MVF_TRY(dropout_cast(A, dz, dgF, m.rows, d.H, d.H, c.p, DropSeed(d.seed, d.seed_dev), SITE_ENC0 + 2 * l + 1, st));
         MVF_TRY(c.linear_dw(m.rows, d.H, d.DFF, dgF, d.H, c.S.p(lname(l, "f")), d.DFF, c.G.f(g + "w.2"), d.DFF,
                             c.G.f(g + "b.2")));
         MVF_TRY(c.linear_dx(A, m.rows, d.H, d.DFF, dgF, d.H, c.S.p(lname(l, "w.2")), d.DFF, df, d.DFF,
@@ -844,7 +853,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         const float* ln1 = c.S.f(lname(l, "ln1"));
         // ... and the masked copy the attention branch consumes (dgA = drop'(dz_out), site 2l) comes out of the same launch
         MVF_TRY(ln_bwd(c.W.f("dr"), c.S.f("z" + std::to_string(2 * l + 1)), ln1, ln1 + m.rows, c.P[b + L_LN1W], dz,
-                       dz_other, c.G.f(g + "ln1w"), c.G.f(g + "ln1b"), m.rows, d.H, st, (float*)dgA, c.p, d.seed,
+                       dz_other, c.G.f(g + "ln1w"), c.G.f(g + "ln1b"), m.rows, d.H, st, (float*)dgA, c.p, DropSeed(d.seed, d.seed_dev),
                        SITE_ENC0 + 2 * l));
         std::swap(dz, dz_other);
         // attention branch: z[2l+1] = z[2l] + drop(Wo ctx + bo)
@@ -861,12 +870,12 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         // the layer below consumes drop'(dz_out) with the site of ITS FFN branch (2(l-1)+1)
         float* next_dgF = l > 0 ? (float*)c.W.p(lname(l - 1, "dgF")) : nullptr;
         MVF_TRY(ln_bwd(c.W.f("dr"), c.S.f("z" + std::to_string(2 * l)), ln0, ln0 + m.rows, c.P[b + L_LN0W], dz, dz_other,
-                       c.G.f(g + "ln0w"), c.G.f(g + "ln0b"), m.rows, d.H, st, next_dgF, c.p, d.seed,
+                       c.G.f(g + "ln0w"), c.G.f(g + "ln0b"), m.rows, d.H, st, next_dgF, c.p, DropSeed(d.seed, d.seed_dev),
                        SITE_ENC0 + 2 * (l - 1) + 1));
         std::swap(dz, dz_other);
       }
       // ---- positional encoding (+dropout) and video_emb ----
-      MVF_TRY(posenc_bwd(A, dz, c.W.p("dh3"), d.BV, d.T, d.E, d.H, c.p, d.seed, st));
+      MVF_TRY(posenc_bwd(A, dz, c.W.p("dh3"), d.BV, d.T, d.E, d.H, c.p, DropSeed(d.seed, d.seed_dev), st));
       const void* xin = d.n_fc ? c.S.p(fname(d.n_fc - 1, "a")) : c.S.p("h0");
       const int64_t ldin = d.n_fc ? d.fc[d.n_fc - 1] : m.ld0;
       MVF_TRY(c.linear_dw(m.R, m.Hin, ldin, c.W.p("dh3"), m.Hin, xin, ldin, c.G.f("g.w.e"), c.Lg.find("g.w.e")->ld,
@@ -878,7 +887,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         MVF_TRY(c.linear_dx(MVF_F32, m.R, m.Hin, C, c.W.p("dh3"), m.Hin, c.S.p("w.e"), c.S.ld("w.e"), c.W.p("da"), C));
         MVF_CHECK_CUDA(cudaMemsetAsync(c.S.p(fname(i, "bsum")), 0, (size_t)2 * C * 8, st));
         MVF_TRY(bn_bwd_stats(c.W.f("da"), C, c.S.f(fname(i, "x")), m.R, C, c.S.f(fname(i, "mi")), c.P[m.iFcG[i]],
-                             c.P[m.iFcBeta[i]], 1, 0.f, d.seed, SITE_FC0 + i + 1, c.S.dbl(fname(i, "bsum")),
+                             c.P[m.iFcBeta[i]], 1, 0.f, DropSeed(d.seed, d.seed_dev), SITE_FC0 + i + 1, c.S.dbl(fname(i, "bsum")),
                              c.G.f("g." + fname(i, "gamma")), c.G.f("g." + fname(i, "beta")), st));
       }
     }
@@ -887,7 +896,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
       const int i = d.n_fc - ph, C = d.fc[i];
       const float pn = (i + 1 < d.n_fc) ? c.p : 0.f;  // dropout that followed this activation
       MVF_TRY(bn_bwd_apply(A, c.W.f("da"), C, c.S.f(fname(i, "x")), m.R, C, c.S.f(fname(i, "mi")), c.P[m.iFcG[i]],
-                           c.P[m.iFcBeta[i]], 1, pn, d.seed, SITE_FC0 + i + 1, c.S.dbl(fname(i, "bsum")),
+                           c.P[m.iFcBeta[i]], 1, pn, DropSeed(d.seed, d.seed_dev), SITE_FC0 + i + 1, c.S.dbl(fname(i, "bsum")),
                            bn_n_global(m, m.R), c.W.p(fname(i, "dx")), C, st));
       d_in = c.W.p(fname(i, "dx"));
       ld_din = C;
@@ -901,7 +910,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         MVF_CHECK_CUDA(cudaMemsetAsync(c.S.p(fname(i - 1, "bsum")), 0, (size_t)2 * Cp * 8, st));
         const float pp = c.p;  // activation i-1 was followed by the dropout of FC layer i
         MVF_TRY(bn_bwd_stats(c.W.f("da"), Cp, c.S.f(fname(i - 1, "x")), m.R, Cp, c.S.f(fname(i - 1, "mi")),
-                             c.P[m.iFcG[i - 1]], c.P[m.iFcBeta[i - 1]], 1, pp, d.seed, SITE_FC0 + i,
+                             c.P[m.iFcG[i - 1]], c.P[m.iFcBeta[i - 1]], 1, pp, DropSeed(d.seed, d.seed_dev), SITE_FC0 + i,
                              c.S.dbl(fname(i - 1, "bsum")), c.G.f("g." + fname(i - 1, "gamma")),
                              c.G.f("g." + fname(i - 1, "beta")), st));
       } else {
@@ -918,7 +927,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         float* gwv = gwk + (size_t)d.SPC * ldg;
         {
           ProfScope ps(3, st);
-          MVF_TRY(ent_finish_bwd(c.W.f("dh0"), m.ld0, c.W.f("dent"), m.R, d.SPC, m.W0, c.p, d.seed, st));
+          MVF_TRY(ent_finish_bwd(c.W.f("dh0"), m.ld0, c.W.f("dent"), m.R, d.SPC, m.W0, c.p, DropSeed(d.seed, d.seed_dev), st));
           // dWv = dEnt^T px, dbv = colsum(dEnt) (forked); d(bk) is analytically zero (a per-entity constant under softmax)
           MVF_TRY(c.linear_dw(m.R, d.SPC, d.C_in, c.W.p("dent"), d.SPC, c.S.p("px"), d.C_in, gwv, ldg, gbkv + o_spc));
           // G = dEnt Wv
@@ -940,7 +949,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
       {
         ProfScope ps(3, st);
         MVF_TRY(xattn_pool_bwd(m.kvt, (int)m.F, d.P, d.E, d.SPC, c.S.p("kv"), c.P[m.iQs], c.P[m.iQb], c.S.f("attn"),
-                               c.W.p("dh0"), m.ld0, c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, d.seed, c.W.p("dkv"),
+                               c.W.p("dh0"), m.ld0, c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, DropSeed(d.seed, d.seed_dev), c.W.p("dkv"),
                                c.G.f("g.Qs"), c.G.f("g.Qb"), gbkv, gbkv + o_spc, st));
       }
       // dW_kv = dKV^T X : 2*SPC x C_in outputs, K = frames*tokens -> split-K across the machine

@@ -21,22 +21,22 @@ int unpack_grads(const UnpackEntry* entries, int n, float scale, cudaStream_t st
 // ---- positional encoding (models/utils.py:113-145) ---------------------------------------------------
 int posenc_table(float* table, int T, int H, int train_frames, cudaStream_t st);
 // z[b, e*T+t, :] = drop(h3[(b*T+t)*E+e, :] + pe[t, :])
-int posenc_add(const float* h3, const float* table, float* z, int BV, int T, int E, int H, float p, uint64_t seed,
+int posenc_add(const float* h3, const float* table, float* z, int BV, int T, int E, int H, float p, DropSeed seed,
                cudaStream_t st);
 // dh3[(b*T+t)*E+e, :] = drop'(dz[b, e*T+t, :])   (out dtype)
-int posenc_bwd(int dtype_out, const float* dz, void* dh3, int BV, int T, int E, int H, float p, uint64_t seed,
+int posenc_bwd(int dtype_out, const float* dz, void* dh3, int BV, int T, int E, int H, float p, DropSeed seed,
                cudaStream_t st);
 
 // ---- LayerNorm with fused residual-add + dropout (models/utils.py:147-159) ----------------------------
 // z_out = z_in + drop(o) (o may be null -> z_out = z_in); r = LN(z_out)*gamma + beta (r may be null -> add only)
 int ln_fwd(int dtype_out, const float* z_in, const float* o, float* z_out, void* r, float* mean, float* rstd,
-           const float* gamma, const float* beta, int64_t rows, int H, float eps, float p, uint64_t seed, int site,
+           const float* gamma, const float* beta, int64_t rows, int H, float eps, float p, DropSeed seed, int site,
            cudaStream_t st);
 // dz_out = dz_in + LN'(dr); dgamma/dbeta accumulated (atomics). dz_in may be null (treated as 0).
 // drop_out (optional): also writes dz_out * dropmask(site) -- the masked gradient the next residual branch consumes.
 int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd, const float* gamma,
            const float* dz_in, float* dz_out, float* dgamma, float* dbeta, int64_t rows, int H, cudaStream_t st,
-           float* drop_out = nullptr, float p = 0.f, uint64_t seed = 0, int site = 0);
+           float* drop_out = nullptr, float p = 0.f, DropSeed seed = 0, int site = 0);
 
 // ---- BatchNorm1d (+ReLU +dropout) in training / eval mode ---------------------------------------------
 // The statistics are produced in three launches so that a multi-GPU caller can all-reduce `sums` in between:
@@ -48,14 +48,14 @@ int bn_finalize(const double* sums, int C, double n_global, float eps, int train
                 float* rvar, int64_t* tracked, float* mi, cudaStream_t st);
 // out = drop(relu?(gamma*(x-mean)*invstd+beta))
 int bn_apply(int dtype_out, const float* x, int64_t R, int C, const float* mi, const float* gamma, const float* beta,
-             int relu, void* out, int64_t ld_out, float p, uint64_t seed, int site, cudaStream_t st);
+             int relu, void* out, int64_t ld_out, float p, DropSeed seed, int site, cudaStream_t st);
 // dy = d_out*drop*relu'(y); bsums[0:C]+=sum dy, [C:2C]+=sum dy*xhat; dgamma/dbeta accumulated from the LOCAL sums
 int bn_bwd_stats(const float* d_out, int64_t ld_d, const float* x, int64_t R, int C, const float* mi,
-                 const float* gamma, const float* beta, int relu, float p, uint64_t seed, int site, double* bsums,
+                 const float* gamma, const float* beta, int relu, float p, DropSeed seed, int site, double* bsums,
                  float* dgamma, float* dbeta, cudaStream_t st);
 // dx = gamma*invstd*(dy - sum(dy)/n - xhat*sum(dy*xhat)/n) with the (all-reduced) bsums and global n
 int bn_bwd_apply(int dtype_out, const float* d_out, int64_t ld_d, const float* x, int64_t R, int C, const float* mi,
-                 const float* gamma, const float* beta, int relu, float p, uint64_t seed, int site, const double* bsums,
+                 const float* gamma, const float* beta, int relu, float p, DropSeed seed, int site, const double* bsums,
                  double n_global, void* dx, int64_t ld_dx, cudaStream_t st);
 
 // ---- misc ------------------------------------------------------------------------------------------------
@@ -72,7 +72,7 @@ int colsum_batched(const ColsumEntry* entries, int n, cudaStream_t st);
 int colsum(int dtype_in, const void* X, int64_t R, int C, int64_t ld, float* out, cudaStream_t st);
 // out = in * dropmask (site) cast to dtype_out; p = 0 -> plain cast
 int dropout_cast(int dtype_out, const float* in, void* out, int64_t rows, int cols, int64_t ld_out, float p,
-                 uint64_t seed, int site, cudaStream_t st);
+                 DropSeed seed, int site, cudaStream_t st);
 int cast_f32(int dtype_out, const float* in, void* out, int64_t n, cudaStream_t st);
 // entity reduction (mvformer.py:181-190): z [BV, E*T, H] -> y [BV*T, H]
 int entity_reduce_fwd(int dtype_out, const float* z, void* y, int32_t* argmax, int BV, int T, int E, int H, int mode,
@@ -86,17 +86,17 @@ int entity_scatter_lin(const float* dzl, float* dz, int BV, int T, int E, int H,
 int l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int D, cudaStream_t st);
 int l2norm_bwd(const float* dy, const float* y, const float* norm, void* dx, int dtype_out, int64_t rows, int D,
                cudaStream_t st);
-int dropout_mask_export(uint64_t seed, int site, int64_t rows, int64_t cols, float p, float* out, cudaStream_t st);
+int dropout_mask_export(DropSeed seed, int site, int64_t rows, int64_t cols, float p, float* out, cudaStream_t st);
 
 // ---- xattn.cu ----------------------------------------------------------------------------------------------
 // ent32 (optional, fp32 [F*E, SPC]): the pooled entities before dropout; when given (and bf16, E <= 4) the single-pass
 // kernels are used -- backward needs it for rowdot[e] = <dEnt[e], ent[e]>.
 int xattn_pool_fwd(int dtype, int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b,
-                   float* attn, void* ent, int64_t ld_ent, float* ent32, int one_hot, float drop_p, uint64_t seed,
+                   float* attn, void* ent, int64_t ld_ent, float* ent32, int one_hot, float drop_p, DropSeed seed,
                    cudaStream_t st);
 int xattn_pool_bwd(int dtype, int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b,
                    const float* attn, const void* d_ent, int64_t ld_ent, const float* ent32, int one_hot, float drop_p,
-                   uint64_t seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv, cudaStream_t st);
+                   DropSeed seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv, cudaStream_t st);
 
 // ---- pool_fold.cu: rank-E folded entity pooling (no K|V tensors; one streaming pass over the tokens per direction) ------
 bool pool_fold_supported(int dtype, int C, int E, int P);
@@ -117,9 +117,9 @@ int pool_fold_mma_fwd(int F, int P, int E, int C, const void* X, const float* Wq
 int pool_fold_mma_bwd(int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,
                       float* dWq, cudaStream_t st);
 // h0 = [drop(ent) | drop(one-hot) | 0]  and its backward
-int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, int E, int one_hot, float p, uint64_t seed,
+int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, int E, int one_hot, float p, DropSeed seed,
                    cudaStream_t st);
-int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SPC, int W, float p, uint64_t seed,
+int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SPC, int W, float p, DropSeed seed,
                    cudaStream_t st);
 
 // ---- attention.cu --------------------------------------------------------------------------------------------

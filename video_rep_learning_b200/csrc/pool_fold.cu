@@ -519,7 +519,7 @@ fold_finish_kernel(const float* __restrict__ dWq, const float* __restrict__ q_s,
 
 // h0[row, :] = [drop(ent[row, :SPC]) | drop(one-hot entity id) | 0 padding]   (mvformer.py:144-151)
 __global__ void ent_finish_fwd_kernel(const float* __restrict__ ent, float* __restrict__ h0, int64_t ld, int64_t R, int SPC,
-                                      int E, int one_hot, float p, float inv_keep, uint64_t seed) {
+                                      int E, int one_hot, float p, float inv_keep, DropSeed seed) {
   const int W = SPC + (one_hot ? E : 0);
   const int64_t total = R * ld;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -534,7 +534,7 @@ __global__ void ent_finish_fwd_kernel(const float* __restrict__ ent, float* __re
 }
 // dEnt[row, c] = drop'(d_h0[row, c]) for c < SPC
 __global__ void ent_finish_bwd_kernel(const float* __restrict__ d_h0, int64_t ld, float* __restrict__ dEnt, int64_t R, int SPC,
-                                      int W, float p, float inv_keep, uint64_t seed) {
+                                      int W, float p, float inv_keep, DropSeed seed) {
   const int64_t total = R * SPC;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / SPC;
@@ -722,7 +722,7 @@ int fold_finish(const float* dWq, const float* q_s, const float* q_b, const floa
   return MVF_OK;
 }
 
-int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, int E, int one_hot, float p, uint64_t seed,
+int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, int E, int one_hot, float p, DropSeed seed,
                    cudaStream_t st) {
   if (R <= 0) return MVF_OK;
   const int64_t total = R * ld;
@@ -732,7 +732,7 @@ int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, 
   return MVF_OK;
 }
 
-int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SPC, int W, float p, uint64_t seed,
+int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SPC, int W, float p, DropSeed seed,
                    cudaStream_t st) {
   if (R <= 0) return MVF_OK;
   const int64_t total = R * SPC;

@@ -13,7 +13,7 @@ template <typename T, int EMAX>
 __global__ void __launch_bounds__(256)
 xattn_fwd_kernel(int P, int E, int SPC, const T* __restrict__ kv, const float* __restrict__ q_s,
                  const float* __restrict__ q_b, float* __restrict__ attn, float* __restrict__ ent, int64_t ld_ent,
-                 int one_hot, float p_drop, float inv_keep, uint64_t seed) {
+                 int one_hot, float p_drop, float inv_keep, DropSeed seed) {
   extern __shared__ float sm[];
   float* Q = sm;                   // [E][SPC]
   float* A = sm + (size_t)E * SPC; // [E][P]
@@ -107,7 +107,7 @@ template <typename T, int EMAX>
 __global__ void __launch_bounds__(256)
 xattn_bwd_kernel(int P, int E, int SPC, const T* __restrict__ kv, const float* __restrict__ q_s,
                  const float* __restrict__ q_b, const float* __restrict__ attn, const float* __restrict__ d_ent,
-                 int64_t ld_ent, int one_hot, float p_drop, float inv_keep, uint64_t seed, T* __restrict__ d_kv,
+                 int64_t ld_ent, int one_hot, float p_drop, float inv_keep, DropSeed seed, T* __restrict__ d_kv,
                  float* __restrict__ d_q_s, float* __restrict__ d_q_b, float* __restrict__ d_bk,
                  float* __restrict__ d_bv) {
   extern __shared__ float sm[];
@@ -236,7 +236,7 @@ template <int EMAX, int CPL>
 __global__ void __launch_bounds__(256, 2)
 xattn_fwd_v2_kernel(int P, int E, int SPC, const bf16* __restrict__ kv, const float* __restrict__ q_s,
                     const float* __restrict__ q_b, float* __restrict__ attn, float* __restrict__ ent, int64_t ld_ent,
-                    float* __restrict__ ent32, int one_hot, float p_drop, float inv_keep, uint64_t seed) {
+                    float* __restrict__ ent32, int one_hot, float p_drop, float inv_keep, DropSeed seed) {
   extern __shared__ __align__(16) float sm[];
   float* Q = sm;                         // [E][SPC]
   float* sc = Q + (size_t)E * SPC;       // [E][P] raw scaled scores, later probabilities
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256, 1)
 xattn_bwd_v2_kernel(int P, int E, int SPC, const bf16* __restrict__ kv, const float* __restrict__ q_s,
                     const float* __restrict__ q_b, const float* __restrict__ attn, const float* __restrict__ d_ent,
                     int64_t ld_ent, const float* __restrict__ ent32, int one_hot, float p_drop, float inv_keep,
-                    uint64_t seed, bf16* __restrict__ d_kv, float* __restrict__ d_q_s, float* __restrict__ d_q_b,
+                    DropSeed seed, bf16* __restrict__ d_kv, float* __restrict__ d_q_s, float* __restrict__ d_q_b,
                     float* __restrict__ d_bk, float* __restrict__ d_bv) {
   extern __shared__ __align__(16) float sm[];
   float* QG = sm;                          // [E][2*SPC]: Q[e] | dEnt[e]  (same chunk numbering as a K|V row)
@@ -522,7 +522,7 @@ static bool v2_ok(int dtype, int E, int SPC, int P, const void* kv, int64_t ld_e
 
 template <int EM, int CPL>
 static int fwd_v2_launch(int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b, float* attn,
-                         void* ent, int64_t ld_ent, float* ent32, int one_hot, float drop_p, uint64_t seed,
+                         void* ent, int64_t ld_ent, float* ent32, int one_hot, float drop_p, DropSeed seed,
                          cudaStream_t st) {
   size_t smem = ((size_t)E * SPC + (size_t)E * P + 16 * EM + 2 * EM + (size_t)8 * E * SPC) * sizeof(float);
   MVF_REQUIRE(smem <= 227 * 1024, MVF_ERR_UNSUPPORTED, "xattn fwd: %zu B of shared memory", smem);
@@ -540,7 +540,7 @@ static int fwd_v2_launch(int F, int P, int E, int SPC, const void* kv, const flo
 template <int EM, int CPL>
 static int bwd_v2_launch(int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b,
                          const float* attn, const void* d_ent, int64_t ld_ent, const float* ent32, int one_hot,
-                         float drop_p, uint64_t seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv,
+                         float drop_p, DropSeed seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv,
                          cudaStream_t st) {
   size_t smem = ((size_t)E * 2 * SPC + (size_t)E * P + EM + (size_t)8 * (E + 1) * 2 * SPC) * sizeof(float);
   MVF_REQUIRE(smem <= 227 * 1024, MVF_ERR_UNSUPPORTED, "xattn bwd: %zu B of shared memory", smem);
@@ -558,7 +558,7 @@ static int bwd_v2_launch(int F, int P, int E, int SPC, const void* kv, const flo
 
 template <typename T>
 static int fwd_t(int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b, float* attn, void* ent,
-                 int64_t ld_ent, int one_hot, float drop_p, uint64_t seed, cudaStream_t st) {
+                 int64_t ld_ent, int one_hot, float drop_p, DropSeed seed, cudaStream_t st) {
   size_t smem = ((size_t)E * SPC + (size_t)E * P) * sizeof(float);
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
 #define LAUNCH_F(EM)                                                                                              \
@@ -578,7 +578,7 @@ static int fwd_t(int F, int P, int E, int SPC, const void* kv, const float* q_s,
 }
 
 int xattn_pool_fwd(int dtype, int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b,
-                   float* attn, void* ent, int64_t ld_ent, float* ent32, int one_hot, float drop_p, uint64_t seed,
+                   float* attn, void* ent, int64_t ld_ent, float* ent32, int one_hot, float drop_p, DropSeed seed,
                    cudaStream_t st) {
   MVF_REQUIRE(E >= 1 && E <= MVF_MAX_ENTITIES, MVF_ERR_UNSUPPORTED, "xattn: %d entities (max %d)", E, MVF_MAX_ENTITIES);
   MVF_REQUIRE(ld_ent >= SPC + (one_hot ? E : 0), MVF_ERR_BAD_ARG, "xattn: ld_ent too small");
@@ -600,7 +600,7 @@ int xattn_pool_fwd(int dtype, int F, int P, int E, int SPC, const void* kv, cons
 
 template <typename T>
 static int bwd_t(int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b, const float* attn,
-                 const void* d_ent, int64_t ld_ent, int one_hot, float drop_p, uint64_t seed, void* d_kv, float* d_q_s,
+                 const void* d_ent, int64_t ld_ent, int one_hot, float drop_p, DropSeed seed, void* d_kv, float* d_q_s,
                  float* d_q_b, float* d_bk, float* d_bv, cudaStream_t st) {
   size_t smem = (2 * (size_t)E * SPC + 2 * (size_t)E * P) * sizeof(float);
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -622,7 +622,7 @@ static int bwd_t(int F, int P, int E, int SPC, const void* kv, const float* q_s,
 
 int xattn_pool_bwd(int dtype, int F, int P, int E, int SPC, const void* kv, const float* q_s, const float* q_b,
                    const float* attn, const void* d_ent, int64_t ld_ent, const float* ent32, int one_hot, float drop_p,
-                   uint64_t seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv, cudaStream_t st) {
+                   DropSeed seed, void* d_kv, float* d_q_s, float* d_q_b, float* d_bk, float* d_bv, cudaStream_t st) {
   MVF_REQUIRE(E >= 1 && E <= MVF_MAX_ENTITIES, MVF_ERR_UNSUPPORTED, "xattn: %d entities (max %d)", E, MVF_MAX_ENTITIES);
   if (F > 0 && ent32 != nullptr && v2_ok(dtype, E, SPC, P, kv, ld_ent) && ((((uintptr_t)d_kv) & 15) == 0)) {
     const int cpl = (2 * SPC / 8 + 31) / 32;

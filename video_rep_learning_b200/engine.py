@@ -131,10 +131,11 @@ class Plan:
             cls._cache[key] = p
         return p
 
-    def desc_with_seed(self, seed: int) -> L.HeadDesc:
+    def desc_with_seed(self, seed: int, seed_dev: Optional[torch.Tensor] = None) -> L.HeadDesc:
         d = L.HeadDesc()
         C.memmove(C.byref(d), C.byref(self.desc), C.sizeof(L.HeadDesc))
         d.seed = seed
+        d.seed_dev = None if seed_dev is None else seed_dev.data_ptr()
         return d
 
     def lookup(self, name: str):
@@ -198,6 +199,7 @@ class CallState:
     project: int = 1                 # 1 MLPHead + normalise, 0 normalise only, 2 MLPHead only
     want_attn: bool = False
     seed: int = 0
+    seed_dev: Optional[torch.Tensor] = None   # device-resident int64 counter added to `seed` in the kernels (graph replay)
     # filled by forward
     plan: Optional[Plan] = None
     head_save: Optional[torch.Tensor] = None
@@ -343,7 +345,7 @@ class HeadFn(torch.autograd.Function):
         with torch.cuda.device(tokens.device):
             plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _world(cs.opts),
                             cs.opts.gemm_backend, cs.opts.pool_mode)
-            d = plan.desc_with_seed(cs.seed)
+            d = plan.desc_with_seed(cs.seed, cs.seed_dev)
             save = torch.empty(plan.save_bytes, dtype=torch.uint8, device=tokens.device)
             ws = _scratch(tokens.device, plan.ws_bytes, "head")
             out = torch.empty(BV, T, cs.spec.emb, dtype=torch.float32, device=tokens.device)
@@ -363,7 +365,7 @@ class HeadFn(torch.autograd.Function):
         mask = mask if ctx.has_mask else None
         plan = cs.plan
         with torch.cuda.device(tokens.device):
-            d = plan.desc_with_seed(ctx.seed)
+            d = plan.desc_with_seed(ctx.seed, cs.seed_dev)
             ws = _scratch(tokens.device, plan.ws_bytes, "head")
             gpack = torch.zeros(plan.gpack_elems, dtype=torch.float32, device=tokens.device)
             full = list(params) + [None] * (len(plan.param_names) - len(params))
@@ -428,7 +430,7 @@ class ModelFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _world(cs.opts),
                             cs.opts.gemm_backend, cs.opts.pool_mode)
-            d = plan.desc_with_seed(cs.seed)
+            d = plan.desc_with_seed(cs.seed, cs.seed_dev)
             save = torch.empty(plan.save_bytes, dtype=torch.uint8, device=dev)
             psave = torch.empty(plan.proj_save_bytes, dtype=torch.uint8, device=dev)
             ws = _scratch(dev, plan.ws_bytes, "head")
@@ -452,7 +454,7 @@ class ModelFn(torch.autograd.Function):
         plan = cs.plan
         dev = tokens.device
         with torch.cuda.device(dev):
-            d = plan.desc_with_seed(ctx.seed)
+            d = plan.desc_with_seed(ctx.seed, cs.seed_dev)
             ws = _scratch(dev, plan.ws_bytes, "head")
             pws = _scratch(dev, plan.proj_ws_bytes, "proj")
             gpack = torch.zeros(plan.gpack_elems, dtype=torch.float32, device=dev)

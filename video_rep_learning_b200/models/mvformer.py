@@ -158,6 +158,7 @@ class MultiEntityTransformerEmbModel(nn.Module):
         self._param_order: Optional[List[str]] = None
         self._param_slots = None
         self.last_call: Optional[engine.CallState] = None
+        self.seed_dev: Optional[torch.Tensor] = None   # set by graph.GraphedTrainStep: device-side dropout counter
 
     # ---- reference API -------------------------------------------------------------------------------
     def set_warmup_status(self, new_status):
@@ -215,7 +216,8 @@ class MultiEntityTransformerEmbModel(nn.Module):
         training = self.training
         seed = engine.new_seed() if (training and self.spec.drop_p > 0) else 0
         return engine.CallState(spec=self.spec, opts=self.run_options, training=training, bn_running=running,
-                                bn_tracked=tracked, project=project, seed=seed)
+                                bn_tracked=tracked, project=project, seed=seed,
+                                seed_dev=self.seed_dev if (training and self.spec.drop_p > 0) else None)
 
     def forward(self, x, video_masks=None, cls_emb=None):
         tokens = self.to_token_major(x.detach())
