@@ -220,6 +220,10 @@ int mvf_pool_fold_fwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t C_in, 
                       float* attn, float* px, mvf_stream_t stream);
 int mvf_pool_fold_bwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t C_in, const void* tokens, const float* g,
                       const float* px, const float* attn, float* d_wq, mvf_stream_t stream);
+/* Same as mvf_pool_fold_bwd with the per-row constants delta[F*E] = <g_row, px_row> supplied by the caller (the fused
+ * head gets them for free as <dEnt_row, ent_row - b_v> while it builds dEnt); delta == NULL -> reduced inside. */
+int mvf_pool_fold_bwd_delta(int dtype, int32_t F, int32_t P, int32_t E, int32_t C_in, const void* tokens, const float* g,
+                            const float* px, const float* attn, const float* delta, float* d_wq, mvf_stream_t stream);
 int mvf_pool_fold_finish(const float* d_wq, const float* q_s, const float* q_b, const float* w_k, int32_t E, int32_t SPC,
                          int32_t C_in, float* d_wk, int64_t ld_dwk, float* d_q_s, float* d_q_b, mvf_stream_t stream);
 

@@ -18,7 +18,9 @@ G = torch.randn(F * E, C, device="cuda", generator=g) * 0.01
 dwq = torch.zeros(E, C, device="cuda")
 L.check(lib.mvf_pool_fold_prep(L.ptr(qs), L.ptr(qb), L.ptr(Wk), E, SPC, C, L.ptr(wq), st))
 fwd = lambda: L.check(lib.mvf_pool_fold_fwd(1, F, P, E, C, L.ptr(X), L.ptr(wq), L.ptr(attn), L.ptr(px), st))
-bwd = lambda: L.check(lib.mvf_pool_fold_bwd(1, F, P, E, C, L.ptr(X), L.ptr(G), L.ptr(px), L.ptr(attn), L.ptr(dwq), st))
+fwd()
+delta = (G * px).sum(-1).contiguous()      # what the fused head gets from ent_finish_bwd: <dEnt, ent - bv> = <G, px>
+bwd = lambda: L.check(lib.mvf_pool_fold_bwd_delta(1, F, P, E, C, L.ptr(X), L.ptr(G), L.ptr(px), L.ptr(attn), L.ptr(delta), L.ptr(dwq), st))
 tok = F * P * C * 2
 for name, fn, nbytes in (("fwd", fwd, tok + F * E * C * 4 + F * E * P * 4), ("bwd", bwd, tok + 2 * F * E * C * 4 + F * E * P * 4)):
     for _ in range(3):

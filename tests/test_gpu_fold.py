@@ -118,6 +118,42 @@ def test_fold_mma_and_cuda_core_paths_agree(monkeypatch):
     assert float((px_m - px_c).abs().max() / px_c.abs().max()) < 5e-6
 
 
+@pytest.mark.parametrize("F,P,E,C", [(9, 196, 3, 2304), (301, 196, 3, 2304), (7, 50, 6, 384), (5, 30, 11, 768), (6, 9, 3, 48)])
+def test_fold_warp_specialised_and_first_generation_kernels_agree(monkeypatch, F, P, E, C):
+    """pool_fold_ws.cu (default) against pool_fold_mma.cu (MVF_FOLD_WS=0): forward outputs, and the backward pass with the
+    caller-supplied delta, with the in-kernel delta, and on the first-generation kernel."""
+    SPC = 64
+    X, qs, qb, Wk, Wv, bk, bv = _mk(F, P, E, C, SPC, torch.bfloat16, seed=8)
+    lib = L.lib()
+    _, attn_w, px_w = _fold_forward(X, qs, qb, Wk)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    G = torch.randn(F * E, C, generator=g, device="cuda") * 0.05
+    delta = (G.double() * px_w.double()).sum(-1).float().contiguous()
+
+    def bwd(with_delta):
+        dwq = torch.zeros(E, C, device="cuda")
+        if with_delta:
+            L.check(lib.mvf_pool_fold_bwd_delta(L.MVF_BF16, F, P, E, C, L.ptr(X), L.ptr(G), L.ptr(px_w), L.ptr(attn_w),
+                                                L.ptr(delta), L.ptr(dwq), _st()))
+        else:
+            L.check(lib.mvf_pool_fold_bwd(L.MVF_BF16, F, P, E, C, L.ptr(X), L.ptr(G), L.ptr(px_w), L.ptr(attn_w), L.ptr(dwq), _st()))
+        torch.cuda.synchronize()
+        return dwq
+
+    d_given, d_inner = bwd(True), bwd(False)
+    monkeypatch.setenv("MVF_FOLD_WS", "0")
+    _, attn_m, px_m = _fold_forward(X, qs, qb, Wk)
+    d_first = bwd(False)
+    assert float((attn_w - attn_m).abs().max()) < 2e-6
+    assert float((px_w - px_m).abs().max() / px_m.abs().max()) < 5e-6
+    # fp64 reference of the streaming pass on the same operands
+    dA = torch.einsum("fec,fpc->fep", G.view(F, E, C).double(), X.double())
+    dS = attn_w.double() * (dA - delta.double().view(F, E, 1))
+    ref = torch.einsum("fep,fpc->ec", dS, X.double())
+    for got in (d_given, d_inner, d_first):
+        assert float((got.double() - ref).norm() / ref.norm()) < 2e-5
+
+
 def test_fold_rejects_unsupported_shapes():
     lib = L.lib()
     x = torch.zeros(2, 4, 44, device="cuda")

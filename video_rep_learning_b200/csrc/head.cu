@@ -396,6 +396,7 @@ static void head_ws_layout(const Model& m, Layout& L) {
     L.add("dent", m.R, d.SPC, RT_F32);
     L.add("G", m.R, d.C_in, RT_F32);
     L.add("dwq", d.E, d.C_in, RT_F32);
+    L.add("pdelta", 1, m.R, RT_F32);
   } else {
     L.add("dkv", m.F * d.P, 2 * d.SPC, m.kvt);
   }
@@ -927,7 +928,9 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         float* gwv = gwk + (size_t)d.SPC * ldg;
         {
           ProfScope ps(3, st);
-          MVF_TRY(ent_finish_bwd(c.W.f("dh0"), m.ld0, c.W.f("dent"), m.R, d.SPC, m.W0, c.p, DropSeed(d.seed, d.seed_dev), st));
+          // dEnt and, from the same pass, delta = <dEnt, ent - bv> (= <G, px>) for the streaming kernel
+          MVF_TRY(ent_finish_bwd(c.W.f("dh0"), m.ld0, c.W.f("dent"), m.R, d.SPC, m.W0, c.p, DropSeed(d.seed, d.seed_dev), st,
+                                 c.S.f("ent32"), c.P[m.ibv], c.W.f("pdelta")));
           // dWv = dEnt^T px, dbv = colsum(dEnt) (forked); d(bk) is analytically zero (a per-entity constant under softmax)
           MVF_TRY(c.linear_dw(m.R, d.SPC, d.C_in, c.W.p("dent"), d.SPC, c.S.p("px"), d.C_in, gwv, ldg, gbkv + o_spc));
           // G = dEnt Wv
@@ -937,7 +940,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         {
           ProfScope ps(1, st);
           MVF_TRY(pool_fold_bwd(m.kvt, (int)m.F, d.P, d.E, d.C_in, tokens, c.W.f("G"), c.S.f("px"), c.S.f("attn"),
-                                c.W.f("dwq"), st));
+                                c.W.f("dwq"), st, c.W.f("pdelta")));
         }
         {
           ProfScope ps(5, st);
@@ -1342,6 +1345,11 @@ int mvf_pool_fold_bwd(int dtype, int32_t F, int32_t P, int32_t E, int32_t C_in, 
                       const float* px, const float* attn, float* d_wq, mvf_stream_t stream) {
   MVF_REQUIRE(tokens && g && px && attn && d_wq, MVF_ERR_BAD_ARG, "pool_fold_bwd: null pointer");
   return pool_fold_bwd(dtype, F, P, E, C_in, tokens, g, px, attn, d_wq, (cudaStream_t)stream);
+}
+int mvf_pool_fold_bwd_delta(int dtype, int32_t F, int32_t P, int32_t E, int32_t C_in, const void* tokens, const float* g,
+                            const float* px, const float* attn, const float* delta, float* d_wq, mvf_stream_t stream) {
+  MVF_REQUIRE(tokens && g && px && attn && d_wq, MVF_ERR_BAD_ARG, "pool_fold_bwd_delta: null pointer");
+  return pool_fold_bwd(dtype, F, P, E, C_in, tokens, g, px, attn, d_wq, (cudaStream_t)stream, delta);
 }
 int mvf_pool_fold_finish(const float* d_wq, const float* q_s, const float* q_b, const float* w_k, int32_t E, int32_t SPC,
                          int32_t C_in, float* d_wk, int64_t ld_dwk, float* d_q_s, float* d_q_b, mvf_stream_t stream) {

@@ -106,8 +106,9 @@ int fold_prep(const float* q_s, const float* q_b, const float* Wk, int E, int SP
 int pool_fold_fwd(int dtype, int F, int P, int E, int C, const void* X, const float* Wq, float* attn, float* px,
                   cudaStream_t st);
 // dWq[E,C] += sum_f (attn * (G X^T - <G, px>)) X              (G = dEnt Wv, [F*E, C] fp32)
+// delta [F*E] = <G_row, px_row> is optional (nullptr: reduced inside the kernels)
 int pool_fold_bwd(int dtype, int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,
-                  float* dWq, cudaStream_t st);
+                  float* dWq, cudaStream_t st, const float* delta = nullptr);
 // dWk += Q^T dWq / sqrt(SPC); dQ_s += dWq Wk^T / sqrt(SPC); dQ_b += column sums of dQ_s
 int fold_finish(const float* dWq, const float* q_s, const float* q_b, const float* Wk, int E, int SPC, int C, float* dWk,
                 int64_t ld_dwk, float* dQs, float* dQb, cudaStream_t st);
@@ -116,11 +117,16 @@ bool pool_fold_mma_supported(int dtype, int C, int P);
 int pool_fold_mma_fwd(int F, int P, int E, int C, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st);
 int pool_fold_mma_bwd(int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,
                       float* dWq, cudaStream_t st);
-// h0 = [drop(ent) | drop(one-hot) | 0]  and its backward
+// warp-specialised second generation of the same two passes (pool_fold_ws.cu): 8-token ring slots, mbarrier-only hand-offs
+bool pool_fold_ws_supported(int dtype, int C, int P);
+int pool_fold_ws_fwd(int F, int P, int E, int C, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st);
+int pool_fold_ws_bwd(int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,
+                     const float* delta, float* dWq, cudaStream_t st);
+// h0 = [drop(ent) | drop(one-hot) | 0]  and its backward (optionally delta[row] = <dEnt[row], ent[row] - bv> = <G_row, px_row>)
 int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, int E, int one_hot, float p, DropSeed seed,
                    cudaStream_t st);
 int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SPC, int W, float p, DropSeed seed,
-                   cudaStream_t st);
+                   cudaStream_t st, const float* ent = nullptr, const float* bv = nullptr, float* delta = nullptr);
 
 // ---- attention.cu --------------------------------------------------------------------------------------------
 int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, void* ctx,

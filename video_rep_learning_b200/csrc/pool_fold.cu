@@ -545,6 +545,26 @@ __global__ void ent_finish_bwd_kernel(const float* __restrict__ d_h0, int64_t ld
   }
 }
 
+// same, one warp per row, plus delta[row] = <dEnt[row, :], ent[row, :] - bv>.  With ent = px Wv^T + bv and G = dEnt Wv this
+// equals <G_row, px_row>, the softmax-Jacobian constant of the folded pooling backward, at SPC instead of C_in MACs per row
+__global__ void __launch_bounds__(256)
+ent_finish_bwd_delta_kernel(const float* __restrict__ d_h0, int64_t ld, float* __restrict__ dEnt, int64_t R, int SPC, int W,
+                            float p, float inv_keep, DropSeed seed, const float* __restrict__ ent,
+                            const float* __restrict__ bv, float* __restrict__ delta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  float acc = 0.f;
+  for (int c = lane; c < SPC; c += 32) {
+    float v = d_h0[row * ld + c];
+    if (p > 0.f) v *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + c), p, inv_keep);
+    dEnt[row * SPC + c] = v;
+    acc = fmaf(v, ent[row * SPC + c] - bv[c], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) delta[row] = acc;
+}
+
 // ---- launch plumbing ---------------------------------------------------------------------------------------------------
 static int g_sms = -1;
 static int num_sms() {
@@ -670,6 +690,13 @@ static bool use_mma(int dtype, int C, int P) {
   return pool_fold_mma_supported(dtype, C, P);
 }
 
+// second-generation warp-specialised kernels (pool_fold_ws.cu) unless MVF_FOLD_WS=0
+static bool use_ws(int dtype, int C, int P) {
+  const char* e = getenv("MVF_FOLD_WS");
+  if (e && atoi(e) == 0) return false;
+  return pool_fold_ws_supported(dtype, C, P);
+}
+
 static int fold_check(int dtype, int F, int P, int E, int C, const void* X) {
   MVF_REQUIRE(pool_fold_supported(dtype, C, E, P), MVF_ERR_UNSUPPORTED,
               "pool_fold: needs C_in (%d) a multiple of 8 and at most 5120, 1 <= E (%d) <= %d", C, E, MVF_MAX_ENTITIES);
@@ -681,7 +708,10 @@ int pool_fold_fwd(int dtype, int F, int P, int E, int C, const void* X, const fl
                   cudaStream_t st) {
   MVF_TRY(fold_check(dtype, F, P, E, C, X));
   if (F == 0) return MVF_OK;
-  if (use_mma(dtype, C, P)) return pool_fold_mma_fwd(F, P, E, C, X, Wq, attn, px, st);
+  if (use_mma(dtype, C, P)) {
+    if (use_ws(dtype, C, P)) return pool_fold_ws_fwd(F, P, E, C, X, Wq, attn, px, st);
+    return pool_fold_mma_fwd(F, P, E, C, X, Wq, attn, px, st);
+  }
   for (int e0 = 0; e0 < E; e0 += 4) {   // entity passes of <= 4 (X is re-streamed per pass; E = 3 in every penn config)
     fold::Geom g{F, P, C, E, e0, 0, C * (dtype == MVF_BF16 ? 2 : 4)};
     const int ne = E - e0 < 4 ? E - e0 : 4;
@@ -692,10 +722,13 @@ int pool_fold_fwd(int dtype, int F, int P, int E, int C, const void* X, const fl
 }
 
 int pool_fold_bwd(int dtype, int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,
-                  float* dWq, cudaStream_t st) {
+                  float* dWq, cudaStream_t st, const float* delta) {
   MVF_TRY(fold_check(dtype, F, P, E, C, X));
   if (F == 0) return MVF_OK;
-  if (use_mma(dtype, C, P)) return pool_fold_mma_bwd(F, P, E, C, X, G, px, attn, dWq, st);
+  if (use_mma(dtype, C, P)) {
+    if (use_ws(dtype, C, P)) return pool_fold_ws_bwd(F, P, E, C, X, G, px, attn, delta, dWq, st);
+    return pool_fold_mma_bwd(F, P, E, C, X, G, px, attn, dWq, st);
+  }
   for (int e0 = 0; e0 < E; e0 += 4) {
     fold::Geom g{F, P, C, E, e0, 0, C * (dtype == MVF_BF16 ? 2 : 4)};
     const int ne = E - e0 < 4 ? E - e0 : 4;
@@ -733,8 +766,14 @@ int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, 
 }
 
 int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SPC, int W, float p, DropSeed seed,
-                   cudaStream_t st) {
+                   cudaStream_t st, const float* ent, const float* bv, float* delta) {
   if (R <= 0) return MVF_OK;
+  if (delta != nullptr && ent != nullptr && bv != nullptr) {
+    fold::ent_finish_bwd_delta_kernel<<<(int)((R + 7) / 8), 256, 0, st>>>(d_h0, ld, dEnt, R, SPC, W, p,
+                                                                         p > 0.f ? 1.f / (1.f - p) : 1.f, seed, ent, bv, delta);
+    MVF_CHECK_LAUNCH();
+    return MVF_OK;
+  }
   const int64_t total = R * SPC;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   fold::ent_finish_bwd_kernel<<<blocks, 256, 0, st>>>(d_h0, ld, dEnt, R, SPC, W, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
