@@ -79,13 +79,12 @@ __device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r
 __device__ __forceinline__ void ldsm_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
-// D[16 x 8] += A[16 x 16] B[16 x 8] with rows 8..15 of A zero (entities are padded 8 -> 16): a1 = a3 = 0
-__device__ __forceinline__ void mma16816_top(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
-  const uint32_t z = 0u;
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a0), "r"(z), "r"(a2), "r"(z), "r"(b0), "r"(b1));
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void mma1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
   asm volatile(
@@ -122,7 +121,7 @@ static Carve carve(int C, int NW, int P, int slots, int ne) {
   Carve c;
   c.ring = (size_t)slots * TG * (C * 2 + 16);
   c.bars = 256;                                        // full[8] empty[8] pready[2] wready[2]
-  c.frag = (size_t)(C / 16) * ne * 4 * 16;             // A fragments of the scores product: [tile][entity][q] x 16 B
+  c.frag = (size_t)(C / 16) * (ne <= 4 ? 4 : 8) * 4 * 16;   // A fragments of the scores product: [tile][entity (4 | 8)][q] x 16 B
   c.partial = (size_t)2 * NW * PT * 4;
   c.wbuf = (size_t)2 * WB * 4;
   c.table = ((size_t)ne * P * 4 + 15) / 16 * 16;
@@ -147,7 +146,7 @@ __device__ __forceinline__ Sm setup(uint8_t* smraw, const Geom& g) {
   s.pready = s.empty + MAX_SLOTS;
   s.wready = s.pready + 2;
   s.frag = reinterpret_cast<uint4*>(smraw + ring_bytes + 256);
-  s.partial = reinterpret_cast<float*>(s.frag + (size_t)(g.C / 16) * g.ne * 4);
+  s.partial = reinterpret_cast<float*>(s.frag + (size_t)(g.C / 16) * (g.ne <= 4 ? 4 : 8) * 4);
   s.wbuf = s.partial + 2 * g.NW * PT;
   s.table = s.wbuf + 2 * WB;
   s.misc = s.table + (((size_t)g.ne * g.P + 3) / 4) * 4;
@@ -186,7 +185,7 @@ __device__ __forceinline__ void producer(const Sm& s, const Geom& g, const bf16*
 // (ch 2q, 2q+1) and (ch 2q+8, 2q+9) of row r8 are the a0 / a2 registers of the m16n8k16 A operand; {hi0, hi1, lo0, lo1} per
 // lane.  Only lanes r8 < ne hold data (the padding rows of A are zero), so a register-resident copy would spend 4*TPW
 // registers per thread on mostly zeros; 16 B per (tile, entity, q) in shared memory cost one 16-byte load per MMA pair.
-template <int TPW>
+template <int TPW, int ES>
 __device__ __forceinline__ void fill_afrag(uint4* fr, const float* __restrict__ M, int64_t stride, int ne, int ch_base, int q,
                                            int r8, float mul) {
   if (r8 < ne) {
@@ -198,35 +197,49 @@ __device__ __forceinline__ void fill_afrag(uint4* fr, const float* __restrict__ 
       uint4 o;
       split2(v0.x * mul, v0.y * mul, o.x, o.z);
       split2(v1.x * mul, v1.y * mul, o.y, o.w);
-      fr[(t * ne + r8) * 4 + q] = o;
+      fr[(t * ES + r8) * 4 + q] = o;
     }
   }
   __syncwarp();
 }
 
-// S^T[ent, tok] partial over this warp's channels -> pw[ent][tok] (rows r8 < ne)
-template <int TPW>
+// S^T[ent, tok] partial over this warp's channels -> pw[ent][tok] (rows r8 < ne).  The entity rows need only 8 of the 16
+// rows of the A operand, so the bf16 hi parts sit in rows 0..7 and the lo parts in rows 8..15: ONE MMA per tile yields both
+// products (accumulator rows r8 and r8 + 8 live in the same lane and are added at the end).  A row only feeds its own
+// output row, so lanes of unused rows simply load the fragment of entity r8 & (ES-1) (or never-written table rows): their
+// results are not stored, and no predication is needed in the loop.
+template <int TPW, int ES>
 __device__ __forceinline__ void scores_phase(uint32_t slot_addr, uint32_t l_off, const uint4* fr, float* pw, int ne, int q,
                                              int r8) {
-  // two independent accumulation chains (lo / hi operand): the warps are decoupled, so other warps fill the MMA latency
-  float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool live = r8 < ne;
-  const uint4* fl = fr + (live ? r8 * 4 + q : 0);
+  float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};   // two chains: even / odd tiles
+  const uint4* fl = fr + (r8 & (ES - 1)) * 4 + q;
 #pragma unroll
   for (int t = 0; t < TPW; ++t) {
     uint32_t b0, b1;
     ldsm_x2(slot_addr + l_off + t * 32, b0, b1);
-    uint4 a = make_uint4(0u, 0u, 0u, 0u);
-    if (live) a = fl[t * ne * 4];
-    mma16816_top(sa, a.z, a.w, b0, b1);
-    mma16816_top(sb, a.x, a.y, b0, b1);
+    const uint4 a = fl[t * ES * 4];                    // {hi0, hi1, lo0, lo1}
+    if (t & 1) mma16816(sb, a.x, a.z, a.y, a.w, b0, b1);
+    else mma16816(sa, a.x, a.z, a.y, a.w, b0, b1);
   }
-  if (live) *reinterpret_cast<float2*>(pw + r8 * TG + 2 * q) = make_float2(sa[0] + sb[0], sa[1] + sb[1]);
+  if (r8 < ne)
+    *reinterpret_cast<float2*>(pw + r8 * TG + 2 * q) = make_float2((sa[0] + sa[2]) + (sb[0] + sb[2]), (sa[1] + sa[3]) + (sb[1] + sb[3]));
 }
 
-// acc[t] (= px^T tile [16 ch, 8 ent]) += X^T tile [16 ch, 8 tok] * w^T [8 tok, 8 ent]
-template <int TPW>
+// acc[t] (= px^T tile [16 ch, 8 columns]) += X^T tile [16 ch, 8 tok] * w^T [8 tok, 8 columns].
+// PACK (at most 4 entities in the pass): columns 0..3 carry the bf16 hi parts of w, columns 4..7 the lo parts, so ONE MMA
+// per tile does both; the two halves of the accumulator are added when it is written out.  Otherwise the columns are the
+// 8 entities and hi / lo take two MMAs.
+template <int TPW, bool PACK>
 __device__ __forceinline__ void pool_phase(uint32_t slot_addr, uint32_t l_off, uint32_t wh, uint32_t wl, float (&acc)[TPW][4]) {
+  if (PACK) {
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      uint32_t a0, a1;
+      ldsm_x2_trans(slot_addr + l_off + t * 32, a0, a1);
+      mma1688(acc[t], a0, a1, wh);                     // the caller passes the lane's hi-or-lo register in wh
+    }
+    return;
+  }
   // tiles in pairs so that the two dependent MMAs of one accumulator are not issued back to back
 #pragma unroll
   for (int t = 0; t + 1 < TPW; t += 2) {
@@ -249,7 +262,7 @@ __device__ __forceinline__ void pool_phase(uint32_t slot_addr, uint32_t l_off, u
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
-template <int TPW>
+template <int TPW, bool PACK>
 __global__ void __launch_bounds__(max_threads(TPW), 1)
 pool_foldw_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, float* __restrict__ attn,
                       float* __restrict__ px, const Geom g) {
@@ -343,12 +356,15 @@ pool_foldw_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, 
 
   // ===== compute warps =====
   const int q = lane & 3, r8 = lane >> 2;
+  const int be = PACK ? (r8 & 3) : r8;                  // entity of this lane's column of the pooling B operand
+  const int e0c = PACK ? ((2 * q) & 3) : 2 * q, e1c = e0c + 1;   // entities of this lane's accumulator columns
   const uint32_t ring_u32 = smem_u32(s.ring);
   const uint32_t slot_bytes = (uint32_t)(TG * g.pitch);
   const uint32_t l_off = (uint32_t)((lane & 7) * g.pitch + (warp * TPW * 16 + ((lane >> 3) & 1) * 8) * 2);
   // the scores live in the log2 domain (log2 e folded into the Wq fragments)
-  uint4* fr = s.frag + (size_t)warp * TPW * g.ne * 4;
-  fill_afrag<TPW>(fr, Wq + (int64_t)g.e0 * g.C, g.C, g.ne, warp * TPW * 16, q, r8, 1.4426950408889634f);
+  constexpr int ES = PACK ? 4 : 8;
+  uint4* fr = s.frag + (size_t)warp * TPW * ES * 4;
+  fill_afrag<TPW, ES>(fr, Wq + (int64_t)g.e0 * g.C, g.C, g.ne, warp * TPW * 16, q, r8, 1.4426950408889634f);
   float acc[TPW][4];
 #pragma unroll
   for (int t = 0; t < TPW; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
@@ -360,7 +376,7 @@ pool_foldw_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, 
   auto score_next = [&](int n1) {
     mbar_wait(&s.full[s_slot], s_use & 1);
     // partial[(n1)&1] was last read for group n1-2; that read finished before wready(n1-2) which this warp has waited on
-    scores_phase<TPW>(ring_u32 + s_slot * slot_bytes, l_off, fr, s.partial + ((n1 & 1) * NW + warp) * PT, g.ne, q, r8);
+    scores_phase<TPW, ES>(ring_u32 + s_slot * slot_bytes, l_off, fr, s.partial + ((n1 & 1) * NW + warp) * PT, g.ne, q, r8);
     __syncwarp();
     if (lane == 0) mbar_arrive(&s.pready[n1 & 1]);
     if (++s_slot == g.slots) { s_slot = 0; ++s_use; }
@@ -372,30 +388,36 @@ pool_foldw_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, 
     const bool last = gi == nG - 1;
     mbar_wait(&s.wready[b], (n >> 1) & 1);
     const float* wb = s.wbuf + b * WB;
-    const float2 w = *reinterpret_cast<const float2*>(wb + r8 * TG + 2 * q);   // rows of padding entities stay zero
-    const float f0 = (2 * q < g.ne) ? wb[64 + 2 * q] : 1.f;
-    const float f1 = (2 * q + 1 < g.ne) ? wb[64 + 2 * q + 1] : 1.f;
+    const float2 w = *reinterpret_cast<const float2*>(wb + be * TG + 2 * q);   // rows of padding entities stay zero
+    const float f0 = (e0c < g.ne) ? wb[64 + e0c] : 1.f;
+    const float f1 = (e1c < g.ne) ? wb[64 + e1c] : 1.f;
     float i0 = 0.f, i1 = 0.f;
-    if (last) { i0 = wb[72 + 2 * q]; i1 = wb[72 + 2 * q + 1]; }
+    if (last) { i0 = wb[72 + e0c]; i1 = wb[72 + e1c]; }
     uint32_t wh, wl;
     split2(w.x, w.y, wh, wl);
+    if (PACK && r8 >= 4) wh = wl;
     // rescale the accumulators when a running maximum moved (columns = entities 2q, 2q+1)
     if (__any_sync(0xffffffffu, f0 != 1.f || f1 != 1.f)) {
 #pragma unroll
       for (int t = 0; t < TPW; ++t) { acc[t][0] *= f0; acc[t][1] *= f1; acc[t][2] *= f0; acc[t][3] *= f1; }
     }
-    pool_phase<TPW>(ring_u32 + p_slot * slot_bytes, l_off, wh, wl, acc);
+    pool_phase<TPW, PACK>(ring_u32 + p_slot * slot_bytes, l_off, wh, wl, acc);
     __syncwarp();
     if (lane == 0) mbar_arrive(&s.empty[p_slot]);
     if (++p_slot == g.slots) p_slot = 0;
     if (last) {
-      const int e0c = 2 * q, e1c = 2 * q + 1;
       float* base = px + ((int64_t)f * g.Etot + g.e0) * g.C + warp * TPW * 16;
+      const bool writer = !PACK || q < 2;
 #pragma unroll
       for (int t = 0; t < TPW; ++t) {
+        float v0 = acc[t][0], v1 = acc[t][1], v2 = acc[t][2], v3 = acc[t][3];
+        if (PACK) {   // hi half (lanes q < 2) + lo half (lanes q >= 2) of the same entity columns
+          v0 += __shfl_xor_sync(0xffffffffu, v0, 2); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 2); v3 += __shfl_xor_sync(0xffffffffu, v3, 2);
+        }
         const int ch = t * 16 + r8;
-        if (e0c < g.ne) { base[(int64_t)e0c * g.C + ch] = acc[t][0] * i0; base[(int64_t)e0c * g.C + ch + 8] = acc[t][2] * i0; }
-        if (e1c < g.ne) { base[(int64_t)e1c * g.C + ch] = acc[t][1] * i1; base[(int64_t)e1c * g.C + ch + 8] = acc[t][3] * i1; }
+        if (writer && e0c < g.ne) { base[(int64_t)e0c * g.C + ch] = v0 * i0; base[(int64_t)e0c * g.C + ch + 8] = v2 * i0; }
+        if (writer && e1c < g.ne) { base[(int64_t)e1c * g.C + ch] = v1 * i1; base[(int64_t)e1c * g.C + ch + 8] = v3 * i1; }
         acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
       }
       gi = 0;
@@ -409,7 +431,7 @@ pool_foldw_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, 
 // =====================================================================================================================
 // backward:  dWq[e, :] += sum_frames sum_p A[e,p] (G_e . x_p - delta_e) x_p,   delta_e = G_e . px_e
 // =====================================================================================================================
-template <int TPW>
+template <int TPW, bool PACK>
 __global__ void __launch_bounds__(max_threads(TPW), 1)
 pool_foldw_bwd_kernel(const bf16* __restrict__ X, const float* __restrict__ G, const float* __restrict__ px,
                       const float* __restrict__ attn, const float* __restrict__ delta, float* __restrict__ dWq, const Geom g) {
@@ -498,10 +520,13 @@ pool_foldw_bwd_kernel(const bf16* __restrict__ X, const float* __restrict__ G, c
 
   // ===== compute warps =====
   const int q = lane & 3, r8 = lane >> 2;
+  const int be = PACK ? (r8 & 3) : r8;                  // entity of this lane's column of the pooling B operand
+  const int e0c = PACK ? ((2 * q) & 3) : 2 * q, e1c = e0c + 1;   // entities of this lane's accumulator columns
   const uint32_t ring_u32 = smem_u32(s.ring);
   const uint32_t slot_bytes = (uint32_t)(TG * g.pitch);
   const uint32_t l_off = (uint32_t)((lane & 7) * g.pitch + (warp * TPW * 16 + ((lane >> 3) & 1) * 8) * 2);
-  uint4* fr = s.frag + (size_t)warp * TPW * g.ne * 4;
+  constexpr int ES = PACK ? 4 : 8;
+  uint4* fr = s.frag + (size_t)warp * TPW * ES * 4;
   float acc[TPW][4];
 #pragma unroll
   for (int t = 0; t < TPW; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
@@ -510,9 +535,9 @@ pool_foldw_bwd_kernel(const bf16* __restrict__ X, const float* __restrict__ G, c
   int64_t s_f = blockIdx.x;    // frame of the next group to score: its G rows are the A operand
   int p_slot = 0;
   auto score_next = [&](int n1) {
-    if (s_gi == 0) fill_afrag<TPW>(fr, G + ((int64_t)s_f * g.Etot + g.e0) * g.C, g.C, g.ne, warp * TPW * 16, q, r8, 1.f);
+    if (s_gi == 0) fill_afrag<TPW, ES>(fr, G + ((int64_t)s_f * g.Etot + g.e0) * g.C, g.C, g.ne, warp * TPW * 16, q, r8, 1.f);
     mbar_wait(&s.full[s_slot], s_use & 1);
-    scores_phase<TPW>(ring_u32 + s_slot * slot_bytes, l_off, fr, s.partial + ((n1 & 1) * NW + warp) * PT, g.ne, q, r8);
+    scores_phase<TPW, ES>(ring_u32 + s_slot * slot_bytes, l_off, fr, s.partial + ((n1 & 1) * NW + warp) * PT, g.ne, q, r8);
     __syncwarp();
     if (lane == 0) mbar_arrive(&s.pready[n1 & 1]);
     if (++s_slot == g.slots) { s_slot = 0; ++s_use; }
@@ -523,22 +548,28 @@ pool_foldw_bwd_kernel(const bf16* __restrict__ X, const float* __restrict__ G, c
     if (n + 1 < total) score_next(n + 1);
     const int b = n & 1;
     mbar_wait(&s.wready[b], (n >> 1) & 1);
-    const float2 w = *reinterpret_cast<const float2*>(s.wbuf + b * WB + r8 * TG + 2 * q);
+    const float2 w = *reinterpret_cast<const float2*>(s.wbuf + b * WB + be * TG + 2 * q);
     uint32_t wh, wl;
     split2(w.x, w.y, wh, wl);
-    pool_phase<TPW>(ring_u32 + p_slot * slot_bytes, l_off, wh, wl, acc);
+    if (PACK && r8 >= 4) wh = wl;
+    pool_phase<TPW, PACK>(ring_u32 + p_slot * slot_bytes, l_off, wh, wl, acc);
     __syncwarp();
     if (lane == 0) mbar_arrive(&s.empty[p_slot]);
     if (++p_slot == g.slots) p_slot = 0;
   }
   if (nF > 0) {
-    const int e0c = 2 * q, e1c = 2 * q + 1;
     float* base = dWq + (int64_t)g.e0 * g.C + warp * TPW * 16;
+    const bool writer = !PACK || q < 2;
 #pragma unroll
     for (int t = 0; t < TPW; ++t) {
+      float v0 = acc[t][0], v1 = acc[t][1], v2 = acc[t][2], v3 = acc[t][3];
+      if (PACK) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, 2); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, 2); v3 += __shfl_xor_sync(0xffffffffu, v3, 2);
+      }
       const int ch = t * 16 + r8;
-      if (e0c < g.ne) { atomicAdd(base + (int64_t)e0c * g.C + ch, acc[t][0]); atomicAdd(base + (int64_t)e0c * g.C + ch + 8, acc[t][2]); }
-      if (e1c < g.ne) { atomicAdd(base + (int64_t)e1c * g.C + ch, acc[t][1]); atomicAdd(base + (int64_t)e1c * g.C + ch + 8, acc[t][3]); }
+      if (writer && e0c < g.ne) { atomicAdd(base + (int64_t)e0c * g.C + ch, v0); atomicAdd(base + (int64_t)e0c * g.C + ch + 8, v2); }
+      if (writer && e1c < g.ne) { atomicAdd(base + (int64_t)e1c * g.C + ch, v1); atomicAdd(base + (int64_t)e1c * g.C + ch + 8, v3); }
     }
   }
 }
@@ -565,6 +596,16 @@ static bool choose_shape(int C, int P, int ne, int* tpw_out, int* nw_out, int* s
     if (nw > max_compute_warps(tpw)) continue;
     const int score = (nw % 4 == 0 ? 100 : 0) + nw;
     if (score > best_score) { best_score = score; best_tpw = tpw; best_nw = nw; }
+  }
+  static int forced_tpw = -1;   // MVF_FOLD_TPW: tiles per compute warp override for A/B measurements
+  if (forced_tpw < 0) {
+    const char* e = getenv("MVF_FOLD_TPW");
+    forced_tpw = e ? atoi(e) : 0;
+  }
+  if (forced_tpw > 0 && CT % forced_tpw == 0 && CT / forced_tpw <= max_compute_warps(forced_tpw)) {
+    bool known = false;
+    for (int tpw : cand) known = known || tpw == forced_tpw;
+    if (known) { best_tpw = forced_tpw; best_nw = CT / forced_tpw; best_score = 0; }
   }
   if (best_score < 0) return false;
   int slots = MAX_SLOTS;
@@ -603,18 +644,30 @@ static int plan(KernelT kernel, Plan& pl, const Geom& g) {
 
 template <int TPW>
 static int fwd_launch(const Geom& g, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st) {
-  static thread_local Plan pl;
-  MVF_TRY(plan(pool_foldw_fwd_kernel<TPW>, pl, g));
-  pool_foldw_fwd_kernel<TPW><<<pl.grid, (g.NW + 2) * 32, pl.smem, st>>>((const bf16*)X, Wq, attn, px, g);
+  if (g.ne <= 4) {
+    static thread_local Plan pl;
+    MVF_TRY(plan(pool_foldw_fwd_kernel<TPW, true>, pl, g));
+    pool_foldw_fwd_kernel<TPW, true><<<pl.grid, (g.NW + 2) * 32, pl.smem, st>>>((const bf16*)X, Wq, attn, px, g);
+  } else {
+    static thread_local Plan pl;
+    MVF_TRY(plan(pool_foldw_fwd_kernel<TPW, false>, pl, g));
+    pool_foldw_fwd_kernel<TPW, false><<<pl.grid, (g.NW + 2) * 32, pl.smem, st>>>((const bf16*)X, Wq, attn, px, g);
+  }
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
 template <int TPW>
 static int bwd_launch(const Geom& g, const void* X, const float* G, const float* px, const float* attn, const float* delta,
                       float* dWq, cudaStream_t st) {
-  static thread_local Plan pl;
-  MVF_TRY(plan(pool_foldw_bwd_kernel<TPW>, pl, g));
-  pool_foldw_bwd_kernel<TPW><<<pl.grid, (g.NW + 2) * 32, pl.smem, st>>>((const bf16*)X, G, px, attn, delta, dWq, g);
+  if (g.ne <= 4) {
+    static thread_local Plan pl;
+    MVF_TRY(plan(pool_foldw_bwd_kernel<TPW, true>, pl, g));
+    pool_foldw_bwd_kernel<TPW, true><<<pl.grid, (g.NW + 2) * 32, pl.smem, st>>>((const bf16*)X, G, px, attn, delta, dWq, g);
+  } else {
+    static thread_local Plan pl;
+    MVF_TRY(plan(pool_foldw_bwd_kernel<TPW, false>, pl, g));
+    pool_foldw_bwd_kernel<TPW, false><<<pl.grid, (g.NW + 2) * 32, pl.smem, st>>>((const bf16*)X, G, px, attn, delta, dWq, g);
+  }
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
