@@ -434,14 +434,14 @@ def run_ours(args):
             if os.path.exists(tp):
                 with open(tp) as f:
                     traffic = json.load(f).get("dram_bytes_per_launch")
-            r = dict(bound="hbm", kernel="pool_foldm_fwd_kernel<12> (folded entity pooling: one streaming pass over the bf16 tokens, mma.sync)",
+            r = dict(bound="hbm", kernel="pool_foldw_fwd_kernel<9,true> (folded entity pooling: one warp-specialised streaming pass over the bf16 tokens, mma.sync)",
                      achieved=achieved, peak=peaks["hbm"], unit="GB/s", frac=achieved / peaks["hbm"], traffic=traffic,
                      peak_source=f"{peaks['source']} hbm_gbs (copy, read+write)", frac_of_nominal_8000=achieved / 8000.0,
                      ms_per_launch=f_ms, launches_timed=len(pr[0]), bytes_per_launch=fwd_bytes)
             if pr[1]:
                 b_ms = mean(pr[1])
                 bwd_bytes = tok_bytes + 2 * F_frames * E * C_in * 4 + F_frames * E * P * 4
-                r["backward_pass"] = dict(kernel="pool_foldm_bwd_kernel<12>", ms_per_launch=b_ms, bytes_per_launch=bwd_bytes,
+                r["backward_pass"] = dict(kernel="pool_foldw_bwd_kernel<9,true>", ms_per_launch=b_ms, bytes_per_launch=bwd_bytes,
                                           achieved=bwd_bytes / (b_ms * 1e-3) / 1e9,
                                           frac=bwd_bytes / (b_ms * 1e-3) / 1e9 / peaks["hbm"])
             r["share_of_step"] = dict(pool_stream_fwd=f_ms / ms, pool_stream_bwd=(mean(pr[1]) / ms) if pr[1] else None,
