@@ -19,6 +19,7 @@ template <typename T, int DK>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict__ keymask, T* __restrict__ ctx,
                 float* __restrict__ lse) {
+  pdl_entry();
   __shared__ __align__(16) float Ks[ATT_TILE][DK];
   __shared__ __align__(16) float Vs[ATT_TILE][DK];
   __shared__ float Ms[ATT_TILE];
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict__ keymask,
                    const T* __restrict__ ctx, const float* __restrict__ lse, const T* __restrict__ d_ctx,
                    T* __restrict__ d_qkv, float* __restrict__ delta) {
+  pdl_entry();
   __shared__ __align__(16) float Ks[ATT_TILE][DK];
   __shared__ __align__(16) float Vs[ATT_TILE][DK];
   __shared__ float Ms[ATT_TILE];
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(int S, int H, const T* __restrict__ qkv, const float* __restrict__ keymask,
                     const float* __restrict__ lse, const T* __restrict__ d_ctx, const float* __restrict__ delta,
                     T* __restrict__ d_qkv) {
+  pdl_entry();
   __shared__ __align__(16) float Qs[ATT_TILE][DK];
   __shared__ __align__(16) float Gs[ATT_TILE][DK];
   __shared__ float Ls[ATT_TILE];
@@ -291,6 +294,7 @@ template <int DK>
 __global__ void __launch_bounds__(512)
 attn_fwd_quad_kernel(int S, int H, const float* __restrict__ qkv, const float* __restrict__ keymask,
                      float* __restrict__ ctx, float* __restrict__ lse) {
+  pdl_entry();
   constexpr int DQ = DK / 4, D4 = DK / 4;
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;
@@ -378,6 +382,7 @@ __global__ void __launch_bounds__(512)
 attn_bwd_quad_kernel(int S, int H, const float* __restrict__ qkv, const float* __restrict__ keymask,
                      const float* __restrict__ ctx, const float* __restrict__ lse, const float* __restrict__ d_ctx,
                      float* __restrict__ d_qkv) {
+  pdl_entry();
   constexpr int DQ = DK / 4, D4 = DK / 4;
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;
@@ -519,7 +524,7 @@ static int fwd_quad_launch(int B, int S, int heads, const void* qkv, const float
     configured = smem;
   }
   const int nt = (int)round_up(4 * S, 32);
-  attn_fwd_quad_kernel<DK><<<dim3(heads, B), nt, smem, st>>>(S, heads * DK, (const float*)qkv, keymask, (float*)ctx, lse);
+  launch_k(attn_fwd_quad_kernel<DK>, dim3(heads, B), nt, smem, st, S, heads * DK, (const float*)qkv, keymask, (float*)ctx, lse);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -533,7 +538,7 @@ static int bwd_quad_launch(int B, int S, int heads, const void* qkv, const float
     configured = smem;
   }
   const int nt = (int)round_up(4 * S, 32);
-  attn_bwd_quad_kernel<DK><<<dim3(heads, B), nt, smem, st>>>(S, heads * DK, (const float*)qkv, keymask, (const float*)ctx, lse,
+  launch_k(attn_bwd_quad_kernel<DK>, dim3(heads, B), nt, smem, st, S, heads * DK, (const float*)qkv, keymask, (const float*)ctx, lse,
                                                              (const float*)d_ctx, (float*)d_qkv);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
@@ -543,7 +548,7 @@ template <typename T, int DK>
 static int fwd_launch(int B, int S, int heads, const void* qkv, const float* keymask, void* ctx, float* lse,
                       cudaStream_t st) {
   dim3 grid(cdiv(S, ATT_THREADS), heads, B);
-  attn_fwd_kernel<T, DK><<<grid, ATT_THREADS, 0, st>>>(S, heads * DK, (const T*)qkv, keymask, (T*)ctx, lse);
+  launch_k(attn_fwd_kernel<T, DK>, grid, ATT_THREADS, 0, st, S, heads * DK, (const T*)qkv, keymask, (T*)ctx, lse);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -551,10 +556,10 @@ template <typename T, int DK>
 static int bwd_launch(int B, int S, int heads, const void* qkv, const float* keymask, const void* ctx, const float* lse,
                       const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st) {
   dim3 grid(cdiv(S, ATT_THREADS), heads, B);
-  attn_bwd_dq_kernel<T, DK><<<grid, ATT_THREADS, 0, st>>>(S, heads * DK, (const T*)qkv, keymask, (const T*)ctx, lse,
+  launch_k(attn_bwd_dq_kernel<T, DK>, grid, ATT_THREADS, 0, st, S, heads * DK, (const T*)qkv, keymask, (const T*)ctx, lse,
                                                           (const T*)d_ctx, (T*)d_qkv, delta);
   MVF_CHECK_LAUNCH();
-  attn_bwd_dkv_kernel<T, DK><<<grid, ATT_THREADS, 0, st>>>(S, heads * DK, (const T*)qkv, keymask, lse, (const T*)d_ctx,
+  launch_k(attn_bwd_dkv_kernel<T, DK>, grid, ATT_THREADS, 0, st, S, heads * DK, (const T*)qkv, keymask, lse, (const T*)d_ctx,
                                                            delta, (T*)d_qkv);
   MVF_CHECK_LAUNCH();
   return MVF_OK;

@@ -46,6 +46,33 @@ void count_launch();  // library-wide kernel launch counter (mvf_launch_count)
     if (_s != MVF_OK) return _s; \
   } while (0)
 
+// ---- programmatic dependent launch ----------------------------------------------------------------------------
+// The step is a chain of ~120 short kernels, each depending on its predecessor.  Every kernel is launched with the
+// programmatic-stream-serialization attribute and calls pdl_entry() before its first global-memory access:
+//   griddepcontrol.wait               blocks until the previous kernel in the stream has completed and flushed its writes;
+//   griddepcontrol.launch_dependents  then lets the NEXT kernel's CTAs be scheduled while this one still runs (they park at
+//                                     their own wait), so launch latency and kernel prologues leave the critical path.
+// Triggering only after the wait keeps the look-ahead at one kernel (no pile-up of parked CTAs).  MVF_PDL=0 launches plainly.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors are picked up by MVF_CHECK_LAUNCH
+}
+
 // ---- scalar conversion ---------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }

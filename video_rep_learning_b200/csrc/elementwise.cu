@@ -18,6 +18,7 @@ struct UnpackTable {
 };
 
 __global__ void pack_kernel(const PackTable tab) {
+  pdl_entry();
   const PackEntry& en = tab.e[blockIdx.y];
   const int64_t total = (int64_t)en.rows * en.ld_dst;
   if (en.dst_bf16 == 0 && en.ld_dst == en.cols && (total & 3) == 0 && ((((uintptr_t)en.src) | ((uintptr_t)en.dst)) & 15) == 0) {
@@ -47,13 +48,14 @@ int pack_params(const PackEntry* entries, int n, cudaStream_t st) {
     PackTable tab;
     tab.n = (n - base < PACK_CHUNK) ? n - base : PACK_CHUNK;
     for (int i = 0; i < tab.n; ++i) tab.e[i] = entries[base + i];
-    pack_kernel<<<dim3(148, tab.n), 256, 0, st>>>(tab);
+    launch_k(pack_kernel, dim3(148, tab.n), 256, 0, st, tab);
     MVF_CHECK_LAUNCH();
   }
   return MVF_OK;
 }
 
 __global__ void unpack_kernel(const UnpackTable tab, float scale) {
+  pdl_entry();
   const UnpackEntry& en = tab.e[blockIdx.y];
   const int64_t total = (int64_t)en.rows * en.cols;
   if (en.ld_src == en.cols && (total & 3) == 0 && ((((uintptr_t)en.src) | ((uintptr_t)en.dst)) & 15) == 0) {
@@ -76,7 +78,7 @@ int unpack_grads(const UnpackEntry* entries, int n, float scale, cudaStream_t st
     UnpackTable tab;
     tab.n = (n - base < PACK_CHUNK) ? n - base : PACK_CHUNK;
     for (int i = 0; i < tab.n; ++i) tab.e[i] = entries[base + i];
-    unpack_kernel<<<dim3(148, tab.n), 256, 0, st>>>(tab, scale);
+    launch_k(unpack_kernel, dim3(148, tab.n), 256, 0, st, tab, scale);
     MVF_CHECK_LAUNCH();
   }
   return MVF_OK;
@@ -86,6 +88,7 @@ int unpack_grads(const UnpackEntry* entries, int n, float scale, cudaStream_t st
 // models/utils.py:113-126: sin on even channels, cos on odd, exponent uses the channel index itself;
 // positions 0..T-1 or numpy.linspace(0, train-1, T) when T != train length.  float64 like numpy.
 __global__ void posenc_table_kernel(float* table, int T, int H, int train_frames) {
+  pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * H) return;
   int t = i / H, c = i % H;
@@ -100,13 +103,14 @@ __global__ void posenc_table_kernel(float* table, int T, int H, int train_frames
   table[i] = (float)((c & 1) ? cos(ang) : sin(ang));
 }
 int posenc_table(float* table, int T, int H, int train_frames, cudaStream_t st) {
-  posenc_table_kernel<<<cdiv((int64_t)T * H, 256), 256, 0, st>>>(table, T, H, train_frames);
+  launch_k(posenc_table_kernel, cdiv((int64_t)T * H, 256), 256, 0, st, table, T, H, train_frames);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
 
 __global__ void posenc_add_kernel(const float* __restrict__ h3, const float* __restrict__ table, float* __restrict__ z,
                                   int BV, int T, int E, int H, float p, float inv_keep, DropSeed seed) {
+  pdl_entry();
   int64_t total = (int64_t)BV * E * T * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % H);
@@ -123,7 +127,7 @@ int posenc_add(const float* h3, const float* table, float* z, int BV, int T, int
                cudaStream_t st) {
   int64_t total = (int64_t)BV * E * T * H;
   int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  posenc_add_kernel<<<grid, 256, 0, st>>>(h3, table, z, BV, T, E, H, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+  launch_k(posenc_add_kernel, grid, 256, 0, st, h3, table, z, BV, T, E, H, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -131,6 +135,7 @@ int posenc_add(const float* h3, const float* table, float* z, int BV, int T, int
 template <typename TO>
 __global__ void posenc_bwd_kernel(const float* __restrict__ dz, TO* __restrict__ dh3, int BV, int T, int E, int H,
                                   float p, float inv_keep, DropSeed seed) {
+  pdl_entry();
   int64_t total = (int64_t)BV * E * T * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % H);
@@ -148,8 +153,8 @@ int posenc_bwd(int dtype_out, const float* dz, void* dh3, int BV, int T, int E, 
   int64_t total = (int64_t)BV * E * T * H;
   int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  if (dtype_out == MVF_BF16) posenc_bwd_kernel<bf16><<<grid, 256, 0, st>>>(dz, (bf16*)dh3, BV, T, E, H, p, ik, seed);
-  else posenc_bwd_kernel<float><<<grid, 256, 0, st>>>(dz, (float*)dh3, BV, T, E, H, p, ik, seed);
+  if (dtype_out == MVF_BF16) launch_k(posenc_bwd_kernel<bf16>, grid, 256, 0, st, dz, (bf16*)dh3, BV, T, E, H, p, ik, seed);
+  else launch_k(posenc_bwd_kernel<float>, grid, 256, 0, st, dz, (float*)dh3, BV, T, E, H, p, ik, seed);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -163,6 +168,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ z
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      int64_t rows, int H, float eps, float p, float inv_keep,
                                                      DropSeed seed, int site) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -202,10 +208,10 @@ int ln_fwd(int dtype_out, const float* z_in, const float* o, float* z_out, void*
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
   int grid = cdiv(rows, 8);
   if (dtype_out == MVF_BF16)
-    ln_fwd_kernel<bf16><<<grid, 256, 0, st>>>(z_in, o, z_out, (bf16*)r, mean, rstd, gamma, beta, rows, H, eps, p, ik,
+    launch_k(ln_fwd_kernel<bf16>, grid, 256, 0, st, z_in, o, z_out, (bf16*)r, mean, rstd, gamma, beta, rows, H, eps, p, ik,
                                               seed, site);
   else
-    ln_fwd_kernel<float><<<grid, 256, 0, st>>>(z_in, o, z_out, (float*)r, mean, rstd, gamma, beta, rows, H, eps, p, ik,
+    launch_k(ln_fwd_kernel<float>, grid, 256, 0, st, z_in, o, z_out, (float*)r, mean, rstd, gamma, beta, rows, H, eps, p, ik,
                                                seed, site);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
@@ -223,6 +229,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      float* __restrict__ dbeta, int64_t rows, int H,
                                                      float* __restrict__ drop_out, float p, float inv_keep, DropSeed seed,
                                                      int site) {
+  pdl_entry();
   extern __shared__ float acc[];  // [8 warps][2][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float gam[VPL], ag[VPL], ab[VPL];
@@ -288,7 +295,7 @@ int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd
   size_t smem = (size_t)8 * 2 * H * sizeof(float);
   MVF_REQUIRE(H % 32 == 0 && H <= 1024 && smem <= 48 * 1024, MVF_ERR_UNSUPPORTED,
               "ln_bwd: hidden size %d must be a multiple of 32 and <= 768", H);
-#define MVF_LNB(V) ln_bwd_kernel<V><<<grid, 256, smem, st>>>(dr, z, mean, rstd, gamma, dz_in, dz_out, dgamma, dbeta, rows, H, drop_out, p, ik, seed, site)
+#define MVF_LNB(V) launch_k(ln_bwd_kernel<V>, grid, 256, smem, st, dr, z, mean, rstd, gamma, dz_in, dz_out, dgamma, dbeta, rows, H, drop_out, p, ik, seed, site)
   switch (H / 32) {
     case 1: MVF_LNB(1); break;
     case 2: MVF_LNB(2); break;
@@ -312,6 +319,7 @@ int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd
 // Column statistics: block = 32 columns x 8 row lanes; double partials, double atomics.
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int64_t R, int C,
                                                        double* __restrict__ sums) {
+  pdl_entry();
   __shared__ double sh[2][8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -336,7 +344,7 @@ int bn_stats(const float* x, int64_t R, int C, double* sums, cudaStream_t st) {
   int gy = cdiv(R, 8 * 16);
   if (gy > 64) gy = 64;
   if (gy < 1) gy = 1;
-  bn_stats_kernel<<<dim3(cdiv(C, 32), gy), 256, 0, st>>>(x, R, C, sums);
+  launch_k(bn_stats_kernel, dim3(cdiv(C, 32), gy), 256, 0, st, x, R, C, sums);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -346,6 +354,7 @@ int bn_stats(const float* x, int64_t R, int C, double* sums, cudaStream_t st) {
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double n, float eps, int training,
                                    float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
                                    int64_t* __restrict__ tracked, float* __restrict__ mi) {
+  pdl_entry();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && training && tracked) *tracked += 1;
   if (c >= C) return;
@@ -367,7 +376,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, doubl
 }
 int bn_finalize(const double* sums, int C, double n_global, float eps, int training, float momentum, float* rmean,
                 float* rvar, int64_t* tracked, float* mi, cudaStream_t st) {
-  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(sums, C, n_global, eps, training, momentum, rmean, rvar, tracked, mi);
+  launch_k(bn_finalize_kernel, cdiv(C, 128), 128, 0, st, sums, C, n_global, eps, training, momentum, rmean, rvar, tracked, mi);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -376,6 +385,7 @@ template <typename TO>
 __global__ void bn_apply_kernel(const float* __restrict__ x, int64_t R, int C, const float* __restrict__ mi,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                                 TO* __restrict__ out, int64_t ld_out, float p, float inv_keep, DropSeed seed, int site) {
+  pdl_entry();
   int64_t total = R * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -392,9 +402,9 @@ int bn_apply(int dtype_out, const float* x, int64_t R, int C, const float* mi, c
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
   if (dtype_out == MVF_BF16)
-    bn_apply_kernel<bf16><<<grid, 256, 0, st>>>(x, R, C, mi, gamma, beta, relu, (bf16*)out, ld_out, p, ik, seed, site);
+    launch_k(bn_apply_kernel<bf16>, grid, 256, 0, st, x, R, C, mi, gamma, beta, relu, (bf16*)out, ld_out, p, ik, seed, site);
   else
-    bn_apply_kernel<float><<<grid, 256, 0, st>>>(x, R, C, mi, gamma, beta, relu, (float*)out, ld_out, p, ik, seed, site);
+    launch_k(bn_apply_kernel<float>, grid, 256, 0, st, x, R, C, mi, gamma, beta, relu, (float*)out, ld_out, p, ik, seed, site);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -405,6 +415,7 @@ bn_bwd_stats_kernel(const float* __restrict__ d_out, int64_t ld_d, const float* 
                     const float* __restrict__ mi, const float* __restrict__ gamma, const float* __restrict__ beta,
                     int relu, float p, float inv_keep, DropSeed seed, int site, double* __restrict__ bsums,
                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_entry();
   __shared__ double sh[2][8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -438,7 +449,7 @@ int bn_bwd_stats(const float* d_out, int64_t ld_d, const float* x, int64_t R, in
   if (gy > 64) gy = 64;
   if (gy < 1) gy = 1;
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  bn_bwd_stats_kernel<<<dim3(cdiv(C, 32), gy), 256, 0, st>>>(d_out, ld_d, x, R, C, mi, gamma, beta, relu, p, ik, seed,
+  launch_k(bn_bwd_stats_kernel, dim3(cdiv(C, 32), gy), 256, 0, st, d_out, ld_d, x, R, C, mi, gamma, beta, relu, p, ik, seed,
                                                              site, bsums, dgamma, dbeta);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
@@ -451,6 +462,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ d_out, int64_t ld_
                                     const float* __restrict__ beta, int relu, float p, float inv_keep, DropSeed seed,
                                     int site, const double* __restrict__ bsums, double n, TO* __restrict__ dx,
                                     int64_t ld_dx) {
+  pdl_entry();
   int64_t total = R * C;
   const float inv_n = (float)(1.0 / n);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -472,10 +484,10 @@ int bn_bwd_apply(int dtype_out, const float* d_out, int64_t ld_d, const float* x
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
   if (dtype_out == MVF_BF16)
-    bn_bwd_apply_kernel<bf16><<<grid, 256, 0, st>>>(d_out, ld_d, x, R, C, mi, gamma, beta, relu, p, ik, seed, site,
+    launch_k(bn_bwd_apply_kernel<bf16>, grid, 256, 0, st, d_out, ld_d, x, R, C, mi, gamma, beta, relu, p, ik, seed, site,
                                                     bsums, n_global, (bf16*)dx, ld_dx);
   else
-    bn_bwd_apply_kernel<float><<<grid, 256, 0, st>>>(d_out, ld_d, x, R, C, mi, gamma, beta, relu, p, ik, seed, site,
+    launch_k(bn_bwd_apply_kernel<float>, grid, 256, 0, st, d_out, ld_d, x, R, C, mi, gamma, beta, relu, p, ik, seed, site,
                                                      bsums, n_global, (float*)dx, ld_dx);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
@@ -485,6 +497,7 @@ int bn_bwd_apply(int dtype_out, const float* d_out, int64_t ld_d, const float* x
 template <typename TI>
 __global__ void __launch_bounds__(256) colsum_kernel(const TI* __restrict__ X, int64_t R, int C, int64_t ld,
                                                      float* __restrict__ out) {
+  pdl_entry();
   __shared__ float sh[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -505,6 +518,7 @@ struct ColsumTable {
   ColsumEntry e[COLSUM_MAX];
 };
 __global__ void __launch_bounds__(256) colsum_batched_kernel(const ColsumTable tab) {
+  pdl_entry();
   const ColsumEntry& en = tab.e[blockIdx.z];
   __shared__ float sh[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -533,7 +547,7 @@ int colsum_batched(const ColsumEntry* entries, int n, cudaStream_t st) {
     }
     int gy = cdiv(maxR, 8 * 32);
     gy = gy > 32 ? 32 : (gy < 1 ? 1 : gy);
-    colsum_batched_kernel<<<dim3(cdiv(maxC, 32), gy, tab.n), 256, 0, st>>>(tab);
+    launch_k(colsum_batched_kernel, dim3(cdiv(maxC, 32), gy, tab.n), 256, 0, st, tab);
     MVF_CHECK_LAUNCH();
   }
   return MVF_OK;
@@ -544,8 +558,8 @@ int colsum(int dtype_in, const void* X, int64_t R, int C, int64_t ld, float* out
   if (gy > 128) gy = 128;
   if (gy < 1) gy = 1;
   dim3 grid(cdiv(C, 32), gy);
-  if (dtype_in == MVF_BF16) colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)X, R, C, ld, out);
-  else colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)X, R, C, ld, out);
+  if (dtype_in == MVF_BF16) launch_k(colsum_kernel<bf16>, grid, 256, 0, st, (const bf16*)X, R, C, ld, out);
+  else launch_k(colsum_kernel<float>, grid, 256, 0, st, (const float*)X, R, C, ld, out);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -553,6 +567,7 @@ int colsum(int dtype_in, const void* X, int64_t R, int C, int64_t ld, float* out
 template <typename TO>
 __global__ void dropout_cast_kernel(const float* __restrict__ in, TO* __restrict__ out, int64_t rows, int cols,
                                     int64_t ld_out, float p, float inv_keep, DropSeed seed, int site) {
+  pdl_entry();
   int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     float v = in[i];
@@ -567,9 +582,9 @@ int dropout_cast(int dtype_out, const float* in, void* out, int64_t rows, int co
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
   if (dtype_out == MVF_BF16)
-    dropout_cast_kernel<bf16><<<grid, 256, 0, st>>>(in, (bf16*)out, rows, cols, ld_out, p, ik, seed, site);
+    launch_k(dropout_cast_kernel<bf16>, grid, 256, 0, st, in, (bf16*)out, rows, cols, ld_out, p, ik, seed, site);
   else
-    dropout_cast_kernel<float><<<grid, 256, 0, st>>>(in, (float*)out, rows, cols, ld_out, p, ik, seed, site);
+    launch_k(dropout_cast_kernel<float>, grid, 256, 0, st, in, (float*)out, rows, cols, ld_out, p, ik, seed, site);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -578,6 +593,7 @@ int cast_f32(int dtype_out, const float* in, void* out, int64_t n, cudaStream_t 
 }
 
 __global__ void dropout_mask_kernel(DropSeed seed, int site, int64_t total, float p, float inv_keep, float* out) {
+  pdl_entry();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = p > 0.f ? drop_scale(seed, site, (uint64_t)i, p, inv_keep) : 1.f;
 }
@@ -585,7 +601,7 @@ int dropout_mask_export(DropSeed seed, int site, int64_t rows, int64_t cols, flo
   int64_t total = rows * cols;
   if (total == 0) return MVF_OK;
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
-  dropout_mask_kernel<<<grid, 256, 0, st>>>(seed, site, total, p, p > 0.f ? 1.f / (1.f - p) : 1.f, out);
+  launch_k(dropout_mask_kernel, grid, 256, 0, st, seed, site, total, p, p > 0.f ? 1.f / (1.f - p) : 1.f, out);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -594,6 +610,7 @@ int dropout_mask_export(DropSeed seed, int site, int64_t rows, int64_t cols, flo
 template <typename TO>
 __global__ void entity_reduce_fwd_kernel(const float* __restrict__ z, TO* __restrict__ y, int32_t* __restrict__ argmax,
                                          int BV, int T, int E, int H, int mode) {
+  pdl_entry();
   int64_t total = (int64_t)BV * T * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % H);
@@ -623,13 +640,14 @@ int entity_reduce_fwd(int dtype_out, const float* z, void* y, int32_t* argmax, i
                       cudaStream_t st) {
   int64_t total = (int64_t)BV * T * H;
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
-  if (dtype_out == MVF_BF16) entity_reduce_fwd_kernel<bf16><<<grid, 256, 0, st>>>(z, (bf16*)y, argmax, BV, T, E, H, mode);
-  else entity_reduce_fwd_kernel<float><<<grid, 256, 0, st>>>(z, (float*)y, argmax, BV, T, E, H, mode);
+  if (dtype_out == MVF_BF16) launch_k(entity_reduce_fwd_kernel<bf16>, grid, 256, 0, st, z, (bf16*)y, argmax, BV, T, E, H, mode);
+  else launch_k(entity_reduce_fwd_kernel<float>, grid, 256, 0, st, z, (float*)y, argmax, BV, T, E, H, mode);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
 __global__ void entity_reduce_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ argmax,
                                          float* __restrict__ dz, int BV, int T, int E, int H, int mode) {
+  pdl_entry();
   int64_t total = (int64_t)BV * E * T * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % H);
@@ -650,7 +668,7 @@ int entity_reduce_bwd(const float* dy, const int32_t* argmax, float* dz, int BV,
                       cudaStream_t st) {
   int64_t total = (int64_t)BV * E * T * H;
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
-  entity_reduce_bwd_kernel<<<grid, 256, 0, st>>>(dy, argmax, dz, BV, T, E, H, mode);
+  launch_k(entity_reduce_bwd_kernel, grid, 256, 0, st, dy, argmax, dz, BV, T, E, H, mode);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -658,6 +676,7 @@ int entity_reduce_bwd(const float* dy, const int32_t* argmax, float* dz, int BV,
 // SMART_FINAL 'lin' (mvformer.py:191-195): zl[b*T+t, e*H+c] = z[b, e*T+t, c]
 template <typename TO>
 __global__ void entity_gather_lin_kernel(const float* __restrict__ z, TO* __restrict__ zl, int BV, int T, int E, int H) {
+  pdl_entry();
   int64_t total = (int64_t)BV * E * T * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % H);
@@ -671,13 +690,14 @@ __global__ void entity_gather_lin_kernel(const float* __restrict__ z, TO* __rest
 int entity_gather_lin(int dtype_out, const float* z, void* zl, int BV, int T, int E, int H, cudaStream_t st) {
   int64_t total = (int64_t)BV * E * T * H;
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
-  if (dtype_out == MVF_BF16) entity_gather_lin_kernel<bf16><<<grid, 256, 0, st>>>(z, (bf16*)zl, BV, T, E, H);
-  else entity_gather_lin_kernel<float><<<grid, 256, 0, st>>>(z, (float*)zl, BV, T, E, H);
+  if (dtype_out == MVF_BF16) launch_k(entity_gather_lin_kernel<bf16>, grid, 256, 0, st, z, (bf16*)zl, BV, T, E, H);
+  else launch_k(entity_gather_lin_kernel<float>, grid, 256, 0, st, z, (float*)zl, BV, T, E, H);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
 __global__ void entity_scatter_lin_kernel(const float* __restrict__ dzl, float* __restrict__ dz, int BV, int T, int E,
                                           int H) {
+  pdl_entry();
   int64_t total = (int64_t)BV * E * T * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % H);
@@ -691,7 +711,7 @@ __global__ void entity_scatter_lin_kernel(const float* __restrict__ dzl, float* 
 int entity_scatter_lin(const float* dzl, float* dz, int BV, int T, int E, int H, cudaStream_t st) {
   int64_t total = (int64_t)BV * E * T * H;
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
-  entity_scatter_lin_kernel<<<grid, 256, 0, st>>>(dzl, dz, BV, T, E, H);
+  launch_k(entity_scatter_lin_kernel, grid, 256, 0, st, dzl, dz, BV, T, E, H);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -699,6 +719,7 @@ int entity_scatter_lin(const float* dzl, float* dz, int BV, int T, int E, int H,
 // F.normalize(x, dim=-1, eps=1e-12): y = x / max(||x||, eps)   (transformer.py:228)
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                          float* __restrict__ norm, int64_t rows, int D) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -710,7 +731,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict
   if (lane == 0) norm[row] = n;
 }
 int l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int D, cudaStream_t st) {
-  l2norm_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, y, norm, rows, D);
+  launch_k(l2norm_fwd_kernel, cdiv(rows, 8), 256, 0, st, x, y, norm, rows, D);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -719,6 +740,7 @@ template <typename TO>
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                                          const float* __restrict__ norm, TO* __restrict__ dx,
                                                          int64_t rows, int D) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -731,8 +753,8 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict
 }
 int l2norm_bwd(const float* dy, const float* y, const float* norm, void* dx, int dtype_out, int64_t rows, int D,
                cudaStream_t st) {
-  if (dtype_out == MVF_BF16) l2norm_bwd_kernel<bf16><<<cdiv(rows, 8), 256, 0, st>>>(dy, y, norm, (bf16*)dx, rows, D);
-  else l2norm_bwd_kernel<float><<<cdiv(rows, 8), 256, 0, st>>>(dy, y, norm, (float*)dx, rows, D);
+  if (dtype_out == MVF_BF16) launch_k(l2norm_bwd_kernel<bf16>, cdiv(rows, 8), 256, 0, st, dy, y, norm, (bf16*)dx, rows, D);
+  else launch_k(l2norm_bwd_kernel<float>, cdiv(rows, 8), 256, 0, st, dy, y, norm, (float*)dx, rows, D);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }

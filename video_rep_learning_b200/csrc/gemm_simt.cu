@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(int M, int N, int K, con
                                                         TC* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
                                                         const TAB* __restrict__ relu_src, int64_t ld_relu, int flags,
                                                         int a_kmajor, int b_kmajor) {
+  pdl_entry();
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int t = threadIdx.x;
@@ -86,7 +87,7 @@ static int launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, c
   dim3 grid(cdiv(N, BN), cdiv(M, BM));
   int64_t sam = a_kmajor ? lda : 1, sak = a_kmajor ? 1 : lda;
   int64_t sbn = b_kmajor ? ldb : 1, sbk = b_kmajor ? 1 : ldb;
-  gemm_simt_kernel<TAB, TC><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, (const TAB*)A, sam, sak, (const TAB*)B, sbn,
+  launch_k(gemm_simt_kernel<TAB, TC>, grid, 256, 0, st, (int)M, (int)N, (int)K, (const TAB*)A, sam, sak, (const TAB*)B, sbn,
                                                   sbk, (TC*)C, ldc, bias, (const TAB*)relu_src, ld_relu, flags,
                                                   a_kmajor, b_kmajor);
   MVF_CHECK_LAUNCH();

@@ -252,6 +252,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) MVF_STAMP(1);
+  // everything above touched only shared / tensor memory and the kernel parameters: with programmatic dependent launch it
+  // overlaps the tail of the previous kernel in the stream; global memory is first read / written below
+  pdl_entry();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -657,7 +660,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   }
   int work = p.tiles_m * p.tiles_n * p.split_k;
   int grid = work < num_sms ? work : num_sms;
-  gemm_tc_kernel<BLOCK_N, STAGES, EB, SPLIT><<<grid, (SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS) + EXTRA_EPI_THREADS, smem, st>>>(ma, mb, mc, p);
+  launch_k(gemm_tc_kernel<BLOCK_N, STAGES, EB, SPLIT>, grid, (SPLIT ? NUM_THREADS_SPLIT : NUM_THREADS) + EXTRA_EPI_THREADS, smem, st, ma, mb, mc, p);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }

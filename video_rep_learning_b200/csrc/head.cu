@@ -25,6 +25,15 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MVF_PDL");
+    on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return on != 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // launch counter + optional CUDA-event timing of the dominant kernels (bench.py's roofline numbers)
 // ------------------------------------------------------------------------------------------------------------

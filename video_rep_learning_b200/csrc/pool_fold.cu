@@ -257,6 +257,7 @@ template <typename T, int E, int NTMAX>
 __global__ void __launch_bounds__(NTMAX, 1)
 pool_fold_fwd_kernel(const T* __restrict__ X, const float* __restrict__ Wq, float* __restrict__ attn,
                      float* __restrict__ px, const Geom g) {
+  pdl_entry();
   constexpr int NV = TG * E;
   MVF_FOLD_SMEM_SETUP();
   float* fin = misc;  // [2][E]: final max, 1/sum
@@ -351,6 +352,7 @@ template <typename T, int E, int NTMAX>
 __global__ void __launch_bounds__(NTMAX, 1)
 pool_fold_bwd_kernel(const T* __restrict__ X, const float* __restrict__ G, const float* __restrict__ px,
                      const float* __restrict__ attn, float* __restrict__ dWq, const Geom g) {
+  pdl_entry();
   constexpr int NV = TG * E;
   MVF_FOLD_SMEM_SETUP();
   float* red = misc;  // [NW][E] partial delta
@@ -438,6 +440,7 @@ constexpr int PREP_SLICES = 32;   // j-slices per CTA: 32 channels x 32 slices =
 __global__ void __launch_bounds__(1024)
 fold_prep_kernel(const float* __restrict__ q_s, const float* __restrict__ q_b, const float* __restrict__ Wk, int E, int SPC,
                  int C, float scale, float* __restrict__ Wq) {
+  pdl_entry();
   extern __shared__ double smd[];
   float* Qf = reinterpret_cast<float*>(smd + (size_t)PREP_SLICES * E * 32);   // [E][SPC] (fp32 sum, like mvformer.py:383)
   double* red = smd;                                                          // [PREP_SLICES][E][32]
@@ -474,6 +477,7 @@ __global__ void __launch_bounds__(256)
 fold_finish_kernel(const float* __restrict__ dWq, const float* __restrict__ q_s, const float* __restrict__ q_b,
                    const float* __restrict__ Wk, int E, int SPC, int C, float scale, float* __restrict__ dWk, int64_t ld_dwk,
                    float* __restrict__ dQs, float* __restrict__ dQb) {
+  pdl_entry();
   __shared__ float red[8][MVF_MAX_ENTITIES];
   const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float qf[MVF_MAX_ENTITIES], dot[MVF_MAX_ENTITIES];
@@ -520,6 +524,7 @@ fold_finish_kernel(const float* __restrict__ dWq, const float* __restrict__ q_s,
 // h0[row, :] = [drop(ent[row, :SPC]) | drop(one-hot entity id) | 0 padding]   (mvformer.py:144-151)
 __global__ void ent_finish_fwd_kernel(const float* __restrict__ ent, float* __restrict__ h0, int64_t ld, int64_t R, int SPC,
                                       int E, int one_hot, float p, float inv_keep, DropSeed seed) {
+  pdl_entry();
   const int W = SPC + (one_hot ? E : 0);
   const int64_t total = R * ld;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -535,6 +540,7 @@ __global__ void ent_finish_fwd_kernel(const float* __restrict__ ent, float* __re
 // dEnt[row, c] = drop'(d_h0[row, c]) for c < SPC
 __global__ void ent_finish_bwd_kernel(const float* __restrict__ d_h0, int64_t ld, float* __restrict__ dEnt, int64_t R, int SPC,
                                       int W, float p, float inv_keep, DropSeed seed) {
+  pdl_entry();
   const int64_t total = R * SPC;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / SPC;
@@ -551,6 +557,7 @@ __global__ void __launch_bounds__(256)
 ent_finish_bwd_delta_kernel(const float* __restrict__ d_h0, int64_t ld, float* __restrict__ dEnt, int64_t R, int SPC, int W,
                             float p, float inv_keep, DropSeed seed, const float* __restrict__ ent,
                             const float* __restrict__ bv, float* __restrict__ delta) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -624,7 +631,7 @@ static int fwd_launch(const Geom& g, const void* X, const float* Wq, float* attn
   MVF_TRY(plan_launch(pool_fold_fwd_kernel<T, E, NTMAX>, cache, g.F, g.P, g.C, E, (int)sizeof(T), L));
   Geom gg = g;
   gg.stages = L.stages;
-  pool_fold_fwd_kernel<T, E, NTMAX><<<L.grid, L.nt, L.smem, st>>>((const T*)X, Wq, attn, px, gg);
+  launch_k(pool_fold_fwd_kernel<T, E, NTMAX>, L.grid, L.nt, L.smem, st, (const T*)X, Wq, attn, px, gg);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -636,7 +643,7 @@ static int bwd_launch(const Geom& g, const void* X, const float* G, const float*
   MVF_TRY(plan_launch(pool_fold_bwd_kernel<T, E, NTMAX>, cache, g.F, g.P, g.C, E, (int)sizeof(T), L));
   Geom gg = g;
   gg.stages = L.stages;
-  pool_fold_bwd_kernel<T, E, NTMAX><<<L.grid, L.nt, L.smem, st>>>((const T*)X, G, px, attn, dWq, gg);
+  launch_k(pool_fold_bwd_kernel<T, E, NTMAX>, L.grid, L.nt, L.smem, st, (const T*)X, G, px, attn, dWq, gg);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -743,14 +750,14 @@ int fold_prep(const float* q_s, const float* q_b, const float* Wk, int E, int SP
   MVF_REQUIRE(smem <= 200 * 1024, MVF_ERR_UNSUPPORTED, "fold_prep: E*SPC too large");
   if (smem > 48 * 1024)
     MVF_CHECK_CUDA(cudaFuncSetAttribute(fold::fold_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fold::fold_prep_kernel<<<cdiv(C, 32), 1024, smem, st>>>(q_s, q_b, Wk, E, SPC, C, (float)(1.0 / sqrt((double)SPC)), Wq);
+  launch_k(fold::fold_prep_kernel, cdiv(C, 32), 1024, smem, st, q_s, q_b, Wk, E, SPC, C, (float)(1.0 / sqrt((double)SPC)), Wq);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
 
 int fold_finish(const float* dWq, const float* q_s, const float* q_b, const float* Wk, int E, int SPC, int C, float* dWk,
                 int64_t ld_dwk, float* dQs, float* dQb, cudaStream_t st) {
-  fold::fold_finish_kernel<<<SPC, 256, 0, st>>>(dWq, q_s, q_b, Wk, E, SPC, C, 1.f / sqrtf((float)SPC), dWk, ld_dwk, dQs, dQb);
+  launch_k(fold::fold_finish_kernel, SPC, 256, 0, st, dWq, q_s, q_b, Wk, E, SPC, C, 1.f / sqrtf((float)SPC), dWk, ld_dwk, dQs, dQb);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -760,7 +767,7 @@ int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, 
   if (R <= 0) return MVF_OK;
   const int64_t total = R * ld;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  fold::ent_finish_fwd_kernel<<<blocks, 256, 0, st>>>(ent, h0, ld, R, SPC, E, one_hot, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+  launch_k(fold::ent_finish_fwd_kernel, blocks, 256, 0, st, ent, h0, ld, R, SPC, E, one_hot, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -769,14 +776,14 @@ int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SP
                    cudaStream_t st, const float* ent, const float* bv, float* delta) {
   if (R <= 0) return MVF_OK;
   if (delta != nullptr && ent != nullptr && bv != nullptr) {
-    fold::ent_finish_bwd_delta_kernel<<<(int)((R + 7) / 8), 256, 0, st>>>(d_h0, ld, dEnt, R, SPC, W, p,
+    launch_k(fold::ent_finish_bwd_delta_kernel, (int)((R + 7) / 8), 256, 0, st, d_h0, ld, dEnt, R, SPC, W, p,
                                                                          p > 0.f ? 1.f / (1.f - p) : 1.f, seed, ent, bv, delta);
     MVF_CHECK_LAUNCH();
     return MVF_OK;
   }
   const int64_t total = R * SPC;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  fold::ent_finish_bwd_kernel<<<blocks, 256, 0, st>>>(d_h0, ld, dEnt, R, SPC, W, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+  launch_k(fold::ent_finish_bwd_kernel, blocks, 256, 0, st, d_h0, ld, dEnt, R, SPC, W, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }

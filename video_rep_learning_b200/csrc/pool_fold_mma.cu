@@ -237,6 +237,7 @@ template <int TPW, int NI>
 __global__ void __launch_bounds__(max_threads(TPW), 1)
 pool_foldm_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, float* __restrict__ attn,
                       float* __restrict__ px, const Geom g) {
+  pdl_entry();
   MVF_FOLDM_SETUP();
   float* fin = misc + warp * 16;   // this warp's copy of [max(8) | 1/sum(8)] at the end of a frame
 
@@ -357,6 +358,7 @@ template <int TPW>
 __global__ void __launch_bounds__(max_threads(TPW), 1)
 pool_foldm_bwd_kernel(const bf16* __restrict__ X, const float* __restrict__ G, const float* __restrict__ px,
                       const float* __restrict__ attn, float* __restrict__ dWq, const Geom g) {
+  pdl_entry();
   MVF_FOLDM_SETUP();
   float* red = misc;   // [NW][8] partial delta (indexing: warp * 16 + e)
 
@@ -493,7 +495,7 @@ template <int TPW, int NI>
 static int fwd_launch_ni(const Geom& g, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st) {
   static thread_local Plan pl;
   MVF_TRY(plan(pool_foldm_fwd_kernel<TPW, NI>, pl, g.F, g.P, g.C, g.NW));
-  pool_foldm_fwd_kernel<TPW, NI><<<pl.grid, (g.NW + 1) * 32, pl.smem, st>>>((const bf16*)X, Wq, attn, px, g);
+  launch_k(pool_foldm_fwd_kernel<TPW, NI>, pl.grid, (g.NW + 1) * 32, pl.smem, st, (const bf16*)X, Wq, attn, px, g);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -511,7 +513,7 @@ static int bwd_launch(const Geom& g, const void* X, const float* G, const float*
                       cudaStream_t st) {
   static thread_local Plan pl;
   MVF_TRY(plan(pool_foldm_bwd_kernel<TPW>, pl, g.F, g.P, g.C, g.NW));
-  pool_foldm_bwd_kernel<TPW><<<pl.grid, (g.NW + 1) * 32, pl.smem, st>>>((const bf16*)X, G, px, attn, dWq, g);
+  launch_k(pool_foldm_bwd_kernel<TPW>, pl.grid, (g.NW + 1) * 32, pl.smem, st, (const bf16*)X, G, px, attn, dWq, g);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }

@@ -160,6 +160,7 @@ __device__ __forceinline__ Sm setup(uint8_t* smraw, const Geom& g) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill before async-proxy bulk copies
+  pdl_entry();   // only shared memory was touched so far: this prologue overlaps the previous kernel's tail
   __syncthreads();
   return s;
 }
@@ -647,11 +648,11 @@ static int fwd_launch(const Geom& g, const void* X, const float* Wq, float* attn
   if (g.ne <= 4) {
     static thread_local Plan pl;
     MVF_TRY(plan(pool_foldw_fwd_kernel<TPW, true>, pl, g));
-    pool_foldw_fwd_kernel<TPW, true><<<pl.grid, (g.NW + 2) * 32, pl.smem, st>>>((const bf16*)X, Wq, attn, px, g);
+    launch_k(pool_foldw_fwd_kernel<TPW, true>, pl.grid, (g.NW + 2) * 32, pl.smem, st, (const bf16*)X, Wq, attn, px, g);
   } else {
     static thread_local Plan pl;
     MVF_TRY(plan(pool_foldw_fwd_kernel<TPW, false>, pl, g));
-    pool_foldw_fwd_kernel<TPW, false><<<pl.grid, (g.NW + 2) * 32, pl.smem, st>>>((const bf16*)X, Wq, attn, px, g);
+    launch_k(pool_foldw_fwd_kernel<TPW, false>, pl.grid, (g.NW + 2) * 32, pl.smem, st, (const bf16*)X, Wq, attn, px, g);
   }
   MVF_CHECK_LAUNCH();
   return MVF_OK;
@@ -662,11 +663,11 @@ static int bwd_launch(const Geom& g, const void* X, const float* G, const float*
   if (g.ne <= 4) {
     static thread_local Plan pl;
     MVF_TRY(plan(pool_foldw_bwd_kernel<TPW, true>, pl, g));
-    pool_foldw_bwd_kernel<TPW, true><<<pl.grid, (g.NW + 2) * 32, pl.smem, st>>>((const bf16*)X, G, px, attn, delta, dWq, g);
+    launch_k(pool_foldw_bwd_kernel<TPW, true>, pl.grid, (g.NW + 2) * 32, pl.smem, st, (const bf16*)X, G, px, attn, delta, dWq, g);
   } else {
     static thread_local Plan pl;
     MVF_TRY(plan(pool_foldw_bwd_kernel<TPW, false>, pl, g));
-    pool_foldw_bwd_kernel<TPW, false><<<pl.grid, (g.NW + 2) * 32, pl.smem, st>>>((const bf16*)X, G, px, attn, delta, dWq, g);
+    launch_k(pool_foldw_bwd_kernel<TPW, false>, pl.grid, (g.NW + 2) * 32, pl.smem, st, (const bf16*)X, G, px, attn, delta, dWq, g);
   }
   MVF_CHECK_LAUNCH();
   return MVF_OK;

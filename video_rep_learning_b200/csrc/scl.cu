@@ -65,6 +65,7 @@ size_t scl_ws_bytes(int Bv, int T, int D) {
 // ---- prep: M = sum(mask), ordered index lists of valid / masked rows, zeroed accumulators --------------------
 // Single CTA, block-wide scan per 1024-row chunk: deterministic order, no host round trip.
 __global__ void scl_prep_kernel(const float* __restrict__ masks, int N, SclWs w, float* loss_out) {
+  pdl_entry();
   // single block, 1024 threads, chunked scan
   __shared__ int scan[1024];
   __shared__ int base_v, base_m;
@@ -112,6 +113,7 @@ __global__ void scl_prep_kernel(const float* __restrict__ masks, int N, SclWs w,
 // (1) per-chunk counts, M (mask sum: integers, exact in fp32 whatever the order), zeroed accumulators;
 // (2) one CTA scans the chunk counts; (3) every chunk scans locally and writes its slice of the ordered lists.
 __global__ void __launch_bounds__(1024) scl_prep_count_kernel(const float* __restrict__ masks, int N, SclWs w, float* loss_out) {
+  pdl_entry();
   __shared__ int cnt[32];
   __shared__ float sum[32];
   const int i = blockIdx.x * 1024 + threadIdx.x;
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(1024) scl_prep_count_kernel(const float* __res
   }
 }
 __global__ void __launch_bounds__(1024) scl_prep_scan_kernel(int N, int nchunks, SclWs w) {
+  pdl_entry();
   // exclusive scan of chunk[0..nchunks) -> chunk[nchunks+1 ..] (valid bases); masked base = 1024*c - valid base
   __shared__ int scan[1024];
   __shared__ int carry;
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(1024) scl_prep_scan_kernel(int N, int nchunks,
   }
 }
 __global__ void __launch_bounds__(1024) scl_prep_write_kernel(const float* __restrict__ masks, int N, int nchunks, SclWs w) {
+  pdl_entry();
   __shared__ int scan[1024];
   const int i = blockIdx.x * 1024 + threadIdx.x;
   const int v = (i < N && masks[i] != 0.f) ? 1 : 0;
@@ -221,6 +225,7 @@ scl_cross_kernel(const float* __restrict__ embs, int D, int T2, float inv_tau_di
                  const int* __restrict__ row_cnt, const int* __restrict__ col_idx, const int* __restrict__ col_cnt,
                  const float* __restrict__ rc_arr, float rc_const, const float* __restrict__ cc_arr, float cc_const,
                  int excl_same_video, float* __restrict__ sum_out, float* __restrict__ vec_out) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   const int Dp = D + 4;
   float* tile = sm;                 // [32][Dp]
@@ -302,6 +307,7 @@ __global__ void __launch_bounds__(256)
 scl_pair_kernel(const float* __restrict__ embs, const int64_t* __restrict__ seq_lens, const int64_t* __restrict__ steps,
                 const float* __restrict__ masks, int T, int D, float tau, float two_var, SclWs w,
                 float* __restrict__ loss_out, float* __restrict__ d_embs) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   const int Dp = D + 4;
   float* tile = sm;            // [32][Dp] partner embeddings of the current column chunk
@@ -464,6 +470,7 @@ __global__ void __launch_bounds__(NT)
 scl_pair_fused_kernel(const float* __restrict__ embs, const int64_t* __restrict__ seq_lens, const int64_t* __restrict__ steps,
                       const float* __restrict__ masks, int T, int D, float tau, float two_var, SclWs w,
                       float* __restrict__ loss_out, float* __restrict__ d_embs) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   const int Dp = D + 4, Tp = T + 1;
   float* E = sm;                          // [2T][Dp]  rows 0..T-1 = view 0, T..2T-1 = view 1
@@ -645,6 +652,7 @@ __global__ void __launch_bounds__(NT)
 scl_pair_fused2_kernel(const float* __restrict__ embs, const int64_t* __restrict__ seq_lens, const int64_t* __restrict__ steps,
                        const float* __restrict__ masks, int T, int D, float tau, float two_var, SclWs w,
                        float* __restrict__ loss_out, float* __restrict__ d_embs) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   const int Dp = D + 4, Tp = T + 1;
   float* E = sm;                          // [2T][Dp]
@@ -846,16 +854,16 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
   MVF_REQUIRE(ws_bytes >= need, MVF_ERR_WORKSPACE, "scl: workspace %zu < %zu bytes", ws_bytes, need);
 
   if (N <= 8192) {
-    scl_prep_kernel<<<1, 1024, 0, st>>>(masks, N, w, loss_out);
+    launch_k(scl_prep_kernel, 1, 1024, 0, st, masks, N, w, loss_out);
     MVF_CHECK_LAUNCH();
   } else {
     const int nchunks = cdiv(N, 1024);
     MVF_CHECK_CUDA(cudaMemsetAsync(w.M, 0, sizeof(float), st));
-    scl_prep_count_kernel<<<nchunks, 1024, 0, st>>>(masks, N, w, loss_out);
+    launch_k(scl_prep_count_kernel, nchunks, 1024, 0, st, masks, N, w, loss_out);
     MVF_CHECK_LAUNCH();
-    scl_prep_scan_kernel<<<1, 1024, 0, st>>>(N, nchunks, w);
+    launch_k(scl_prep_scan_kernel, 1, 1024, 0, st, N, nchunks, w);
     MVF_CHECK_LAUNCH();
-    scl_prep_write_kernel<<<nchunks, 1024, 0, st>>>(masks, N, nchunks, w);
+    launch_k(scl_prep_write_kernel, nchunks, 1024, 0, st, masks, N, nchunks, w);
     MVF_CHECK_LAUNCH();
   }
 
@@ -876,12 +884,12 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
   const bool batch = negative_type == MVF_NEG_BATCH_NOSELF;
   // Z extras
   if (quirk) {
-    scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.masked, w.counts + 1,
+    launch_k(scl_cross_kernel, cross_grid, 256, smem, st, embs, D, T2, temperature, w.valid, w.counts, w.masked, w.counts + 1,
                                                     nullptr, 1.f, nullptr, 1e-6f, 0, w.zext, nullptr);
     MVF_CHECK_LAUNCH();
   }
   if (batch) {
-    scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.valid, w.counts,
+    launch_k(scl_cross_kernel, cross_grid, 256, smem, st, embs, D, T2, temperature, w.valid, w.counts, w.valid, w.counts,
                                                     nullptr, 1.f, nullptr, 1.f, 1, w.zext, nullptr);
     MVF_CHECK_LAUNCH();
   }
@@ -901,7 +909,7 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
         MVF_CHECK_CUDA(cudaFuncSetAttribute(scl_pair_fused2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2smem));
         configured = f2smem;
       }
-      scl_pair_fused2_kernel<256><<<Bv, 256, f2smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
+      launch_k(scl_pair_fused2_kernel<256>, Bv, 256, f2smem, st, embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
                                                           w, loss_out, d_embs);
     } else {
       static size_t configured = 0;
@@ -909,7 +917,7 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
         MVF_CHECK_CUDA(cudaFuncSetAttribute(scl_pair_fused2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2smem));
         configured = f2smem;
       }
-      scl_pair_fused2_kernel<128><<<Bv, 128, f2smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
+      launch_k(scl_pair_fused2_kernel<128>, Bv, 128, f2smem, st, embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
                                                           w, loss_out, d_embs);
     }
     MVF_CHECK_LAUNCH();
@@ -920,7 +928,7 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
         MVF_CHECK_CUDA(cudaFuncSetAttribute(scl_pair_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         configured = fsmem;
       }
-      scl_pair_fused_kernel<256><<<Bv, 256, fsmem, st>>>(embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
+      launch_k(scl_pair_fused_kernel<256>, Bv, 256, fsmem, st, embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
                                                          w, loss_out, d_embs);
     } else {
       static size_t configured = 0;
@@ -928,17 +936,17 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
         MVF_CHECK_CUDA(cudaFuncSetAttribute(scl_pair_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         configured = fsmem;
       }
-      scl_pair_fused_kernel<128><<<Bv, 128, fsmem, st>>>(embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
+      launch_k(scl_pair_fused_kernel<128>, Bv, 128, fsmem, st, embs, seq_lens, steps, masks, T, D, temperature, 2.f * label_variance,
                                                          w, loss_out, d_embs);
     }
     MVF_CHECK_LAUNCH();
   } else {
     const int pair_grid = Bv * 2 * cdiv(T, 8);
-    scl_pair_kernel<0><<<pair_grid, 256, smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature,
+    launch_k(scl_pair_kernel<0>, pair_grid, 256, smem, st, embs, seq_lens, steps, masks, T, D, temperature,
                                                      2.f * label_variance, w, loss_out, nullptr);
     MVF_CHECK_LAUNCH();
     if (d_embs) {
-      scl_pair_kernel<1><<<pair_grid, 256, smem, st>>>(embs, seq_lens, steps, masks, T, D, temperature,
+      launch_k(scl_pair_kernel<1>, pair_grid, 256, smem, st, embs, seq_lens, steps, masks, T, D, temperature,
                                                        2.f * label_variance, w, loss_out, d_embs);
       MVF_CHECK_LAUNCH();
     }
@@ -946,19 +954,19 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
   if (d_embs) {
     if (quirk) {
       // rows valid i, columns masked k: dE_i += c_i 1e-6 e^{l_ik} e_k / tau
-      scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.masked,
+      launch_k(scl_cross_kernel, cross_grid, 256, smem, st, embs, D, T2, temperature, w.valid, w.counts, w.masked,
                                                       w.counts + 1, w.c, 1.f, nullptr, 1e-6f, 0, nullptr, d_embs);
       MVF_CHECK_LAUNCH();
       // rows masked k, columns valid i: dE_k += 1e-6 sum_i c_i e^{l_ik} e_i / tau
-      scl_cross_kernel<<<cross_grid_tall, 256, smem, st>>>(embs, D, T2, temperature, w.masked, w.counts + 1, w.valid,
+      launch_k(scl_cross_kernel, cross_grid_tall, 256, smem, st, embs, D, T2, temperature, w.masked, w.counts + 1, w.valid,
                                                            w.counts, nullptr, 1e-6f, w.c, 1.f, 0, nullptr, d_embs);
       MVF_CHECK_LAUNCH();
     }
     if (batch) {
-      scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.valid, w.counts,
+      launch_k(scl_cross_kernel, cross_grid, 256, smem, st, embs, D, T2, temperature, w.valid, w.counts, w.valid, w.counts,
                                                       w.c, 1.f, nullptr, 1.f, 1, nullptr, d_embs);
       MVF_CHECK_LAUNCH();
-      scl_cross_kernel<<<cross_grid, 256, smem, st>>>(embs, D, T2, temperature, w.valid, w.counts, w.valid, w.counts,
+      launch_k(scl_cross_kernel, cross_grid, 256, smem, st, embs, D, T2, temperature, w.valid, w.counts, w.valid, w.counts,
                                                       nullptr, 1.f, w.c, 1.f, 1, nullptr, d_embs);
       MVF_CHECK_LAUNCH();
     }

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256)
 xattn_fwd_kernel(int P, int E, int SPC, const T* __restrict__ kv, const float* __restrict__ q_s,
                  const float* __restrict__ q_b, float* __restrict__ attn, float* __restrict__ ent, int64_t ld_ent,
                  int one_hot, float p_drop, float inv_keep, DropSeed seed) {
+  pdl_entry();
   extern __shared__ float sm[];
   float* Q = sm;                   // [E][SPC]
   float* A = sm + (size_t)E * SPC; // [E][P]
@@ -110,6 +111,7 @@ xattn_bwd_kernel(int P, int E, int SPC, const T* __restrict__ kv, const float* _
                  int64_t ld_ent, int one_hot, float p_drop, float inv_keep, DropSeed seed, T* __restrict__ d_kv,
                  float* __restrict__ d_q_s, float* __restrict__ d_q_b, float* __restrict__ d_bk,
                  float* __restrict__ d_bv) {
+  pdl_entry();
   extern __shared__ float sm[];
   float* Q = sm;                        // [E][SPC]
   float* dEnt = Q + (size_t)E * SPC;    // [E][SPC]
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(256, 2)
 xattn_fwd_v2_kernel(int P, int E, int SPC, const bf16* __restrict__ kv, const float* __restrict__ q_s,
                     const float* __restrict__ q_b, float* __restrict__ attn, float* __restrict__ ent, int64_t ld_ent,
                     float* __restrict__ ent32, int one_hot, float p_drop, float inv_keep, DropSeed seed) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   float* Q = sm;                         // [E][SPC]
   float* sc = Q + (size_t)E * SPC;       // [E][P] raw scaled scores, later probabilities
@@ -369,6 +372,7 @@ xattn_bwd_v2_kernel(int P, int E, int SPC, const bf16* __restrict__ kv, const fl
                     int64_t ld_ent, const float* __restrict__ ent32, int one_hot, float p_drop, float inv_keep,
                     DropSeed seed, bf16* __restrict__ d_kv, float* __restrict__ d_q_s, float* __restrict__ d_q_b,
                     float* __restrict__ d_bk, float* __restrict__ d_bv) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   float* QG = sm;                          // [E][2*SPC]: Q[e] | dEnt[e]  (same chunk numbering as a K|V row)
   float* A = QG + (size_t)E * 2 * SPC;     // [E][P]
@@ -532,7 +536,7 @@ static int fwd_v2_launch(int F, int P, int E, int SPC, const void* kv, const flo
     cfgd = true;
   }
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  xattn_fwd_v2_kernel<EM, CPL><<<F, 256, smem, st>>>(P, E, SPC, (const bf16*)kv, q_s, q_b, attn, (float*)ent, ld_ent, ent32,
+  launch_k(xattn_fwd_v2_kernel<EM, CPL>, F, 256, smem, st, P, E, SPC, (const bf16*)kv, q_s, q_b, attn, (float*)ent, ld_ent, ent32,
                                                      one_hot, drop_p, ik, seed);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
@@ -550,7 +554,7 @@ static int bwd_v2_launch(int F, int P, int E, int SPC, const void* kv, const flo
     cfgd = true;
   }
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  xattn_bwd_v2_kernel<EM, CPL><<<F, 256, smem, st>>>(P, E, SPC, (const bf16*)kv, q_s, q_b, attn, (const float*)d_ent, ld_ent,
+  launch_k(xattn_bwd_v2_kernel<EM, CPL>, F, 256, smem, st, P, E, SPC, (const bf16*)kv, q_s, q_b, attn, (const float*)d_ent, ld_ent,
                                                      ent32, one_hot, drop_p, ik, seed, (bf16*)d_kv, d_q_s, d_q_b, d_bk, d_bv);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
@@ -566,7 +570,7 @@ static int fwd_t(int F, int P, int E, int SPC, const void* kv, const float* q_s,
     if (smem > 48 * 1024)                                                                                         \
       MVF_CHECK_CUDA(cudaFuncSetAttribute(xattn_fwd_kernel<T, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                           (int)smem));                                                            \
-    xattn_fwd_kernel<T, EM><<<F, 256, smem, st>>>(P, E, SPC, (const T*)kv, q_s, q_b, attn, (float*)ent, ld_ent, one_hot, \
+    launch_k(xattn_fwd_kernel<T, EM>, F, 256, smem, st, P, E, SPC, (const T*)kv, q_s, q_b, attn, (float*)ent, ld_ent, one_hot, \
                                                   drop_p, ik, seed);                                              \
   } while (0)
   if (E <= 4) LAUNCH_F(4);
@@ -609,7 +613,7 @@ static int bwd_t(int F, int P, int E, int SPC, const void* kv, const float* q_s,
     if (smem > 48 * 1024)                                                                                         \
       MVF_CHECK_CUDA(cudaFuncSetAttribute(xattn_bwd_kernel<T, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                           (int)smem));                                                            \
-    xattn_bwd_kernel<T, EM><<<F, 256, smem, st>>>(P, E, SPC, (const T*)kv, q_s, q_b, attn, (const float*)d_ent, ld_ent, \
+    launch_k(xattn_bwd_kernel<T, EM>, F, 256, smem, st, P, E, SPC, (const T*)kv, q_s, q_b, attn, (const float*)d_ent, ld_ent, \
                                                   one_hot, drop_p, ik, seed, (T*)d_kv, d_q_s, d_q_b, d_bk, d_bv); \
   } while (0)
   if (E <= 4) LAUNCH_B(4);
