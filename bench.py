@@ -274,7 +274,7 @@ def run_ours(args):
         region from extra replays, one synchronisation per replay."""
         from video_rep_learning_b200.graph import GraphedTrainStep
         head_opts.pool_mode = pool_mode
-        gs = GraphedTrainStep(model, algo, Bv, T, P, C_in, dtype=torch.bfloat16, device=dev)
+        gs = GraphedTrainStep(model, algo, Bv, T, P, C_in, dtype=torch.bfloat16, device=dev, micro_batches=args.micro_batches)
         gs.adopt_tokens(tokens_dev)
         gs.set_inputs(seq_lens=seq_lens_d, steps=steps_d, masks=masks_d)
         gs.capture(profile=True)
@@ -316,14 +316,22 @@ def run_ours(args):
     else:
         try:
             main_run = graph_region(pool_default, args.steps, max(args.warmup, 3), True)
-            graph_note = "one cudaGraphLaunch per step (GraphedTrainStep)"
+            graph_note = "one cudaGraphLaunch per step (GraphedTrainStep)" + (
+                f", views run as {args.micro_batches} slices on {args.micro_batches} streams inside the graph" if args.micro_batches > 1 else "")
             eager_run = timed_region(pool_default, max(3, min(args.steps, 20)), 3, False)
+            if args.micro_batches > 1:
+                # the pooling kernels of the slices queue behind each other on different streams, so an event pair around
+                # one of them also times its wait for SMs: the roofline figures come from the un-split eager leg below
+                # (same kernels, same tokens, whole batch per launch, events on the launching stream)
+                main_run["prof"] = eager_run["prof"]
+                main_run["prof_ms_step"] = eager_run["ms_step"]
         except Exception as e:  # capture refused (e.g. a collective that cannot be captured): fall back to eager launches
             graph_note = f"capture failed, eager launches timed instead: {type(e).__name__}: {str(e)[:200]}"
             torch.cuda.synchronize()
             main_run = timed_region(pool_default, args.steps, max(args.warmup, 3), True)
     ms_step, launches, prof, clk, final_loss = (main_run["ms_step"], main_run["launches"], main_run["prof"],
                                                 main_run["clocks"], main_run["loss"])
+    prof_ms_step = main_run.get("prof_ms_step", ms_step)
     value = world * Bv / (ms_step / 1e3)
     dense_run = None
     if args.pool == "folded" and not args.no_dense and world == 1:
@@ -449,7 +457,11 @@ def run_ours(args):
                                       pool_rest_bwd=((mean(pr[3]) or 0) + (mean(pr[5]) or 0)) / ms if pr[3] else None)
             return r
 
-        roof = dense_roofline(prof, ms_step) if args.pool == "dense" else folded_roofline(prof, ms_step)
+        roof = dense_roofline(prof, prof_ms_step) if args.pool == "dense" else folded_roofline(prof, prof_ms_step)
+        if roof is not None:
+            roof["timed_in"] = ("eager leg of this run: the un-split step issued kernel by kernel (CUDA events on the launching stream, "
+                                f"{prof_ms_step:.3f} ms/step); share_of_step is relative to that leg") if "prof_ms_step" in main_run \
+                else "the timed region of `value`"
         dense = None
         if dense_run is not None:
             dms = dense_run["ms_step"]
@@ -499,6 +511,7 @@ def main():
     ap.add_argument("--pool", default="folded", choices=["folded", "dense"],
                     help="entity pooling: folded (default product path) or dense (as written: K|V GEMM + attention)")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--micro-batches", type=int, default=1, help="slices of the captured step (1 = un-split)")
     ap.add_argument("--no-dense", action="store_true", help="skip the short as-written (dense pooling) comparison leg")
     args = ap.parse_args()
     if args.impl == "reference":

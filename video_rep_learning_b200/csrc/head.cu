@@ -81,14 +81,17 @@ struct ProfScope {
 // forked onto a second stream and overlap the dX chain on the caller's stream (joined before every return)
 // ------------------------------------------------------------------------------------------------------------
 struct SideCtl {
+  cudaStream_t owner = nullptr;   // caller stream this side stream is paired with
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[64];
   int n_ev = 0, next = 0;
 };
-constexpr int MAX_DEVICES = 64;
-static SideCtl g_side[MAX_DEVICES];   // one side stream + event ring per device (streams and events are device-bound)
+constexpr int MAX_DEVICES = 64, SIDE_PER_DEV = 4;
+// one side stream + event ring per (device, caller stream): concurrent micro-batches on different caller streams fork onto
+// different side streams (streams and events are device-bound).  More than SIDE_PER_DEV caller streams share the last slot.
+static SideCtl g_side[MAX_DEVICES][SIDE_PER_DEV];
 static std::mutex g_side_mu;
-static int side_acquire(cudaStream_t* s, int* dev_out) {
+static int side_acquire(cudaStream_t caller, cudaStream_t* s, int* dev_out) {
   static int enabled = -1;  // MVF_SIDE_STREAM=0 keeps everything on the caller's stream (debugging / A-B timing)
   if (enabled < 0) {
     const char* e = getenv("MVF_SIDE_STREAM");
@@ -101,19 +104,24 @@ static int side_acquire(cudaStream_t* s, int* dev_out) {
   MVF_CHECK_CUDA(cudaGetDevice(&dev));
   MVF_REQUIRE(dev >= 0 && dev < MAX_DEVICES, MVF_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
   std::lock_guard<std::mutex> lk(g_side_mu);
-  SideCtl& c = g_side[dev];
+  int slot = SIDE_PER_DEV - 1;
+  for (int i = 0; i < SIDE_PER_DEV; ++i) {
+    if (g_side[dev][i].stream == nullptr || g_side[dev][i].owner == caller) { slot = i; break; }
+  }
+  SideCtl& c = g_side[dev][slot];
   if (c.stream == nullptr) {
     MVF_CHECK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 64; ++i) MVF_CHECK_CUDA(cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming));
     c.n_ev = 64;
+    c.owner = caller;
   }
   *s = c.stream;
-  *dev_out = dev;
+  *dev_out = dev * SIDE_PER_DEV + slot;
   return MVF_OK;
 }
-static cudaEvent_t side_event(int dev) {
+static cudaEvent_t side_event(int handle) {
   std::lock_guard<std::mutex> lk(g_side_mu);
-  SideCtl& c = g_side[dev];
+  SideCtl& c = g_side[handle / SIDE_PER_DEV][handle % SIDE_PER_DEV];
   cudaEvent_t e = c.ev[c.next];
   c.next = (c.next + 1) % c.n_ev;
   return e;
@@ -1268,7 +1276,7 @@ int mvf_head_backward(const mvf_head_desc* d, const float* const* params, const 
   Ctx c;
   MVF_TRY(make_ctx(d, c, false, save, save_bytes, ws, ws_bytes, gpack, params, (cudaStream_t)stream));
   MVF_REQUIRE(tokens != nullptr && d_emb != nullptr && gpack != nullptr, MVF_ERR_BAD_ARG, "null tokens / d_emb / gpack");
-  MVF_TRY(side_acquire(&c.side, &c.side_dev));
+  MVF_TRY(side_acquire(c.st, &c.side, &c.side_dev));
   int rc = head_backward_impl(c, tokens, mask, d_emb, phase_begin, phase_end);
   if (rc != MVF_OK) c.join();  // never leave forked work un-joined, even on an error path
   return rc;
@@ -1291,7 +1299,7 @@ int mvf_proj_backward(const mvf_head_desc* d, const float* const* params, const 
   MVF_REQUIRE(d_out != nullptr && d_emb != nullptr, MVF_ERR_BAD_ARG, "null d_out / d_emb");
   MVF_REQUIRE(!project || gpack != nullptr, MVF_ERR_BAD_ARG, "null gpack");
   // the forward stores the normalised rows in `ehat` for both modes
-  MVF_TRY(side_acquire(&c.side, &c.side_dev));
+  MVF_TRY(side_acquire(c.st, &c.side, &c.side_dev));
   int rc = proj_backward_impl(c, d_out, project, d_emb, c.S.f("ehat"), phase_begin, phase_end);
   if (rc != MVF_OK) c.join();
   return rc;

@@ -57,6 +57,11 @@ class RunOptions:
     process_group: Optional[object] = None
     scl_quirk: bool = True          # keep the 1e-6 weight on masked columns (algos/scl.py:80)
     pool_mode: int = L.POOL_AUTO    # entity pooling: AUTO -> folded (no K|V tensors); POOL_DENSE = as written in the reference
+    micro_batches: int = 1          # >1: the step's views are cut into that many slices which run on separate CUDA streams
+                                    # with BatchNorm statistics combined at the phase cuts (same results as the unsplit
+                                    # step up to re-association).  The chain behind the pooling is ~100 short, latency-bound
+                                    # kernels, so two slices overlap almost perfectly -- but the host enqueues twice the
+                                    # calls, so this is meant for CUDA-graph replay (graph.GraphedTrainStep turns it on)
 
 
 def _world(opts: RunOptions) -> int:
@@ -418,6 +423,147 @@ class ProjFn(torch.autograd.Function):
         return (d_emb, None) + pg
 
 
+_mb_stream_cache: Dict[tuple, List[torch.cuda.Stream]] = {}
+
+
+def _mb_streams(dev: torch.device, n: int) -> List[torch.cuda.Stream]:
+    key = (dev, n)
+    ss = _mb_stream_cache.get(key)
+    if ss is None:
+        ss = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        _mb_stream_cache[key] = ss
+    return ss
+
+
+def _combine_stats(bufs: List[torch.Tensor], streams: List[torch.cuda.Stream], cs: CallState, dist_world: int):
+    """Sum the slices' BatchNorm statistic buffers (and, across ranks, all-reduce the sum) and hand the total back to every
+    slice: the in-GPU analogue of parallel.sync_stats_.  Slice 0's stream does the arithmetic; the others wait for it."""
+    s0 = streams[0]
+    for s in streams[1:]:
+        s0.wait_stream(s)
+    with torch.cuda.stream(s0):
+        for b in bufs[1:]:
+            bufs[0].add_(b)
+        if dist_world > 1 and cs.opts.sync_bn:
+            parallel.sync_stats_(bufs[0], cs.opts.process_group)
+        for b in bufs[1:]:
+            b.copy_(bufs[0])
+    for s in streams[1:]:
+        s.wait_stream(s0)
+
+
+class _Split:
+    """State of a micro-batched step (forward -> backward)."""
+    def __init__(self):
+        self.plan = None
+        self.saves: List[torch.Tensor] = []
+        self.psaves: List[torch.Tensor] = []
+        self.n = 1
+
+
+def _split_forward(cs: CallState, tokens, mask, params, nmb: int):
+    dev = tokens.device
+    BV, T, P, Cin = tokens.shape
+    hb = BV // nmb
+    dist_world = _world(cs.opts)
+    eff_world = nmb * (dist_world if cs.opts.sync_bn else 1)
+    plan = Plan.get(cs.spec, hb, T, P, _mvf_dtype(tokens), cs.training, mask is not None, eff_world, cs.opts.gemm_backend,
+                    cs.opts.pool_mode)
+    lib = L.lib()
+    cur = torch.cuda.current_stream(dev)
+    streams = _mb_streams(dev, nmb)
+    emb = torch.empty(BV, T, cs.spec.emb, dtype=torch.float32, device=dev)
+    out = torch.empty(BV, T, cs.spec.emb, dtype=torch.float32, device=dev)
+    sp = _Split()
+    sp.plan, sp.n = plan, nmb
+    sp.saves = [torch.empty(plan.save_bytes, dtype=torch.uint8, device=dev) for _ in range(nmb)]
+    sp.psaves = [torch.empty(plan.proj_save_bytes, dtype=torch.uint8, device=dev) for _ in range(nmb)]
+    wss = [_scratch(dev, plan.ws_bytes, f"head{h}") for h in range(nmb)]
+    pwss = [_scratch(dev, plan.proj_ws_bytes, f"proj{h}") for h in range(nmb)]
+    arr = L.ptr_array(list(params))
+    descs = [plan.desc_with_seed(cs.seed + h, cs.seed_dev) for h in range(nmb)]
+    # running statistics are updated by slice 0 only (every slice sees the same global batch statistics)
+    rm = L.ptr_array(cs.bn_running) if cs.bn_running else None
+    tr = L.ptr_array(cs.bn_tracked) if cs.bn_tracked else None
+    toks = [tokens[h * hb:(h + 1) * hb] for h in range(nmb)]
+    msks = [None if mask is None else mask[h * hb:(h + 1) * hb] for h in range(nmb)]
+    embs = [emb[h * hb:(h + 1) * hb] for h in range(nmb)]
+    outs = [out[h * hb:(h + 1) * hb] for h in range(nmb)]
+    for s in streams:
+        s.wait_stream(cur)
+    n_fc = plan.n_fc
+    for ph in range(n_fc + 1):
+        for h in range(nmb):
+            with torch.cuda.stream(streams[h]):
+                L.check(lib.mvf_head_forward(C.byref(descs[h]), arr, rm if h == 0 else None, tr if h == 0 else None,
+                                             L.ptr(toks[h]), L.ptr(msks[h]), L.ptr(sp.saves[h]), sp.saves[h].numel(),
+                                             L.ptr(wss[h]), wss[h].numel(), L.ptr(embs[h]), None, ph, ph + 1,
+                                             streams[h].cuda_stream), "mvf_head_forward")
+        if ph < n_fc:
+            _combine_stats([plan.bn_stat(sv, ph, False) for sv in sp.saves], streams, cs, dist_world)
+    project = int(cs.project)
+    cuts = [(0, 1), (1, 2)] if project else [(0, L.PHASE_ALL)]
+    for ci, (p0, p1) in enumerate(cuts):
+        for h in range(nmb):
+            with torch.cuda.stream(streams[h]):
+                L.check(lib.mvf_proj_forward(C.byref(descs[h]), arr, rm if h == 0 else None, tr if h == 0 else None,
+                                             L.ptr(embs[h]), project, L.ptr(sp.psaves[h]), sp.psaves[h].numel(),
+                                             L.ptr(pwss[h]), pwss[h].numel(), L.ptr(outs[h]), p0, p1,
+                                             streams[h].cuda_stream), "mvf_proj_forward")
+        if project and ci == 0:
+            _combine_stats([plan.bn_stat(sv, n_fc, False) for sv in sp.psaves], streams, cs, dist_world)
+    for s in streams:
+        cur.wait_stream(s)
+    return out, sp, arr
+
+
+def _split_backward(cs: CallState, sp: _Split, tokens, mask, params, arr, d_out, seed):
+    dev = tokens.device
+    nmb, plan = sp.n, sp.plan
+    BV = tokens.shape[0]
+    hb = BV // nmb
+    dist_world = _world(cs.opts)
+    lib = L.lib()
+    cur = torch.cuda.current_stream(dev)
+    streams = _mb_streams(dev, nmb)
+    d_out = d_out.contiguous().float()
+    d_emb = torch.empty(d_out.shape, dtype=torch.float32, device=dev)
+    gpacks = [torch.zeros(plan.gpack_elems, dtype=torch.float32, device=dev) for _ in range(nmb)]
+    wss = [_scratch(dev, plan.ws_bytes, f"head{h}") for h in range(nmb)]
+    pwss = [_scratch(dev, plan.proj_ws_bytes, f"proj{h}") for h in range(nmb)]
+    descs = [plan.desc_with_seed(seed + h, cs.seed_dev) for h in range(nmb)]
+    toks = [tokens[h * hb:(h + 1) * hb] for h in range(nmb)]
+    msks = [None if mask is None else mask[h * hb:(h + 1) * hb] for h in range(nmb)]
+    douts = [d_out[h * hb:(h + 1) * hb] for h in range(nmb)]
+    dembs = [d_emb[h * hb:(h + 1) * hb] for h in range(nmb)]
+    for s in streams:
+        s.wait_stream(cur)
+    n_fc = plan.n_fc
+    project = int(cs.project)
+    cuts = [(0, 1), (1, 2)] if project else [(0, L.PHASE_ALL)]
+    for ci, (p0, p1) in enumerate(cuts):
+        for h in range(nmb):
+            with torch.cuda.stream(streams[h]):
+                L.check(lib.mvf_proj_backward(C.byref(descs[h]), arr, L.ptr(douts[h]), project, L.ptr(sp.psaves[h]),
+                                              sp.psaves[h].numel(), L.ptr(pwss[h]), pwss[h].numel(), L.ptr(gpacks[h]),
+                                              L.ptr(dembs[h]), p0, p1, streams[h].cuda_stream), "mvf_proj_backward")
+        if project and ci == 0:
+            _combine_stats([plan.bn_stat(sv, n_fc, True) for sv in sp.psaves], streams, cs, dist_world)
+    for ph in range(n_fc + 1):
+        for h in range(nmb):
+            with torch.cuda.stream(streams[h]):
+                L.check(lib.mvf_head_backward(C.byref(descs[h]), arr, L.ptr(toks[h]), L.ptr(msks[h]), L.ptr(dembs[h]),
+                                              L.ptr(sp.saves[h]), sp.saves[h].numel(), L.ptr(wss[h]), wss[h].numel(),
+                                              L.ptr(gpacks[h]), ph, ph + 1, streams[h].cuda_stream), "mvf_head_backward")
+        if ph < n_fc:
+            _combine_stats([plan.bn_stat(sv, n_fc - 1 - ph, True) for sv in sp.saves], streams, cs, dist_world)
+    for s in streams:
+        cur.wait_stream(s)
+    for g in gpacks[1:]:
+        gpacks[0].add_(g)
+    return gpacks[0], descs[0]
+
+
 class ModelFn(torch.autograd.Function):
     """Head + projection (+normalise) as ONE autograd node: one flat gradient buffer, one all-reduce."""
 
@@ -427,6 +573,15 @@ class ModelFn(torch.autograd.Function):
         BV, T, P, Cin = tokens.shape
         mask = _prep_mask(mask, BV, T, tokens.device)
         dev = tokens.device
+        nmb = int(cs.opts.micro_batches)
+        if nmb > 1 and cs.training and BV % nmb == 0 and BV // nmb >= 1:
+            with torch.cuda.device(dev):
+                out, sp, arr = _split_forward(cs, tokens, mask, params, nmb)
+            cs.plan, cs.head_save, cs.proj_save = sp.plan, sp.saves[-1], sp.psaves[-1]
+            ctx.cs, ctx.seed, ctx.split = cs, cs.seed, sp
+            ctx.tokens, ctx.mask, ctx.params, ctx.param_ptrs = tokens, mask, params, arr
+            return out
+        ctx.split = None
         with torch.cuda.device(dev):
             plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _world(cs.opts),
                             cs.opts.gemm_backend, cs.opts.pool_mode)
@@ -453,6 +608,11 @@ class ModelFn(torch.autograd.Function):
         tokens, mask, params = ctx.tokens, ctx.mask, ctx.params
         plan = cs.plan
         dev = tokens.device
+        if ctx.split is not None:
+            with torch.cuda.device(dev):
+                gpack, d = _split_backward(cs, ctx.split, tokens, mask, params, ctx.param_ptrs, d_out, ctx.seed)
+                grads = _finish_grads(cs, ctx.split.plan, d, gpack, list(params))
+            return (None, None, None) + tuple(grads)
         with torch.cuda.device(dev):
             d = plan.desc_with_seed(ctx.seed, cs.seed_dev)
             ws = _scratch(dev, plan.ws_bytes, "head")

@@ -14,6 +14,9 @@ What has to be static for a replay, and how it is kept so:
   * parameters are read through raw pointers, so in-place optimizer updates are picked up; re-assigning a parameter
     tensor needs a new capture;
   * `.grad` of every head parameter is a view of one flat buffer in the graph's private pool, rewritten by each replay;
+  * optionally (micro_batches > 1) the views run as slices on separate streams with BatchNorm statistics summed at the
+    phase cuts and SCL on the whole batch -- same results as the unsplit step up to re-association (slower on B200 at
+    the bench shape, see __init__);
   * dropout: kernel arguments are frozen at capture, so the per-step seed is `base + *seed_dev` with `seed_dev` a device
     counter advanced inside the graph (csrc/common.cuh DropSeed) -- every replay draws a fresh mask.
 """
@@ -29,7 +32,7 @@ from . import engine
 
 class GraphedTrainStep:
     def __init__(self, model, algo, Bv: int, T: int, P: int, C_in: int, dtype=torch.bfloat16,
-                 device: Optional[torch.device] = None, warmup: int = 3, project: bool = True):
+                 device: Optional[torch.device] = None, warmup: int = 3, project: bool = True, micro_batches: int = 1):
         self.model, self.algo = model, algo
         self.Bv, self.T = Bv, T
         self.project = project
@@ -44,6 +47,11 @@ class GraphedTrainStep:
         self.params: List[torch.nn.Parameter] = [p for n, p in model.named_parameters() if "backbone" not in n]
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.warmup = warmup
+        # optional: run the views as `micro_batches` slices on separate streams (engine.RunOptions.micro_batches).  Measured
+        # at BASELINE configs[1] on B200: 2 slices 2.03 ms/step, 4 slices 2.35 ms vs 1.85 ms un-split -- the chain kernels
+        # are bound by what they move, not only by latency, so the slices do not overlap enough to pay for the extra
+        # statistics exchanges.  Kept (and tested) as an option; off by default.
+        self.micro_batches = micro_batches if (micro_batches > 1 and (2 * Bv) % micro_batches == 0) else 1
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss: Optional[torch.Tensor] = None
         self.grads: List[Optional[torch.Tensor]] = []
@@ -82,6 +90,14 @@ class GraphedTrainStep:
         after a replay)."""
         embed = self.model.embed
         embed.seed_dev = self.seed_dev
+        opts = self.model.run_options
+        prev_mb, opts.micro_batches = opts.micro_batches, self.micro_batches
+        try:
+            return self._capture(profile)
+        finally:
+            opts.micro_batches = prev_mb
+
+    def _capture(self, profile: bool) -> "GraphedTrainStep":
         cur = torch.cuda.current_stream(self.device)
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(cur)
