@@ -112,6 +112,52 @@ def test_temporal_attention_fwd_bwd(B, S, heads, dk, masked, dtype):
     assert H.rel_l2(d_qkv.float().cpu(), want) < (2e-5 if dtype == torch.float32 else 3e-2)
 
 
+@pytest.mark.parametrize("B,S,heads,masked", [(3, 60, 8, True), (2, 64, 8, False), (2, 17, 2, True), (5, 33, 4, True), (1, 1, 1, False)])
+def test_temporal_attention_tensor_core_path(monkeypatch, B, S, heads, masked):
+    """attention_tc.cu (S <= 64, d_k = 32; bf16 hi/lo operand splits on mma.sync), forced through MVF_ATTN_TC=2, against the
+    fp64 formulation -- including a view whose keys are all masked except one and a partially filled last warp."""
+    monkeypatch.setenv("MVF_ATTN_TC", "2")
+    dk = 32
+    Hd = heads * dk
+    g = torch.Generator().manual_seed(B * S + heads)
+    qkv = torch.randn(B * S, 3 * Hd, generator=g) * 0.7
+    km = None
+    if masked:
+        km = (torch.rand(B, S, generator=g) > 0.25).float()
+        km[:, 0] = 1
+        km[0, 1:] = 0                      # a single valid key
+    x = qkv.double().view(B, S, 3, heads, dk).requires_grad_(True)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    sc = q @ k.transpose(-1, -2) / np.sqrt(dk)
+    if km is not None:
+        sc = sc.masked_fill(km[:, None, None, :] == 0, -float("inf"))
+    ctx_ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, Hd)
+    lse_ref = torch.logsumexp(sc, -1)
+    d_ctx = torch.randn(B * S, Hd, generator=g)
+    (ctx_ref * d_ctx.double()).sum().backward()
+    dev = "cuda"
+    qkv_d = qkv.to(dev)
+    ctx = torch.full((B * S, Hd), float("nan"), device=dev)
+    lse = torch.full((B, heads, S), float("nan"), device=dev)
+    kmd = None if km is None else km.to(dev)
+    L.check(L.lib().mvf_attention_fwd(L.MVF_F32, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse), _stream()))
+    torch.cuda.synchronize()
+    assert float((ctx.cpu().double() - ctx_ref.detach()).abs().max()) < 2e-5 * max(1.0, float(ctx_ref.abs().max()))
+    assert float((lse.cpu().double() - lse_ref.detach()).abs().max()) < 2e-5
+    d_qkv = torch.full_like(qkv_d, float("nan"))
+    delta = torch.empty(B, heads, S, device=dev)
+    L.check(L.lib().mvf_attention_bwd(L.MVF_F32, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse),
+                                      L.ptr(d_ctx.to(dev)), L.ptr(d_qkv), L.ptr(delta), _stream()))
+    torch.cuda.synchronize()
+    assert H.rel_l2(d_qkv.cpu(), x.grad.reshape(B * S, 3 * Hd)) < 5e-5
+    # the exact CUDA-core kernels stay the default of the stand-alone entry point
+    monkeypatch.setenv("MVF_ATTN_TC", "1")
+    ctx2 = torch.empty_like(ctx)
+    L.check(L.lib().mvf_attention_fwd(L.MVF_F32, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx2), L.ptr(lse), _stream()))
+    torch.cuda.synchronize()
+    assert float((ctx2.cpu().double() - ctx_ref.detach()).abs().max()) < 2e-6 * max(1.0, float(ctx_ref.abs().max()))
+
+
 def test_dropout_mask_is_counter_based_and_unbiased():
     n_r, n_c, p = 1000, 257, 0.1
     a = torch.empty(n_r, n_c, device="cuda")

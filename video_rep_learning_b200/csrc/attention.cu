@@ -583,9 +583,10 @@ static int bwd_launch(int B, int S, int heads, const void* qkv, const float* key
   } while (0)
 
 int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, void* ctx,
-                  float* lse, cudaStream_t st) {
+                  float* lse, cudaStream_t st, bool allow_split) {
   if (B <= 0 || S <= 0) return MVF_OK;
   MVF_REQUIRE(B <= 65535 && heads <= 65535, MVF_ERR_BAD_ARG, "attention: grid too large");
+  if (attention_tc_ok(dtype, S, dk, heads * dk, qkv, ctx, allow_split)) return attention_tc_fwd(B, S, heads, qkv, keymask, ctx, lse, st);
   if (quad_ok(dtype, S, dk, qkv, ctx) && (heads * dk) % 4 == 0) {
     if (dk == 32) return fwd_quad_launch<32>(B, S, heads, qkv, keymask, ctx, lse, st);
     return fwd_quad_launch<64>(B, S, heads, qkv, keymask, ctx, lse, st);
@@ -593,9 +594,11 @@ int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, c
   DISPATCH_DK(fwd_launch, B, S, heads, qkv, keymask, ctx, lse, st);
 }
 int attention_bwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, const void* ctx,
-                  const float* lse, const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st) {
+                  const float* lse, const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st, bool allow_split) {
   if (B <= 0 || S <= 0) return MVF_OK;
   MVF_REQUIRE(B <= 65535 && heads <= 65535, MVF_ERR_BAD_ARG, "attention: grid too large");
+  if (attention_tc_ok(dtype, S, dk, heads * dk, qkv, d_qkv, allow_split) && ((((uintptr_t)ctx) | ((uintptr_t)d_ctx)) & 15) == 0)
+    return attention_tc_bwd(B, S, heads, qkv, keymask, ctx, lse, d_ctx, d_qkv, st);
   if (quad_ok(dtype, S, dk, qkv, d_qkv) && (heads * dk) % 4 == 0 && ((((uintptr_t)ctx) | ((uintptr_t)d_ctx)) & 15) == 0) {
     if (dk == 32) return bwd_quad_launch<32>(B, S, heads, qkv, keymask, ctx, lse, d_ctx, d_qkv, st);
     return bwd_quad_launch<64>(B, S, heads, qkv, keymask, ctx, lse, d_ctx, d_qkv, st);

@@ -780,7 +780,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       MVF_TRY(c.linear(A, m.rows, 3 * d.H, d.H, c.S.p(lname(l, "r0")), d.H, c.S.p(lname(l, "w.qkv")), d.H,
                        c.S.f(lname(l, "b.qkv")), c.S.p(lname(l, "qkv")), 3 * d.H, 0, lname(l, "w.qkv").c_str()));
       MVF_TRY(attention_fwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
-                            c.S.f(lname(l, "lse")), st));
+                            c.S.f(lname(l, "lse")), st, m.tc));
       MVF_TRY(c.linear(MVF_F32, m.rows, d.H, d.H, c.S.p(lname(l, "ctx")), d.H, c.S.p(lname(l, "w.o")), d.H, c.P[b + L_BO],
                        o, d.H, 0, lname(l, "w.o").c_str()));
       float* ln1 = c.S.f(lname(l, "ln1"));
@@ -879,7 +879,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
                             c.G.f(g + "b.o")));
         MVF_TRY(c.linear_dx(A, m.rows, d.H, d.H, dgA, d.H, c.S.p(lname(l, "w.o")), d.H, c.W.p("dctx"), d.H));
         MVF_TRY(attention_bwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
-                              c.S.f(lname(l, "lse")), c.W.p("dctx"), dqkv, c.W.f("delta"), st));
+                              c.S.f(lname(l, "lse")), c.W.p("dctx"), dqkv, c.W.f("delta"), st, m.tc));
         MVF_TRY(c.linear_dw(m.rows, 3 * d.H, d.H, dqkv, 3 * d.H, c.S.p(lname(l, "r0")), d.H, c.G.f(g + "w.qkv"),
                             d.H, c.G.f(g + "b.qkv")));
         MVF_TRY(c.linear_dx(MVF_F32, m.rows, 3 * d.H, d.H, dqkv, 3 * d.H, c.S.p(lname(l, "w.qkv")), d.H,

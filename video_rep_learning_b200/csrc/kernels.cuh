@@ -129,10 +129,16 @@ int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SP
                    cudaStream_t st, const float* ent = nullptr, const float* bv = nullptr, float* delta = nullptr);
 
 // ---- attention.cu --------------------------------------------------------------------------------------------
+// allow_split: the caller accepts operands split into bf16 hi + lo (2^-16 relative) -> tensor-core kernels of attention_tc.cu
+// for S <= 64, d_k = 32; otherwise (and always for exact-fp32 callers) the CUDA-core kernels
 int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, void* ctx,
-                  float* lse, cudaStream_t st);
+                  float* lse, cudaStream_t st, bool allow_split = false);
 int attention_bwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, const void* ctx,
-                  const float* lse, const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st);
+                  const float* lse, const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st, bool allow_split = false);
+bool attention_tc_ok(int dtype, int S, int dk, int H, const void* qkv, const void* other, bool allow_split);
+int attention_tc_fwd(int B, int S, int heads, const void* qkv, const float* keymask, void* ctx, float* lse, cudaStream_t st);
+int attention_tc_bwd(int B, int S, int heads, const void* qkv, const float* keymask, const void* ctx, const float* lse,
+                     const void* d_ctx, void* d_qkv, cudaStream_t st);
 
 // ---- scl.cu ----------------------------------------------------------------------------------------------------
 size_t scl_ws_bytes(int Bv, int T, int D);
