@@ -34,7 +34,9 @@ struct SclWs {
   int* valid;     // [N]
   int* masked;    // [N]
   int* chunk;     // [2 * (nchunks + 1)] valid / masked counts per 1024-row chunk, then their exclusive scans (large N only)
+  float* mex;     // [n_valid x n_masked] 1e-6 e^{l_rk} of (valid row, masked column) pairs (N <= SCL_MEX_MAXN only, else null)
 };
+constexpr int SCL_MEX_MAXN = 4096;   // the stored matrix has at most N^2 / 4 entries: 16.8 MB at this N
 
 static size_t scl_ws_layout(int N, SclWs* w, char* base) {
   size_t off = 0;
@@ -53,7 +55,8 @@ static size_t scl_ws_layout(int N, SclWs* w, char* base) {
   int* valid = (int*)take(sizeof(int) * N);
   int* masked = (int*)take(sizeof(int) * N);
   int* chunk = (int*)take(sizeof(int) * 2 * ((size_t)(N + 1023) / 1024 + 1));
-  if (w) { w->chunk = chunk; }
+  float* mex = N <= SCL_MEX_MAXN ? (float*)take(sizeof(float) * ((size_t)N * N / 4 + 1)) : nullptr;
+  if (w) { w->chunk = chunk; w->mex = mex; }
   if (w) { w->M = M; w->Z = Z; w->g = g; w->den = den; w->c = c; w->zext = zext; w->counts = counts; w->valid = valid; w->masked = masked; }
   return off;
 }
@@ -289,6 +292,118 @@ scl_cross_kernel(const float* __restrict__ embs, int D, int T2, float inv_tau_di
         for (int k = 0; k < SCL_MAXD / 32; ++k) {
           const int d = lane + 32 * k;
           if (d < D && acc[k] != 0.f) atomicAdd(vec_out + (int64_t)r * D + d, __fdiv_rn(rc * acc[k], inv_tau_div));
+        }
+      }
+    }
+  }
+}
+
+// ---- masked-column passes with the exp matrix kept (scl.py:80 quirk; small batches) -----------------------------------
+// The three generic cross passes above recompute the (valid row, masked column) dot products and exponentials three
+// times and accumulate with atomics.  For N <= SCL_MEX_MAXN the matrix x_rk = 1e-6 e^{l_rk} is computed ONCE, stored
+// ([n_valid x n_masked], a few hundred KB at the named shapes) and reused:
+//   scl_mex_kernel    x_rk and its row sums (-> zext), 8 valid rows per CTA, no column split, no atomics on the matrix
+//   scl_mgrad_kernel  after the pair kernel has produced c_r:   role A (valid rows, warp per row)  dE_r += c_r sum_k x_rk e_k / tau
+//                                                               role B (masked rows, CTA per row)  dE_k += sum_r c_r x_rk e_r / tau
+// Every output row is owned by one warp / CTA, so the updates are plain read-modify-writes.
+__global__ void __launch_bounds__(256)
+scl_mex_kernel(const float* __restrict__ embs, int D, float tau, SclWs w) {
+  pdl_entry();
+  extern __shared__ __align__(16) float sm[];
+  const int Dp = D + 4;
+  float* tile = sm;                 // [32][Dp]
+  float* er = tile + 32 * Dp;       // [8][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = w.counts[0], nm = w.counts[1];
+  if (nv == 0 || nm == 0) return;
+  for (int rb = blockIdx.x; rb * 8 < nv; rb += gridDim.x) {
+    const int rslot = rb * 8 + warp;
+    const bool ractive = rslot < nv;
+    const int r = ractive ? w.valid[rslot] : 0;
+    __syncthreads();
+    for (int d = lane; d < D; d += 32) er[warp * D + d] = ractive ? embs[(int64_t)r * D + d] : 0.f;
+    float rsum = 0.f;
+    for (int c0 = blockIdx.y * 32; c0 < nm; c0 += 32 * gridDim.y) {   // column tiles are split over blockIdx.y
+      __syncthreads();
+      load_tile(tile, Dp, embs, D, w.masked, c0, nm, 0);
+      __syncthreads();
+      const float dot = dot4(er + warp * D, tile + lane * Dp, D);
+      if (ractive && c0 + lane < nm) {
+        const float x = 1e-6f * expf(__fdiv_rn(dot, tau));
+        w.mex[(size_t)rslot * nm + c0 + lane] = x;
+        rsum += x;
+      }
+    }
+    rsum = warp_sum(rsum);
+    if (ractive && lane == 0 && rsum != 0.f) atomicAdd(w.zext + r, rsum);
+  }
+}
+
+// One CTA = 8 output rows (a warp each) x one share (blockIdx.y) of the 32-row tiles of the other side, staged in shared
+// memory.  role A (blockIdx.x < gridA): outputs = valid rows r, other side = masked rows k, weight c_r x_rk;
+// role B: outputs = masked rows k, other side = valid rows r, same weight.  dE accumulates with one atomicAdd per element
+// and share.
+__global__ void __launch_bounds__(256)
+scl_mgrad_kernel(const float* __restrict__ embs, int D, float tau, SclWs w, int gridA, float* __restrict__ d_embs) {
+  pdl_entry();
+  extern __shared__ __align__(16) float sm[];
+  const int Dp = D + 4;
+  float* tile = sm;                 // [32][Dp]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = w.counts[0], nm = w.counts[1];
+  if (nv == 0 || nm == 0) return;
+  const bool roleA = (int)blockIdx.x < gridA;
+  const int nout = roleA ? nv : nm, nin = roleA ? nm : nv;
+  const int* out_idx = roleA ? w.valid : w.masked;
+  const int* in_idx = roleA ? w.masked : w.valid;
+  const int gx = roleA ? gridA : (int)gridDim.x - gridA;
+  const int bx = roleA ? (int)blockIdx.x : (int)blockIdx.x - gridA;
+  const int D4 = D >> 2;
+  for (int ob = bx; ob * 8 < nout; ob += gx) {
+    const int oslot = ob * 8 + warp;
+    const bool oactive = oslot < nout;
+    const int orow = oactive ? out_idx[oslot] : 0;
+    const float co = (roleA && oactive) ? w.c[orow] : 1.f;
+    float4 acc[SCL_MAXD / 128];
+#pragma unroll
+    for (int u = 0; u < SCL_MAXD / 128; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i0 = blockIdx.y * 32; i0 < nin; i0 += 32 * gridDim.y) {
+      __syncthreads();
+      load_tile(tile, Dp, embs, D, in_idx, i0, nin, 0);
+      // this lane's weight for inner row i0 + lane
+      float x = 0.f;
+      if (oactive && i0 + lane < nin) {
+        if (roleA) x = co * w.mex[(size_t)oslot * nm + i0 + lane];
+        else x = w.c[in_idx[i0 + lane]] * w.mex[(size_t)(i0 + lane) * nm + oslot];
+      }
+      __syncthreads();
+      if (__any_sync(0xffffffffu, x != 0.f)) {
+        for (int jj = 0; jj < 32; ++jj) {
+          const float xj = __shfl_sync(0xffffffffu, x, jj);
+          if (xj != 0.f) {
+#pragma unroll
+            for (int u = 0; u < SCL_MAXD / 128; ++u) {
+              const int d4 = lane + 32 * u;
+              if (d4 < D4) {
+                const float4 e = *reinterpret_cast<const float4*>(tile + jj * Dp + 4 * d4);
+                acc[u].x = fmaf(xj, e.x, acc[u].x); acc[u].y = fmaf(xj, e.y, acc[u].y);
+                acc[u].z = fmaf(xj, e.z, acc[u].z); acc[u].w = fmaf(xj, e.w, acc[u].w);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (oactive) {
+      float* out = d_embs + (int64_t)orow * D;
+#pragma unroll
+      for (int u = 0; u < SCL_MAXD / 128; ++u) {
+        const int d4 = lane + 32 * u;
+        if (d4 < D4) {
+          if (acc[u].x != 0.f) atomicAdd(out + 4 * d4, __fdiv_rn(acc[u].x, tau));
+          if (acc[u].y != 0.f) atomicAdd(out + 4 * d4 + 1, __fdiv_rn(acc[u].y, tau));
+          if (acc[u].z != 0.f) atomicAdd(out + 4 * d4 + 2, __fdiv_rn(acc[u].z, tau));
+          if (acc[u].w != 0.f) atomicAdd(out + 4 * d4 + 3, __fdiv_rn(acc[u].w, tau));
         }
       }
     }
@@ -883,7 +998,11 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
   const int T2 = 2 * T;
   const bool batch = negative_type == MVF_NEG_BATCH_NOSELF;
   // Z extras
-  if (quirk) {
+  const bool use_mex = quirk && w.mex != nullptr;
+  if (use_mex) {
+    launch_k(scl_mex_kernel, dim3(cx, 8), 256, smem, st, embs, D, temperature, w);
+    MVF_CHECK_LAUNCH();
+  } else if (quirk) {
     launch_k(scl_cross_kernel, cross_grid, 256, smem, st, embs, D, T2, temperature, w.valid, w.counts, w.masked, w.counts + 1,
                                                     nullptr, 1.f, nullptr, 1e-6f, 0, w.zext, nullptr);
     MVF_CHECK_LAUNCH();
@@ -952,7 +1071,14 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
     }
   }
   if (d_embs) {
-    if (quirk) {
+    if (use_mex) {
+      // both masked-column gradient terms from the stored matrix, one launch (roles by block index)
+      // role A: valid output rows with the few masked tiles in one share each; role B: the masked output rows, whose many
+      // valid inner tiles are what the 8 shares of blockIdx.y split (role A CTAs with blockIdx.y past their tiles exit)
+      const int gridA = cx, gridB = cx < 64 ? cx : 64;
+      launch_k(scl_mgrad_kernel, dim3(gridA + gridB, 8), 256, smem, st, embs, D, temperature, w, gridA, d_embs);
+      MVF_CHECK_LAUNCH();
+    } else if (quirk) {
       // rows valid i, columns masked k: dE_i += c_i 1e-6 e^{l_ik} e_k / tau
       launch_k(scl_cross_kernel, cross_grid, 256, smem, st, embs, D, T2, temperature, w.valid, w.counts, w.masked,
                                                       w.counts + 1, w.c, 1.f, nullptr, 1e-6f, 0, nullptr, d_embs);
