@@ -121,7 +121,7 @@ static Carve carve(int C, int NW, int P, int slots, int ne) {
   Carve c;
   c.ring = (size_t)slots * TG * (C * 2 + 16);
   c.bars = 256;                                        // full[8] empty[8] pready[2] wready[2]
-  c.frag = (size_t)(C / 16) * (ne <= 4 ? 4 : 8) * 4 * 16;   // A fragments of the scores product: [tile][entity (4 | 8)][q] x 16 B
+  c.frag = (size_t)(C / 16) * ne * 4 * 16;             // A fragments of the scores product: [tile][entity][q] x 16 B
   c.partial = (size_t)2 * NW * PT * 4;
   c.wbuf = (size_t)2 * WB * 4;
   c.table = ((size_t)ne * P * 4 + 15) / 16 * 16;
@@ -146,7 +146,7 @@ __device__ __forceinline__ Sm setup(uint8_t* smraw, const Geom& g) {
   s.pready = s.empty + MAX_SLOTS;
   s.wready = s.pready + 2;
   s.frag = reinterpret_cast<uint4*>(smraw + ring_bytes + 256);
-  s.partial = reinterpret_cast<float*>(s.frag + (size_t)(g.C / 16) * (g.ne <= 4 ? 4 : 8) * 4);
+  s.partial = reinterpret_cast<float*>(s.frag + (size_t)(g.C / 16) * g.ne * 4);
   s.wbuf = s.partial + 2 * g.NW * PT;
   s.table = s.wbuf + 2 * WB;
   s.misc = s.table + (((size_t)g.ne * g.P + 3) / 4) * 4;
@@ -186,7 +186,7 @@ __device__ __forceinline__ void producer(const Sm& s, const Geom& g, const bf16*
 // (ch 2q, 2q+1) and (ch 2q+8, 2q+9) of row r8 are the a0 / a2 registers of the m16n8k16 A operand; {hi0, hi1, lo0, lo1} per
 // lane.  Only lanes r8 < ne hold data (the padding rows of A are zero), so a register-resident copy would spend 4*TPW
 // registers per thread on mostly zeros; 16 B per (tile, entity, q) in shared memory cost one 16-byte load per MMA pair.
-template <int TPW, int ES>
+template <int TPW>
 __device__ __forceinline__ void fill_afrag(uint4* fr, const float* __restrict__ M, int64_t stride, int ne, int ch_base, int q,
                                            int r8, float mul) {
   if (r8 < ne) {
@@ -198,7 +198,7 @@ __device__ __forceinline__ void fill_afrag(uint4* fr, const float* __restrict__ 
       uint4 o;
       split2(v0.x * mul, v0.y * mul, o.x, o.z);
       split2(v1.x * mul, v1.y * mul, o.y, o.w);
-      fr[(t * ES + r8) * 4 + q] = o;
+      fr[(t * ne + r8) * 4 + q] = o;
     }
   }
   __syncwarp();
@@ -207,18 +207,22 @@ __device__ __forceinline__ void fill_afrag(uint4* fr, const float* __restrict__ 
 // S^T[ent, tok] partial over this warp's channels -> pw[ent][tok] (rows r8 < ne).  The entity rows need only 8 of the 16
 // rows of the A operand, so the bf16 hi parts sit in rows 0..7 and the lo parts in rows 8..15: ONE MMA per tile yields both
 // products (accumulator rows r8 and r8 + 8 live in the same lane and are added at the end).  A row only feeds its own
-// output row, so lanes of unused rows simply load the fragment of entity r8 & (ES-1) (or never-written table rows): their
-// results are not stored, and no predication is needed in the loop.
-template <int TPW, int ES>
+// output row, so the registers of lanes that own padding rows may hold anything: their results are not stored.
+template <int TPW>
 __device__ __forceinline__ void scores_phase(uint32_t slot_addr, uint32_t l_off, const uint4* fr, float* pw, int ne, int q,
                                              int r8) {
   float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};   // two chains: even / odd tiles
-  const uint4* fl = fr + (r8 & (ES - 1)) * 4 + q;
+  // lanes whose A rows are padding (r8 >= ne) skip the load: predicated-off quarter warps issue no shared-memory
+  // wavefronts (the fragment loads were half of the kernel's shared-memory traffic), and their registers are don't-care
+  const bool loader = r8 < ne;
+  const uint4* fl = fr + (loader ? r8 * 4 + q : 0);
+  const int tstride = ne * 4;
+  uint4 a = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
   for (int t = 0; t < TPW; ++t) {
     uint32_t b0, b1;
     ldsm_x2(slot_addr + l_off + t * 32, b0, b1);
-    const uint4 a = fl[t * ES * 4];                    // {hi0, hi1, lo0, lo1}
+    if (loader) a = fl[t * tstride];                   // {hi0, hi1, lo0, lo1}
     if (t & 1) mma16816(sb, a.x, a.z, a.y, a.w, b0, b1);
     else mma16816(sa, a.x, a.z, a.y, a.w, b0, b1);
   }
@@ -363,9 +367,8 @@ pool_foldw_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, 
   const uint32_t slot_bytes = (uint32_t)(TG * g.pitch);
   const uint32_t l_off = (uint32_t)((lane & 7) * g.pitch + (warp * TPW * 16 + ((lane >> 3) & 1) * 8) * 2);
   // the scores live in the log2 domain (log2 e folded into the Wq fragments)
-  constexpr int ES = PACK ? 4 : 8;
-  uint4* fr = s.frag + (size_t)warp * TPW * ES * 4;
-  fill_afrag<TPW, ES>(fr, Wq + (int64_t)g.e0 * g.C, g.C, g.ne, warp * TPW * 16, q, r8, 1.4426950408889634f);
+  uint4* fr = s.frag + (size_t)warp * TPW * g.ne * 4;
+  fill_afrag<TPW>(fr, Wq + (int64_t)g.e0 * g.C, g.C, g.ne, warp * TPW * 16, q, r8, 1.4426950408889634f);
   float acc[TPW][4];
 #pragma unroll
   for (int t = 0; t < TPW; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
@@ -377,7 +380,7 @@ pool_foldw_fwd_kernel(const bf16* __restrict__ X, const float* __restrict__ Wq, 
   auto score_next = [&](int n1) {
     mbar_wait(&s.full[s_slot], s_use & 1);
     // partial[(n1)&1] was last read for group n1-2; that read finished before wready(n1-2) which this warp has waited on
-    scores_phase<TPW, ES>(ring_u32 + s_slot * slot_bytes, l_off, fr, s.partial + ((n1 & 1) * NW + warp) * PT, g.ne, q, r8);
+    scores_phase<TPW>(ring_u32 + s_slot * slot_bytes, l_off, fr, s.partial + ((n1 & 1) * NW + warp) * PT, g.ne, q, r8);
     __syncwarp();
     if (lane == 0) mbar_arrive(&s.pready[n1 & 1]);
     if (++s_slot == g.slots) { s_slot = 0; ++s_use; }
@@ -526,8 +529,7 @@ pool_foldw_bwd_kernel(const bf16* __restrict__ X, const float* __restrict__ G, c
   const uint32_t ring_u32 = smem_u32(s.ring);
   const uint32_t slot_bytes = (uint32_t)(TG * g.pitch);
   const uint32_t l_off = (uint32_t)((lane & 7) * g.pitch + (warp * TPW * 16 + ((lane >> 3) & 1) * 8) * 2);
-  constexpr int ES = PACK ? 4 : 8;
-  uint4* fr = s.frag + (size_t)warp * TPW * ES * 4;
+  uint4* fr = s.frag + (size_t)warp * TPW * g.ne * 4;
   float acc[TPW][4];
 #pragma unroll
   for (int t = 0; t < TPW; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
@@ -536,9 +538,9 @@ pool_foldw_bwd_kernel(const bf16* __restrict__ X, const float* __restrict__ G, c
   int64_t s_f = blockIdx.x;    // frame of the next group to score: its G rows are the A operand
   int p_slot = 0;
   auto score_next = [&](int n1) {
-    if (s_gi == 0) fill_afrag<TPW, ES>(fr, G + ((int64_t)s_f * g.Etot + g.e0) * g.C, g.C, g.ne, warp * TPW * 16, q, r8, 1.f);
+    if (s_gi == 0) fill_afrag<TPW>(fr, G + ((int64_t)s_f * g.Etot + g.e0) * g.C, g.C, g.ne, warp * TPW * 16, q, r8, 1.f);
     mbar_wait(&s.full[s_slot], s_use & 1);
-    scores_phase<TPW, ES>(ring_u32 + s_slot * slot_bytes, l_off, fr, s.partial + ((n1 & 1) * NW + warp) * PT, g.ne, q, r8);
+    scores_phase<TPW>(ring_u32 + s_slot * slot_bytes, l_off, fr, s.partial + ((n1 & 1) * NW + warp) * PT, g.ne, q, r8);
     __syncwarp();
     if (lane == 0) mbar_arrive(&s.pready[n1 & 1]);
     if (++s_slot == g.slots) { s_slot = 0; ++s_use; }
