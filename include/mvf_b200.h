@@ -227,6 +227,15 @@ int mvf_pool_fold_bwd_delta(int dtype, int32_t F, int32_t P, int32_t E, int32_t 
 int mvf_pool_fold_finish(const float* d_wq, const float* q_s, const float* q_b, const float* w_k, int32_t E, int32_t SPC,
                          int32_t C_in, float* d_wk, int64_t ld_dwk, float* d_q_s, float* d_q_b, mvf_stream_t stream);
 
+/* Cross-rank sum of a small float64 buffer (BatchNorm statistics, replaces the SyncBatchNorm exchange of train.py:283)
+ * over NVLink peer memory: bufs_dev = DEVICE array of `world` pointers to the ranks' symmetric buffers of
+ * mvf_peer_buffer_bytes() bytes each (zero-filled before first use; e.g. torch.distributed._symmetric_memory),
+ * counter = this rank's device-resident exchange counter (starts at 0, advanced by the kernel: graph-replayable).
+ * Every rank must call it the same number of times in the same order; the result is bitwise identical on all ranks. */
+size_t mvf_peer_buffer_bytes(void);
+int mvf_peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int32_t rank, int32_t world, uint32_t* counter,
+                     mvf_stream_t stream);
+
 /* a5/a8 temporal self-attention core (utils.py:11-44 with the [B,1,1,S] key mask): qkv [B*S, 3*H]
  * (Q | K | V, head h at columns h*dk), keymask [B,S] fp32 or NULL -> ctx [B*S, H], lse [B,heads,S] fp32. */
 int mvf_attention_fwd(int dtype, int32_t B, int32_t S, int32_t heads, int32_t dk, const void* qkv,

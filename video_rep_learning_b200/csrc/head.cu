@@ -1376,6 +1376,11 @@ int mvf_pool_fold_finish(const float* d_wq, const float* q_s, const float* q_b, 
   return fold_finish(d_wq, q_s, q_b, w_k, E, SPC, C_in, d_wk, ld_dwk, d_q_s, d_q_b, (cudaStream_t)stream);
 }
 
+size_t mvf_peer_buffer_bytes(void) { return peer_buffer_bytes(); }
+int mvf_peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int32_t rank, int32_t world, uint32_t* counter,
+                     mvf_stream_t stream) {
+  return peer_sum_f64(local, n, bufs_dev, rank, world, counter, (cudaStream_t)stream);
+}
 int mvf_attention_fwd(int dtype, int32_t B, int32_t S, int32_t heads, int32_t dk, const void* qkv, const float* keymask,
                       void* ctx, float* lse, mvf_stream_t stream) {
   MVF_REQUIRE(qkv && ctx && lse, MVF_ERR_BAD_ARG, "attention fwd: null pointer");

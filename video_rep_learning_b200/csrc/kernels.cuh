@@ -128,6 +128,10 @@ int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, 
 int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SPC, int W, float p, DropSeed seed,
                    cudaStream_t st, const float* ent = nullptr, const float* bv = nullptr, float* delta = nullptr);
 
+// ---- peer.cu: sum of small float64 buffers over NVLink peer memory (BatchNorm statistics across ranks) ----------------
+size_t peer_buffer_bytes();
+int peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int rank, int world, uint32_t* counter, cudaStream_t st);
+
 // ---- attention.cu --------------------------------------------------------------------------------------------
 // allow_split: the caller accepts operands split into bf16 hi + lo (2^-16 relative) -> tensor-core kernels of attention_tc.cu
 // for S <= 64, d_k = 32; otherwise (and always for exact-fp32 callers) the CUDA-core kernels
