@@ -227,6 +227,18 @@ int mvf_pool_fold_bwd_delta(int dtype, int32_t F, int32_t P, int32_t E, int32_t 
 int mvf_pool_fold_finish(const float* d_wq, const float* q_s, const float* q_b, const float* w_k, int32_t E, int32_t SPC,
                          int32_t C_in, float* d_wk, int64_t ld_dwk, float* d_q_s, float* d_q_b, mvf_stream_t stream);
 
+/* Fused optimizer tail: gradient unscale (inv_scale, AMP GradScaler train.py:124-127), global-norm
+ * clipping (torch.nn.utils.clip_grad_norm_, OPTIMIZER.GRAD_CLIP train.py:126,151; max_norm <= 0 disables it) and Adam
+ * (adamw = 0, L2 weight decay folded into the gradient) or AdamW (adamw = 1) as built by utils/optimizer.py:60-73, over
+ * n_tensors fp32 tensors.  params / grads / m / v: HOST arrays of device pointers, numel: host array; lr_dev (float) and
+ * step_dev (int64, advanced by the call) are DEVICE scalars so that the launches are CUDA-graph replayable; norm_out
+ * (device float, may be NULL) receives the pre-clip gradient norm; ws: mvf_opt_ws_bytes(n_tensors) bytes of scratch. */
+size_t mvf_opt_ws_bytes(int32_t n_tensors);
+int mvf_opt_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* m, float* const* v,
+                      const int64_t* numel, const float* lr_dev, int64_t* step_dev, double beta1, double beta2, float eps,
+                      float weight_decay, int32_t adamw, float max_norm, float inv_scale, float* norm_out, void* ws,
+                      size_t ws_bytes, mvf_stream_t stream);
+
 /* Cross-rank sum of a small float64 buffer (BatchNorm statistics, replaces the SyncBatchNorm exchange of train.py:283)
  * over NVLink peer memory: bufs_dev = DEVICE array of `world` pointers to the ranks' symmetric buffers of
  * mvf_peer_buffer_bytes() bytes each (zero-filled before first use; e.g. torch.distributed._symmetric_memory),

@@ -80,6 +80,9 @@ _PROTOS = {
     "mvf_pool_fold_bwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvf_pool_fold_bwd_delta": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvf_pool_fold_finish": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "mvf_opt_ws_bytes": (_sz, [_i32]),
+    "mvf_opt_adam_step": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _f32, _f32, _i32, _f32, _f32, _vp, _vp,
+                                    _sz, _vp]),
     "mvf_peer_buffer_bytes": (_sz, []),
     "mvf_peer_sum_f64": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     "mvf_attention_fwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

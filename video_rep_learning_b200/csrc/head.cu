@@ -1376,6 +1376,14 @@ int mvf_pool_fold_finish(const float* d_wq, const float* q_s, const float* q_b, 
   return fold_finish(d_wq, q_s, q_b, w_k, E, SPC, C_in, d_wk, ld_dwk, d_q_s, d_q_b, (cudaStream_t)stream);
 }
 
+size_t mvf_opt_ws_bytes(int32_t n_tensors) { return opt_ws_bytes(n_tensors); }
+int mvf_opt_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* m, float* const* v,
+                      const int64_t* numel, const float* lr_dev, int64_t* step_dev, double beta1, double beta2, float eps,
+                      float weight_decay, int32_t adamw, float max_norm, float inv_scale, float* norm_out, void* ws,
+                      size_t ws_bytes, mvf_stream_t stream) {
+  return opt_adam_step(n_tensors, params, grads, m, v, numel, lr_dev, step_dev, beta1, beta2, eps, weight_decay, adamw, max_norm,
+                       inv_scale, norm_out, ws, ws_bytes, (cudaStream_t)stream);
+}
 size_t mvf_peer_buffer_bytes(void) { return peer_buffer_bytes(); }
 int mvf_peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int32_t rank, int32_t world, uint32_t* counter,
                      mvf_stream_t stream) {

@@ -128,6 +128,12 @@ int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, 
 int ent_finish_bwd(const float* d_h0, int64_t ld, float* dEnt, int64_t R, int SPC, int W, float p, DropSeed seed,
                    cudaStream_t st, const float* ent = nullptr, const float* bv = nullptr, float* delta = nullptr);
 
+// ---- optim.cu: fused clip + Adam / AdamW over a list of tensors -----------------------------------------------------------
+size_t opt_ws_bytes(int n_tensors);
+int opt_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* m, float* const* v,
+                  const int64_t* numel, const float* lr_dev, int64_t* step_dev, double beta1, double beta2, float eps, float wd,
+                  int adamw, float max_norm, float inv_scale, float* norm_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // ---- peer.cu: sum of small float64 buffers over NVLink peer memory (BatchNorm statistics across ranks) ----------------
 size_t peer_buffer_bytes();
 int peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int rank, int world, uint32_t* counter, cudaStream_t st);

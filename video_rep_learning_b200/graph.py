@@ -32,7 +32,8 @@ from . import engine
 
 class GraphedTrainStep:
     def __init__(self, model, algo, Bv: int, T: int, P: int, C_in: int, dtype=torch.bfloat16,
-                 device: Optional[torch.device] = None, warmup: int = 3, project: bool = True, micro_batches: int = 1):
+                 device: Optional[torch.device] = None, warmup: int = 3, project: bool = True, micro_batches: int = 1,
+                 optimizer=None):
         self.model, self.algo = model, algo
         self.Bv, self.T = Bv, T
         self.project = project
@@ -47,6 +48,8 @@ class GraphedTrainStep:
         self.params: List[torch.nn.Parameter] = [p for n, p in model.named_parameters() if "backbone" not in n]
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.warmup = warmup
+        # optional fused optimizer tail (optim.FusedAdam): clip + Adam captured at the end of the same graph
+        self.optimizer = optimizer
         # optional: run the views as `micro_batches` slices on separate streams (engine.RunOptions.micro_batches).  Measured
         # at BASELINE configs[1] on B200: 2 slices 2.03 ms/step, 4 slices 2.35 ms vs 1.85 ms un-split -- the chain kernels
         # are bound by what they move, not only by latency, so the slices do not overlap enough to pay for the extra
@@ -81,6 +84,8 @@ class GraphedTrainStep:
         embs = self.model.forward_tokens(self.tokens, video_masks=self.masks, project=self.project)
         loss = self.algo.compute_sequence_loss(embs.view(self.Bv, 2, self.T, -1), self.seq_lens, self.steps, self.masks)["loss"]
         loss.backward()
+        if self.optimizer is not None:
+            self.optimizer.step()
         return loss
 
     def capture(self, profile: bool = False) -> "GraphedTrainStep":
