@@ -184,6 +184,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # --overlap: the chain's gradient all-reduce runs beside the pooling backward, which leaves --reserve-sms SMs free
+        # for it: keep NCCL's CTA count within that
+        if args.overlap:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.reserve_sms))
         dist.init_process_group("nccl", device_id=dev)
     Bv, T, P, C_in = WORKLOAD["videos_per_gpu"], WORKLOAD["T"], WORKLOAD["P"], WORKLOAD["c_in"]
     BV = 2 * Bv
@@ -224,6 +228,8 @@ def run_ours(args):
 
     lib = L.lib()
     head_opts = model.run_options
+    head_opts.overlap_grad_allreduce = bool(args.overlap)
+    head_opts.pool_bwd_reserve_sms = args.reserve_sms
 
     def timed_region(pool_mode, steps, warmup, sample_clocks):
         """W untimed + K timed steps with the tokens resident in HBM; CUDA events; max over ranks."""
@@ -512,6 +518,9 @@ def main():
                     help="entity pooling: folded (default product path) or dense (as written: K|V GEMM + attention)")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--micro-batches", type=int, default=1, help="slices of the captured step (1 = un-split)")
+    ap.add_argument("--overlap", action="store_true",
+                    help="multi-GPU: all-reduce the chain's gradients beside the pooling backward (measured slower; default off)")
+    ap.add_argument("--reserve-sms", type=int, default=16, help="SMs the pooling backward leaves to the overlapped all-reduce")
     ap.add_argument("--no-dense", action="store_true", help="skip the short as-written (dense pooling) comparison leg")
     args = ap.parse_args()
     if args.impl == "reference":

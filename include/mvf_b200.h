@@ -113,6 +113,12 @@ int mvf_bn_info(const mvf_head_desc* d, int idx, char* name, size_t name_cap, in
 size_t mvf_save_bytes(const mvf_head_desc* d);    /* activations kept from forward for backward         */
 size_t mvf_ws_bytes(const mvf_head_desc* d);      /* scratch, free to reuse after each call returns     */
 size_t mvf_gpack_elems(const mvf_head_desc* d);   /* flat fp32 gradient buffer (the all-reduce payload)  */
+/* Leading elements of the flat gradient buffer that only the LAST backward phase (n_fc + 1: the pooling backward) writes;
+ * everything behind them is final when phase n_fc returns, so its all-reduce can overlap the pooling kernel. */
+size_t mvf_gpack_pool_elems(const mvf_head_desc* d);
+/* Number of SMs the streaming pooling-backward kernel leaves free for a collective running beside it (0 = none);
+ * returns the previous setting. */
+int mvf_pool_bwd_reserve_sms(int32_t n);
 size_t mvf_proj_save_bytes(const mvf_head_desc* d); /* same two, for mvf_proj_forward / mvf_proj_backward */
 size_t mvf_proj_ws_bytes(const mvf_head_desc* d);
 /* Named views into the head save buffer (stage outputs), into the projection save buffer ("proj:<name>")
@@ -128,7 +134,9 @@ int mvf_bn_stat_lookup(const mvf_head_desc* d, int bn_idx, int backward, size_t*
 /* ---- a2-a9: MultiEntityTransformerEmbModel.forward / backward (models/mvformer.py:128-200) --------- */
 /* Phases: the chain is cut at every BatchNorm statistic so that a caller with world_size > 1 can all-reduce
  * the statistics buffer in between.  [0, MVF_PHASE_ALL) runs everything. Head forward has n_fc + 1 phases:
- * phase i ends after the partial statistics of fc BatchNorm i are written.  Head backward mirrors it. */
+ * phase i ends after the partial statistics of fc BatchNorm i are written.  Head backward mirrors it (phase i ends after
+ * the partial sums of BatchNorm n_fc-1-i) and has one more phase, n_fc + 1: the pooling backward (see
+ * mvf_gpack_pool_elems). */
 #define MVF_PHASE_ALL 255
 
 /* tokens [BV*T*P, C_in] token-major contiguous (dtype = d->dtype); mask [BV,T] fp32 or NULL;

@@ -58,6 +58,8 @@ _PROTOS = {
     "mvf_save_bytes": (_sz, [_pd]),
     "mvf_ws_bytes": (_sz, [_pd]),
     "mvf_gpack_elems": (_sz, [_pd]),
+    "mvf_gpack_pool_elems": (_sz, [_pd]),
+    "mvf_pool_bwd_reserve_sms": (C.c_int, [_i32]),
     "mvf_proj_save_bytes": (_sz, [_pd]),
     "mvf_proj_ws_bytes": (_sz, [_pd]),
     "mvf_save_lookup": (C.c_int, [_pd, C.c_char_p, C.POINTER(_sz), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),

@@ -819,7 +819,9 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
   const int A = m.act;
   cudaStream_t st = c.st;
   MVF_REQUIRE(d.training, MVF_ERR_BAD_ARG, "backward needs training = 1 (batch statistics were not saved in eval mode)");
-  const int n_ph = d.n_fc + 1;
+  // phases 0 .. n_fc are cut at the BatchNorm statistics (as in forward); the pooling backward is a phase of its own
+  // (n_fc + 1) so that a multi-GPU caller can start all-reducing the chain's gradients while it runs
+  const int n_ph = d.n_fc + 2;
   if (ph1 > n_ph) ph1 = n_ph;
   for (int ph = ph0; ph < ph1; ++ph) {
     const void* d_in;   // gradient w.r.t. the output of the FC Linear handled in this phase (act dtype)
@@ -909,7 +911,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
                              c.G.f("g." + fname(i, "gamma")), c.G.f("g." + fname(i, "beta")), st));
       }
     }
-    if (ph >= 1) {
+    if (ph >= 1 && ph <= d.n_fc) {
       // BatchNorm i = n_fc - ph: finish its backward with the (all-reduced) sums, then the Linear in front of it
       const int i = d.n_fc - ph, C = d.fc[i];
       const float pn = (i + 1 < d.n_fc) ? c.p : 0.f;  // dropout that followed this activation
@@ -1209,6 +1211,16 @@ static size_t layout_total(const mvf_head_desc* d, int which) {
 size_t mvf_save_bytes(const mvf_head_desc* d) { return layout_total(d, 0); }
 size_t mvf_ws_bytes(const mvf_head_desc* d) { return layout_total(d, 1); }
 size_t mvf_gpack_elems(const mvf_head_desc* d) { return layout_total(d, 2) / 4; }
+size_t mvf_gpack_pool_elems(const mvf_head_desc* d) {
+  // the regions written by the pooling phase of backward (g.Qs, g.Qb, g.w.kv, g.b.kv) lead the buffer
+  Model m;
+  if (build_model(d, m) != MVF_OK) return 0;
+  Layout L;
+  gpack_layout(m, L);
+  const auto* r = L.find(d->n_fc > 0 ? ("g." + fname(0, "w")).c_str() : "g.w.e");
+  return r ? r->off / 4 : 0;
+}
+int mvf_pool_bwd_reserve_sms(int32_t n) { return pool_fold_reserve_sms(n); }
 size_t mvf_proj_save_bytes(const mvf_head_desc* d) { return layout_total(d, 3); }
 size_t mvf_proj_ws_bytes(const mvf_head_desc* d) { return layout_total(d, 4); }
 

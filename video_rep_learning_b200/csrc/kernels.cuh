@@ -122,6 +122,8 @@ bool pool_fold_ws_supported(int dtype, int C, int P);
 int pool_fold_ws_fwd(int F, int P, int E, int C, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st);
 int pool_fold_ws_bwd(int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,
                      const float* delta, float* dWq, cudaStream_t st);
+// SMs the streaming backward kernel leaves free (a collective running beside it gets them); returns the previous value
+int pool_fold_reserve_sms(int n);
 // h0 = [drop(ent) | drop(one-hot) | 0]  and its backward (optionally delta[row] = <dEnt[row], ent[row] - bv> = <G_row, px_row>)
 int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, int E, int one_hot, float p, DropSeed seed,
                    cudaStream_t st);

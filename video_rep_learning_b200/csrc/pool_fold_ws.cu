@@ -626,20 +626,24 @@ static bool choose_shape(int C, int P, int ne, int* tpw_out, int* nw_out, int* s
   return true;
 }
 
+static int g_reserve_sms = 0;   // SMs left free by the backward kernel (pool_fold_reserve_sms)
+
 struct Plan {
-  int F = -1, P = -1, C = -1, ne = -1, slots = -1;
+  int F = -1, P = -1, C = -1, ne = -1, slots = -1, reserve = -1;
   int grid = 0;
   size_t smem = 0;
 };
 
 template <typename KernelT>
-static int plan(KernelT kernel, Plan& pl, const Geom& g) {
-  if (pl.F == g.F && pl.P == g.P && pl.C == g.C && pl.ne == g.ne && pl.slots == g.slots) return MVF_OK;
+static int plan(KernelT kernel, Plan& pl, const Geom& g, int reserve = 0) {
+  if (pl.F == g.F && pl.P == g.P && pl.C == g.C && pl.ne == g.ne && pl.slots == g.slots && pl.reserve == reserve) return MVF_OK;
   Carve cv = carve(g.C, g.NW, g.P, g.slots, g.ne);
   MVF_REQUIRE(cv.total <= 227 * 1024, MVF_ERR_UNSUPPORTED, "pool_fold_ws: %d channels need %zu B of shared memory", g.C, cv.total);
   MVF_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total));
-  const int sms = num_sms();
+  int sms = num_sms() - reserve;
+  if (sms < 1) sms = 1;
   pl.grid = g.F < sms ? g.F : sms;     // one persistent CTA per SM (the ring takes most of the shared memory)
+  pl.reserve = reserve;
   pl.smem = cv.total;
   pl.F = g.F; pl.P = g.P; pl.C = g.C; pl.ne = g.ne; pl.slots = g.slots;
   return MVF_OK;
@@ -664,11 +668,11 @@ static int bwd_launch(const Geom& g, const void* X, const float* G, const float*
                       float* dWq, cudaStream_t st) {
   if (g.ne <= 4) {
     static thread_local Plan pl;
-    MVF_TRY(plan(pool_foldw_bwd_kernel<TPW, true>, pl, g));
+    MVF_TRY(plan(pool_foldw_bwd_kernel<TPW, true>, pl, g, g_reserve_sms));
     launch_k(pool_foldw_bwd_kernel<TPW, true>, pl.grid, (g.NW + 2) * 32, pl.smem, st, (const bf16*)X, G, px, attn, delta, dWq, g);
   } else {
     static thread_local Plan pl;
-    MVF_TRY(plan(pool_foldw_bwd_kernel<TPW, false>, pl, g));
+    MVF_TRY(plan(pool_foldw_bwd_kernel<TPW, false>, pl, g, g_reserve_sms));
     launch_k(pool_foldw_bwd_kernel<TPW, false>, pl.grid, (g.NW + 2) * 32, pl.smem, st, (const bf16*)X, G, px, attn, delta, dWq, g);
   }
   MVF_CHECK_LAUNCH();
@@ -676,6 +680,12 @@ static int bwd_launch(const Geom& g, const void* X, const float* G, const float*
 }
 
 }  // namespace foldw
+
+int pool_fold_reserve_sms(int n) {
+  const int prev = foldw::g_reserve_sms;
+  foldw::g_reserve_sms = n < 0 ? 0 : n;
+  return prev;
+}
 
 bool pool_fold_ws_supported(int dtype, int C, int P) {
   int tpw, nw, slots;
