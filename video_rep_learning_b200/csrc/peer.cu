@@ -35,23 +35,27 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int PEER_THREADS = 1024;
+
+__global__ void __launch_bounds__(PEER_THREADS)
 peer_sum_f64_kernel(double* __restrict__ local, int n, uint8_t* const* __restrict__ bufs, int rank, int world,
                     uint32_t* __restrict__ counter) {
   pdl_entry();
   __shared__ uint32_t s_epoch;
+  __shared__ uint8_t* s_buf[64];
   if (threadIdx.x == 0) s_epoch = *counter + 1u;
+  if ((int)threadIdx.x < world) s_buf[threadIdx.x] = bufs[threadIdx.x];
   __syncthreads();
   const uint32_t epoch = s_epoch;
   const size_t slot = PEER_FLAG_BYTES + (size_t)(epoch & 1u) * PEER_STAGE_N * sizeof(double);
-  double* mine = reinterpret_cast<double*>(bufs[rank] + slot);
+  double* mine = reinterpret_cast<double*>(s_buf[rank] + slot);
   for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = local[i];
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < world) {
     // flag [rank] in peer threadIdx.x's buffer: "rank's slot of this exchange is complete"
-    st_release_sys(reinterpret_cast<uint32_t*>(bufs[threadIdx.x]) + rank, epoch);
-    const uint32_t* flag = reinterpret_cast<const uint32_t*>(bufs[rank]) + threadIdx.x;
+    st_release_sys(reinterpret_cast<uint32_t*>(s_buf[threadIdx.x]) + rank, epoch);
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(s_buf[rank]) + threadIdx.x;
     uint32_t spins = 0;
     while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
       if (++spins > (1u << 27)) {
@@ -61,9 +65,19 @@ peer_sum_f64_kernel(double* __restrict__ local, int n, uint8_t* const* __restric
     }
   }
   __syncthreads();
+  // all peer loads of an element are issued before the first addition (eight NVLink round trips in flight instead of
+  // one after the other); the additions keep rank order, so every rank computes the bitwise identical total
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double t = 0.0;
-    for (int p = 0; p < world; ++p) t += ld_relaxed_sys_f64(reinterpret_cast<const double*>(bufs[p] + slot) + i);
+    for (int p0 = 0; p0 < world; p0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        v[q] = (p0 + q < world) ? ld_relaxed_sys_f64(reinterpret_cast<const double*>(s_buf[p0 + q] + slot) + i) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (p0 + q < world) t += v[q];
+    }
     local[i] = t;
   }
   if (threadIdx.x == 0) *counter = epoch;
@@ -76,7 +90,7 @@ int peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int rank, int 
   MVF_REQUIRE(n >= 0 && n <= PEER_STAGE_N, MVF_ERR_UNSUPPORTED, "peer_sum: %lld values > %d", (long long)n, PEER_STAGE_N);
   MVF_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, MVF_ERR_BAD_ARG, "peer_sum: rank %d of %d", rank, world);
   if (n == 0) return MVF_OK;
-  launch_k(peer_sum_f64_kernel, 1, 256, 0, st, local, (int)n, (uint8_t* const*)bufs_dev, rank, world, counter);
+  launch_k(peer_sum_f64_kernel, 1, PEER_THREADS, 0, st, local, (int)n, (uint8_t* const*)bufs_dev, rank, world, counter);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
