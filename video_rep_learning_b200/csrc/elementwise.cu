@@ -202,10 +202,106 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ z
   }
 }
 
+// Same, for H = 128 * V4 with 16-byte aligned rows: the row lives in registers (V4 float4 per lane), every array is touched
+// once with 16-byte accesses (the generic kernel re-reads z_out from memory for the variance and for the output).
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(bf16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a);
+  u.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+template <typename TO, int V4>
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ z_in, const float* __restrict__ o,
+                                                         float* __restrict__ z_out, TO* __restrict__ r,
+                                                         float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         int64_t rows, float eps, float p, float inv_keep, DropSeed seed,
+                                                         int site) {
+  pdl_entry();
+  constexpr int H = 128 * V4;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* zi = z_in + row * H;
+  float* zo = z_out + row * H;
+  float4 v[V4];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < V4; ++k) {
+    const int c = 4 * (lane + 32 * k);
+    v[k] = *reinterpret_cast<const float4*>(zi + c);
+    if (o) {
+      float4 ov = *reinterpret_cast<const float4*>(o + row * H + c);
+      if (p > 0.f) {
+        const uint64_t idx = (uint64_t)(row * H + c);
+        ov.x *= drop_scale(seed, site, idx, p, inv_keep);
+        ov.y *= drop_scale(seed, site, idx + 1, p, inv_keep);
+        ov.z *= drop_scale(seed, site, idx + 2, p, inv_keep);
+        ov.w *= drop_scale(seed, site, idx + 3, p, inv_keep);
+      }
+      v[k].x += ov.x; v[k].y += ov.y; v[k].z += ov.z; v[k].w += ov.w;
+    }
+    if (o || zo != zi) *reinterpret_cast<float4*>(zo + c) = v[k];
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  if (r == nullptr) return;
+  s = warp_sum(s);
+  const float mean = s / (float)H;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < V4; ++k) {
+    const float a = v[k].x - mean, b = v[k].y - mean, c2 = v[k].z - mean, d = v[k].w - mean;
+    ss += (a * a + b * b) + (c2 * c2 + d * d);
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / (float)H + eps);
+#pragma unroll
+  for (int k = 0; k < V4; ++k) {
+    const int c = 4 * (lane + 32 * k);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    store4(r + row * H + c, make_float4((v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y,
+                                        (v[k].z - mean) * rstd * g.z + b.z, (v[k].w - mean) * rstd * g.w + b.w));
+  }
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+template <typename TO>
+static bool ln_fwd_vec(const float* z_in, const float* o, float* z_out, TO* r, float* mean, float* rstd, const float* gamma,
+                       const float* beta, int64_t rows, int H, float eps, float p, float ik, DropSeed seed, int site,
+                       cudaStream_t st) {
+  const uintptr_t al = (uintptr_t)z_in | (uintptr_t)o | (uintptr_t)z_out | (uintptr_t)r | (uintptr_t)gamma | (uintptr_t)beta;
+  if (H % 128 != 0 || H > 1024 || (al & 15) != 0) return false;
+  const int grid = cdiv(rows, 8);
+#define MVF_LNF(V) launch_k(ln_fwd_vec_kernel<TO, V>, grid, 256, 0, st, z_in, o, z_out, r, mean, rstd, gamma, beta, rows, eps, p, ik, seed, site)
+  switch (H / 128) {
+    case 1: MVF_LNF(1); return true;
+    case 2: MVF_LNF(2); return true;
+    case 3: MVF_LNF(3); return true;
+    case 4: MVF_LNF(4); return true;
+    case 6: MVF_LNF(6); return true;
+    case 8: MVF_LNF(8); return true;
+    default: return false;
+  }
+#undef MVF_LNF
+}
+
 int ln_fwd(int dtype_out, const float* z_in, const float* o, float* z_out, void* r, float* mean, float* rstd,
            const float* gamma, const float* beta, int64_t rows, int H, float eps, float p, DropSeed seed, int site,
            cudaStream_t st) {
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (r != nullptr && rows > 0) {
+    const bool done = dtype_out == MVF_BF16 ? ln_fwd_vec<bf16>(z_in, o, z_out, (bf16*)r, mean, rstd, gamma, beta, rows, H, eps, p, ik, seed, site, st)
+                                            : ln_fwd_vec<float>(z_in, o, z_out, (float*)r, mean, rstd, gamma, beta, rows, H, eps, p, ik, seed, site, st);
+    if (done) {
+      MVF_CHECK_LAUNCH();
+      return MVF_OK;
+    }
+  }
   int grid = cdiv(rows, 8);
   if (dtype_out == MVF_BF16)
     launch_k(ln_fwd_kernel<bf16>, grid, 256, 0, st, z_in, o, z_out, (bf16*)r, mean, rstd, gamma, beta, rows, H, eps, p, ik,
