@@ -10,10 +10,12 @@ dropout 0.1 (training mode), synthetic tokens, deterministic synthetic parameter
 32 videos (weak scaling; N = 8 is BASELINE configs[2]'s global batch of 256), BatchNorm statistics are exchanged
 across ranks and the flat head-gradient buffer is all-reduced once per step over NCCL.
 
-One JSON line on stdout (rank 0).  `value` = videos/s with tokens already resident in HBM; `e2e` = videos/s
+One JSON line on stdout (rank 0).  `value` = videos/s with tokens already resident in HBM, the step (forward, SCL,
+backward, cross-rank exchanges) captured once as a CUDA graph and replayed (`launch_mode`; `eager` = the same step issued
+kernel by kernel through the drop-in Python API, `--eager` makes that the timed leg); `e2e` = videos/s
 through the public Python API (model + algos.SCL) with the step's tokens copied from pinned host memory inside
 the timed region and the loss read back; `roofline` = the dominant kernel timed with CUDA events on its launching
-stream inside the timed steps: with the default folded entity pooling that is the streaming pooling pass over the
+stream inside the timed steps (event-record nodes of the graph): with the default folded entity pooling that is the streaming pooling pass over the
 tokens (HBM-bound, against the measured copy bandwidth); `dense_path` = the same step with the pooling evaluated as
 written in the reference (K|V projection GEMM on tcgen05 + attention over K|V), with the GEMM's fraction of the
 measured cuBLAS bf16 peak; `cpu_baseline` = the CPU oracle port of the reference algorithm on this host's cores on
