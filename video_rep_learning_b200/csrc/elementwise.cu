@@ -2,6 +2,8 @@
 // +dropout), BatchNorm1d (+ReLU +dropout) with split statistics (so the statistics can be all-reduced across
 // ranks between two launches), column sums for bias gradients, entity reduction, L2 normalisation.
 // All fp32 math; outputs optionally bf16 when they feed a tensor-core GEMM.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace mvf {
@@ -381,6 +383,86 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   }
 }
 
+// Same for H = 128 * V4 with 16-byte aligned rows: lane owns 4 consecutive columns per float4 (16-byte accesses).
+template <int V4>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict__ dr, const float* __restrict__ z,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         const float* __restrict__ gamma, const float* __restrict__ dz_in,
+                                                         float* __restrict__ dz_out, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta, int64_t rows,
+                                                         float* __restrict__ drop_out, float p, float inv_keep, DropSeed seed,
+                                                         int site) {
+  pdl_entry();
+  constexpr int H = 128 * V4;
+  extern __shared__ __align__(16) float acc[];  // [8 warps][2][H]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 gam[V4], ag[V4], ab[V4];
+#pragma unroll
+  for (int k = 0; k < V4; ++k) {
+    gam[k] = *reinterpret_cast<const float4*>(gamma + 4 * (lane + 32 * k));
+    ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
+    const float m = mean[row], rs = rstd[row];
+    float4 d[V4], xh[V4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < V4; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      d[k] = *reinterpret_cast<const float4*>(dr + row * H + c);
+      const float4 zv = *reinterpret_cast<const float4*>(z + row * H + c);
+      xh[k] = make_float4((zv.x - m) * rs, (zv.y - m) * rs, (zv.z - m) * rs, (zv.w - m) * rs);
+      const float gx = d[k].x * gam[k].x, gy = d[k].y * gam[k].y, gz = d[k].z * gam[k].z, gw = d[k].w * gam[k].w;
+      s1 += (gx + gy) + (gz + gw);
+      s2 += (gx * xh[k].x + gy * xh[k].y) + (gz * xh[k].z + gw * xh[k].w);
+      ag[k].x += d[k].x * xh[k].x; ag[k].y += d[k].y * xh[k].y; ag[k].z += d[k].z * xh[k].z; ag[k].w += d[k].w * xh[k].w;
+      ab[k].x += d[k].x; ab[k].y += d[k].y; ab[k].z += d[k].z; ab[k].w += d[k].w;
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+    for (int k = 0; k < V4; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      float4 v = make_float4(rs * (d[k].x * gam[k].x - s1 - xh[k].x * s2), rs * (d[k].y * gam[k].y - s1 - xh[k].y * s2),
+                             rs * (d[k].z * gam[k].z - s1 - xh[k].z * s2), rs * (d[k].w * gam[k].w - s1 - xh[k].w * s2));
+      if (dz_in) {
+        const float4 a = *reinterpret_cast<const float4*>(dz_in + row * H + c);
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      }
+      *reinterpret_cast<float4*>(dz_out + row * H + c) = v;
+      if (drop_out) {
+        float4 o = v;
+        if (p > 0.f) {
+          const uint64_t idx = (uint64_t)(row * H + c);
+          o.x *= drop_scale(seed, site, idx, p, inv_keep);
+          o.y *= drop_scale(seed, site, idx + 1, p, inv_keep);
+          o.z *= drop_scale(seed, site, idx + 2, p, inv_keep);
+          o.w *= drop_scale(seed, site, idx + 3, p, inv_keep);
+        }
+        *reinterpret_cast<float4*>(drop_out + row * H + c) = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V4; ++k) {
+    const int c = 4 * (lane + 32 * k);
+    *reinterpret_cast<float4*>(acc + (size_t)warp * 2 * H + c) = ag[k];
+    *reinterpret_cast<float4*>(acc + (size_t)warp * 2 * H + H + c) = ab[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      g += acc[(size_t)w * 2 * H + c];
+      b += acc[(size_t)w * 2 * H + H + c];
+    }
+    atomicAdd(dgamma + c, g);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
 int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd, const float* gamma,
            const float* dz_in, float* dz_out, float* dgamma, float* dbeta, int64_t rows, int H, cudaStream_t st,
            float* drop_out, float p, DropSeed seed, int site) {
@@ -391,6 +473,31 @@ int ln_bwd(const float* dr, const float* z, const float* mean, const float* rstd
   size_t smem = (size_t)8 * 2 * H * sizeof(float);
   MVF_REQUIRE(H % 32 == 0 && H <= 1024 && smem <= 48 * 1024, MVF_ERR_UNSUPPORTED,
               "ln_bwd: hidden size %d must be a multiple of 32 and <= 768", H);
+  {
+    const uintptr_t al = (uintptr_t)dr | (uintptr_t)z | (uintptr_t)gamma | (uintptr_t)dz_in | (uintptr_t)dz_out | (uintptr_t)drop_out;
+    static int vec_on = -1;   // MVF_LN_VEC=0: scalar kernels only (A/B)
+    if (vec_on < 0) {
+      const char* e = getenv("MVF_LN_VEC");
+      vec_on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (vec_on && H % 128 == 0 && (al & 15) == 0) {
+#define MVF_LNBV(V) launch_k(ln_bwd_vec_kernel<V>, grid, 256, smem, st, dr, z, mean, rstd, gamma, dz_in, dz_out, dgamma, dbeta, rows, drop_out, p, ik, seed, site)
+      bool done = true;
+      switch (H / 128) {
+        case 1: MVF_LNBV(1); break;
+        case 2: MVF_LNBV(2); break;
+        case 3: MVF_LNBV(3); break;
+        case 4: MVF_LNBV(4); break;
+        case 6: MVF_LNBV(6); break;
+        default: done = false; break;
+      }
+#undef MVF_LNBV
+      if (done) {
+        MVF_CHECK_LAUNCH();
+        return MVF_OK;
+      }
+    }
+  }
 #define MVF_LNB(V) launch_k(ln_bwd_kernel<V>, grid, 256, smem, st, dr, z, mean, rstd, gamma, dz_in, dz_out, dgamma, dbeta, rows, H, drop_out, p, ik, seed, site)
   switch (H / 32) {
     case 1: MVF_LNB(1); break;
