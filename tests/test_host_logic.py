@@ -166,3 +166,35 @@ def test_cfg_container_semantics():
     assert cfg.A.C.D == 2
     with pytest.raises(AttributeError):
         _ = cfg.missing
+
+
+def test_optimizer_tail_and_graph_step_have_no_cpu_path():
+    """optim.FusedAdam / graph.GraphedTrainStep: host-side contract only (the arithmetic is tested on the GPU box) -- CPU
+    tensors are refused loudly, mixed hyper-parameters across groups are refused, construct_optimizer mirrors
+    utils/optimizer.py:60-73."""
+    import pytest
+    import torch
+    from video_rep_learning_b200.graph import GraphedTrainStep
+    from video_rep_learning_b200.optim import FusedAdam, construct_optimizer
+
+    cfg = small_cfg(drop=0.0)
+    w = torch.nn.Parameter(torch.zeros(4, 4))
+    w.grad = torch.ones(4, 4)
+    opt = FusedAdam([w], lr=1e-3, max_grad_norm=10.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()
+    a, b = torch.nn.Parameter(torch.zeros(2)), torch.nn.Parameter(torch.zeros(2))
+    a.grad, b.grad = torch.ones(2), torch.ones(2)
+    mixed = FusedAdam([{"params": [a], "lr": 1e-3}, {"params": [b], "lr": 1e-2}])
+    with pytest.raises(NotImplementedError):
+        mixed.step()
+    from video_rep_learning_b200.models import build_model
+    m = build_model(cfg, backbone=DummyBackbone())
+    o = construct_optimizer(m, cfg)
+    n_head = sum(1 for n, p in m.named_parameters() if "backbone" not in n)
+    assert sum(len(g["params"]) for g in o.param_groups) == n_head
+    assert o.max_grad_norm == float(cfg.OPTIMIZER.GRAD_CLIP) and not o.adamw
+    assert o.param_groups[0]["weight_decay"] == cfg.OPTIMIZER.WEIGHT_DECAY
+    from video_rep_learning_b200.algos import get_algo
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GraphedTrainStep(m, get_algo(cfg), 2, 8, 9, 48, device=torch.device("cpu"))
