@@ -42,6 +42,15 @@ METRIC = "training videos/sec (head+SCL fwd/bwd)"
 UNIT = "videos/s"
 
 
+def workload_config(world: int) -> dict:
+    """The `config` object of the JSON line (both arms print the same one)."""
+    Bv = WORKLOAD["videos_per_gpu"]
+    return dict(workload=WORKLOAD["name"], videos_per_gpu=Bv, global_videos=Bv * world, frames=WORKLOAD["T"], views=2,
+                patch_tokens=WORKLOAD["P"], token_channels=WORKLOAD["c_in"], entities=WORKLOAD["entities"], dropout=0.1,
+                l2="inputs (1.16 GB of tokens per step) larger than L2; no flush needed",
+                parallelism=f"dp{world} (video shards; BN statistics + one flat gradient all-reduce)")
+
+
 def flops_per_video(T=20, P=196, c_in=2304, E=3, SPC=384, FC=512, H=256, DFF=1024, L=3, D=128, PS=128):
     """SURVEY.md section 8d formula (as-written dense contractions, 2 FLOP/MAC)."""
     F2 = 2 * T
@@ -149,14 +158,17 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 4
-    # warm-up + steps, each step = one fwd+bwd over `sample` videos of the workload shape
-    times = cpu_step_time(sample, max(1, min(args.steps, 5)), threads)
+    sample = WORKLOAD["videos_per_gpu"]
+    # warm-up + steps, each step = one fwd+bwd over the workload's batch (32 videos); at most 8 timed steps (~1.2 s each on
+    # the GPU box's 16 cores) so that the run ends within a minute whatever --steps says
+    times = cpu_step_time(sample, max(1, min(args.steps, 8)), threads)
     ms = 1e3 * statistics.mean(times)
     v = sample / (ms / 1e3)
     out = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=len(times), warmup=1,
                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-               config=dict(workload=WORKLOAD["name"], note="CPU oracle port of the reference algorithm; fp32"),
+               config=dict(workload_config(max(1, args.gpus)),
+                           note="CPU arm: oracle port of the reference algorithm on the host cores of rank 0, fp32, dropout 0, "
+                                "one step = the workload's 32-video batch"),
                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind="port",
                                  sample=f"{sample} videos x 20 frames x 2 views of the cfg2 shape per step, {len(times)} steps"),
                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -481,18 +493,15 @@ def run_ours(args):
         cpu = None
         if not args.no_cpu:
             threads = os.cpu_count() or 1
-            sample = 2
-            times = cpu_step_time(sample, 2, threads)
+            sample = 16       # half of the workload's batch per iteration: ~10 s of CPU work with the warm-up on 16 cores
+            times = cpu_step_time(sample, 6, threads)
             cms = statistics.mean(times)
             cpu = dict(value=sample / cms, unit=UNIT, cores=threads, kind="port",
                        sample=f"{sample} videos of the cfg2 shape (fp32 oracle port), {len(times)} timed iterations after 1 warm-up")
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                    data="synthetic",
-                   config=dict(workload=WORKLOAD["name"], videos_per_gpu=Bv, global_videos=Bv * world, frames=T, views=2,
-                               patch_tokens=P, token_channels=C_in, entities=3, dropout=0.1,
-                               l2="inputs (1.16 GB of tokens per step) larger than L2; no flush needed",
-                               parallelism=f"dp{world} (video shards; BN statistics + one flat gradient all-reduce)"),
+                   config=workload_config(world),
                    as_written_tflops=whole, gflop_per_video_as_written=fl["total"] / 1e9, loss=final_loss,
                    pooling=args.pool, launch_mode=("eager" if args.eager else "cuda_graph"), launch_note=graph_note,
                    eager=None if eager_run is None else dict(
