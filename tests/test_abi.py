@@ -54,6 +54,11 @@ def test_param_table_is_reference_state_dict_order(kw):
     assert plan.bn_names == O.bn_buffer_names(hc)
     assert plan.gpack_elems >= sum(r * c for r, c in plan.param_shapes)
     assert plan.save_bytes > 0 and plan.ws_bytes > 0 and plan.proj_save_bytes > 0
+    # the regions of the pooling parameters (Q_s, Q_s_b, W_k | W_v, b_k | b_v) lead the flat gradient buffer: what the last
+    # backward phase writes, and what an overlapped all-reduce must leave for the end
+    pool_params = hc.n_entities * hc.pool_channels + hc.pool_channels + 2 * hc.pool_channels * hc.c_in + 2 * hc.pool_channels
+    assert pool_params <= plan.gpack_pool_elems < plan.gpack_elems
+    assert plan.gpack_pool_elems - pool_params < 4 * 64 + 2 * hc.pool_channels * 8      # only alignment padding in between
 
 
 def test_layout_lookup_and_bn_stat_regions():
