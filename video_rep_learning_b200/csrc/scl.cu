@@ -1021,7 +1021,11 @@ int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps
     fused_on = e ? atoi(e) : 2;
   }
   const size_t f2smem = scl_fused2_smem(T, D);
-  if (fused_on >= 2 && f2smem <= 200 * 1024) {
+  if (scl_pair_tc_enabled(T, D)) {
+    // prototype (MVF_SCL_TC=1): tensor-core per-pair kernel, see scl_tc.cu
+    MVF_TRY(scl_pair_tc(embs, seq_lens, steps, masks, Bv, T, D, temperature, 2.f * label_variance, w.M, w.zext, w.c, loss_out,
+                        d_embs, st));
+  } else if (fused_on >= 2 && f2smem <= 200 * 1024) {
     if (T * T >= 2048) {
       static size_t configured = 0;
       if (f2smem > configured) {
