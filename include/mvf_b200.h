@@ -97,6 +97,7 @@ uint64_t mvf_launch_count(void);
  * DENSE pooling: tag 0 K|V projection GEMM, 1 its weight-gradient GEMM, 2 cross-attention pooling fwd, 3 its bwd.
  * FOLDED pooling: tag 0 streaming pooling pass fwd, 1 streaming pass bwd, 2 the rest of the forward pooling block
  * (Wq fold, px Wv^T GEMM, dropout/one-hot), 3 the rest of its backward (dEnt, G and dWv GEMMs, dWk/dQ finish).
+ * Both modes: tag 6 temporal self-attention forward (one bracket per encoder layer), 7 its backward, 8 SCL (loss + gradient).
  * mvf_profile_read synchronises on the recorded events and returns the durations in milliseconds. */
 int mvf_profile_enable(int on);
 int mvf_profile_read(int tag, float* ms, int cap, int* n);

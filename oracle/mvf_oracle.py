@@ -221,7 +221,7 @@ def entity_mlp(P, buf, ent: Tensor, cfg: HeadCfg, training: bool, new_buf, drop_
     BV, T, E, SPC = ent.shape
     x = ent
     if cfg.one_hot == "pool":                                   # mvformer.py:144-149
-        eye = torch.eye(E, dtype=ent.dtype).expand(BV, T, E, E)
+        eye = torch.eye(E, dtype=ent.dtype, device=ent.device).expand(BV, T, E, E)
         x = torch.cat([x, eye], dim=-1)
     x = x.reshape(BV * T * E, x.shape[-1])
     for i in range(len(cfg.fc_channels)):
@@ -238,6 +238,17 @@ def entity_mlp(P, buf, ent: Tensor, cfg: HeadCfg, training: bool, new_buf, drop_
 # --------------------------------------------------------------------------------------------------
 # a8: temporal encoder (models/utils.py:47-108, 147-159, 176-242)
 # --------------------------------------------------------------------------------------------------
+ATTN_LEAN_ELEMS = 1 << 27   # score elements above which the oracle's attention runs view by view (memory only)
+
+
+def _attention_core(q: Tensor, k: Tensor, v: Tensor, keymask: Optional[Tensor], dk: int) -> Tensor:
+    """attention() of models/utils.py:11-44 with the [B,1,1,S] key mask, dropout p = 0."""
+    sc = q @ k.transpose(-1, -2) / np.sqrt(dk)                                   # utils.py:17-18
+    if keymask is not None:
+        sc = sc.masked_fill(keymask[:, None, None, :] == 0, -float("inf"))      # utils.py:20-21
+    return torch.softmax(sc, dim=-1) @ v
+
+
 def encoder_layer(P, pre: str, z: Tensor, keymask: Optional[Tensor], cfg: HeadCfg, drop=None) -> Tensor:
     """Pre-LN block: z + MHA(LN z); z + FFN(LN z).  keymask [BV,S] (1 = attend, 0 = -inf)."""
     BV, S, H = z.shape
@@ -248,10 +259,15 @@ def encoder_layer(P, pre: str, z: Tensor, keymask: Optional[Tensor], cfg: HeadCf
     q = F.linear(r, P[a + "linear_Q2d.weight"], P[a + "linear_Q2d.bias"]).view(BV, S, nh, dk).transpose(1, 2)
     k = F.linear(r, P[a + "linear_K2d.weight"], P[a + "linear_K2d.bias"]).view(BV, S, nh, dk).transpose(1, 2)
     v = F.linear(r, P[a + "linear_V2d.weight"], P[a + "linear_V2d.bias"]).view(BV, S, nh, dk).transpose(1, 2)
-    sc = q @ k.transpose(-1, -2) / np.sqrt(dk)                                   # utils.py:17-18
-    if keymask is not None:
-        sc = sc.masked_fill(keymask[:, None, None, :] == 0, -float("inf"))      # utils.py:20-21
-    ctx = torch.softmax(sc, dim=-1) @ v
+    if BV * nh * S * S > ATTN_LEAN_ELEMS and BV > 1:
+        # long sequences (S = E*T up to thousands): the [BV, heads, S, S] score tensors of all views and layers would be
+        # kept for backward; evaluate view by view under activation checkpointing instead (same arithmetic)
+        from torch.utils.checkpoint import checkpoint
+        ctx = torch.cat([checkpoint(_attention_core, q[b:b + 1], k[b:b + 1], v[b:b + 1],
+                                    None if keymask is None else keymask[b:b + 1], dk, use_reentrant=False)
+                         for b in range(BV)], dim=0)
+    else:
+        ctx = _attention_core(q, k, v, keymask, dk)
     ctx = ctx.transpose(1, 2).reshape(BV, S, H)
     o = F.linear(ctx, P[a + "linear_d2Q.weight"], P[a + "linear_d2Q.bias"])
     if drop is not None:
@@ -285,12 +301,12 @@ def head_forward(P: Dict[str, Tensor], buf: Optional[Dict[str, Tensor]], tokens:
     ent, attn = xattn_pool(P, tokens, cfg)
     h3 = entity_mlp(P, buf, ent, cfg, training, new_buf, drop_masks)             # [BV,T,E,Hin]
     z = h3.permute(0, 2, 1, 3)                                                   # [BV,E,T,Hin]  mvformer.py:155-157
-    pe = torch.from_numpy(pos_table_for(cfg, T, z.shape[-1])).to(z.dtype)        # utils.py:136-143
+    pe = torch.from_numpy(pos_table_for(cfg, T, z.shape[-1])).to(device=z.device, dtype=z.dtype)   # utils.py:136-143
     z = z + pe[None, None]
     if drop_masks is not None and "pos" in drop_masks:
         z = z * drop_masks["pos"].reshape(BV, E, T, -1)
     if cfg.one_hot == "enc":                                                     # mvformer.py:162-168
-        eye = torch.eye(E, dtype=z.dtype)[None, :, None, :].expand(BV, E, T, E)
+        eye = torch.eye(E, dtype=z.dtype, device=z.device)[None, :, None, :].expand(BV, E, T, E)
         z = torch.cat([z, eye], dim=-1)
     z = z.reshape(BV, E * T, z.shape[-1])                                        # s = e*T + t   mvformer.py:170
     keymask = None
@@ -376,7 +392,7 @@ def scl_loss_dense(embs: Tensor, seq_lens: Tensor, steps: Tensor, masks: Tensor,
     # the dtype of the embeddings, then cast with .type_as(logits) (scl.py:62, 85)
     dist = torch.abs(st[:, None] / L[:, None] * L[None, :] - st[None, :])        # scl.py:62
     dist = dist.masked_fill(mm == 0, 1e6)                                        # scl.py:63
-    idx = torch.arange(N)
+    idx = torch.arange(N, device=e.device)
     vid, view = idx // (V * T), (idx // T) % V
     same_vid = vid[:, None] == vid[None, :]
     same_view = same_vid & (view[:, None] == view[None, :])

@@ -1,9 +1,12 @@
-"""Import the reference's own hot-path modules (build container only).  TEST INFRASTRUCTURE ONLY.
+"""Import the reference's own hot-path modules.  TEST / BASELINE INFRASTRUCTURE ONLY.
 
-/root/reference does not exist on the GPU box, so nothing in `-m gpu` tests, smoke() or bench.py
-may import this file.  It is used by tests/golden/make_golden.py (to generate the committed golden
-vectors) and by the `not gpu` test that re-checks the oracle against the live reference when the
-tree is present.
+Two locations are tried: /root/reference/CARL_MVF (build container) and, on the GPU box where that tree does not
+exist, `baseline/_ref/CARL_MVF` -- an UNMODIFIED copy of the handful of reference files on the hot path that
+`__graft_entry__.build()` places there (git-ignored, shipped by gpurun; never part of the repository history).
+It is used by tests/golden/make_golden.py (to generate the committed golden vectors), by the `not gpu` test that
+re-checks the oracle against the live reference, and by the baseline arms of bench.py (`--impl reference`,
+`--impl reference-gpu`), which time the reference's own modules.  Nothing in the product path, the `-m gpu` parity
+tests or smoke() imports this file.
 
 A plain `import models` fails (timm / iopath / easydict are not installed), so
 the four files on the hot path are loaded by path under stub parent packages.
@@ -19,7 +22,40 @@ import types
 import torch
 import yaml
 
-REF_ROOT = os.environ.get("MVF_REFERENCE_ROOT", "/root/reference/CARL_MVF")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VENDORED_ROOT = os.path.join(_REPO, "baseline", "_ref", "CARL_MVF")
+# files of the reference that the hot path (and its samplers / configs) needs; copied verbatim by vendor_reference()
+VENDOR_FILES = ("models/utils.py", "models/mvformer.py", "models/resnet_c2d.py", "algos/scl.py",
+                "datasets/dataset_splits.py", "datasets/data_augment.py", "datasets/penn_action.py", "datasets/finegym.py",
+                "datasets/pouring.py", "configs_mvf/penn_mvf.yml", "configs_mvf/fg99_mvf.yml", "configs_mvf/k400_mvf.yml",
+                "configs_mvf/ablate_dinoB8_fwb3.yml")
+
+
+def _default_root() -> str:
+    env = os.environ.get("MVF_REFERENCE_ROOT")
+    if env:
+        return env
+    live = "/root/reference/CARL_MVF"
+    return live if os.path.isfile(os.path.join(live, "models", "mvformer.py")) else VENDORED_ROOT
+
+
+REF_ROOT = _default_root()
+
+
+def vendor_reference(src_root: str = "/root/reference/CARL_MVF") -> bool:
+    """Copy the unmodified hot-path files of the reference into baseline/_ref (git-ignored) so that the baseline arms of
+    bench.py can run the reference's own code on the GPU box.  No-op when the reference tree is absent."""
+    import shutil
+    if not os.path.isfile(os.path.join(src_root, "models", "mvformer.py")):
+        return False
+    for rel in VENDOR_FILES:
+        src, dst = os.path.join(src_root, rel), os.path.join(VENDORED_ROOT, rel)
+        if not os.path.isfile(src):
+            continue
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if not os.path.isfile(dst) or os.path.getmtime(dst) < os.path.getmtime(src) or os.path.getsize(dst) != os.path.getsize(src):
+            shutil.copyfile(src, dst)
+    return True
 
 
 def available() -> bool:
@@ -86,9 +122,16 @@ def load_reference():
     _load("datasets.dataset_splits", "datasets/dataset_splits.py")
     rc = _load("models.resnet_c2d", "models/resnet_c2d.py")
     scl = _load("ref_algos_scl", "algos/scl.py")
-    if not torch.cuda.is_available():
-        # mvformer.py:145 calls torch.eye(device=x.get_device()); get_device() is -1 on CPU tensors.
-        torch.Tensor.get_device = lambda self: self.device
+    # mvformer.py:145 calls torch.eye(device=x.get_device()); get_device() is -1 on CPU tensors -> hand back the device
+    # object for CPU tensors (CUDA tensors keep their ordinal), so that the same modules run on either side
+    if not getattr(torch.Tensor.get_device, "_mvf_patched", False):
+        _orig_get_device = torch.Tensor.get_device
+
+        def _get_device(self):
+            return self.device if self.device.type == "cpu" else _orig_get_device(self)
+
+        _get_device._mvf_patched = True
+        torch.Tensor.get_device = _get_device
     _loaded.update(dict(utils=mu, mvformer=mv, resnet_c2d=rc, scl=scl,
                         MultiEntityTransformerEmbModel=mv.MultiEntityTransformerEmbModel,
                         MLPHead=rc.MLPHead, SCL=scl.SCL))

@@ -1,0 +1,68 @@
+#!/bin/bash
+# One GPU-box visit of round 2.  Usage: scripts/gpu_r2.sh [tests] [smoke] [bench] [bench4] [bench5] [ref] [launches] ...
+# Everything is logged under gpurun_out/ (merged back by gpurun).
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+free -g | head -2 >> gpurun_out/gpu.txt; nproc >> gpurun_out/gpu.txt
+S=gpurun_out/summary.txt
+for stage in "$@"; do
+  echo "=== $stage === $(date +%T)" | tee -a $S
+  case $stage in
+    tests)
+      for f in test_gpu_gemm test_gpu_fold test_gpu_blocks test_gpu_scl test_gpu_model test_gpu_dropin test_gpu_graph test_gpu_optim test_gpu_multi test_gpu_fullsize; do
+        [ -f tests/$f.py ] || continue
+        timeout 1500 python -m pytest tests/$f.py -m gpu -q -s --timeout=1200 -p no:cacheprovider > gpurun_out/$f.log 2>&1
+        echo "$f exit $? :: $(tail -n 1 gpurun_out/$f.log)" | tee -a $S
+      done ;;
+    tests_extra)
+      for f in $(ls tests/test_gpu_*.py | sed 's#tests/##; s#\.py##'); do
+        case $f in test_gpu_gemm|test_gpu_fold|test_gpu_blocks|test_gpu_scl|test_gpu_model|test_gpu_dropin|test_gpu_graph|test_gpu_optim|test_gpu_multi|test_gpu_fullsize) continue;; esac
+        timeout 1500 python -m pytest tests/$f.py -m gpu -q -s --timeout=1200 -p no:cacheprovider > gpurun_out/$f.log 2>&1
+        echo "$f exit $? :: $(tail -n 1 gpurun_out/$f.log)" | tee -a $S
+      done ;;
+    file:*)
+      f=${stage#file:}
+      timeout 1500 python -m pytest tests/$f.py -m gpu -q -s --timeout=1200 -p no:cacheprovider > gpurun_out/$f.log 2>&1
+      echo "$f exit $? :: $(tail -n 1 gpurun_out/$f.log)" | tee -a $S ;;
+    smoke)
+      timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "exit $?" | tee -a $S
+      tail -n 4 gpurun_out/smoke.log | tee -a $S ;;
+    bench)
+      timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; echo "exit $?" | tee -a $S ;;
+    bench4)
+      timeout 900 python bench.py --workload finegym_cfg4 --steps 20 --warmup 5 > gpurun_out/bench_cfg4.json 2> gpurun_out/bench_cfg4.err; echo "exit $?" | tee -a $S ;;
+    bench5)
+      timeout 1200 python bench.py --workload long_cfg5 --steps 10 --warmup 3 > gpurun_out/bench_cfg5.json 2> gpurun_out/bench_cfg5.err; echo "exit $?" | tee -a $S ;;
+    quick)
+      timeout 600 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu --no-dense --no-refgpu --no-parity > gpurun_out/quick_cfg2.json 2> gpurun_out/quick_cfg2.err; echo "exit $?" | tee -a $S ;;
+    quick4)
+      timeout 600 python bench.py --workload finegym_cfg4 --steps 20 --warmup 5 --no-e2e --no-cpu --no-dense --no-refgpu --no-parity > gpurun_out/quick_cfg4.json 2> gpurun_out/quick_cfg4.err; echo "exit $?" | tee -a $S ;;
+    quick5)
+      timeout 600 python bench.py --workload long_cfg5 --steps 10 --warmup 3 --no-e2e --no-cpu --no-dense --no-refgpu --no-parity > gpurun_out/quick_cfg5.json 2> gpurun_out/quick_cfg5.err; echo "exit $?" | tee -a $S ;;
+    ref)
+      timeout 900 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "exit $?" | tee -a $S ;;
+    launches|launches4|launches5)
+      wl=penn_cfg2; [ $stage = launches4 ] && wl=finegym_cfg4; [ $stage = launches5 ] && wl=long_cfg5
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 1200 --csv --log-file gpurun_out/$stage.csv \
+        python bench.py --workload $wl --eager --steps 2 --warmup 3 --no-e2e --no-cpu --no-dense --no-refgpu --no-parity > gpurun_out/$stage.log 2>&1
+      echo "exit $?" | tee -a $S ;;
+    *) echo "unknown stage $stage" | tee -a $S ;;
+  esac
+done
+for f in gpurun_out/bench_cfg*.json gpurun_out/quick_cfg*.json; do [ -f $f ] && python - "$f" <<'PY' | tee -a $S
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    r = d.get("roofline") or {}
+    print(sys.argv[1], "value %.1f ms %.3f launches %s | roofline %s frac %.3f | parity %s | e2e %s | refgpu %s" % (
+        d["value"], d["ms_per_step"], d.get("gpu_launches"), (r.get("kernel") or "")[:40], r.get("frac") or 0,
+        {k: (round(v, 6) if isinstance(v, float) else v) for k, v in (d.get("parity") or {}).items() if k in ("loss_rel", "emb_rel", "grad_rel", "ok")},
+        (d.get("e2e") or {}).get("value"), {k: round(v["value"], 1) for k, v in (d.get("reference_gpu") or {}).items() if isinstance(v, dict) and "value" in v}))
+    print("   share", {k: round(v, 3) for k, v in (r.get("share_of_step") or {}).items() if v})
+except Exception as e:
+    print(sys.argv[1], "unreadable:", e)
+PY
+done
+exit 0

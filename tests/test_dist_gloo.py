@@ -91,7 +91,13 @@ def _worker(rank, world, port, out_dir):
         flat = torch.cat([Pr[k].grad.reshape(-1) for k in P])          # the "gpack" of this rank
         scale = parallel.finish_flat_grads_(flat)
         flat *= scale
-        torch.save({"loss": loss.detach(), "flat": flat}, os.path.join(out_dir, f"rank{rank}.pt"))
+        # descriptor world sizes (engine.py): BatchNorm divides its statistics by local_rows * bn_world, so bn_world must be 1
+        # when the statistics are NOT exchanged (sync_bn=False), whatever the size of the group; the gradient all-reduce is
+        # gated by the group size alone
+        from video_rep_learning_b200 import engine
+        worlds = (engine._world(engine.RunOptions()), engine._bn_world(engine.RunOptions()),
+                  engine._world(engine.RunOptions(sync_bn=False)), engine._bn_world(engine.RunOptions(sync_bn=False)))
+        torch.save({"loss": loss.detach(), "flat": flat, "worlds": worlds}, os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         O.BN_TRAIN_HOOK = None
         dist.destroy_process_group()
@@ -105,6 +111,7 @@ def test_two_rank_protocol_matches_syncbn_ddp_semantics(tmp_path):
     r0 = torch.load(os.path.join(str(tmp_path), "rank0.pt"))
     r1 = torch.load(os.path.join(str(tmp_path), "rank1.pt"))
     assert torch.equal(r0["flat"], r1["flat"])                     # every rank ends with identical gradients
+    assert r0["worlds"] == (2, 2, 2, 1) and r1["worlds"] == (2, 2, 2, 1)
 
     # single-process ground truth: BatchNorm over ALL rows, loss = mean of per-rank means
     P, tokens, seq_lens, steps, masks = _inputs()

@@ -1,9 +1,15 @@
-"""GPU: the BASELINE.json shapes at full size (per-GPU shards), checked through size-independent properties -- the oracle
-cannot run them in seconds.  (1) the folded and the as-written (dense tcgen05) pooling are two evaluations of the same
-function: embeddings, loss and gradients agree; (2) the loss and every gradient are finite, the embeddings unit-norm;
-(3) a second evaluation with the same seed reproduces the step up to the order of the split-K reductions;
-(4) the gradient of a frozen direction: d loss / d (scale of an embedding row) = 0 (the loss only sees unit vectors), i.e.
-    <dE_i, e_i> = 0 for the gradient SCL hands back."""
+"""GPU: the BASELINE.json shapes at full size (the per-GPU shards bench.py runs), whole step against the CPU oracle.
+
+For each of cfg2 (Penn, 32 videos x 20 frames, 3 entities), cfg4 (FineGym, 8 videos x 80 frames, 6 entities, FC 1536, D 256,
+avg; temporal attention over S = 480) and cfg5 (4 videos x 240 frames, 16 entities; S = 3840):
+  (1) bf16 tokens (the bench path: folded pooling, tensor-core chain) against the reference algorithm evaluated in fp64 on
+      the SAME bf16-rounded tokens: embeddings, loss and the concatenated gradient within 2e-2 (north-star tolerance);
+  (2) fp32 tokens (exact-FMA path) against the fp64 oracle: 1e-5 on embeddings and loss, 2e-5 on the concatenated gradient
+      (fp32 accumulation over K = 2304 channels / S = 3840 keys; measured values are printed);
+  (3) the as-written (dense tcgen05 K|V GEMM) pooling agrees with the folded one at the bf16 operand level.
+The oracle evaluates long sequences view by view under activation checkpointing (oracle.ATTN_LEAN_ELEMS), so the
+S = 3840 case needs a few GB of host memory, not tens.
+"""
 import pytest
 import torch
 
@@ -15,64 +21,72 @@ pytestmark = pytest.mark.gpu
 
 # per-GPU shards of BASELINE configs[1..4]: (name, HeadCfg kwargs, videos, T, P)
 SHAPES = [
-    ("cfg2_penn_vitb16x3", dict(c_in=2304, train_frames=20), 8, 20, 196),
-    ("cfg4_finegym_T80_E6", dict(c_in=2304, n_entities=6, fc_channels=(1536, 1536), emb=256, final="avg", train_frames=80), 2, 80, 196),
-    ("cfg5_long_T240_E16", dict(c_in=2304, n_entities=16, train_frames=240), 1, 240, 196),
+    ("cfg2_penn_vitb16x3", dict(c_in=2304, train_frames=20), 32, 20, 196),
+    ("cfg4_finegym_T80_E6", dict(c_in=2304, n_entities=6, fc_channels=(1536, 1536), emb=256, final="avg", train_frames=80), 8, 80, 196),
+    ("cfg5_long_T240_E16", dict(c_in=2304, n_entities=16, train_frames=240), 4, 240, 196),
 ]
 
 
-@pytest.mark.parametrize("name,kw,Bv,T,P", SHAPES, ids=[s[0] for s in SHAPES])
-def test_full_size_properties(name, kw, Bv, T, P):
+def _inputs(kw, Bv, T, P):
     hc = O.HeadCfg(**kw)
     Pm = O.init_params(hc, seed=3)
     g = torch.Generator().manual_seed(5)
-    tokens = torch.randn(2 * Bv, T, P, hc.c_in, generator=g).bfloat16()
+    tokens = torch.randn(2 * Bv, T, P, hc.c_in, generator=g)
     _, seq_lens, steps, masks = O.synth_batch(Bv, T, 1, 1, seed=6)
+    return hc, Pm, tokens, seq_lens, steps, masks
+
+
+@pytest.mark.parametrize("name,kw,Bv,T,P", SHAPES, ids=[s[0] for s in SHAPES])
+def test_full_size_bf16_step_matches_oracle_on_same_operands(name, kw, Bv, T, P):
+    hc, Pm, tokens, seq_lens, steps, masks = _inputs(kw, Bv, T, P)
     keys = list(Pm.keys())
-    run = lambda pm: H.run_cuda(hc, Pm, None, tokens, masks, seq_lens, steps, dtype=torch.bfloat16, pool_mode=pm, drop_p=0.1, seed=77)
-    a = run(L.POOL_FOLDED)
-    ga = H.grad_vector(a["grads"], keys)
-    assert torch.isfinite(a["e"]).all() and torch.isfinite(a["loss"]) and torch.isfinite(ga).all()
-    assert float(a["loss"]) > 0
-    assert float((a["e"].double().norm(dim=-1) - 1).abs().max()) < 1e-5
-    # Not bit-reproducible by design: split-K partial sums are reduced in arrival order (TMA reduce-add).  That noise is
-    # 7e-8 where it is born (ent32) but this randomly initialised MLP + BatchNorm amplifies it 40x by h3 and SCL's 1/tau
-    # another 60x on the gradient (scripts/diag_determinism.py: px/attn 0, ent32 7e-8, h3 3e-6, e 9e-6, gradient 6e-4).
-    b = run(L.POOL_FOLDED)
-    assert H.rel_l2(b["e"], a["e"]) < 1e-4 and H.rel_l2(H.grad_vector(b["grads"], keys), ga) < 5e-3
-    d = run(L.POOL_DENSE)
-    # dense rounds W_k|W_v and K|V to bf16, folded does not: agreement at the bf16 operand level
-    assert H.rel_l2(d["e"], a["e"]) < 2e-2
-    assert abs(float(d["loss"]) - float(a["loss"])) / float(a["loss"]) < 2e-2
-    assert H.rel_l2(H.grad_vector(d["grads"], keys), ga) < 1e-1
+    tok16 = tokens.bfloat16()
+    ref = H.run_oracle_quantized(hc, Pm, tok16, masks, seq_lens, steps, kv_bf16=False)
+    got = H.run_cuda(hc, Pm, None, tok16, masks, seq_lens, steps, dtype=torch.bfloat16, pool_mode=L.POOL_FOLDED)
+    ee = H.rel_l2(got["e"], ref["e"])
+    le = abs(float(got["loss"]) - float(ref["loss"])) / float(ref["loss"])
+    ge = H.rel_l2(H.grad_vector(got["grads"], keys), H.grad_vector(ref["grads"], keys))
+    print(f"{name} bf16 tokens vs fp64 oracle on the same operands: embeddings {ee:.2e} loss {le:.2e} gradient {ge:.2e}")
+    assert ee < 2e-2 and le < 2e-2 and ge < 2e-2, (ee, le, ge)
+    assert float((got["e"].double().norm(dim=-1) - 1).abs().max()) < 1e-5
+    # the as-written pooling (K|V GEMM on tcgen05, W_k|W_v and K|V rounded to bf16) is another evaluation of the same function
+    d = H.run_cuda(hc, Pm, None, tok16, masks, seq_lens, steps, dtype=torch.bfloat16, pool_mode=L.POOL_DENSE)
+    assert H.rel_l2(d["e"], got["e"]) < 2e-2
+    assert abs(float(d["loss"]) - float(got["loss"])) / float(got["loss"]) < 2e-2
+    assert H.rel_l2(H.grad_vector(d["grads"], keys), H.grad_vector(got["grads"], keys)) < 1e-1
+
+
+@pytest.mark.parametrize("name,kw,Bv,T,P", SHAPES, ids=[s[0] for s in SHAPES])
+def test_full_size_fp32_step_matches_oracle(name, kw, Bv, T, P):
+    hc, Pm, tokens, seq_lens, steps, masks = _inputs(kw, Bv, T, P)
+    keys = list(Pm.keys())
+    ref = H.run_oracle(hc, Pm, None, tokens, masks, seq_lens, steps, dtype=torch.float64)
+    got = H.run_cuda(hc, Pm, None, tokens, masks, seq_lens, steps, dtype=torch.float32)
+    ee = H.rel_l2(got["e"], ref["e"])
+    le = abs(float(got["loss"]) - float(ref["loss"])) / float(ref["loss"])
+    ge = H.rel_l2(H.grad_vector(got["grads"], keys), H.grad_vector(ref["grads"], keys))
+    print(f"{name} fp32 tokens vs fp64 oracle: embeddings {ee:.2e} loss {le:.2e} gradient {ge:.2e}")
+    assert ee < 1e-5 and le < 1e-5 and ge < 2e-5, (ee, le, ge)
 
 
 @pytest.mark.parametrize("Bv,T,D", [(32, 20, 128), (8, 80, 256), (4, 240, 128)])
-def test_scl_gradient_is_tangent_and_matches_finite_difference(Bv, T, D):
-    """Named SCL shapes: loss finite; a central finite difference along a random direction matches <dE, direction>."""
+def test_scl_named_shapes_match_oracle(Bv, T, D):
+    """SCL at the named shapes (loss + gradient) against the dense N x N oracle in fp64."""
     lib = L.lib()
-    g = torch.Generator(device="cuda").manual_seed(T + D)
-    e = torch.nn.functional.normalize(torch.randn(Bv, 2, T, D, device="cuda", generator=g), dim=-1).contiguous()
+    g = torch.Generator().manual_seed(T + D)
+    e = torch.nn.functional.normalize(torch.randn(Bv, 2, T, D, generator=g), dim=-1).contiguous()
     _, seq_lens, steps, masks = O.synth_batch(Bv, T, 1, 1, seed=9)
+    e64 = e.double().requires_grad_(True)
+    ref = O.scl_loss_dense(e64, seq_lens, steps, masks.double())
+    ref.backward()
+    ed = e.cuda()
     sl, st, mk = seq_lens.cuda(), steps.cuda(), masks.view(Bv, 2, T).cuda()
     nb = lib.mvf_scl_ws_bytes(Bv, T, D)
     ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
-
-    def f(x, want_grad):
-        loss = torch.empty((), device="cuda")
-        dE = torch.empty_like(x) if want_grad else None
-        L.check(lib.mvf_scl_fwd_bwd(L.ptr(x), L.ptr(sl), L.ptr(st), L.ptr(mk), Bv, T, D, 0.1, 10.0, 0, 1, L.ptr(loss), L.ptr(dE),
-                                    L.ptr(ws), nb, torch.cuda.current_stream().cuda_stream))
-        torch.cuda.synchronize()
-        return float(loss), dE
-
-    loss, dE = f(e, True)
-    assert loss > 0 and torch.isfinite(dE).all()
-    u = torch.randn(e.shape, device="cuda", generator=g)
-    u = u / u.norm()
-    eps = 2e-2
-    lp, _ = f((e + eps * u).contiguous(), False)
-    lm, _ = f((e - eps * u).contiguous(), False)
-    fd = (lp - lm) / (2 * eps)
-    an = float((dE.double() * u.double()).sum())
-    assert abs(fd - an) < 2e-2 * max(abs(an), 1e-3) + 2e-4, (fd, an)
+    loss = torch.empty((), device="cuda")
+    dE = torch.empty_like(ed)
+    L.check(lib.mvf_scl_fwd_bwd(L.ptr(ed), L.ptr(sl), L.ptr(st), L.ptr(mk), Bv, T, D, 0.1, 10.0, 0, 1, L.ptr(loss), L.ptr(dE),
+                                L.ptr(ws), nb, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert H.rel_l2(dE, e64.grad) < 1e-5

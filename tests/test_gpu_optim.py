@@ -64,6 +64,30 @@ def test_unscale_factor_and_state_dict_round_trip():
         assert float((p - q).abs().max()) <= 1e-6 * max(1.0, float(p.abs().max()))
     sd = oa.state_dict()
     assert len(sd["state"]) == len(ps) and "exp_avg" in sd["state"][0]
+    # the step count travels with the checkpoint (bias correction after a resume) ...
+    assert float(sd["state"][0]["step"]) == 1.0
+    c = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    oc = FusedAdam(c, lr=1e-3, max_grad_norm=5.0)
+    oc.load_state_dict(sd)
+    assert oc.step_count == 1
+    for p, q, g in zip(a, c, gs[1]):
+        p.grad = g.clone()
+        q.grad = g.clone()
+    oa.step()
+    oc.step()
+    assert oc.step_count == 2
+    for p, q in zip(a, c):
+        assert float((p - q).abs().max()) <= 1e-7 * max(1.0, float(p.abs().max()))
+    # ... and a torch.optim.Adam checkpoint (per-parameter 'step' tensors) is accepted
+    ref_p = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref = torch.optim.Adam(ref_p, lr=1e-3)
+    for _ in range(3):
+        for p, g in zip(ref_p, gs[2]):
+            p.grad = g.clone()
+        ref.step()
+    od = FusedAdam([torch.nn.Parameter(p.detach().clone()) for p in ref_p], lr=1e-3)
+    od.load_state_dict(ref.state_dict())
+    assert od.step_count == 3
 
 
 def test_optimizer_tail_inside_the_step_graph():
@@ -85,10 +109,27 @@ def test_optimizer_tail_inside_the_step_graph():
     for grp in opt.param_groups:
         grp["lr"] = 2e-3
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
-    gs = GraphedTrainStep(model, algo, Bv, T, P, Cc, dtype=torch.float32, optimizer=opt, warmup=1)
+    gs = GraphedTrainStep(model, algo, Bv, T, P, Cc, dtype=torch.float32, optimizer=opt, warmup=2)
     gs.capture()
-    model.load_state_dict(sd0)                        # the warm-up steps of capture() already moved the parameters
+    # capturing (eager warm-up steps on whatever is in the static buffers) leaves no trace on the training state:
+    # parameters, BatchNorm running statistics / counters, Adam moments and the step counter are as before
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd0[k]), k
+    assert opt.step_count == 0
+    assert all(float(st["exp_avg"].abs().max()) == 0.0 for st in opt.state.values())
     losses = [float(gs(tokens, seq_lens.cuda(), steps.cuda(), masks.cuda())) for _ in range(6)]
     assert losses[-1] < losses[0]
-    assert opt.step_count >= 6 and float(opt.grad_norm) > 0
+    assert opt.step_count == 6 and float(opt.grad_norm) > 0
+    # a scheduler changing the learning rate between replays is honoured: lr = 0 freezes the parameters
+    for grp in opt.param_groups:
+        grp["lr"] = 0.0
+    before = [p.detach().clone() for p in gs.params]
+    gs()
+    torch.cuda.synchronize()
+    assert all(torch.equal(p.detach(), b) for p, b in zip(gs.params, before))
+    for grp in opt.param_groups:
+        grp["lr"] = 2e-3
+    gs()
+    torch.cuda.synchronize()
+    assert any(not torch.equal(p.detach(), b) for p, b in zip(gs.params, before))
     gs.release()

@@ -40,7 +40,7 @@ bool pdl_enabled() {
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
-constexpr int PROF_TAGS = 6, PROF_CAP = 512;
+constexpr int PROF_TAGS = 10, PROF_CAP = 512;
 static int g_prof_on = 0;
 static cudaEvent_t g_prof_ev[PROF_TAGS][PROF_CAP][2];
 static int g_prof_n[PROF_TAGS] = {0};
@@ -779,8 +779,11 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
                      c.P[b + L_LN0B], m.rows, d.H, d.ln_eps, c.p, DropSeed(d.seed, d.seed_dev), pend_site, st));
       MVF_TRY(c.linear(A, m.rows, 3 * d.H, d.H, c.S.p(lname(l, "r0")), d.H, c.S.p(lname(l, "w.qkv")), d.H,
                        c.S.f(lname(l, "b.qkv")), c.S.p(lname(l, "qkv")), 3 * d.H, 0, lname(l, "w.qkv").c_str()));
-      MVF_TRY(attention_fwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
-                            c.S.f(lname(l, "lse")), st, m.tc));
+      {
+        ProfScope ps(6, st);
+        MVF_TRY(attention_fwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
+                              c.S.f(lname(l, "lse")), st, m.tc));
+      }
       MVF_TRY(c.linear(MVF_F32, m.rows, d.H, d.H, c.S.p(lname(l, "ctx")), d.H, c.S.p(lname(l, "w.o")), d.H, c.P[b + L_BO],
                        o, d.H, 0, lname(l, "w.o").c_str()));
       float* ln1 = c.S.f(lname(l, "ln1"));
@@ -880,8 +883,11 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         MVF_TRY(c.linear_dw(m.rows, d.H, d.H, dgA, d.H, c.S.p(lname(l, "ctx")), d.H, c.G.f(g + "w.o"), d.H,
                             c.G.f(g + "b.o")));
         MVF_TRY(c.linear_dx(A, m.rows, d.H, d.H, dgA, d.H, c.S.p(lname(l, "w.o")), d.H, c.W.p("dctx"), d.H));
-        MVF_TRY(attention_bwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
-                              c.S.f(lname(l, "lse")), c.W.p("dctx"), dqkv, c.W.f("delta"), st, m.tc));
+        {
+          ProfScope ps(7, st);
+          MVF_TRY(attention_bwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
+                                c.S.f(lname(l, "lse")), c.W.p("dctx"), dqkv, c.W.f("delta"), st, m.tc));
+        }
         MVF_TRY(c.linear_dw(m.rows, 3 * d.H, d.H, dqkv, 3 * d.H, c.S.p(lname(l, "r0")), d.H, c.G.f(g + "w.qkv"),
                             d.H, c.G.f(g + "b.qkv")));
         MVF_TRY(c.linear_dx(MVF_F32, m.rows, 3 * d.H, d.H, dqkv, 3 * d.H, c.S.p(lname(l, "w.qkv")), d.H,
@@ -1330,6 +1336,7 @@ size_t mvf_scl_ws_bytes(int32_t Bv, int32_t T, int32_t D) { return scl_ws_bytes(
 int mvf_scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps, const float* masks, int32_t Bv,
                     int32_t T, int32_t D, float temperature, float label_variance, int32_t negative_type, int32_t quirk,
                     float* loss_out, float* d_embs, void* ws, size_t ws_bytes, mvf_stream_t stream) {
+  ProfScope ps(8, (cudaStream_t)stream);
   return scl_fwd_bwd(embs, seq_lens, steps, masks, Bv, T, D, temperature, label_variance, negative_type, quirk, loss_out,
                      d_embs, ws, ws_bytes, (cudaStream_t)stream);
 }

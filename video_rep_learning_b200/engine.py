@@ -63,17 +63,20 @@ class RunOptions:
                                           # all-reduce at the end -- the SMs the HBM-bound pooling kernel gives up cost as
                                           # much as the hidden transfer saves -- so it is off by default
     pool_bwd_reserve_sms: int = 16        # SMs that kernel leaves to the collective while they overlap
-    micro_batches: int = 1          # >1: the step's views are cut into that many slices which run on separate CUDA streams
-                                    # with BatchNorm statistics combined at the phase cuts (same results as the unsplit
-                                    # step up to re-association).  The chain behind the pooling is ~100 short, latency-bound
-                                    # kernels, so two slices overlap almost perfectly -- but the host enqueues twice the
-                                    # calls, so this is meant for CUDA-graph replay (graph.GraphedTrainStep turns it on)
+
 
 
 def _world(opts: RunOptions) -> int:
+    """Ranks of the process group: gates (and scales) the gradient all-reduce."""
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(opts.process_group)
     return 1
+
+
+def _bn_world(opts: RunOptions) -> int:
+    """Ranks whose rows enter one BatchNorm statistic: the descriptor's world_size (it divides the summed statistics by
+    local_rows * world_size).  Without sync_bn every rank normalises with its own batch, whatever the group size."""
+    return _world(opts) if opts.sync_bn else 1
 
 
 class Plan:
@@ -181,6 +184,11 @@ def _scratch(device: torch.device, nbytes: int, tag: str) -> torch.Tensor:
         t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
         _ws_cache[key] = t
     return t
+
+
+def scratch_tensors(device: torch.device) -> List[torch.Tensor]:
+    """The cached scratch workspaces currently in use on `device` (graph.GraphedTrainStep pins them while its graph lives)."""
+    return [t for (dev, _tag), t in _ws_cache.items() if dev == device]
 
 
 def _stream() -> int:
@@ -334,7 +342,7 @@ def _finish_grads(cs: CallState, plan: Plan, d, gpack: torch.Tensor, params: Seq
     """One all-reduce of the flat gradient buffer (SUM), then scatter * 1/world into per-parameter tensors.
     The per-parameter gradients are views of ONE dense buffer (one allocation per step instead of one per parameter).
     reduced_from: elements [reduced_from:] were already all-reduced (overlapped with the pooling backward)."""
-    if plan.world > 1 and cs.opts.allreduce_grads:
+    if _world(cs.opts) > 1 and cs.opts.allreduce_grads:
         scale = parallel.finish_flat_grads_(gpack if reduced_from is None else gpack[:reduced_from], cs.opts.process_group)
     else:
         scale = 1.0
@@ -379,7 +387,7 @@ class HeadFn(torch.autograd.Function):
         BV, T, P, Cin = tokens.shape
         mask = _prep_mask(mask, BV, T, tokens.device)
         with torch.cuda.device(tokens.device):
-            plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _world(cs.opts),
+            plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _bn_world(cs.opts),
                             cs.opts.gemm_backend, cs.opts.pool_mode)
             d = plan.desc_with_seed(cs.seed, cs.seed_dev)
             save = torch.empty(plan.save_bytes, dtype=torch.uint8, device=tokens.device)
@@ -421,7 +429,7 @@ class ProjFn(torch.autograd.Function):
         embc = emb.contiguous().float()
         with torch.cuda.device(emb.device):
             plan = Plan.get(cs.spec, BV, T, 1, L.MVF_F32 if cs.opts.gemm_backend != L.GEMM_TCGEN05 else L.MVF_BF16,
-                            cs.training, False, _world(cs.opts), cs.opts.gemm_backend, cs.opts.pool_mode)
+                            cs.training, False, _bn_world(cs.opts), cs.opts.gemm_backend, cs.opts.pool_mode)
             d = plan.desc_with_seed(0)
             save = torch.empty(plan.proj_save_bytes, dtype=torch.uint8, device=emb.device)
             ws = _scratch(emb.device, plan.proj_ws_bytes, "proj")
@@ -454,152 +462,6 @@ class ProjFn(torch.autograd.Function):
         return (d_emb, None) + pg
 
 
-_mb_stream_cache: Dict[tuple, List[torch.cuda.Stream]] = {}
-
-
-def _mb_streams(dev: torch.device, n: int) -> List[torch.cuda.Stream]:
-    key = (dev, n)
-    ss = _mb_stream_cache.get(key)
-    if ss is None:
-        ss = [torch.cuda.Stream(device=dev) for _ in range(n)]
-        _mb_stream_cache[key] = ss
-    return ss
-
-
-def _combine_stats(bufs: List[torch.Tensor], streams: List[torch.cuda.Stream], cs: CallState, dist_world: int):
-    """Sum the slices' BatchNorm statistic buffers (and, across ranks, all-reduce the sum) and hand the total back to every
-    slice: the in-GPU analogue of parallel.sync_stats_.  Slice 0's stream does the arithmetic; the others wait for it."""
-    s0 = streams[0]
-    for s in streams[1:]:
-        s0.wait_stream(s)
-    with torch.cuda.stream(s0):
-        for b in bufs[1:]:
-            bufs[0].add_(b)
-        if dist_world > 1 and cs.opts.sync_bn:
-            parallel.sync_stats_(bufs[0], cs.opts.process_group)
-        for b in bufs[1:]:
-            b.copy_(bufs[0])
-    for s in streams[1:]:
-        s.wait_stream(s0)
-
-
-class _Split:
-    """State of a micro-batched step (forward -> backward)."""
-    def __init__(self):
-        self.plan = None
-        self.saves: List[torch.Tensor] = []
-        self.psaves: List[torch.Tensor] = []
-        self.n = 1
-
-
-def _split_forward(cs: CallState, tokens, mask, params, nmb: int):
-    dev = tokens.device
-    BV, T, P, Cin = tokens.shape
-    hb = BV // nmb
-    dist_world = _world(cs.opts)
-    eff_world = nmb * (dist_world if cs.opts.sync_bn else 1)
-    plan = Plan.get(cs.spec, hb, T, P, _mvf_dtype(tokens), cs.training, mask is not None, eff_world, cs.opts.gemm_backend,
-                    cs.opts.pool_mode)
-    lib = L.lib()
-    cur = torch.cuda.current_stream(dev)
-    streams = _mb_streams(dev, nmb)
-    emb = torch.empty(BV, T, cs.spec.emb, dtype=torch.float32, device=dev)
-    out = torch.empty(BV, T, cs.spec.emb, dtype=torch.float32, device=dev)
-    sp = _Split()
-    sp.plan, sp.n = plan, nmb
-    sp.saves = [torch.empty(plan.save_bytes, dtype=torch.uint8, device=dev) for _ in range(nmb)]
-    sp.psaves = [torch.empty(plan.proj_save_bytes, dtype=torch.uint8, device=dev) for _ in range(nmb)]
-    wss = [_scratch(dev, plan.ws_bytes, f"head{h}") for h in range(nmb)]
-    pwss = [_scratch(dev, plan.proj_ws_bytes, f"proj{h}") for h in range(nmb)]
-    arr = L.ptr_array(list(params))
-    descs = [plan.desc_with_seed(cs.seed + h, cs.seed_dev) for h in range(nmb)]
-    # running statistics are updated by slice 0 only (every slice sees the same global batch statistics)
-    rm = L.ptr_array(cs.bn_running) if cs.bn_running else None
-    tr = L.ptr_array(cs.bn_tracked) if cs.bn_tracked else None
-    toks = [tokens[h * hb:(h + 1) * hb] for h in range(nmb)]
-    msks = [None if mask is None else mask[h * hb:(h + 1) * hb] for h in range(nmb)]
-    embs = [emb[h * hb:(h + 1) * hb] for h in range(nmb)]
-    outs = [out[h * hb:(h + 1) * hb] for h in range(nmb)]
-    for s in streams:
-        s.wait_stream(cur)
-    n_fc = plan.n_fc
-    for ph in range(n_fc + 1):
-        for h in range(nmb):
-            with torch.cuda.stream(streams[h]):
-                L.check(lib.mvf_head_forward(C.byref(descs[h]), arr, rm if h == 0 else None, tr if h == 0 else None,
-                                             L.ptr(toks[h]), L.ptr(msks[h]), L.ptr(sp.saves[h]), sp.saves[h].numel(),
-                                             L.ptr(wss[h]), wss[h].numel(), L.ptr(embs[h]), None, ph, ph + 1,
-                                             streams[h].cuda_stream), "mvf_head_forward")
-        if ph < n_fc:
-            _combine_stats([plan.bn_stat(sv, ph, False) for sv in sp.saves], streams, cs, dist_world)
-    project = int(cs.project)
-    cuts = [(0, 1), (1, 2)] if project else [(0, L.PHASE_ALL)]
-    for ci, (p0, p1) in enumerate(cuts):
-        for h in range(nmb):
-            with torch.cuda.stream(streams[h]):
-                L.check(lib.mvf_proj_forward(C.byref(descs[h]), arr, rm if h == 0 else None, tr if h == 0 else None,
-                                             L.ptr(embs[h]), project, L.ptr(sp.psaves[h]), sp.psaves[h].numel(),
-                                             L.ptr(pwss[h]), pwss[h].numel(), L.ptr(outs[h]), p0, p1,
-                                             streams[h].cuda_stream), "mvf_proj_forward")
-        if project and ci == 0:
-            _combine_stats([plan.bn_stat(sv, n_fc, False) for sv in sp.psaves], streams, cs, dist_world)
-    for s in streams:
-        cur.wait_stream(s)
-    return out, sp, arr
-
-
-def _split_backward(cs: CallState, sp: _Split, tokens, mask, params, arr, d_out, seed):
-    dev = tokens.device
-    nmb, plan = sp.n, sp.plan
-    BV = tokens.shape[0]
-    hb = BV // nmb
-    dist_world = _world(cs.opts)
-    lib = L.lib()
-    cur = torch.cuda.current_stream(dev)
-    streams = _mb_streams(dev, nmb)
-    d_out = d_out.contiguous().float()
-    d_emb = torch.empty(d_out.shape, dtype=torch.float32, device=dev)
-    gpacks = [torch.zeros(plan.gpack_elems, dtype=torch.float32, device=dev) for _ in range(nmb)]
-    wss = [_scratch(dev, plan.ws_bytes, f"head{h}") for h in range(nmb)]
-    pwss = [_scratch(dev, plan.proj_ws_bytes, f"proj{h}") for h in range(nmb)]
-    descs = [plan.desc_with_seed(seed + h, cs.seed_dev) for h in range(nmb)]
-    toks = [tokens[h * hb:(h + 1) * hb] for h in range(nmb)]
-    msks = [None if mask is None else mask[h * hb:(h + 1) * hb] for h in range(nmb)]
-    douts = [d_out[h * hb:(h + 1) * hb] for h in range(nmb)]
-    dembs = [d_emb[h * hb:(h + 1) * hb] for h in range(nmb)]
-    for s in streams:
-        s.wait_stream(cur)
-    n_fc = plan.n_fc
-    project = int(cs.project)
-    cuts = [(0, 1), (1, 2)] if project else [(0, L.PHASE_ALL)]
-    for ci, (p0, p1) in enumerate(cuts):
-        for h in range(nmb):
-            with torch.cuda.stream(streams[h]):
-                L.check(lib.mvf_proj_backward(C.byref(descs[h]), arr, L.ptr(douts[h]), project, L.ptr(sp.psaves[h]),
-                                              sp.psaves[h].numel(), L.ptr(pwss[h]), pwss[h].numel(), L.ptr(gpacks[h]),
-                                              L.ptr(dembs[h]), p0, p1, streams[h].cuda_stream), "mvf_proj_backward")
-        if project and ci == 0:
-            _combine_stats([plan.bn_stat(sv, n_fc, True) for sv in sp.psaves], streams, cs, dist_world)
-    for ph in range(n_fc + 1):
-        for h in range(nmb):
-            with torch.cuda.stream(streams[h]):
-                L.check(lib.mvf_head_backward(C.byref(descs[h]), arr, L.ptr(toks[h]), L.ptr(msks[h]), L.ptr(dembs[h]),
-                                              L.ptr(sp.saves[h]), sp.saves[h].numel(), L.ptr(wss[h]), wss[h].numel(),
-                                              L.ptr(gpacks[h]), ph, ph + 1, streams[h].cuda_stream), "mvf_head_backward")
-        if ph < n_fc:
-            _combine_stats([plan.bn_stat(sv, n_fc - 1 - ph, True) for sv in sp.saves], streams, cs, dist_world)
-    for h in range(nmb):                      # the pooling backward is a phase of its own
-        with torch.cuda.stream(streams[h]):
-            L.check(lib.mvf_head_backward(C.byref(descs[h]), arr, L.ptr(toks[h]), L.ptr(msks[h]), L.ptr(dembs[h]),
-                                          L.ptr(sp.saves[h]), sp.saves[h].numel(), L.ptr(wss[h]), wss[h].numel(),
-                                          L.ptr(gpacks[h]), n_fc + 1, n_fc + 2, streams[h].cuda_stream), "mvf_head_backward")
-    for s in streams:
-        cur.wait_stream(s)
-    for g in gpacks[1:]:
-        gpacks[0].add_(g)
-    return gpacks[0], descs[0]
-
-
 class ModelFn(torch.autograd.Function):
     """Head + projection (+normalise) as ONE autograd node: one flat gradient buffer, one all-reduce."""
 
@@ -609,17 +471,8 @@ class ModelFn(torch.autograd.Function):
         BV, T, P, Cin = tokens.shape
         mask = _prep_mask(mask, BV, T, tokens.device)
         dev = tokens.device
-        nmb = int(cs.opts.micro_batches)
-        if nmb > 1 and cs.training and BV % nmb == 0 and BV // nmb >= 1:
-            with torch.cuda.device(dev):
-                out, sp, arr = _split_forward(cs, tokens, mask, params, nmb)
-            cs.plan, cs.head_save, cs.proj_save = sp.plan, sp.saves[-1], sp.psaves[-1]
-            ctx.cs, ctx.seed, ctx.split = cs, cs.seed, sp
-            ctx.tokens, ctx.mask, ctx.params, ctx.param_ptrs = tokens, mask, params, arr
-            return out
-        ctx.split = None
         with torch.cuda.device(dev):
-            plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _world(cs.opts),
+            plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _bn_world(cs.opts),
                             cs.opts.gemm_backend, cs.opts.pool_mode)
             d = plan.desc_with_seed(cs.seed, cs.seed_dev)
             save = torch.empty(plan.save_bytes, dtype=torch.uint8, device=dev)
@@ -644,11 +497,6 @@ class ModelFn(torch.autograd.Function):
         tokens, mask, params = ctx.tokens, ctx.mask, ctx.params
         plan = cs.plan
         dev = tokens.device
-        if ctx.split is not None:
-            with torch.cuda.device(dev):
-                gpack, d = _split_backward(cs, ctx.split, tokens, mask, params, ctx.param_ptrs, d_out, ctx.seed)
-                grads = _finish_grads(cs, ctx.split.plan, d, gpack, list(params))
-            return (None, None, None) + tuple(grads)
         with torch.cuda.device(dev):
             d = plan.desc_with_seed(ctx.seed, cs.seed_dev)
             ws = _scratch(dev, plan.ws_bytes, "head")

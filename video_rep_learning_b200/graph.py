@@ -14,9 +14,6 @@ What has to be static for a replay, and how it is kept so:
   * parameters are read through raw pointers, so in-place optimizer updates are picked up; re-assigning a parameter
     tensor needs a new capture;
   * `.grad` of every head parameter is a view of one flat buffer in the graph's private pool, rewritten by each replay;
-  * optionally (micro_batches > 1) the views run as slices on separate streams with BatchNorm statistics summed at the
-    phase cuts and SCL on the whole batch -- same results as the unsplit step up to re-association (slower on B200 at
-    the bench shape, see __init__);
   * dropout: kernel arguments are frozen at capture, so the per-step seed is `base + *seed_dev` with `seed_dev` a device
     counter advanced inside the graph (csrc/common.cuh DropSeed) -- every replay draws a fresh mask.
 """
@@ -32,8 +29,7 @@ from . import engine
 
 class GraphedTrainStep:
     def __init__(self, model, algo, Bv: int, T: int, P: int, C_in: int, dtype=torch.bfloat16,
-                 device: Optional[torch.device] = None, warmup: int = 3, project: bool = True, micro_batches: int = 1,
-                 optimizer=None):
+                 device: Optional[torch.device] = None, warmup: int = 3, project: bool = True, optimizer=None):
         self.model, self.algo = model, algo
         self.Bv, self.T = Bv, T
         self.project = project
@@ -50,14 +46,10 @@ class GraphedTrainStep:
         self.warmup = warmup
         # optional fused optimizer tail (optim.FusedAdam): clip + Adam captured at the end of the same graph
         self.optimizer = optimizer
-        # optional: run the views as `micro_batches` slices on separate streams (engine.RunOptions.micro_batches).  Measured
-        # at BASELINE configs[1] on B200: 2 slices 2.03 ms/step, 4 slices 2.35 ms vs 1.85 ms un-split -- the chain kernels
-        # are bound by what they move, not only by latency, so the slices do not overlap enough to pay for the extra
-        # statistics exchanges.  Kept (and tested) as an option; off by default.
-        self.micro_batches = micro_batches if (micro_batches > 1 and (2 * Bv) % micro_batches == 0) else 1
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss: Optional[torch.Tensor] = None
         self.grads: List[Optional[torch.Tensor]] = []
+        self._scratch_refs: List[torch.Tensor] = []
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------------------
@@ -95,24 +87,51 @@ class GraphedTrainStep:
         after a replay)."""
         embed = self.model.embed
         embed.seed_dev = self.seed_dev
-        opts = self.model.run_options
-        prev_mb, opts.micro_batches = opts.micro_batches, self.micro_batches
-        try:
-            return self._capture(profile)
-        finally:
-            opts.micro_batches = prev_mb
+        return self._capture(profile)
+
+    def _snapshot_state(self):
+        """Everything the eager warm-up steps mutate besides scratch: parameters (optimizer), BatchNorm running statistics
+        and counters, the optimizer's moments and step counter.  Restored after the warm-up, so capturing is free of side
+        effects on the training state whatever is in the static input buffers at that point."""
+        snap = dict(params=[p.detach().clone() for p in self.params],
+                    buffers=[(b, b.detach().clone()) for n, b in self.model.named_buffers() if "backbone" not in n])
+        if self.optimizer is not None:
+            snap["opt"] = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.optimizer.state.get(p, {}).items()}
+                           for p in self.params}
+            snap["opt_step"] = getattr(self.optimizer, "step_count", None)
+        return snap
+
+    def _restore_state(self, snap):
+        with torch.no_grad():
+            for p, v in zip(self.params, snap["params"]):
+                p.copy_(v)
+            for b, v in snap["buffers"]:
+                b.copy_(v)
+            if self.optimizer is not None:
+                for p in self.params:
+                    st, old = self.optimizer.state.get(p), snap["opt"].get(id(p), {})
+                    if not st:
+                        continue
+                    for k, v in st.items():
+                        if torch.is_tensor(v):               # in place: the captured launches hold these pointers
+                            v.copy_(old[k]) if k in old else v.zero_()
+                if snap.get("opt_step") is not None and hasattr(self.optimizer, "set_step_count"):
+                    self.optimizer.set_step_count(snap["opt_step"])
 
     def _capture(self, profile: bool) -> "GraphedTrainStep":
         cur = torch.cuda.current_stream(self.device)
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(cur)
+        snap = self._snapshot_state()
         with torch.cuda.stream(s):
             for _ in range(max(self.warmup, 1)):
                 for p in self.params:
                     p.grad = None
                 self._eager_step()
+            self._restore_state(snap)
         cur.wait_stream(s)
         torch.cuda.synchronize(self.device)
+        del snap
         for p in self.params:
             p.grad = None
         lib = L.lib()
@@ -126,13 +145,18 @@ class GraphedTrainStep:
         self.launches_per_step = int(lib.mvf_launch_count() - n0)
         self.graph = g
         self.grads = [p.grad for p in self.params]
+        # the captured launches hold raw pointers into the engine's cached scratch workspaces: keep those tensors alive for as
+        # long as the graph is, even if a later eager call (e.g. whole-video evaluation) makes the cache grow a replacement
+        self._scratch_refs = engine.scratch_tensors(self.device)
         return self
 
     def __call__(self, tokens=None, seq_lens=None, steps=None, masks=None) -> torch.Tensor:
         """Run one step.  Returns the (static) loss tensor; `.grad` of the head parameters holds this step's gradients."""
+        self.set_inputs(tokens, seq_lens, steps, masks)
         if self.graph is None:
             self.capture()
-        self.set_inputs(tokens, seq_lens, steps, masks)
+        if self.optimizer is not None and hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()       # a scheduler may have changed param_groups[...]['lr'] since the last replay
         self.graph.replay()
         for p, gr in zip(self.params, self.grads):
             if p.grad is not gr:
@@ -143,5 +167,6 @@ class GraphedTrainStep:
         self.graph = None
         self.loss = None
         self.grads = []
+        self._scratch_refs = []
         if self.model.embed.seed_dev is self.seed_dev:
             self.model.embed.seed_dev = None

@@ -207,7 +207,6 @@ class MultiEntityTransformerEmbModel(nn.Module):
         ca = self.pooling.cross_att
         if not ca.visual or cs.head_save is None:
             return
-        # head_save is the save buffer of the slice that holds the last view (the whole batch unless micro-batched)
         attn = cs.plan.region(cs.head_save, "attn").view(-1, T, self.spec.n_entities, P)
         ca.attn_matrix = attn[-1].detach()
         ca.attn_holder(ca.attn_matrix)

@@ -4,8 +4,10 @@
 `optimizer.step()` of the Adam / AdamW built by `utils/optimizer.py:60-73` -- in PyTorch ~4 launches per parameter tensor
 (56 tensors) plus a host sync for the clip factor.  `FusedAdam` does the same arithmetic in two launches over all tensors
 (csrc/optim.cu), with the step count and the learning rate in device memory so that the tail can be captured at the end
-of the step graph (`graph.GraphedTrainStep(..., optimizer=opt)`).  It is a `torch.optim.Optimizer`: param groups, `lr`
-schedulers (`utils/optimizer.py:construct_scheduler`) and `state_dict()` work as usual.
+of the step graph (`graph.GraphedTrainStep(..., optimizer=opt)`).  It is a `torch.optim.Optimizer`: param groups and `lr`
+schedulers (`utils/optimizer.py:construct_scheduler`) work as usual -- under graph replay the new learning rate is copied to the
+device scalar by `sync_lr()` before each replay -- and `state_dict()` / `load_state_dict()` carry the step count as a
+per-parameter `step` entry, interchangeable with `torch.optim.Adam` checkpoints.
 """
 from __future__ import annotations
 
@@ -26,14 +28,49 @@ class FusedAdam(torch.optim.Optimizer):
         self.adamw = bool(adamw)
         self.grad_norm: Optional[torch.Tensor] = None      # pre-clip global gradient norm of the last step (device scalar)
         self._dev_state = {}
+        self._pending_step: Optional[int] = None            # step count loaded from a checkpoint before the device state exists
 
     def _group_state(self, gi: int, device: torch.device):
         st = self._dev_state.get(gi)
         if st is None:
             st = dict(lr=torch.zeros(1, dtype=torch.float32, device=device), lr_host=None,
                       step=torch.zeros(1, dtype=torch.int64, device=device), ws=None)
+            if self._pending_step is not None:
+                st["step"].fill_(int(self._pending_step))
+                self._pending_step = None
             self._dev_state[gi] = st
         return st
+
+    def sync_lr(self):
+        """Copy param_groups[0]['lr'] into the device-resident scalar the kernels read.  step() does this itself; a CUDA-graph
+        replay never runs step(), so graph.GraphedTrainStep calls it before every replay (outside the captured region)."""
+        st = self._dev_state.get(0)
+        lr = self.param_groups[0]["lr"]
+        if st is not None and st["lr_host"] != lr:
+            st["lr"].fill_(float(lr))
+            st["lr_host"] = lr
+
+    # ---- checkpointing: the step count lives on the device; mirror it into the per-parameter state like torch.optim.Adam ----
+    def set_step_count(self, t: int):
+        st = self._dev_state.get(0)
+        if st is None:
+            self._pending_step = int(t)
+        else:
+            st["step"].fill_(int(t))
+
+    def state_dict(self):
+        t = float(self.step_count)
+        for p, st in self.state.items():
+            if "exp_avg" in st:
+                st["step"] = torch.tensor(t, dtype=torch.float32)
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        # our own checkpoints and torch.optim.Adam / AdamW checkpoints both carry a per-parameter 'step'
+        steps = [float(st["step"]) for st in self.state.values() if "step" in st]
+        if steps:
+            self.set_step_count(int(round(max(steps))))
 
     @torch.no_grad()
     def step(self, closure=None, inv_scale: float = 1.0):
@@ -90,7 +127,9 @@ class FusedAdam(torch.optim.Optimizer):
     @property
     def step_count(self) -> int:
         st = self._dev_state.get(0)
-        return 0 if st is None else int(st["step"].item())
+        if st is None:
+            return int(self._pending_step or 0)
+        return int(st["step"].item())
 
 
 def construct_optimizer(model, cfg) -> FusedAdam:
