@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MVF_ABI_VERSION 2
+#define MVF_ABI_VERSION 3
 
 typedef void* mvf_stream_t; /* cudaStream_t */
 
@@ -258,12 +258,17 @@ int mvf_peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int32_t ra
                      mvf_stream_t stream);
 
 /* a5/a8 temporal self-attention core (utils.py:11-44 with the [B,1,1,S] key mask): qkv [B*S, 3*H]
- * (Q | K | V, head h at columns h*dk), keymask [B,S] fp32 or NULL -> ctx [B*S, H], lse [B,heads,S] fp32. */
+ * (Q | K | V, head h at columns h*dk), keymask [B,S] fp32 or NULL -> ctx [B*S, H], lse [B,heads,S] fp32.
+ * ws == NULL: exact fp32 arithmetic on CUDA cores (the parity mode).  ws != NULL (mvf_attention_ws_bytes bytes,
+ * 1024-byte aligned; fp32 data, dk = 32): tensor-core kernels on bf16 hi|lo operand splits (~2^-16 relative) --
+ * mma.sync for S <= 64, tcgen05 / TMEM / TMA flash-attention kernels for longer sequences (the mode the fused head
+ * uses on the tensor-core backend). */
+size_t mvf_attention_ws_bytes(int32_t B, int32_t S, int32_t heads, int32_t dk);
 int mvf_attention_fwd(int dtype, int32_t B, int32_t S, int32_t heads, int32_t dk, const void* qkv,
-                      const float* keymask, void* ctx, float* lse, mvf_stream_t stream);
+                      const float* keymask, void* ctx, float* lse, void* ws, size_t ws_bytes, mvf_stream_t stream);
 int mvf_attention_bwd(int dtype, int32_t B, int32_t S, int32_t heads, int32_t dk, const void* qkv,
                       const float* keymask, const void* ctx, const float* lse, const void* d_ctx, void* d_qkv,
-                      float* ws_delta, mvf_stream_t stream);
+                      float* ws_delta, void* ws, size_t ws_bytes, mvf_stream_t stream);
 
 /* The dropout keep-mask (pre-scaled by 1/(1-p)) the kernels use at `site` for a [rows, cols] tensor; lets
  * tests feed identical masks to the oracle.  Sites: 0 fc0 input, 1.. fc_i input, 8 pos-enc,

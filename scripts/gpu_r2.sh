@@ -41,6 +41,16 @@ for stage in "$@"; do
       timeout 600 python bench.py --workload finegym_cfg4 --steps 20 --warmup 5 --no-e2e --no-cpu --no-dense --no-refgpu --no-parity > gpurun_out/quick_cfg4.json 2> gpurun_out/quick_cfg4.err; echo "exit $?" | tee -a $S ;;
     quick5)
       timeout 600 python bench.py --workload long_cfg5 --steps 10 --warmup 3 --no-e2e --no-cpu --no-dense --no-refgpu --no-parity > gpurun_out/quick_cfg5.json 2> gpurun_out/quick_cfg5.err; echo "exit $?" | tee -a $S ;;
+    diag)
+      timeout 900 python scripts/diag_fullsize.py 32 20 3 512 > gpurun_out/diag_fullsize.txt 2>&1
+      timeout 900 python scripts/diag_fullsize.py 8 20 3 512 >> gpurun_out/diag_fullsize.txt 2>&1
+      echo "exit $?" | tee -a $S; grep "grad rel" gpurun_out/diag_fullsize.txt | tee -a $S ;;
+    ncu:*)
+      # ncu:<kernel regex>:<workload>  -> one full capture of the matching kernel
+      spec=${stage#ncu:}; kre=${spec%%:*}; wl=${spec#*:}
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kre -s 6 -c 2 -f -o gpurun_out/ncu_${kre}_$wl \
+        python bench.py --workload $wl --eager --steps 2 --warmup 3 --no-e2e --no-cpu --no-dense --no-refgpu --no-parity > gpurun_out/ncu_${kre}_$wl.log 2>&1
+      echo "exit $?" | tee -a $S ;;
     ref)
       timeout 900 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "exit $?" | tee -a $S ;;
     launches|launches4|launches5)

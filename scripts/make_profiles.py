@@ -86,31 +86,36 @@ def unit_bytes(v, unit_row):
     return v
 
 
-os.makedirs(PR, exist_ok=True)
-launch_table(os.path.join(GO, "launches.csv"), os.path.join(PR, f"{TAG}_launches_step_cold.txt"),
-             "ncu --metrics gpu__time_duration.sum --clock-control none; bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-dense (cfg2, bf16, folded pooling)")
-launch_table(os.path.join(GO, "launches_warm.csv"), os.path.join(PR, f"{TAG}_launches_step_warm.txt"),
-             "same with --cache-control none (L2 state carried between kernels, as in the real step)")
-ncu_summary("prof_fold_fwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_pool_fold_fwd.txt"), "pool_foldm_fwd_kernel<12> (first generation, MVF_FOLD_WS=0) at the bench shape (1280 frames x 196 tokens x 2304 ch, bf16, E=3)")
-ncu_summary("prof_fold_bwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_pool_fold_bwd.txt"), "pool_foldm_bwd_kernel<12> (first generation) at the bench shape")
-v = ncu_summary("prof_foldw_fwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_pool_foldw_fwd.txt"), "pool_foldw_fwd_kernel<9,true> (warp-specialised, default) at the bench shape (1280 frames x 196 tokens x 2304 ch, bf16, E=3)")
-ncu_summary("prof_foldw_bwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_pool_foldw_bwd.txt"), "pool_foldw_bwd_kernel<9,true> at the bench shape")
-ncu_summary("prof_attn_tc_bwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_attn_tc_bwd.txt"), "attn_tc_bwd_kernel (64 views x 8 heads, S = 60, d_k = 32)")
-ncu_summary("prof_gemm_split3.ncu-rep", os.path.join(PR, f"{TAG}_ncu_gemm_bf16x3_3840x512x512.txt"), "gemm_tc_kernel<256,4,4,true> (bf16x3, 3840 x 512 x 512)")
-ncu_summary("prof_kv_fwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_kv_proj_fwd_dense.txt"), "gemm_tc_kernel<256,4,2,false> dense K|V projection forward (250880 x 768 x 2304, bf16)")
-for name in ("fold_bench.txt", "scl_bench.txt", "bench_2gpu_graph.json", "bench_8gpu.json", "bench_reference.json", "host_cost.txt", "gemm_dbg.txt", "gemm_bench.txt", "diag_cfg1.txt", "bench.json",
-             "bench_quick.json", "bench_2gpu.json", "pytest_summary.txt", "smoke.log"):
-    src = os.path.join(GO, name)
-    if os.path.exists(src):
-        shutil.copy(src, os.path.join(PR, f"{TAG}_{name}"))
-if v and "dram__bytes_read.sum" in v:
-    def to_bytes(x):
-        num, _, unit = x.partition(" ")
-        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
-        return float(num.replace(",", "")) * mult
-    tr = to_bytes(v["dram__bytes_read.sum"]) + to_bytes(v["dram__bytes_write.sum"])
-    with open(os.path.join(PR, "pool_fold_fwd_traffic.json"), "w") as f:
-        json.dump({"kernel": "pool_foldw_fwd_kernel<9,true> (cfg2: 1280 frames x 196 tokens x 2304 channels, bf16, E=3)",
-                   "dram_bytes_per_launch": tr,
-                   "source": f"profiles/{TAG}_ncu_pool_foldw_fwd.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}, f, indent=1)
-print("profiles/ updated:", sorted(os.listdir(PR)))
+def main():
+    os.makedirs(PR, exist_ok=True)
+    launch_table(os.path.join(GO, "launches.csv"), os.path.join(PR, f"{TAG}_launches_step_cold.txt"),
+                 "ncu --metrics gpu__time_duration.sum --clock-control none; bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-dense (cfg2, bf16, folded pooling)")
+    launch_table(os.path.join(GO, "launches_warm.csv"), os.path.join(PR, f"{TAG}_launches_step_warm.txt"),
+                 "same with --cache-control none (L2 state carried between kernels, as in the real step)")
+    ncu_summary("prof_fold_fwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_pool_fold_fwd.txt"), "pool_foldm_fwd_kernel<12> (first generation, MVF_FOLD_WS=0) at the bench shape (1280 frames x 196 tokens x 2304 ch, bf16, E=3)")
+    ncu_summary("prof_fold_bwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_pool_fold_bwd.txt"), "pool_foldm_bwd_kernel<12> (first generation) at the bench shape")
+    v = ncu_summary("prof_foldw_fwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_pool_foldw_fwd.txt"), "pool_foldw_fwd_kernel<9,true> (warp-specialised, default) at the bench shape (1280 frames x 196 tokens x 2304 ch, bf16, E=3)")
+    ncu_summary("prof_foldw_bwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_pool_foldw_bwd.txt"), "pool_foldw_bwd_kernel<9,true> at the bench shape")
+    ncu_summary("prof_attn_tc_bwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_attn_tc_bwd.txt"), "attn_tc_bwd_kernel (64 views x 8 heads, S = 60, d_k = 32)")
+    ncu_summary("prof_gemm_split3.ncu-rep", os.path.join(PR, f"{TAG}_ncu_gemm_bf16x3_3840x512x512.txt"), "gemm_tc_kernel<256,4,4,true> (bf16x3, 3840 x 512 x 512)")
+    ncu_summary("prof_kv_fwd.ncu-rep", os.path.join(PR, f"{TAG}_ncu_kv_proj_fwd_dense.txt"), "gemm_tc_kernel<256,4,2,false> dense K|V projection forward (250880 x 768 x 2304, bf16)")
+    for name in ("fold_bench.txt", "scl_bench.txt", "bench_2gpu_graph.json", "bench_8gpu.json", "bench_reference.json", "host_cost.txt", "gemm_dbg.txt", "gemm_bench.txt", "diag_cfg1.txt", "bench.json",
+                 "bench_quick.json", "bench_2gpu.json", "pytest_summary.txt", "smoke.log"):
+        src = os.path.join(GO, name)
+        if os.path.exists(src):
+            shutil.copy(src, os.path.join(PR, f"{TAG}_{name}"))
+    if v and "dram__bytes_read.sum" in v:
+        def to_bytes(x):
+            num, _, unit = x.partition(" ")
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
+            return float(num.replace(",", "")) * mult
+        tr = to_bytes(v["dram__bytes_read.sum"]) + to_bytes(v["dram__bytes_write.sum"])
+        with open(os.path.join(PR, "pool_fold_fwd_traffic.json"), "w") as f:
+            json.dump({"kernel": "pool_foldw_fwd_kernel<9,true> (cfg2: 1280 frames x 196 tokens x 2304 channels, bf16, E=3)",
+                       "dram_bytes_per_launch": tr,
+                       "source": f"profiles/{TAG}_ncu_pool_foldw_fwd.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}, f, indent=1)
+    print("profiles/ updated:", sorted(os.listdir(PR)))
+
+
+if __name__ == "__main__":
+    main()

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/mvf_b200.h but not exported"
     assert set(declared) == set(L.EXPORTED_SYMBOLS), set(declared) ^ set(L.EXPORTED_SYMBOLS)
-    assert lib.mvf_version() == 2
+    assert lib.mvf_version() == 3
 
 
 def test_struct_layout_matches_header():

@@ -98,7 +98,7 @@ def test_temporal_attention_fwd_bwd(B, S, heads, dk, masked, dtype):
     ctx = torch.empty(B * S, Hd, dtype=dtype, device=dev)
     lse = torch.empty(B, heads, S, device=dev)
     kmd = None if km is None else km.to(dev)
-    L.check(L.lib().mvf_attention_fwd(md, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse), _stream()))
+    L.check(L.lib().mvf_attention_fwd(md, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse), None, 0, _stream()))
     torch.cuda.synchronize()
     tol = 2e-6 if dtype == torch.float32 else 1.5e-2
     assert float((ctx.float().cpu().double() - ctx_ref.detach()).abs().max()) < tol * max(1.0, float(ctx_ref.abs().max()))
@@ -106,56 +106,111 @@ def test_temporal_attention_fwd_bwd(B, S, heads, dk, masked, dtype):
     delta = torch.empty(B, heads, S, device=dev)
     d_ctx_d = d_ctx.to(dev)
     L.check(L.lib().mvf_attention_bwd(md, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse),
-                                      L.ptr(d_ctx_d), L.ptr(d_qkv), L.ptr(delta), _stream()))
+                                      L.ptr(d_ctx_d), L.ptr(d_qkv), L.ptr(delta), None, 0, _stream()))
     torch.cuda.synchronize()
     want = x.grad.reshape(B * S, 3 * Hd)
     assert H.rel_l2(d_qkv.float().cpu(), want) < (2e-5 if dtype == torch.float32 else 3e-2)
 
 
-@pytest.mark.parametrize("B,S,heads,masked", [(3, 60, 8, True), (2, 64, 8, False), (2, 17, 2, True), (5, 33, 4, True), (1, 1, 1, False)])
-def test_temporal_attention_tensor_core_path(monkeypatch, B, S, heads, masked):
-    """attention_tc.cu (S <= 64, d_k = 32; bf16 hi/lo operand splits on mma.sync), forced through MVF_ATTN_TC=2, against the
-    fp64 formulation -- including a view whose keys are all masked except one and a partially filled last warp."""
-    monkeypatch.setenv("MVF_ATTN_TC", "2")
+def _attention_reference(qkv, km, B, S, heads, dk, d_ctx):
+    """fp64 statement of attention() (models/utils.py:11-44) + autograd, one (view, head) at a time to bound memory."""
+    Hd = heads * dk
+    x = qkv.double().view(B, S, 3, heads, dk).requires_grad_(True)
+    ctx_ref = torch.empty(B, S, heads, dk, dtype=torch.float64)
+    lse_ref = torch.empty(B, heads, S, dtype=torch.float64)
+    g = d_ctx.double().view(B, S, heads, dk)
+    grads = torch.zeros_like(x)
+    for b in range(B):
+        for h in range(heads):
+            xb = x[b, :, :, h].detach().clone().requires_grad_(True)          # [S, 3, dk]
+            sc = xb[:, 0] @ xb[:, 1].t() / np.sqrt(dk)
+            if km is not None:
+                sc = sc.masked_fill(km[b][None, :] == 0, -float("inf"))
+            o = torch.softmax(sc, -1) @ xb[:, 2]
+            (o * g[b, :, h]).sum().backward()
+            ctx_ref[b, :, h] = o.detach()
+            lse_ref[b, h] = torch.logsumexp(sc.detach(), -1)
+            grads[b, :, :, h] = xb.grad
+    return ctx_ref.reshape(B * S, Hd), lse_ref, grads.reshape(B * S, 3 * Hd)
+
+
+def _run_attention_tc(qkv, km, B, S, heads, dk, d_ctx):
+    dev = "cuda"
+    Hd = heads * dk
+    qkv_d = qkv.to(dev)
+    ctx = torch.full((B * S, Hd), float("nan"), device=dev)
+    lse = torch.full((B, heads, S), float("nan"), device=dev)
+    kmd = None if km is None else km.to(dev)
+    nb = L.lib().mvf_attention_ws_bytes(B, S, heads, dk)
+    assert nb > 0
+    ws = torch.empty(nb + 1024, dtype=torch.uint8, device=dev)
+    wsp = (ws.data_ptr() + 1023) // 1024 * 1024
+    L.check(L.lib().mvf_attention_fwd(L.MVF_F32, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse), wsp, nb, _stream()))
+    torch.cuda.synchronize()
+    d_qkv = torch.full_like(qkv_d, float("nan"))
+    delta = torch.empty(B, heads, S, device=dev)
+    L.check(L.lib().mvf_attention_bwd(L.MVF_F32, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse),
+                                      L.ptr(d_ctx.to(dev)), L.ptr(d_qkv), L.ptr(delta), wsp, nb, _stream()))
+    torch.cuda.synchronize()
+    return ctx.cpu(), lse.cpu(), d_qkv.cpu()
+
+
+def _attention_case(B, S, heads, masked, seed_extra=0):
     dk = 32
     Hd = heads * dk
-    g = torch.Generator().manual_seed(B * S + heads)
+    g = torch.Generator().manual_seed(B * S + heads + seed_extra)
     qkv = torch.randn(B * S, 3 * Hd, generator=g) * 0.7
     km = None
     if masked:
         km = (torch.rand(B, S, generator=g) > 0.25).float()
         km[:, 0] = 1
-        km[0, 1:] = 0                      # a single valid key
-    x = qkv.double().view(B, S, 3, heads, dk).requires_grad_(True)
-    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
-    sc = q @ k.transpose(-1, -2) / np.sqrt(dk)
-    if km is not None:
-        sc = sc.masked_fill(km[:, None, None, :] == 0, -float("inf"))
-    ctx_ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, Hd)
-    lse_ref = torch.logsumexp(sc, -1)
+        km[0, 1:] = 0                      # view 0: a single valid key
+        if B > 1 and S > 70:
+            km[1, S // 2:] = 0             # view 1: the whole tail padded (ragged sequence), key tiles with no valid key
     d_ctx = torch.randn(B * S, Hd, generator=g)
-    (ctx_ref * d_ctx.double()).sum().backward()
-    dev = "cuda"
-    qkv_d = qkv.to(dev)
-    ctx = torch.full((B * S, Hd), float("nan"), device=dev)
-    lse = torch.full((B, heads, S), float("nan"), device=dev)
-    kmd = None if km is None else km.to(dev)
-    L.check(L.lib().mvf_attention_fwd(L.MVF_F32, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse), _stream()))
-    torch.cuda.synchronize()
-    assert float((ctx.cpu().double() - ctx_ref.detach()).abs().max()) < 2e-5 * max(1.0, float(ctx_ref.abs().max()))
-    assert float((lse.cpu().double() - lse_ref.detach()).abs().max()) < 2e-5
-    d_qkv = torch.full_like(qkv_d, float("nan"))
-    delta = torch.empty(B, heads, S, device=dev)
-    L.check(L.lib().mvf_attention_bwd(L.MVF_F32, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx), L.ptr(lse),
-                                      L.ptr(d_ctx.to(dev)), L.ptr(d_qkv), L.ptr(delta), _stream()))
-    torch.cuda.synchronize()
-    assert H.rel_l2(d_qkv.cpu(), x.grad.reshape(B * S, 3 * Hd)) < 5e-5
-    # the exact CUDA-core kernels stay the default of the stand-alone entry point
-    monkeypatch.setenv("MVF_ATTN_TC", "1")
-    ctx2 = torch.empty_like(ctx)
-    L.check(L.lib().mvf_attention_fwd(L.MVF_F32, B, S, heads, dk, L.ptr(qkv_d), L.ptr(kmd), L.ptr(ctx2), L.ptr(lse), _stream()))
-    torch.cuda.synchronize()
-    assert float((ctx2.cpu().double() - ctx_ref.detach()).abs().max()) < 2e-6 * max(1.0, float(ctx_ref.abs().max()))
+    return dk, qkv, km, d_ctx
+
+
+@pytest.mark.parametrize("B,S,heads,masked", [(3, 60, 8, True), (2, 64, 8, False), (2, 17, 2, True), (5, 33, 4, True), (1, 1, 1, False)])
+def test_temporal_attention_tensor_core_path(B, S, heads, masked):
+    """attention_tc.cu (S <= 64, d_k = 32; bf16 hi/lo operand splits on mma.sync) -- what the C ABI runs when a split-operand
+    workspace is supplied -- against the fp64 formulation, including a view whose keys are all masked except one and a
+    partially filled last warp."""
+    dk, qkv, km, d_ctx = _attention_case(B, S, heads, masked)
+    ctx_ref, lse_ref, want = _attention_reference(qkv, km, B, S, heads, dk, d_ctx)
+    ctx, lse, d_qkv = _run_attention_tc(qkv, km, B, S, heads, dk, d_ctx)
+    assert float((ctx.double() - ctx_ref).abs().max()) < 2e-5 * max(1.0, float(ctx_ref.abs().max()))
+    assert float((lse.double() - lse_ref).abs().max()) < 2e-5
+    assert H.rel_l2(d_qkv, want) < 5e-5
+
+
+@pytest.mark.parametrize("B,S,heads,masked", [(2, 65, 2, True), (2, 128, 8, False), (3, 200, 4, True), (16, 480, 8, True),
+                                              (2, 1000, 2, True), (2, 3840, 2, True), (1, 6000, 1, False)])
+def test_temporal_attention_tcgen05_long_sequences(B, S, heads, masked):
+    """attention_fa.cu: flash-attention forward, dQ and dK/dV on tcgen05 / TMEM / TMA (bf16 hi|lo operand splits) for S > 64:
+    cfg4 (S = 480), cfg5 (S = 3840) and whole-video evaluation lengths, ragged key masks, tiles with no valid key, sequence
+    lengths that are not multiples of the 64 / 128 tile sizes -- against the fp64 formulation."""
+    dk, qkv, km, d_ctx = _attention_case(B, S, heads, masked, seed_extra=7)
+    ctx_ref, lse_ref, want = _attention_reference(qkv, km, B, S, heads, dk, d_ctx)
+    ctx, lse, d_qkv = _run_attention_tc(qkv, km, B, S, heads, dk, d_ctx)
+    assert torch.isfinite(ctx).all() and torch.isfinite(d_qkv).all()
+    assert float((ctx.double() - ctx_ref).abs().max()) < 2e-5 * max(1.0, float(ctx_ref.abs().max()))
+    assert float((lse.double() - lse_ref).abs().max()) < 2e-5
+    err = H.rel_l2(d_qkv, want)
+    print(f"tcgen05 attention B {B} S {S} heads {heads}: ctx max err {float((ctx.double() - ctx_ref).abs().max()):.2e} d_qkv rel {err:.2e}")
+    assert err < 5e-5
+
+
+@pytest.mark.parametrize("B,S,heads", [(2, 17, 2), (3, 60, 8), (1, 64, 1)])
+def test_temporal_attention_tcgen05_short_sequences_forced(monkeypatch, B, S, heads):
+    """MVF_ATTN_FA=2 sends every length through the tcgen05 kernels: a single, partially filled key tile."""
+    monkeypatch.setenv("MVF_ATTN_FA", "2")
+    dk, qkv, km, d_ctx = _attention_case(B, S, heads, True, seed_extra=3)
+    ctx_ref, lse_ref, want = _attention_reference(qkv, km, B, S, heads, dk, d_ctx)
+    ctx, lse, d_qkv = _run_attention_tc(qkv, km, B, S, heads, dk, d_ctx)
+    assert float((ctx.double() - ctx_ref).abs().max()) < 2e-5 * max(1.0, float(ctx_ref.abs().max()))
+    assert float((lse.double() - lse_ref).abs().max()) < 2e-5
+    assert H.rel_l2(d_qkv, want) < 5e-5
 
 
 def test_dropout_mask_is_counter_based_and_unbiased():

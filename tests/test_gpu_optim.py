@@ -1,5 +1,7 @@
 """GPU: the fused optimizer tail (csrc/optim.cu, optim.FusedAdam) against torch.nn.utils.clip_grad_norm_ +
 torch.optim.Adam / AdamW on the same tensors (train.py:124-133,151-155; utils/optimizer.py:60-73)."""
+import copy
+
 import pytest
 import torch
 
@@ -68,7 +70,7 @@ def test_unscale_factor_and_state_dict_round_trip():
     assert float(sd["state"][0]["step"]) == 1.0
     c = [torch.nn.Parameter(p.detach().clone()) for p in a]
     oc = FusedAdam(c, lr=1e-3, max_grad_norm=5.0)
-    oc.load_state_dict(sd)
+    oc.load_state_dict(copy.deepcopy(sd))      # as after torch.save / torch.load: load_state_dict itself aliases same-device tensors
     assert oc.step_count == 1
     for p, q, g in zip(a, c, gs[1]):
         p.grad = g.clone()

@@ -87,8 +87,9 @@ _PROTOS = {
                                     _sz, _vp]),
     "mvf_peer_buffer_bytes": (_sz, []),
     "mvf_peer_sum_f64": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),
-    "mvf_attention_fwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "mvf_attention_bwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvf_attention_ws_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "mvf_attention_fwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mvf_attention_bwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mvf_dropout_mask": (C.c_int, [_u64, _i32, _i64, _i64, _f32, _vp, _vp]),
 }
 

@@ -1,7 +1,8 @@
 // Temporal multi-head self-attention core (models/utils.py:11-44, 87-103): softmax(Q K^T / sqrt(dk) + keymask) V
 // per (view, head), streaming over key tiles with an online softmax so the [S,S] score matrix never reaches
 // HBM (the reference materialises [BV,8,S,S]).  fp32 math on CUDA cores: with dk = 32 the exp, not the MMA, is
-// the bound; a tcgen05 version only pays at S >= ~1k and is a later-round item.
+// the bound.  These are the exact-fp32 kernels (fp32 tokens / parity mode); on the tensor-core
+// backend S <= 64 runs in attention_tc.cu (mma.sync) and longer sequences in attention_fa.cu (tcgen05 / TMEM / TMA).
 //
 // Layout: qkv [B*S, 3*H] rows = (view, token), columns Q | K | V with head h at [h*dk, (h+1)*dk).
 // One thread owns one query row (forward, dQ) or one key row (dK/dV); key/query tiles are staged in shared
@@ -582,10 +583,15 @@ static int bwd_launch(int B, int S, int heads, const void* qkv, const float* key
     return MVF_ERR_UNSUPPORTED;                                                                \
   } while (0)
 
+size_t attention_ws_bytes(int B, int S, int heads, int dk) {
+  return (dk == 32 && tc_available()) ? attention_fa_ws_bytes(B, S, heads) : 0;
+}
 int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, void* ctx,
-                  float* lse, cudaStream_t st, bool allow_split) {
+                  float* lse, cudaStream_t st, bool allow_split, void* ws, size_t ws_bytes) {
   if (B <= 0 || S <= 0) return MVF_OK;
   MVF_REQUIRE(B <= 65535 && heads <= 65535, MVF_ERR_BAD_ARG, "attention: grid too large");
+  if (attention_fa_ok(dtype, S, dk, heads * dk, allow_split, ws, ws_bytes, B, heads) && ((((uintptr_t)qkv) | ((uintptr_t)ctx)) & 15) == 0)
+    return attention_fa_fwd(B, S, heads, qkv, keymask, ctx, lse, ws, st);
   if (attention_tc_ok(dtype, S, dk, heads * dk, qkv, ctx, allow_split)) return attention_tc_fwd(B, S, heads, qkv, keymask, ctx, lse, st);
   if (quad_ok(dtype, S, dk, qkv, ctx) && (heads * dk) % 4 == 0) {
     if (dk == 32) return fwd_quad_launch<32>(B, S, heads, qkv, keymask, ctx, lse, st);
@@ -594,9 +600,13 @@ int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, c
   DISPATCH_DK(fwd_launch, B, S, heads, qkv, keymask, ctx, lse, st);
 }
 int attention_bwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, const void* ctx,
-                  const float* lse, const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st, bool allow_split) {
+                  const float* lse, const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st, bool allow_split, void* ws,
+                  size_t ws_bytes) {
   if (B <= 0 || S <= 0) return MVF_OK;
   MVF_REQUIRE(B <= 65535 && heads <= 65535, MVF_ERR_BAD_ARG, "attention: grid too large");
+  if (attention_fa_ok(dtype, S, dk, heads * dk, allow_split, ws, ws_bytes, B, heads) &&
+      ((((uintptr_t)qkv) | ((uintptr_t)ctx) | ((uintptr_t)d_ctx) | ((uintptr_t)d_qkv)) & 15) == 0)
+    return attention_fa_bwd(B, S, heads, qkv, keymask, ctx, lse, d_ctx, d_qkv, ws, st);
   if (attention_tc_ok(dtype, S, dk, heads * dk, qkv, d_qkv, allow_split) && ((((uintptr_t)ctx) | ((uintptr_t)d_ctx)) & 15) == 0)
     return attention_tc_bwd(B, S, heads, qkv, keymask, ctx, lse, d_ctx, d_qkv, st);
   if (quad_ok(dtype, S, dk, qkv, d_qkv) && (heads * dk) % 4 == 0 && ((((uintptr_t)ctx) | ((uintptr_t)d_ctx)) & 15) == 0) {

@@ -405,6 +405,11 @@ static void head_ws_layout(const Model& m, Layout& L) {
   L.add("dr", m.rows, d.H, RT_F32);
   L.add("dctx", m.rows, d.H, A);
   L.add("delta", (int64_t)d.BV * d.heads, m.S, RT_F32);
+  if (m.tc && d.heads > 0 && d.H / d.heads == 32) {
+    // split-operand scratch of the tcgen05 attention kernels (attention_fa.cu); 1024-byte aligned inside the region
+    const size_t fa = attention_ws_bytes(d.BV, (int)m.S, d.heads, 32);
+    if (fa > 0) L.add("fa", 1, (int64_t)(fa + 1024) / 4, RT_F32);
+  }
   L.add("dh3", m.R, m.Hin, A);
   L.add("da", m.R, maxfc, RT_F32);
   for (int i = 0; i < d.n_fc; ++i) L.add(fname(i, "dx"), m.R, d.fc[i], A);
@@ -529,6 +534,18 @@ struct Ctx {
               int64_t ldb, void* C, int64_t ldc, const float* bias, int flags, int split_k) const {
     return gemm_dispatch(backend, m.kvt, dtype_c, akm, bkm, M, N, K, A, lda, B, ldb, C, ldc, bias, nullptr, 0, flags,
                          split_k, st);
+  }
+  // 1024-byte aligned scratch of the tcgen05 attention kernels inside the "fa" region of the scratch buffer (or null)
+  void* fa_ws() const {
+    const Region* r = Lw.find("fa");
+    if (r == nullptr) return nullptr;
+    return (void*)(((uintptr_t)(W.base + r->off) + 1023) & ~(uintptr_t)1023);
+  }
+  size_t fa_ws_bytes() const {
+    const Region* r = Lw.find("fa");
+    if (r == nullptr) return 0;
+    const uintptr_t b0 = (uintptr_t)(W.base + r->off), b1 = (b0 + 1023) & ~(uintptr_t)1023;
+    return (size_t)r->cols * 4 - (size_t)(b1 - b0);
   }
   int fork() {
     if (!side) return MVF_OK;
@@ -782,7 +799,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       {
         ProfScope ps(6, st);
         MVF_TRY(attention_fwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
-                              c.S.f(lname(l, "lse")), st, m.tc));
+                              c.S.f(lname(l, "lse")), st, m.tc, c.fa_ws(), c.fa_ws_bytes()));
       }
       MVF_TRY(c.linear(MVF_F32, m.rows, d.H, d.H, c.S.p(lname(l, "ctx")), d.H, c.S.p(lname(l, "w.o")), d.H, c.P[b + L_BO],
                        o, d.H, 0, lname(l, "w.o").c_str()));
@@ -886,7 +903,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         {
           ProfScope ps(7, st);
           MVF_TRY(attention_bwd(A, d.BV, (int)m.S, d.heads, dk, c.S.p(lname(l, "qkv")), keymask, c.S.p(lname(l, "ctx")),
-                                c.S.f(lname(l, "lse")), c.W.p("dctx"), dqkv, c.W.f("delta"), st, m.tc));
+                                c.S.f(lname(l, "lse")), c.W.p("dctx"), dqkv, c.W.f("delta"), st, m.tc, c.fa_ws(), c.fa_ws_bytes()));
         }
         MVF_TRY(c.linear_dw(m.rows, 3 * d.H, d.H, dqkv, 3 * d.H, c.S.p(lname(l, "r0")), d.H, c.G.f(g + "w.qkv"),
                             d.H, c.G.f(g + "b.qkv")));
@@ -1408,16 +1425,18 @@ int mvf_peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int32_t ra
                      mvf_stream_t stream) {
   return peer_sum_f64(local, n, bufs_dev, rank, world, counter, (cudaStream_t)stream);
 }
+size_t mvf_attention_ws_bytes(int32_t B, int32_t S, int32_t heads, int32_t dk) { return attention_ws_bytes(B, S, heads, dk); }
 int mvf_attention_fwd(int dtype, int32_t B, int32_t S, int32_t heads, int32_t dk, const void* qkv, const float* keymask,
-                      void* ctx, float* lse, mvf_stream_t stream) {
+                      void* ctx, float* lse, void* ws, size_t ws_bytes, mvf_stream_t stream) {
   MVF_REQUIRE(qkv && ctx && lse, MVF_ERR_BAD_ARG, "attention fwd: null pointer");
-  return attention_fwd(dtype, B, S, heads, dk, qkv, keymask, ctx, lse, (cudaStream_t)stream);
+  return attention_fwd(dtype, B, S, heads, dk, qkv, keymask, ctx, lse, (cudaStream_t)stream, ws != nullptr, ws, ws_bytes);
 }
 int mvf_attention_bwd(int dtype, int32_t B, int32_t S, int32_t heads, int32_t dk, const void* qkv, const float* keymask,
-                      const void* ctx, const float* lse, const void* d_ctx, void* d_qkv, float* ws_delta,
-                      mvf_stream_t stream) {
+                      const void* ctx, const float* lse, const void* d_ctx, void* d_qkv, float* ws_delta, void* ws,
+                      size_t ws_bytes, mvf_stream_t stream) {
   MVF_REQUIRE(qkv && ctx && lse && d_ctx && d_qkv && ws_delta, MVF_ERR_BAD_ARG, "attention bwd: null pointer");
-  return attention_bwd(dtype, B, S, heads, dk, qkv, keymask, ctx, lse, d_ctx, d_qkv, ws_delta, (cudaStream_t)stream);
+  return attention_bwd(dtype, B, S, heads, dk, qkv, keymask, ctx, lse, d_ctx, d_qkv, ws_delta, (cudaStream_t)stream,
+                       ws != nullptr, ws, ws_bytes);
 }
 
 int mvf_dropout_mask(uint64_t seed, int32_t site, int64_t rows, int64_t cols, float p, float* out, mvf_stream_t stream) {

@@ -143,10 +143,20 @@ int peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int rank, int 
 // ---- attention.cu --------------------------------------------------------------------------------------------
 // allow_split: the caller accepts operands split into bf16 hi + lo (2^-16 relative) -> tensor-core kernels of attention_tc.cu
 // for S <= 64, d_k = 32; otherwise (and always for exact-fp32 callers) the CUDA-core kernels
+// ws / ws_bytes (optional, attention_ws_bytes): scratch for the split operands of the tcgen05 kernels (attention_fa.cu, S > 64)
+size_t attention_ws_bytes(int B, int S, int heads, int dk);
 int attention_fwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, void* ctx,
-                  float* lse, cudaStream_t st, bool allow_split = false);
+                  float* lse, cudaStream_t st, bool allow_split = false, void* ws = nullptr, size_t ws_bytes = 0);
 int attention_bwd(int dtype, int B, int S, int heads, int dk, const void* qkv, const float* keymask, const void* ctx,
-                  const float* lse, const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st, bool allow_split = false);
+                  const float* lse, const void* d_ctx, void* d_qkv, float* delta, cudaStream_t st, bool allow_split = false,
+                  void* ws = nullptr, size_t ws_bytes = 0);
+// attention_fa.cu: flash-attention forward / dQ / dK,dV on tcgen05 (d_k = 32, fp32 qkv, bf16 hi|lo operand splits)
+size_t attention_fa_ws_bytes(int B, int S, int heads);
+bool attention_fa_ok(int dtype, int S, int dk, int H, bool allow_split, const void* ws, size_t ws_bytes, int B, int heads);
+int attention_fa_fwd(int B, int S, int heads, const void* qkv, const float* keymask, void* ctx, float* lse, void* ws,
+                     cudaStream_t st);
+int attention_fa_bwd(int B, int S, int heads, const void* qkv, const float* keymask, const void* ctx, const float* lse,
+                     const void* d_ctx, void* d_qkv, void* ws, cudaStream_t st);
 bool attention_tc_ok(int dtype, int S, int dk, int H, const void* qkv, const void* other, bool allow_split);
 int attention_tc_fwd(int B, int S, int heads, const void* qkv, const float* keymask, void* ctx, float* lse, cudaStream_t st);
 int attention_tc_bwd(int B, int S, int heads, const void* qkv, const float* keymask, const void* ctx, const float* lse,
