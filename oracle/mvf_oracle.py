@@ -49,6 +49,8 @@ class HeadCfg:
     ln_eps: float = 1e-5
     bn_eps: float = 1e-5
     bn_momentum: float = 0.1
+    pool_kind: str = "lstp"     # "lstp": LearnableTokenPooling (entity cross-attention); "fwb": FIXED_WIDTH_BASELINE (FWBPooling)
+    cls_dim: int = 0            # fwb: width of the CLS embedding = OUT_CHANNEL / len(SMART_FEATS) (mvformer.py:441-447)
 
 
 def param_shapes(cfg: HeadCfg) -> Dict[str, Tuple[int, ...]]:
@@ -58,13 +60,17 @@ def param_shapes(cfg: HeadCfg) -> Dict[str, Tuple[int, ...]]:
     """
     E, SPC, H = cfg.n_entities, cfg.pool_channels, cfg.hidden
     s: Dict[str, Tuple[int, ...]] = {}
-    p = "embed.pooling.cross_att."
-    s[p + "Q_s"] = (1, E, SPC)
-    s[p + "Q_s_b"] = (SPC,)
-    s[p + "linear_K2d.weight"] = (SPC, cfg.c_in)
-    s[p + "linear_K2d.bias"] = (SPC,)
-    s[p + "linear_V2d.weight"] = (SPC, cfg.c_in)
-    s[p + "linear_V2d.bias"] = (SPC,)
+    if cfg.pool_kind == "fwb":                                   # FWBPooling.lin_conv (mvformer.py:449-451)
+        s["embed.pooling.lin_conv.weight"] = (SPC * E, cfg.cls_dim)
+        s["embed.pooling.lin_conv.bias"] = (SPC * E,)
+    else:
+        p = "embed.pooling.cross_att."
+        s[p + "Q_s"] = (1, E, SPC)
+        s[p + "Q_s_b"] = (SPC,)
+        s[p + "linear_K2d.weight"] = (SPC, cfg.c_in)
+        s[p + "linear_K2d.bias"] = (SPC,)
+        s[p + "linear_V2d.weight"] = (SPC, cfg.c_in)
+        s[p + "linear_V2d.bias"] = (SPC,)
     cin = SPC + (E if cfg.one_hot == "pool" else 0)
     for i, ch in enumerate(cfg.fc_channels):
         lin, bn = 4 * i + 1, 4 * i + 2
@@ -184,6 +190,14 @@ def xattn_pool(P: Dict[str, Tensor], tokens: Tensor, cfg: HeadCfg) -> Tuple[Tens
     return ent, attn
 
 
+def fwb_pool(P: Dict[str, Tensor], cls_emb: Tensor, BV: int, T: int, cfg: HeadCfg) -> Tensor:
+    """FIXED_WIDTH_BASELINE (FWBPooling.forward, mvformer.py:455-462): the patch tokens are ignored; one Linear maps the
+    CLS embedding of every frame [BV*T, cls_dim] to SPC*E channels, reshaped [frames, SPC, E] -- "entity" e of channel c
+    is output column c*E + e.  Returns ent [BV,T,E,SPC]."""
+    y = F.linear(cls_emb, P["embed.pooling.lin_conv.weight"], P["embed.pooling.lin_conv.bias"])
+    return y.reshape(BV, T, cfg.pool_channels, cfg.n_entities).permute(0, 1, 3, 2)
+
+
 # --------------------------------------------------------------------------------------------------
 # a6: per-entity MLP (mvformer.py:70-86, 144-153)
 # --------------------------------------------------------------------------------------------------
@@ -287,7 +301,7 @@ def encoder_layer(P, pre: str, z: Tensor, keymask: Optional[Tensor], cfg: HeadCf
 def head_forward(P: Dict[str, Tensor], buf: Optional[Dict[str, Tensor]], tokens: Tensor,
                  video_masks: Optional[Tensor], cfg: HeadCfg, training: bool = True,
                  drop_masks: Optional[Dict[str, Tensor]] = None,
-                 return_aux: bool = False):
+                 return_aux: bool = False, cls_emb: Optional[Tensor] = None):
     """tokens [BV,T,Ptok,C_in] token-major; video_masks [BV,1,T] or [BV,T] or None -> emb [BV,T,D].
 
     Equivalent to MultiEntityTransformerEmbModel.forward on x = tokens.permute(0,1,3,2).reshape(BV,T,C,h,w).
@@ -298,7 +312,10 @@ def head_forward(P: Dict[str, Tensor], buf: Optional[Dict[str, Tensor]], tokens:
     BV, T, Ptok, C = tokens.shape
     E, H = cfg.n_entities, cfg.hidden
     new_buf: Dict[str, Tensor] = {}
-    ent, attn = xattn_pool(P, tokens, cfg)
+    if cfg.pool_kind == "fwb":
+        ent, attn = fwb_pool(P, cls_emb, BV, T, cfg), None
+    else:
+        ent, attn = xattn_pool(P, tokens, cfg)
     h3 = entity_mlp(P, buf, ent, cfg, training, new_buf, drop_masks)             # [BV,T,E,Hin]
     z = h3.permute(0, 2, 1, 3)                                                   # [BV,E,T,Hin]  mvformer.py:155-157
     pe = torch.from_numpy(pos_table_for(cfg, T, z.shape[-1])).to(device=z.device, dtype=z.dtype)   # utils.py:136-143

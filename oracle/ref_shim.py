@@ -191,8 +191,14 @@ def cfg_from_headcfg(hc, yml: str = "penn_mvf.yml"):
                         HIDDEN_SIZE=hc.hidden, D_FF=hc.d_ff, NUM_HEADS=hc.n_heads, NUM_LAYERS=hc.n_layers,
                         EMBEDDING_SIZE=hc.emb, SMART_ONE_HOT=hc.one_hot, SMART_FINAL=hc.final,
                         FC_DROPOUT_RATE=hc.drop_p, PROJECTION_SIZE=hc.proj)
-    # SMART_FEATS only matters for dynamic tokens; keep a single layer so d_dyn_in == c_in.
+    # SMART_FEATS only matters for the width of the CLS embedding (dynamic tokens / FIXED_WIDTH_BASELINE): d_dyn_in =
+    # OUT_CHANNEL / number of feature layers (mvformer.py:441-447); a single layer keeps d_dyn_in == c_in.
     cfg.MODEL.EMBEDDER_MODEL.SMART_FEATS = "11"
+    if getattr(hc, "pool_kind", "lstp") == "fwb":
+        cfg.MODEL.EMBEDDER_MODEL.FIXED_WIDTH_BASELINE = True
+        n = hc.c_in // hc.cls_dim
+        assert n * hc.cls_dim == hc.c_in
+        cfg.MODEL.EMBEDDER_MODEL.SMART_FEATS = ",".join(str(11 - i) for i in range(n)) if n > 1 else "11"
     return cfg
 
 

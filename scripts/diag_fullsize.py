@@ -27,5 +27,5 @@ rows = []
 for k in keys:
     a, b = r["grads"][k].double(), o["grads"][k]
     rows.append((float((a - b).norm()) / G, k, float(b.norm()) / G, float((a - b).norm() / (b.norm() + 1e-300))))
-for err, k, share, rel in sorted(rows, reverse=True)[:14]:
+for err, k, share, rel in (rows if os.environ.get("DIAG_ALL") else sorted(rows, reverse=True)[:14]):
     print(f"   {k:58s} |g|/|G| {share:.2e}  err/|G| {err:.2e}  rel {rel:.2e}")

@@ -42,8 +42,8 @@ for stage in "$@"; do
     quick5)
       timeout 600 python bench.py --workload long_cfg5 --steps 10 --warmup 3 --no-e2e --no-cpu --no-dense --no-refgpu --no-parity > gpurun_out/quick_cfg5.json 2> gpurun_out/quick_cfg5.err; echo "exit $?" | tee -a $S ;;
     diag)
-      timeout 900 python scripts/diag_fullsize.py 32 20 3 512 > gpurun_out/diag_fullsize.txt 2>&1
-      timeout 900 python scripts/diag_fullsize.py 8 20 3 512 >> gpurun_out/diag_fullsize.txt 2>&1
+      DIAG_ALL=1 timeout 900 python scripts/diag_fullsize.py 32 20 3 512 > gpurun_out/diag_fullsize.txt 2>&1
+      MVF_SIMT_CHUNK=0 timeout 900 python scripts/diag_fullsize.py 32 20 3 512 >> gpurun_out/diag_fullsize.txt 2>&1
       echo "exit $?" | tee -a $S; grep "grad rel" gpurun_out/diag_fullsize.txt | tee -a $S ;;
     ncu:*)
       # ncu:<kernel regex>:<workload>  -> one full capture of the matching kernel

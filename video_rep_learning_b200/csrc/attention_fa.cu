@@ -37,7 +37,6 @@ constexpr int BK = 64;      // columns per inner tile
 constexpr int DK = 32;
 constexpr int ROW = 128;    // bytes per operand row (64 bf16)
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
 
 __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
@@ -45,6 +44,29 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
   const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// 2^x on the MUFU (ex2.approx.ftz: 2^-inf = +0); exp2f() wraps the same instruction in range fix-ups the kernels do not need
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void split8(const float* v, uint4& h, uint4& l) {
+  split2(v[0], v[1], h.x, l.x);
+  split2(v[2], v[3], h.y, l.y);
+  split2(v[4], v[5], h.z, l.z);
+  split2(v[6], v[7], h.w, l.w);
+}
+__device__ __forceinline__ void store_chunk(uint8_t* tile_hi, uint8_t* tile_lo, int r, int chunk, const uint4& h, const uint4& l) {
+  const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(tile_hi + off) = h;
+  *reinterpret_cast<uint4*>(tile_lo + off) = l;
+}
+constexpr int MAX_MASK_WORDS = 512;    // S <= 16384
+// the view's key-mask words -> shared memory (called by the `n` softmax threads, ids 0..n-1, after pdl_entry)
+__device__ __forceinline__ void load_mask_words(uint32_t* smask, const uint32_t* __restrict__ mb, int words, int tid, int n) {
+  for (int i = tid; i < words + 2; i += n) smask[i] = i < words ? __ldg(mb + i) : 0u;
 }
 
 // 1-D bulk copy global -> shared, completion on an mbarrier (bytes % 16 == 0, both addresses 16-byte aligned)
@@ -119,8 +141,8 @@ __global__ void __launch_bounds__(256) fa_prep_kernel(const PrepArgs a, int S, i
   }
 }
 
-// backward row statistics: L2[slab][Sq] = lse * log2(e) (+inf where the row has no valid key or is padding, so that
-// 2^(s - L2) = 0) and D[slab][Sq] = <dO_i, O_i> over the head's channels
+// backward row statistics: L2[slab][Sq] = -lse * log2(e) (-inf where the row has no valid key or is padding, so that
+// 2^(s + L2) = 0) and D[slab][Sq] = <dO_i, O_i> / sqrt(dk) over the head's channels
 __global__ void __launch_bounds__(256) fa_stats_kernel(const float* __restrict__ ctx, const float* __restrict__ d_ctx,
                                                        const float* __restrict__ lse, float* __restrict__ L2,
                                                        float* __restrict__ Dl, int S, int Sq, int heads, int H) {
@@ -139,13 +161,13 @@ __global__ void __launch_bounds__(256) fa_stats_kernel(const float* __restrict__
   dl += __shfl_xor_sync(0xffffffffu, dl, 2);
   dl += __shfl_xor_sync(0xffffffffu, dl, 4);
   if (c4 == 0 && i < Sq) {
-    float l2 = INFINITY;
+    float l2 = -INFINITY;
     if (i < S) {
       const float lv = lse[slab * S + i];
-      l2 = (lv == -INFINITY) ? INFINITY : lv * LOG2E;
+      l2 = (lv == -INFINITY) ? -INFINITY : -lv * LOG2E;
     }
     L2[slab * Sq + i] = l2;
-    Dl[slab * Sq + i] = dl;
+    Dl[slab * Sq + i] = dl * rsqrtf((float)DK);
   }
 }
 
@@ -176,18 +198,6 @@ __device__ __forceinline__ void mma_tsplit(uint32_t tmem_d, uint32_t sa_hi, uint
     umma<2>(tmem_d, dah + o, dbh + o, idesc, 1u);
   }
 }
-// eight fp32 values -> one 16-byte chunk of the hi tile and one of the lo tile (row r of a SWIZZLE_128B K-major tile)
-__device__ __forceinline__ void store_split8(uint8_t* tile_hi, uint8_t* tile_lo, int r, int chunk, const float* v) {
-  uint4 h, l;
-  split2(v[0], v[1], h.x, l.x);
-  split2(v[2], v[3], h.y, l.y);
-  split2(v[4], v[5], h.z, l.z);
-  split2(v[6], v[7], h.w, l.w);
-  const int off = r * ROW + ((chunk ^ (r & 7)) << 4);
-  *reinterpret_cast<uint4*>(tile_hi + off) = h;
-  *reinterpret_cast<uint4*>(tile_lo + off) = l;
-}
-
 struct Params {
   int S, Sq, heads, H;
   int mask_words;
@@ -209,6 +219,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
               const __grid_constant__ CUtensorMap map_vt, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint32_t smask[MAX_MASK_WORDS + 2];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 16384;
@@ -305,12 +316,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const int row = q * 32 + lane;
     const int qi = q0 + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float scale2 = LOG2E * rsqrtf((float)DK);
-    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+    const float scale = rsqrtf((float)DK), scale2 = LOG2E * scale;
+    load_mask_words(smask, p.maskbits + (int64_t)b * p.mask_words, p.mask_words, threadIdx.x - 64, 128);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;   // m: running maximum of the RAW scores (the scale is folded into the FFMA)
     float O[DK];
 #pragma unroll
     for (int c = 0; c < DK; ++c) O[c] = 0.f;
-    const uint32_t* mb = p.maskbits + (int64_t)b * p.mask_words;
     for (int j = 0; j < nt; ++j) {
       const int st = j & 1;
       mbar_wait(&s_full[st], (j >> 1) & 1, 17);
@@ -322,27 +334,26 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
-      const uint32_t w0 = (2 * j < p.mask_words) ? __ldg(mb + 2 * j) : 0u;
-      const uint32_t w1 = (2 * j + 1 < p.mask_words) ? __ldg(mb + 2 * j + 1) : 0u;
-      float tmax = -INFINITY;
+      const uint32_t w0 = smask[2 * j], w1 = smask[2 * j + 1];
+      if ((w0 & w1) != 0xffffffffu) {   // warp-uniform: only tiles that contain masked / out-of-range keys pay for the selects
 #pragma unroll
-      for (int c = 0; c < BK; ++c) {
-        const bool ok = ((c < 32 ? w0 : w1) >> (c & 31)) & 1u;
-        const float sv = ok ? __uint_as_float(r[c]) * scale2 : -INFINITY;
-        r[c] = __float_as_uint(sv);
-        tmax = fmaxf(tmax, sv);
+        for (int c = 0; c < BK; ++c)
+          if (!(((c < 32 ? w0 : w1) >> (c & 31)) & 1u)) r[c] = 0xff800000u;   // -inf
       }
-      const float m_new = fmaxf(m, tmax);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m - m_use);
-      float rs = 0.f;
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < BK; ++c) mx[c & 3] = fmaxf(mx[c & 3], __uint_as_float(r[c]));
+      const float m_new = fmaxf(fmaxf(m, fmaxf(mx[0], mx[1])), fmaxf(mx[2], mx[3]));
+      const float nms = -((m_new == -INFINITY) ? 0.f : m_new) * scale2;
+      const float alpha = ex2(fmaf(m, scale2, nms));
+      float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < BK; ++c) {
-        const float pv = exp2f(__uint_as_float(r[c]) - m_use);
+        const float pv = ex2(fmaf(__uint_as_float(r[c]), scale2, nms));
         r[c] = __float_as_uint(pv);
-        rs += pv;
+        rs[c & 3] += pv;
       }
-      l = l * alpha + rs;
+      l = fmaf(l, alpha, (rs[0] + rs[1]) + (rs[2] + rs[3]));
       m = m_new;
       if (j > 0) {   // the P V product of the previous tile (it has also released the P tiles)
         mbar_wait(o_full, (j - 1) & 1, 18);
@@ -351,7 +362,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         tmem_ld32(lane_addr + 2 * BK, t);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < DK; ++c) O[c] = O[c] * alpha_prev + __uint_as_float(t[c]);
+        for (int c = 0; c < DK; ++c) O[c] = fmaf(O[c], alpha_prev, __uint_as_float(t[c]));
         tcgen05_fence_before();
       }
 #pragma unroll
@@ -359,7 +370,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * ch + e]);
-        store_split8(sPh, sPl, row, ch, v);
+        uint4 hh, ll;
+        split8(v, hh, ll);
+        store_chunk(sPh, sPl, row, ch, hh, ll);
       }
       fence_proxy_async_smem();
       mbar_arrive(p_full);
@@ -372,7 +385,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       tmem_ld32(lane_addr + 2 * BK, t);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < DK; ++c) O[c] = O[c] * alpha_prev + __uint_as_float(t[c]);
+      for (int c = 0; c < DK; ++c) O[c] = fmaf(O[c], alpha_prev, __uint_as_float(t[c]));
     }
     if (qi < p.S) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
@@ -380,7 +393,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
       for (int c = 0; c < DK; c += 4)
         *reinterpret_cast<float4*>(o + c) = make_float4(O[c] * inv, O[c + 1] * inv, O[c + 2] * inv, O[c + 3] * inv);
-      p.lse[(int64_t)slab * p.S + qi] = m * LN2 + logf(l);
+      p.lse[(int64_t)slab * p.S + qi] = m * scale + logf(l);
     }
   }
   tcgen05_fence_before();
@@ -402,6 +415,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                  const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                  const __grid_constant__ CUtensorMap map_kt, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint32_t smask[MAX_MASK_WORDS + 2];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
   uint8_t* sG = sQ + 16384;
@@ -503,14 +517,15 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const int qi = q0 + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float scale = rsqrtf((float)DK), scale2 = scale * LOG2E;
-    // rows past S (Sq is a multiple of 64, q0 + row may still exceed it): +inf -> every weight 0
-    const float L = qi < p.Sq ? __ldg(p.L2 + (int64_t)slab * p.Sq + qi) : INFINITY;
-    const float D = qi < p.Sq ? __ldg(p.Dl + (int64_t)slab * p.Sq + qi) : 0.f;
-    const uint32_t* mb = p.maskbits + (int64_t)b * p.mask_words;
+    // rows past S (Sq is a multiple of 64, q0 + row may still exceed it): -inf -> every weight 0
+    const float NL = qi < p.Sq ? __ldg(p.L2 + (int64_t)slab * p.Sq + qi) : -INFINITY;   // -lse * log2(e)
+    const float Dn = qi < p.Sq ? -__ldg(p.Dl + (int64_t)slab * p.Sq + qi) : 0.f;        // -delta / sqrt(dk)
+    load_mask_words(smask, p.maskbits + (int64_t)b * p.mask_words, p.mask_words, threadIdx.x - 64, 128);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int j = 0; j < nt; ++j) {
       mbar_wait(sd_full, j & 1, 27);
-      mbar_wait(ds_empty, (j & 1) ^ 1, 28);
       tcgen05_fence_after();
+      uint4 hh[8], ll[8];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t rs_[32], rp[32];
@@ -522,20 +537,24 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(sd_empty);
         }
-        const uint32_t w = (2 * j + half < p.mask_words) ? __ldg(mb + 2 * j + half) : 0u;
+        const uint32_t w = smask[2 * j + half];
+        const bool full = w == 0xffffffffu;   // warp-uniform
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int c = 8 * ch + e;
-            const bool ok = (w >> c) & 1u;
-            const float pw = ok ? exp2f(__uint_as_float(rs_[c]) * scale2 - L) : 0.f;
-            v[e] = pw * (__uint_as_float(rp[c]) - D) * scale;
+            float pw = ex2(fmaf(__uint_as_float(rs_[c]), scale2, NL));
+            if (!full) pw = ((w >> c) & 1u) ? pw : 0.f;
+            v[e] = pw * fmaf(__uint_as_float(rp[c]), scale, Dn);
           }
-          store_split8(sDh, sDl, row, half * 4 + ch, v);
+          split8(v, hh[half * 4 + ch], ll[half * 4 + ch]);
         }
       }
+      mbar_wait(ds_empty, (j & 1) ^ 1, 28);   // the dQ product of the previous tile has released the dS tiles
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) store_chunk(sDh, sDl, row, ch, hh[ch], ll[ch]);
       fence_proxy_async_smem();
       mbar_arrive(ds_full);
     }
@@ -682,6 +701,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float scale = rsqrtf((float)DK), scale2 = scale * LOG2E;
     const bool key_ok = ki < p.S && ((__ldg(p.maskbits + (int64_t)b * p.mask_words + (ki >> 5)) >> (ki & 31)) & 1u);
+    const bool all_ok = __all_sync(0xffffffffu, key_ok);   // warp-uniform: no per-element selects for fully valid warps
     for (int j = 0; j < nq; ++j) {
       const int st = j & 1;
       const uint8_t* s = sSt + st * STAGE_PITCH;
@@ -695,9 +715,9 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sd_empty[st]);
-      const float4* Ls = reinterpret_cast<const float4*>(s + 4 * 8192) + wg * 8;
-      const float4* Ds = reinterpret_cast<const float4*>(s + 4 * 8192 + 256) + wg * 8;
-      mbar_wait(pd_empty, (j & 1) ^ 1, 36);
+      const float4* Ls = reinterpret_cast<const float4*>(s + 4 * 8192) + wg * 8;          // -lse * log2(e) of the 32 queries
+      const float4* Ds = reinterpret_cast<const float4*>(s + 4 * 8192 + 256) + wg * 8;    // delta / sqrt(dk)
+      uint4 ph[4], pl[4], dh[4], dl[4];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         float pv[8], dv[8];
@@ -708,13 +728,20 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = 8 * ch + 4 * e4 + e;
-            const float pw = key_ok ? exp2f(__uint_as_float(rs_[c]) * scale2 - Lx[e]) : 0.f;
+            float pw = ex2(fmaf(__uint_as_float(rs_[c]), scale2, Lx[e]));
+            if (!all_ok) pw = key_ok ? pw : 0.f;
             pv[4 * e4 + e] = pw;
-            dv[4 * e4 + e] = pw * (__uint_as_float(rp[c]) - Dx[e]) * scale;
+            dv[4 * e4 + e] = pw * fmaf(__uint_as_float(rp[c]), scale, -Dx[e]);
           }
         }
-        store_split8(sPh, sPl, row, wg * 4 + ch, pv);
-        store_split8(sDh, sDl, row, wg * 4 + ch, dv);
+        split8(pv, ph[ch], pl[ch]);
+        split8(dv, dh[ch], dl[ch]);
+      }
+      mbar_wait(pd_empty, (j & 1) ^ 1, 36);   // the dV / dK products of the previous tile have released the P^T / dS^T tiles
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        store_chunk(sPh, sPl, row, wg * 4 + ch, ph[ch], pl[ch]);
+        store_chunk(sDh, sDl, row, wg * 4 + ch, dh[ch], dl[ch]);
       }
       fence_proxy_async_smem();
       mbar_arrive(pd_full);
@@ -803,6 +830,7 @@ bool attention_fa_ok(int dtype, int S, int dk, int H, bool allow_split, const vo
   const int mode = attn_fa_mode();
   if (mode == 0 || !allow_split || ws == nullptr) return false;
   if (mode == 1 && S <= 64) return false;
+  if (S > 32 * fa::MAX_MASK_WORDS) return false;
   return dtype == MVF_F32 && dk == fa::DK && H == heads * dk && H % 4 == 0 && tc_available() &&
          ws_bytes >= attention_fa_ws_bytes(B, S, heads) && ((uintptr_t)ws & 1023) == 0;
 }

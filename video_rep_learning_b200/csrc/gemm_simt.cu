@@ -3,6 +3,8 @@
 // Role: (1) the fp32 parity path (1e-5 relative needs true fp32 FMA; bf16/tf32 tensor cores cannot give it),
 // (2) the on-device cross-check for the tcgen05 GEMM in tests.  It is NOT the throughput path: in bf16 mode
 // every contraction goes through gemm_tc.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mvf {
@@ -14,19 +16,24 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(int M, int N, int K, con
                                                         int64_t sak, const TAB* __restrict__ B, int64_t sbn, int64_t sbk,
                                                         TC* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
                                                         const TAB* __restrict__ relu_src, int64_t ld_relu, int flags,
-                                                        int a_kmajor, int b_kmajor) {
+                                                        int a_kmajor, int b_kmajor, int chunk_iters) {
   pdl_entry();
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int t = threadIdx.x;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int ty = t / 16, tx = t % 16;
+  // Blocked summation: a single fp32 accumulator running over a long K (the weight gradients sum over thousands of
+  // entity rows, with heavy cancellation) loses ~K * 2^-24 relative to the partial sums; fp32 partial sums over
+  // chunk_iters * BK terms folded into float64 totals keep the parity mode at the 1e-6 level for any K.
   float acc[4][4];
+  double tot[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.0; }
 
+  int it = 0;
   for (int k0 = 0; k0 < K; k0 += BK) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -59,7 +66,20 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(int M, int N, int K, con
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
+    if (chunk_iters > 0 && ++it == chunk_iters) {
+      it = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tot[i][j] += (double)acc[i][j]; acc[i][j] = 0.f; }
+    }
     __syncthreads();
+  }
+  if (chunk_iters > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = (float)(tot[i][j] + (double)acc[i][j]);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -87,9 +107,14 @@ static int launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, c
   dim3 grid(cdiv(N, BN), cdiv(M, BM));
   int64_t sam = a_kmajor ? lda : 1, sak = a_kmajor ? 1 : lda;
   int64_t sbn = b_kmajor ? ldb : 1, sbk = b_kmajor ? 1 : ldb;
+  static int chunk = -1;   // MVF_SIMT_CHUNK: BK-steps per fp32 partial sum (0 = one running fp32 sum; A/B measurements)
+  if (chunk < 0) {
+    const char* e = getenv("MVF_SIMT_CHUNK");
+    chunk = e ? atoi(e) : 4;
+  }
   launch_k(gemm_simt_kernel<TAB, TC>, grid, 256, 0, st, (int)M, (int)N, (int)K, (const TAB*)A, sam, sak, (const TAB*)B, sbn,
                                                   sbk, (TC*)C, ldc, bias, (const TAB*)relu_src, ld_relu, flags,
-                                                  a_kmajor, b_kmajor);
+                                                  a_kmajor, b_kmajor, K > 4 * BK * (chunk > 0 ? chunk : 1) ? chunk : 0);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
