@@ -44,6 +44,10 @@ enum mvf_negative { MVF_NEG_SINGLE_NOSELF = 0, MVF_NEG_BATCH_NOSELF = 1 };
  * never formed: one HBM-bound streaming pass over the tokens per direction, identical results up to fp32
  * re-association.  DENSE: as written in the reference (K|V projection GEMM on tcgen05, then attention over K|V). */
 enum mvf_pool_mode { MVF_POOL_AUTO = 0, MVF_POOL_DENSE = 1, MVF_POOL_FOLDED = 2 };
+/* Which pooling module feeds the per-entity MLP.  LSTP: LearnableTokenPooling (entity cross-attention, mvformer.py:207-266).
+ * FWB: FIXED_WIDTH_BASELINE (FWBPooling, mvformer.py:421-462; configs_mvf/ablate_dinoB8_fwb{3,5}.yml): the patch tokens are
+ * ignored and one Linear(cls_dim -> SPC*E) of each frame's CLS embedding is reshaped [frames, SPC, E]. */
+enum mvf_pool_kind { MVF_POOLKIND_LSTP = 0, MVF_POOLKIND_FWB = 1 };
 
 #define MVF_MAX_FC 4
 #define MVF_MAX_ENTITIES 16
@@ -84,6 +88,10 @@ typedef struct mvf_head_desc {
   const uint64_t* seed_dev; /* optional DEVICE counter added to `seed` inside the kernels (NULL = none): */
                         /* a CUDA-graph-captured step freezes `seed`, so the caller advances *seed_dev  */
                         /* on the device once per replay to keep drawing fresh dropout masks            */
+  int32_t pool_kind;    /* mvf_pool_kind                                                            */
+  int32_t cls_dim;      /* FWB: width of the CLS embedding (OUT_CHANNEL / number of SMART_FEATS layers) */
+  const float* cls_emb; /* FWB: DEVICE [BV*T, cls_dim] fp32 CLS embeddings of the frames, rows in the order the */
+                        /* reference hands them over (transformer.py:200,217); frozen, no gradient         */
 } mvf_head_desc;
 
 /* ---- library / bookkeeping ------------------------------------------------------------------------ */

@@ -18,6 +18,7 @@ ONEHOT = {"none": 0, "pool": 1, "enc": 2}
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 NEG = {"single_noself": 0, "batch_noself": 1}
 POOL_AUTO, POOL_DENSE, POOL_FOLDED = 0, 1, 2
+POOLKIND = {"lstp": 0, "fwb": 1}
 PHASE_ALL = 255
 GEMM_RELU, GEMM_ACCUM, GEMM_RELUMASK, GEMM_SPLIT3, GEMM_B_PRESPLIT = 1, 2, 4, 8, 16
 MAX_FC = 4
@@ -35,6 +36,7 @@ class HeadDesc(C.Structure):
         ("gemm_backend", C.c_int32), ("world_size", C.c_int32), ("pool_mode", C.c_int32),
         ("drop_p", C.c_float), ("ln_eps", C.c_float), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
         ("seed", C.c_uint64), ("seed_dev", C.c_void_p),
+        ("pool_kind", C.c_int32), ("cls_dim", C.c_int32), ("cls_emb", C.c_void_p),
     ]
 
 

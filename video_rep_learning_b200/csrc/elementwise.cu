@@ -23,7 +23,7 @@ __global__ void pack_kernel(const PackTable tab) {
   pdl_entry();
   const PackEntry& en = tab.e[blockIdx.y];
   const int64_t total = (int64_t)en.rows * en.ld_dst;
-  if (en.dst_bf16 == 0 && en.ld_dst == en.cols && (total & 3) == 0 && ((((uintptr_t)en.src) | ((uintptr_t)en.dst)) & 15) == 0) {
+  if (en.perm_n <= 1 && en.dst_bf16 == 0 && en.ld_dst == en.cols && (total & 3) == 0 && ((((uintptr_t)en.src) | ((uintptr_t)en.dst)) & 15) == 0) {
     // plain fp32 copy of a dense matrix: 16-byte vectors, no index arithmetic
     const float4* s4 = reinterpret_cast<const float4*>(en.src);
     float4* d4 = reinterpret_cast<float4*>(en.dst);
@@ -32,7 +32,12 @@ __global__ void pack_kernel(const PackTable tab) {
   }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int r = (int)(i / en.ld_dst), c = (int)(i - (int64_t)r * en.ld_dst);
-    float v = c < en.cols ? en.src[(int64_t)r * en.cols + c] : 0.f;
+    int rs = r, cs = c;
+    if (en.perm_n > 1) {   // interleaved source rows (FWBPooling: output channel c*E + e feeds entity e, channel c)
+      if (en.rows > 1) rs = (r % en.perm_n) * (en.rows / en.perm_n) + r / en.perm_n;
+      else if (c < en.cols) cs = (c % en.perm_n) * (en.cols / en.perm_n) + c / en.perm_n;
+    }
+    float v = c < en.cols ? en.src[(int64_t)rs * en.cols + cs] : 0.f;
     if (en.dst_bf16 == 2) {
       // "pre-split" container for the bf16x3 GEMM: every 32-float block of a row holds [hi(32) | lo(32)] bf16
       const bf16 hi = __float2bfloat16_rn(v);
@@ -60,7 +65,7 @@ __global__ void unpack_kernel(const UnpackTable tab, float scale) {
   pdl_entry();
   const UnpackEntry& en = tab.e[blockIdx.y];
   const int64_t total = (int64_t)en.rows * en.cols;
-  if (en.ld_src == en.cols && (total & 3) == 0 && ((((uintptr_t)en.src) | ((uintptr_t)en.dst)) & 15) == 0) {
+  if (en.perm_n <= 1 && en.ld_src == en.cols && (total & 3) == 0 && ((((uintptr_t)en.src) | ((uintptr_t)en.dst)) & 15) == 0) {
     const float4* s4 = reinterpret_cast<const float4*>(en.src);
     float4* d4 = reinterpret_cast<float4*>(en.dst);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (total >> 2); i += (int64_t)gridDim.x * blockDim.x) {
@@ -71,6 +76,10 @@ __global__ void unpack_kernel(const UnpackTable tab, float scale) {
   }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int r = (int)(i / en.cols), c = (int)(i - (int64_t)r * en.cols);
+    if (en.perm_n > 1) {
+      if (en.rows > 1) r = (r % en.perm_n) * (en.rows / en.perm_n) + r / en.perm_n;
+      else c = (c % en.perm_n) * (en.cols / en.perm_n) + c / en.perm_n;
+    }
     en.dst[i] = scale * en.src[(int64_t)r * en.ld_src + c];
   }
 }

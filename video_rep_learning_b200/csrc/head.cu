@@ -148,6 +148,8 @@ struct Model {
   int kvt;     // dtype of tokens, W_k|W_v, K|V and dK|dV (the 96 % of the FLOPs): d.dtype
   bool tc;     // chain GEMMs on tcgen05 (bf16 tokens or an explicit TCGEN05 backend): forward weights are also packed pre-split
   bool fold;   // rank-E folded pooling (pool_fold.cu): no K|V tensors, one streaming pass over the tokens per direction
+  bool fwb;    // FIXED_WIDTH_BASELINE: FWBPooling (one Linear of the CLS embedding) instead of the entity cross-attention
+  int iWlc, iblc;
   std::vector<ParamInfo> params;
   // indices into params
   int iQs, iQb, iWk, ibk, iWv, ibv;
@@ -218,13 +220,23 @@ static int build_model(const mvf_head_desc* dp, Model& m) {
     m.fold = pm == MVF_POOL_FOLDED || (pm == MVF_POOL_AUTO && ok);
   }
   m.params.clear();
-  const std::string ca = "embed.pooling.cross_att.";
-  m.iQs = add_param(m, ca + "Q_s", d.E, d.SPC);
-  m.iQb = add_param(m, ca + "Q_s_b", 1, d.SPC);
-  m.iWk = add_param(m, ca + "linear_K2d.weight", d.SPC, d.C_in);
-  m.ibk = add_param(m, ca + "linear_K2d.bias", 1, d.SPC);
-  m.iWv = add_param(m, ca + "linear_V2d.weight", d.SPC, d.C_in);
-  m.ibv = add_param(m, ca + "linear_V2d.bias", 1, d.SPC);
+  MVF_REQUIRE(d.pool_kind == MVF_POOLKIND_LSTP || d.pool_kind == MVF_POOLKIND_FWB, MVF_ERR_BAD_ARG, "pool_kind %d", d.pool_kind);
+  m.fwb = d.pool_kind == MVF_POOLKIND_FWB;
+  m.iQs = m.iQb = m.iWk = m.ibk = m.iWv = m.ibv = m.iWlc = m.iblc = -1;
+  if (m.fwb) {
+    MVF_REQUIRE(d.cls_dim > 0 && d.cls_dim % 4 == 0, MVF_ERR_BAD_ARG, "FIXED_WIDTH_BASELINE needs cls_dim (%d) > 0, a multiple of 4", d.cls_dim);
+    m.fold = false;
+    m.iWlc = add_param(m, "embed.pooling.lin_conv.weight", (int64_t)d.SPC * d.E, d.cls_dim);
+    m.iblc = add_param(m, "embed.pooling.lin_conv.bias", 1, (int64_t)d.SPC * d.E);
+  } else {
+    const std::string ca = "embed.pooling.cross_att.";
+    m.iQs = add_param(m, ca + "Q_s", d.E, d.SPC);
+    m.iQb = add_param(m, ca + "Q_s_b", 1, d.SPC);
+    m.iWk = add_param(m, ca + "linear_K2d.weight", d.SPC, d.C_in);
+    m.ibk = add_param(m, ca + "linear_K2d.bias", 1, d.SPC);
+    m.iWv = add_param(m, ca + "linear_V2d.weight", d.SPC, d.C_in);
+    m.ibv = add_param(m, ca + "linear_V2d.bias", 1, d.SPC);
+  }
   int cin = m.W0;
   for (int i = 0; i < d.n_fc; ++i) {
     MVF_REQUIRE(d.fc[i] > 0, MVF_ERR_BAD_ARG, "fc[%d] = %d", i, d.fc[i]);
@@ -312,7 +324,12 @@ static std::string fname(int i, const char* s) { return "fc" + std::to_string(i)
 static void head_save_layout(const Model& m, Layout& L) {
   const mvf_head_desc& d = m.d;
   const int A = m.act;
-  if (m.fold) {
+  if (m.fwb) {
+    // lin_conv with its output rows regrouped entity-major: row e*SPC + c of "w.lc" = row c*E + e of the parameter
+    L.add("w.lc", (int64_t)d.E * d.SPC, d.cls_dim, A);
+    L.add("b.lc", 1, (int64_t)d.E * d.SPC, RT_F32);
+    if (m.tc) add_split(L, "w.lc", (int64_t)d.E * d.SPC, d.cls_dim);
+  } else if (m.fold) {
     L.add("wq", d.E, d.C_in, RT_F32);
     if (m.tc) add_split(L, "w.v", d.SPC, d.C_in);
   } else {
@@ -346,9 +363,11 @@ static void head_save_layout(const Model& m, Layout& L) {
     L.add("w.lin", d.H, (int64_t)d.E * d.H, A);
     if (m.tc) add_split(L, "w.lin", d.H, (int64_t)d.E * d.H);
   }
-  if (m.fold) L.add("px", m.R, d.C_in, RT_F32);      // attention-pooled tokens: the only C_in-wide activation kept
-  else L.add("kv", m.F * d.P, 2 * d.SPC, m.kvt);
-  L.add("attn", m.F * d.E, d.P, RT_F32);
+  if (!m.fwb) {
+    if (m.fold) L.add("px", m.R, d.C_in, RT_F32);      // attention-pooled tokens: the only C_in-wide activation kept
+    else L.add("kv", m.F * d.P, 2 * d.SPC, m.kvt);
+    L.add("attn", m.F * d.E, d.P, RT_F32);
+  }
   L.add("h0", m.R, m.W0, A, m.ld0);
   L.add("ent32", m.R, d.SPC, RT_F32);
   for (int i = 0; i < d.n_fc; ++i) {
@@ -414,7 +433,9 @@ static void head_ws_layout(const Model& m, Layout& L) {
   L.add("da", m.R, maxfc, RT_F32);
   for (int i = 0; i < d.n_fc; ++i) L.add(fname(i, "dx"), m.R, d.fc[i], A);
   L.add("dh0", m.R, m.W0, A, m.ld0);
-  if (m.fold) {
+  if (m.fwb) {
+    L.add("dent", m.R, d.SPC, RT_F32);
+  } else if (m.fold) {
     L.add("dent", m.R, d.SPC, RT_F32);
     L.add("G", m.R, d.C_in, RT_F32);
     L.add("dwq", d.E, d.C_in, RT_F32);
@@ -454,10 +475,15 @@ static void proj_ws_layout(const Model& m, Layout& L) {
 // flat gradient buffer: one region per packed parameter group (fp32), head + projection together
 static void gpack_layout(const Model& m, Layout& L) {
   const mvf_head_desc& d = m.d;
-  L.add("g.Qs", d.E, d.SPC, RT_F32);
-  L.add("g.Qb", 1, d.SPC, RT_F32);
-  L.add("g.w.kv", 2 * d.SPC, d.C_in, RT_F32, round_up(d.C_in, 8));
-  L.add("g.b.kv", 1, 2 * d.SPC, RT_F32);
+  if (m.fwb) {
+    L.add("g.w.lc", (int64_t)d.E * d.SPC, d.cls_dim, RT_F32);   // entity-major row order, un-permuted when scattered
+    L.add("g.b.lc", 1, (int64_t)d.E * d.SPC, RT_F32);
+  } else {
+    L.add("g.Qs", d.E, d.SPC, RT_F32);
+    L.add("g.Qb", 1, d.SPC, RT_F32);
+    L.add("g.w.kv", 2 * d.SPC, d.C_in, RT_F32, round_up(d.C_in, 8));
+    L.add("g.b.kv", 1, 2 * d.SPC, RT_F32);
+  }
   int cin_ld = m.ld0;
   for (int i = 0; i < d.n_fc; ++i) {
     L.add("g." + fname(i, "w"), d.fc[i], i == 0 ? m.W0 : d.fc[i - 1], RT_F32, cin_ld);
@@ -656,8 +682,19 @@ static int pack_head_weights(Ctx& c) {
     char* dst = c.S.base + r->off + (size_t)row0 * r->ld * 4;
     e.push_back(PackEntry{c.P[pidx], dst, (int)pi.rows, (int)pi.cols, (int)r->ld, 2});
   };
+  if (m.fwb) {
+    const Region* rw = c.Ls.find("w.lc");
+    const Region* rb = c.Ls.find("b.lc");
+    const ParamInfo& pw = m.params[m.iWlc];
+    e.push_back(PackEntry{c.P[m.iWlc], c.S.base + rw->off, (int)pw.rows, (int)pw.cols, (int)rw->ld, 0, d.SPC});
+    e.push_back(PackEntry{c.P[m.iblc], c.S.base + rb->off, 1, (int)pw.rows, (int)pw.rows, 0, d.SPC});
+    if (m.tc) {
+      const Region* rs = c.Ls.find("w.lc.s");
+      e.push_back(PackEntry{c.P[m.iWlc], c.S.base + rs->off, (int)pw.rows, (int)pw.cols, (int)rs->ld, 2, d.SPC});
+    }
+  }
   if (m.fold) split("w.v", m.iWv);
-  if (!m.fold) {
+  if (!m.fold && !m.fwb) {
     mat("w.kv", m.iWk, 0);
     mat("w.kv", m.iWv, d.SPC);
     vec("b.kv", m.ibk, 0);
@@ -705,8 +742,16 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
   for (int ph = ph0; ph < ph1; ++ph) {
     if (ph == 0) {
       MVF_TRY(pack_head_weights(c));
-      float* attn = c.S.f("attn");
-      if (m.fold) {
+      float* attn = m.fwb ? nullptr : c.S.f("attn");
+      if (m.fwb) {
+        // FWBPooling (mvformer.py:455-462): ent[(f, e), c] = lin_conv(cls[f])[c*E + e]; with the weight rows regrouped
+        // entity-major the [F, E*SPC] product IS the [F*E, SPC] entity matrix
+        MVF_REQUIRE(d.cls_emb != nullptr, MVF_ERR_BAD_ARG, "FIXED_WIDTH_BASELINE needs the CLS embeddings (desc.cls_emb)");
+        const int64_t NE = (int64_t)d.E * d.SPC;
+        MVF_TRY(c.linear(MVF_F32, m.F, NE, d.cls_dim, d.cls_emb, d.cls_dim, c.S.p("w.lc"), d.cls_dim, c.S.f("b.lc"), c.S.p("ent32"), NE, 0, "w.lc"));
+        MVF_TRY(ent_finish_fwd(c.S.f("ent32"), c.S.f("h0"), m.ld0, m.R, d.SPC, d.E, d.one_hot == MVF_ONEHOT_POOL, c.p,
+                               DropSeed(d.seed, d.seed_dev), st));
+      } else if (m.fold) {
         // a3-a5 folded: Wq = Q Wk / sqrt(SPC); one streaming pass over the tokens (online softmax + pooling of X);
         // the value projection is applied to the E pooled rows per frame instead of the P token rows
         {
@@ -737,7 +782,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
                                  m.ld0, c.S.f("ent32"), d.one_hot == MVF_ONEHOT_POOL, c.p, DropSeed(d.seed, d.seed_dev), st));
         }
       }
-      if (attn_out)
+      if (attn_out && attn)
         MVF_CHECK_CUDA(cudaMemcpyAsync(attn_out, attn, (size_t)m.F * d.E * d.P * 4, cudaMemcpyDeviceToDevice, st));
     }
     // input of FC layer `ph` (or of video_emb when ph == n_fc)
@@ -962,6 +1007,14 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
     }
     if (ph == n_ph - 1) {
       // ---- entity cross-attention pooling and the K|V projection weight gradient ----
+      if (m.fwb) {
+        MVF_REQUIRE(d.cls_emb != nullptr, MVF_ERR_BAD_ARG, "FIXED_WIDTH_BASELINE needs the CLS embeddings (desc.cls_emb)");
+        const int64_t NE = (int64_t)d.E * d.SPC;
+        MVF_TRY(ent_finish_bwd(c.W.f("dh0"), m.ld0, c.W.f("dent"), m.R, d.SPC, m.W0, c.p, DropSeed(d.seed, d.seed_dev), st));
+        // d(lin_conv) in entity-major row order: dW' = dEnt[F, E*SPC]^T cls, db' = column sums (cls is frozen: no dX)
+        MVF_TRY(c.linear_dw(m.F, NE, d.cls_dim, c.W.p("dent"), NE, d.cls_emb, d.cls_dim, c.G.f("g.w.lc"), d.cls_dim, c.G.f("g.b.lc")));
+        continue;
+      }
       const int o_spc = d.SPC;
       float* gbkv = c.G.f("g.b.kv");
       if (m.fold) {
@@ -1102,19 +1155,24 @@ static int unpack_impl(const Model& m, const Layout& Lg, const float* gpack, flo
                        cudaStream_t st) {
   const mvf_head_desc& d = m.d;
   std::vector<UnpackEntry> e;
-  auto add = [&](const std::string& reg, int pidx, int64_t row0 = 0, int64_t col0 = 0) {
+  auto add = [&](const std::string& reg, int pidx, int64_t row0 = 0, int64_t col0 = 0, int perm_n = 0) {
     if (pidx < 0 || grads[pidx] == nullptr) return;
     const Region* r = Lg.find(reg);
     const ParamInfo& pi = m.params[pidx];
     const float* src = (const float*)((const char*)gpack + r->off) + row0 * r->ld + col0;
-    e.push_back(UnpackEntry{src, grads[pidx], (int)pi.rows, (int)pi.cols, (int)r->ld});
+    e.push_back(UnpackEntry{src, grads[pidx], (int)pi.rows, (int)pi.cols, (int)r->ld, perm_n});
   };
-  add("g.Qs", m.iQs);
-  add("g.Qb", m.iQb);
-  add("g.w.kv", m.iWk, 0);
-  add("g.w.kv", m.iWv, d.SPC);
-  add("g.b.kv", m.ibk, 0, 0);
-  add("g.b.kv", m.ibv, 0, d.SPC);
+  if (m.fwb) {
+    add("g.w.lc", m.iWlc, 0, 0, d.E);     // parameter row c*E + e <- entity-major row e*SPC + c
+    add("g.b.lc", m.iblc, 0, 0, d.E);
+  } else {
+    add("g.Qs", m.iQs);
+    add("g.Qb", m.iQb);
+    add("g.w.kv", m.iWk, 0);
+    add("g.w.kv", m.iWv, d.SPC);
+    add("g.b.kv", m.ibk, 0, 0);
+    add("g.b.kv", m.ibv, 0, d.SPC);
+  }
   for (int i = 0; i < d.n_fc; ++i) {
     add("g." + fname(i, "w"), m.iFcW[i]);
     add("g." + fname(i, "b"), m.iFcB[i]);
@@ -1300,7 +1358,7 @@ int mvf_head_forward(const mvf_head_desc* d, const float* const* params, float* 
                      mvf_stream_t stream) {
   Ctx c;
   MVF_TRY(make_ctx(d, c, false, save, save_bytes, ws, ws_bytes, nullptr, params, (cudaStream_t)stream));
-  MVF_REQUIRE(tokens != nullptr && out_emb != nullptr, MVF_ERR_BAD_ARG, "null tokens / output");
+  MVF_REQUIRE((tokens != nullptr || d->pool_kind == MVF_POOLKIND_FWB) && out_emb != nullptr, MVF_ERR_BAD_ARG, "null tokens / output");
   MVF_REQUIRE(!d->has_mask || mask != nullptr, MVF_ERR_BAD_ARG, "has_mask set but mask is null");
   return head_forward_impl(c, bn_running, bn_tracked, tokens, mask, out_emb, attn_out, phase_begin, phase_end);
 }
@@ -1310,7 +1368,8 @@ int mvf_head_backward(const mvf_head_desc* d, const float* const* params, const 
                       int phase_begin, int phase_end, mvf_stream_t stream) {
   Ctx c;
   MVF_TRY(make_ctx(d, c, false, save, save_bytes, ws, ws_bytes, gpack, params, (cudaStream_t)stream));
-  MVF_REQUIRE(tokens != nullptr && d_emb != nullptr && gpack != nullptr, MVF_ERR_BAD_ARG, "null tokens / d_emb / gpack");
+  MVF_REQUIRE((tokens != nullptr || d->pool_kind == MVF_POOLKIND_FWB) && d_emb != nullptr && gpack != nullptr, MVF_ERR_BAD_ARG,
+              "null tokens / d_emb / gpack");
   MVF_TRY(side_acquire(c.st, &c.side, &c.side_dev));
   int rc = head_backward_impl(c, tokens, mask, d_emb, phase_begin, phase_end);
   if (rc != MVF_OK) c.join();  // never leave forked work un-joined, even on an error path

@@ -9,12 +9,14 @@ struct PackEntry {
   const float* src;  // fp32 [rows, cols] contiguous
   void* dst;         // [rows, ld_dst] in dst dtype, zero padded
   int rows, cols, ld_dst, dst_bf16;  // dst_bf16: 0 fp32, 1 bf16, 2 pre-split bf16 hi|lo blocks (ld_dst floats, multiple of 32)
+  int perm_n;        // > 1: destination row r (column c for a vector) comes from source row (r % perm_n) * (rows / perm_n) + r / perm_n
 };
 int pack_params(const PackEntry* entries, int n, cudaStream_t st);
 struct UnpackEntry {
   const float* src;  // gpack + offset, [rows, ld_src]
   float* dst;        // [rows, cols] contiguous
   int rows, cols, ld_src;
+  int perm_n;        // > 1: destination row r (column c for a vector) comes from source row (r % perm_n) * (rows / perm_n) + r / perm_n
 };
 int unpack_grads(const UnpackEntry* entries, int n, float scale, cudaStream_t st);
 

@@ -46,6 +46,8 @@ class HeadSpec:
     ln_eps: float = 1e-5
     bn_eps: float = 1e-5
     bn_momentum: float = 0.1
+    pool_kind: str = "lstp"     # "lstp" LearnableTokenPooling | "fwb" FIXED_WIDTH_BASELINE (FWBPooling on the CLS embedding)
+    cls_dim: int = 0            # fwb: width of the CLS embedding
 
 
 @dataclass
@@ -106,6 +108,8 @@ class Plan:
         d.gemm_backend = backend
         d.world_size = world
         d.pool_mode = pool_mode
+        d.pool_kind = L.POOLKIND[spec.pool_kind]
+        d.cls_dim = spec.cls_dim
         d.drop_p = spec.drop_p
         d.ln_eps, d.bn_eps, d.bn_momentum = spec.ln_eps, spec.bn_eps, spec.bn_momentum
         d.seed = 0
@@ -146,11 +150,13 @@ class Plan:
             cls._cache[key] = p
         return p
 
-    def desc_with_seed(self, seed: int, seed_dev: Optional[torch.Tensor] = None) -> L.HeadDesc:
+    def desc_with_seed(self, seed: int, seed_dev: Optional[torch.Tensor] = None,
+                       cls_emb: Optional[torch.Tensor] = None) -> L.HeadDesc:
         d = L.HeadDesc()
         C.memmove(C.byref(d), C.byref(self.desc), C.sizeof(L.HeadDesc))
         d.seed = seed
         d.seed_dev = None if seed_dev is None else seed_dev.data_ptr()
+        d.cls_emb = None if cls_emb is None else cls_emb.data_ptr()
         return d
 
     def lookup(self, name: str):
@@ -220,6 +226,7 @@ class CallState:
     want_attn: bool = False
     seed: int = 0
     seed_dev: Optional[torch.Tensor] = None   # device-resident int64 counter added to `seed` in the kernels (graph replay)
+    cls_emb: Optional[torch.Tensor] = None    # FIXED_WIDTH_BASELINE: [BV*T, cls_dim] fp32 CLS embeddings of the frames
     # filled by forward
     plan: Optional[Plan] = None
     head_save: Optional[torch.Tensor] = None
@@ -371,6 +378,18 @@ def _prep_tokens(tokens: torch.Tensor) -> torch.Tensor:
     return tokens.contiguous()
 
 
+def _prep_cls(cs: "CallState", frames: int) -> Optional[torch.Tensor]:
+    """FIXED_WIDTH_BASELINE input: contiguous fp32 [frames, cls_dim] on the device (kept on the call state for backward)."""
+    if cs.spec.pool_kind != "fwb":
+        return None
+    if cs.cls_emb is None:
+        raise ValueError("FIXED_WIDTH_BASELINE: the head needs cls_emb (the CLS embedding of every frame)")
+    c = cs.cls_emb.detach().reshape(frames, cs.spec.cls_dim).float().contiguous()
+    _require_cuda(c, "cls_emb")
+    cs.cls_emb = c
+    return c
+
+
 def _prep_mask(mask: Optional[torch.Tensor], BV: int, T: int, device) -> Optional[torch.Tensor]:
     if mask is None:
         return None
@@ -389,7 +408,7 @@ class HeadFn(torch.autograd.Function):
         with torch.cuda.device(tokens.device):
             plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _bn_world(cs.opts),
                             cs.opts.gemm_backend, cs.opts.pool_mode)
-            d = plan.desc_with_seed(cs.seed, cs.seed_dev)
+            d = plan.desc_with_seed(cs.seed, cs.seed_dev, _prep_cls(cs, BV * T))
             save = torch.empty(plan.save_bytes, dtype=torch.uint8, device=tokens.device)
             ws = _scratch(tokens.device, plan.ws_bytes, "head")
             out = torch.empty(BV, T, cs.spec.emb, dtype=torch.float32, device=tokens.device)
@@ -409,7 +428,7 @@ class HeadFn(torch.autograd.Function):
         mask = mask if ctx.has_mask else None
         plan = cs.plan
         with torch.cuda.device(tokens.device):
-            d = plan.desc_with_seed(ctx.seed, cs.seed_dev)
+            d = plan.desc_with_seed(ctx.seed, cs.seed_dev, cs.cls_emb)
             ws = _scratch(tokens.device, plan.ws_bytes, "head")
             gpack = torch.zeros(plan.gpack_elems, dtype=torch.float32, device=tokens.device)
             full = list(params) + [None] * (len(plan.param_names) - len(params))
@@ -474,7 +493,7 @@ class ModelFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             plan = Plan.get(cs.spec, BV, T, P, _mvf_dtype(tokens), cs.training, mask is not None, _bn_world(cs.opts),
                             cs.opts.gemm_backend, cs.opts.pool_mode)
-            d = plan.desc_with_seed(cs.seed, cs.seed_dev)
+            d = plan.desc_with_seed(cs.seed, cs.seed_dev, _prep_cls(cs, BV * T))
             save = torch.empty(plan.save_bytes, dtype=torch.uint8, device=dev)
             psave = torch.empty(plan.proj_save_bytes, dtype=torch.uint8, device=dev)
             ws = _scratch(dev, plan.ws_bytes, "head")
@@ -498,7 +517,7 @@ class ModelFn(torch.autograd.Function):
         plan = cs.plan
         dev = tokens.device
         with torch.cuda.device(dev):
-            d = plan.desc_with_seed(ctx.seed, cs.seed_dev)
+            d = plan.desc_with_seed(ctx.seed, cs.seed_dev, cs.cls_emb)
             ws = _scratch(dev, plan.ws_bytes, "head")
             pws = _scratch(dev, plan.proj_ws_bytes, "proj")
             gpack = torch.zeros(plan.gpack_elems, dtype=torch.float32, device=dev)

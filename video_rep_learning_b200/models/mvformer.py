@@ -47,7 +47,20 @@ def head_spec_from_cfg(cfg) -> engine.HeadSpec:
         final=str(_get(em, "SMART_FINAL", "max")),
         train_frames=int(cfg.TRAIN.NUM_FRAMES),
         drop_p=float(em.FC_DROPOUT_RATE),
+        pool_kind="fwb" if _get(em, "FIXED_WIDTH_BASELINE", False) else "lstp",
+        cls_dim=_cls_width(cfg) if _get(em, "FIXED_WIDTH_BASELINE", False) else 0,
     )
+
+
+def _cls_width(cfg) -> int:
+    """d_dyn_in of mvformer.py:226-232 / 441-447: OUT_CHANNEL divided by the number of SMART_FEATS layers."""
+    em = cfg.MODEL.EMBEDDER_MODEL
+    d = int(cfg.MODEL.BASE_MODEL.OUT_CHANNEL)
+    if "SMART_FEATS" in em:
+        sfl = str(em.SMART_FEATS)
+        if "," in sfl:
+            d = int(d / len(sfl.split(",")))
+    return d
 
 
 class LSTPCrossAtt(_FusedOnly):
@@ -107,6 +120,21 @@ class LearnableTokenPooling(_FusedOnly):
                                       d_model_V=self.in_c, d_model=self.spc, d_dyn_in=d_dyn_in)
 
 
+class FWBPooling(_FusedOnly):
+    """FIXED_WIDTH_BASELINE (mvformer.py:421-462): `lin_conv` maps the CLS embedding of a frame to SPC * tokens channels;
+    parameter container only -- the product runs inside the fused head (csrc/head.cu, pool_kind FWB)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        em = cfg.MODEL.EMBEDDER_MODEL
+        self.nst = int(_get(em, "SMART_TOKENS", 5))
+        self.nsdt = int(_get(em, "SMART_DYNAMIC_TOKENS", 0))
+        self.spc = int(_get(em, "SMART_POOL_CHANNELS", 384))
+        self.in_c = int(cfg.MODEL.BASE_MODEL.OUT_CHANNEL)
+        self.lin_conv = nn.Linear(_cls_width(cfg), self.spc * (self.nst + self.nsdt))
+
+
 class MultiEntityTransformerEmbModel(nn.Module):
     """Drop-in for CARL_MVF/models/mvformer.py:15 (`model.embed`)."""
 
@@ -125,14 +153,14 @@ class MultiEntityTransformerEmbModel(nn.Module):
         if self.one_hot_pos == "pool":
             in_channels += self.nst + self.nsdt
         self.fwb = bool(_get(em, "FIXED_WIDTH_BASELINE", False))
-        if self.fwb:
-            raise NotImplementedError(f"FIXED_WIDTH_BASELINE is {_NEXT_ROUND}")
+        if self.fwb and self.nsdt > 0:
+            raise NotImplementedError(f"FIXED_WIDTH_BASELINE with SMART_DYNAMIC_TOKENS > 0 is {_NEXT_ROUND}")
         cap_scalar = em.CAPACITY_SCALAR
         fc_params = em.FC_LAYERS if "FC_LAYERS" in em else None
         self.embedding_size = em.EMBEDDING_SIZE
         hidden_channels = em.HIDDEN_SIZE
 
-        self.pooling = LearnableTokenPooling(cfg)
+        self.pooling = FWBPooling(cfg) if self.fwb else LearnableTokenPooling(cfg)
         if fc_params is None:
             self.fc_layers = nn.Identity()
         else:
@@ -204,6 +232,8 @@ class MultiEntityTransformerEmbModel(nn.Module):
 
     def _publish_attention(self, cs: engine.CallState, BV: int, T: int, P: int):
         """attn_matrix of the LAST video-view, [T, E, P], pushed through attn_holder for forward hooks."""
+        if self.fwb:
+            return                           # no attention maps: the patch tokens are not used
         ca = self.pooling.cross_att
         if not ca.visual or cs.head_save is None:
             return
@@ -211,18 +241,19 @@ class MultiEntityTransformerEmbModel(nn.Module):
         ca.attn_matrix = attn[-1].detach()
         ca.attn_holder(ca.attn_matrix)
 
-    def make_call_state(self, project: bool = False) -> engine.CallState:
+    def make_call_state(self, project: bool = False, cls_emb=None) -> engine.CallState:
         running, tracked = self.bn_buffers()
         training = self.training
         seed = engine.new_seed() if (training and self.spec.drop_p > 0) else 0
         return engine.CallState(spec=self.spec, opts=self.run_options, training=training, bn_running=running,
                                 bn_tracked=tracked, project=project, seed=seed,
-                                seed_dev=self.seed_dev if (training and self.spec.drop_p > 0) else None)
+                                seed_dev=self.seed_dev if (training and self.spec.drop_p > 0) else None,
+                                cls_emb=cls_emb if self.fwb else None)
 
     def forward(self, x, video_masks=None, cls_emb=None):
         tokens = self.to_token_major(x.detach())
         BV, T, P, _ = tokens.shape
-        cs = self.make_call_state()
+        cs = self.make_call_state(cls_emb=cls_emb)
         out = engine.HeadFn.apply(tokens, video_masks, cs, *self.head_params())
         self.last_call = cs
         self._publish_attention(cs, BV, T, P)

@@ -101,12 +101,15 @@ class TransformerModel(nn.Module):
     def run_options(self) -> engine.RunOptions:
         return self.embed.run_options
 
-    def backbone_tokens(self, x: torch.Tensor) -> torch.Tensor:
+    def backbone_tokens(self, x: torch.Tensor, with_cls: bool = False):
         """frames [BV,T,3,H,W] -> patch tokens [BV,T,P,C_in] (token-major, CLS dropped), chunked over frames like
-        transformer.py:175-189 (FRAMES_PER_BATCH), backbone in eval mode under no_grad."""
+        transformer.py:175-189 (FRAMES_PER_BATCH), backbone in eval mode under no_grad.  with_cls: also the CLS embeddings
+        [BV*T, C] concatenated chunk by chunk exactly as transformer.py:200,217 does (chunk-major rows -- with T >
+        FRAMES_PER_BATCH that differs from the video-major order the head assumes; the reference's own behaviour is kept)."""
         BV, T, c, h, w = x.shape
         fpb = self.cfg.MODEL.BASE_MODEL.FRAMES_PER_BATCH
         out = None
+        cls_chunks = []
         self.backbone.eval()
         for i in range(int(math.ceil(float(T) / fpb))):
             t0 = i * fpb
@@ -115,26 +118,37 @@ class TransformerModel(nn.Module):
             with torch.no_grad():
                 toks, _cls = self.backbone(cur)
             toks = self.res_finetune(toks)
+            if with_cls:
+                cls_chunks.append(_cls)
             n, ntok, C = toks.shape
             if out is None:
                 out = torch.empty(BV, T, ntok - 1, C, dtype=toks.dtype, device=toks.device)
             out[:, t0:t1] = toks[:, 1:, :].reshape(BV, t1 - t0, ntok - 1, C)   # drop CLS, keep token-major
+        if with_cls:
+            return out, torch.cat(cls_chunks, dim=0)
         return out
 
     def forward(self, x, num_frames=None, video_masks=None, project=False, classification=False):
         if classification:
             raise NotImplementedError("classification head is out of scope")
-        tokens = self.backbone_tokens(x) if x.dim() == 5 and x.shape[2] == 3 else self.embed.to_token_major(x)
-        return self.forward_tokens(tokens, video_masks=video_masks, project=project)
+        cls_emb = None
+        if x.dim() == 5 and x.shape[2] == 3:
+            if self.embed.fwb:
+                tokens, cls_emb = self.backbone_tokens(x, with_cls=True)
+            else:
+                tokens = self.backbone_tokens(x)
+        else:
+            tokens = self.embed.to_token_major(x)
+        return self.forward_tokens(tokens, video_masks=video_masks, project=project, cls_emb=cls_emb)
 
-    def forward_tokens(self, tokens, video_masks=None, project=False):
+    def forward_tokens(self, tokens, video_masks=None, project=False, cls_emb=None):
         """The hot path proper: patch tokens [BV,T,P,C_in] -> embeddings [BV,T,D] (transformer.py:219-230)."""
         cfg = self.cfg
         BV, T, P, _ = tokens.shape
         use_proj = bool(cfg.MODEL.PROJECTION and project)
         if not use_proj and not cfg.MODEL.L2_NORMALIZE:
-            return self.embed(tokens, video_masks=video_masks)
-        cs = self.embed.make_call_state(project=1 if use_proj else 0)
+            return self.embed(tokens, video_masks=video_masks, cls_emb=cls_emb)
+        cs = self.embed.make_call_state(project=1 if use_proj else 0, cls_emb=cls_emb)
         params = list(self.embed.head_params())
         if cfg.MODEL.PROJECTION:
             params += self.ssl_projection.proj_params()
