@@ -13,13 +13,13 @@ from oracle import mvf_oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def meta():
-    with open(os.path.join(GOLDEN, "meta.json")) as f:
+def meta(fname="meta.json"):
+    with open(os.path.join(GOLDEN, fname)) as f:
         return json.load(f)
 
 
-def load_case(name):
-    m = meta()["cases"][name]
+def load_case(name, meta_file="meta.json"):
+    m = meta(meta_file)["cases"][name]
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     kw = dict(m["head_cfg"])
     kw["fc_channels"] = tuple(kw["fc_channels"])
@@ -36,7 +36,8 @@ def spec_from_headcfg(hc: O.HeadCfg, drop_p: Optional[float] = None):
                            fc_channels=tuple(hc.fc_channels), hidden=hc.hidden, d_ff=hc.d_ff, n_heads=hc.n_heads,
                            n_layers=hc.n_layers, emb=hc.emb, proj=hc.proj, one_hot=hc.one_hot, final=hc.final,
                            train_frames=hc.train_frames, drop_p=hc.drop_p if drop_p is None else drop_p,
-                           ln_eps=hc.ln_eps, bn_eps=hc.bn_eps, bn_momentum=hc.bn_momentum)
+                           ln_eps=hc.ln_eps, bn_eps=hc.bn_eps, bn_momentum=hc.bn_momentum,
+                           pool_kind=getattr(hc, "pool_kind", "lstp"), cls_dim=getattr(hc, "cls_dim", 0))
 
 
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
@@ -50,7 +51,7 @@ def grad_vector(g: Dict[str, torch.Tensor], keys):
 
 def run_cuda(hc: O.HeadCfg, P: Dict[str, torch.Tensor], buf: Optional[Dict[str, torch.Tensor]], tokens, masks, seq_lens,
              steps, *, dtype=torch.float32, negative_type="single_noself", training=True, drop_p=0.0, seed=0,
-             backend=0, quirk=True, project=True, device="cuda", pool_mode=0):
+             backend=0, quirk=True, project=True, device="cuda", pool_mode=0, cls_emb=None):
     """One step of the CUDA path through engine.ModelFn + engine.SCLFn.  Returns a dict with emb (head output),
     e (normalised projection), loss, grads (by reference state_dict name), new BN buffers, the CallState."""
     from video_rep_learning_b200 import engine
@@ -66,7 +67,8 @@ def run_cuda(hc: O.HeadCfg, P: Dict[str, torch.Tensor], buf: Optional[Dict[str, 
         tracked.append(buf[pre + ".num_batches_tracked"].to(dev).clone())
     opts = engine.RunOptions(gemm_backend=backend, scl_quirk=quirk, pool_mode=pool_mode)
     cs = engine.CallState(spec=spec, opts=opts, training=training, bn_running=running, bn_tracked=tracked,
-                          project=1 if project else 0, seed=seed)
+                          project=1 if project else 0, seed=seed,
+                          cls_emb=None if cls_emb is None else cls_emb.to(dev).float())
     tok = tokens.to(dev).to(dtype)
     m = None if masks is None else masks.to(dev)
     out = engine.ModelFn.apply(tok, m, cs, *params)
@@ -91,18 +93,18 @@ def run_cuda(hc: O.HeadCfg, P: Dict[str, torch.Tensor], buf: Optional[Dict[str, 
 
 
 def run_oracle(hc: O.HeadCfg, P, buf, tokens, masks, seq_lens, steps, *, dtype=torch.float64,
-               negative_type="single_noself", drop_masks=None):
+               negative_type="single_noself", drop_masks=None, cls_emb=None):
     Pr = {k: v.clone().to(dtype).requires_grad_(True) for k, v in P.items()}
     b2 = None if buf is None else {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in buf.items()}
     emb, nb, aux = O.head_forward(Pr, b2, tokens.to(dtype), None if masks is None else masks.to(dtype), hc, True,
-                                  drop_masks, return_aux=True)
+                                  drop_masks, return_aux=True, cls_emb=None if cls_emb is None else cls_emb.to(dtype))
     e, nb2 = O.proj_forward(Pr, b2, emb, hc, True)
     nb.update(nb2)
     Bv, T = tokens.shape[0] // 2, tokens.shape[1]
     loss = O.scl_loss_dense(e.view(Bv, 2, T, -1), seq_lens, steps, masks.to(dtype), negative_type=negative_type)
     loss.backward()
     return dict(emb=emb.detach(), e=e.detach(), loss=loss.detach(), grads={k: v.grad for k, v in Pr.items()}, bufs=nb,
-                aux={k: v.detach() for k, v in aux.items()})
+                aux={k: v.detach() for k, v in aux.items() if v is not None})
 
 
 def run_oracle_quantized(hc, P, tokens, masks, seq_lens, steps, negative_type="single_noself", kv_bf16=True):

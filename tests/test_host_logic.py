@@ -98,12 +98,20 @@ def test_seeded_init_identical_to_reference(yml_like):
 
 
 def test_unsupported_branches_fail_loudly():
-    for key, val in (("SMART_DYNAMIC_TOKENS", 2), ("VAL_PASS", True), ("SMART_DISJOINT", True), ("SMART_LN_KEYS", True),
-                     ("FIXED_WIDTH_BASELINE", True)):
+    for key, val in (("SMART_DYNAMIC_TOKENS", 2), ("VAL_PASS", True), ("SMART_DISJOINT", True), ("SMART_LN_KEYS", True)):
         cfg = small_cfg()
         cfg.MODEL.EMBEDDER_MODEL[key] = val
         with pytest.raises(NotImplementedError):
             MultiEntityTransformerEmbModel(cfg)
+    # FIXED_WIDTH_BASELINE (configs_mvf/ablate_dinoB8_fwb{3,5}.yml) is built: FWBPooling.lin_conv replaces the cross-attention
+    cfg = small_cfg()
+    cfg.MODEL.EMBEDDER_MODEL.FIXED_WIDTH_BASELINE = True
+    fwb = MultiEntityTransformerEmbModel(cfg)
+    keys = set(fwb.state_dict().keys())
+    assert "pooling.lin_conv.weight" in keys and not any("cross_att" in k for k in keys)
+    assert fwb.spec.pool_kind == "fwb" and fwb.spec.cls_dim > 0
+    assert tuple(fwb.pooling.lin_conv.weight.shape) == (fwb.spec.pool_channels * fwb.spec.n_entities, fwb.spec.cls_dim)
+    assert fwb.head_param_names()[:2] == ["pooling.lin_conv.weight", "pooling.lin_conv.bias"]
     with pytest.raises(NotImplementedError):
         MultiEntityTransformerEmbModel(small_cfg(one_hot="enc"))
     cfg = small_cfg()

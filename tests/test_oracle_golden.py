@@ -127,3 +127,17 @@ def test_oracle_against_live_reference():
     assert abs(float(o["loss"]) - float(loss)) / float(loss) < 1e-5
     keys = list(P.keys())
     assert H.rel_l2(H.grad_vector(o["grads"], keys), H.grad_vector(g, keys)) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["f2_fwb", "f2_fwb_e5_avg"])
+def test_oracle_matches_reference_golden_optional_branches(name):
+    """SURVEY.md section 8f-2 branches: the oracle restatement against reference-generated fixtures (make_golden_f2.py)."""
+    m, hc, z, P, G, B = H.load_case(name, "meta_f2.json")
+    tokens, masks = torch.from_numpy(z["tokens"]), torch.from_numpy(z["masks"])
+    seq_lens, steps = torch.from_numpy(z["seq_lens"]), torch.from_numpy(z["steps"])
+    cls_emb = torch.from_numpy(z["cls_emb"]) if "cls_emb" in z.files else None
+    o = H.run_oracle(hc, P, None, tokens, masks, seq_lens, steps, dtype=torch.float64, cls_emb=cls_emb)
+    keys = list(P.keys())
+    assert H.rel_l2(o["e"], torch.from_numpy(z["ref_e"])) < 1e-5
+    assert abs(float(o["loss"]) - float(z["ref_loss"])) / float(z["ref_loss"]) < 1e-5
+    assert H.rel_l2(H.grad_vector(o["grads"], keys), H.grad_vector(G, keys)) < 1e-5

@@ -64,10 +64,6 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// shared-state-space accesses by 32-bit address (generic-pointer stores to shared memory go through the L1TEX address path)
-__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -588,10 +584,10 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 // backward, rows = keys: dK, dV
 // =====================================================================================================================
 constexpr int DKV_THREADS = 320;   // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 columns 0..31, warps 6..9 columns 32..63
-constexpr int DKV_NS = 4;
+constexpr int DKV_NS = 3;
 constexpr int DKV_STAGE = 2 * T64 + 512;    // bytes landing per stage: Q, G tiles (row-split) | L2[64], D[64]
 constexpr int DKV_PITCH = 2 * T64 + 1024;   // keeps every tile of every stage 1024-byte aligned
-constexpr int DKV_SMEM = 2 * T128 + DKV_NS * DKV_PITCH + 4 * T128;   // K, V | ring | P^T hi, lo, dS^T hi, lo
+constexpr int DKV_SMEM = 2 * T128 + DKV_NS * DKV_PITCH + 8 * T128;   // K, V | ring | 2 x (P^T hi, lo, dS^T hi, lo)
 
 __global__ void __launch_bounds__(DKV_THREADS, 1)
 fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -600,20 +596,18 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;
   uint8_t* sV = sK + T128;
-  uint8_t* sSt = sV + T128;                 // [4] stages
-  uint8_t* sPh = sSt + DKV_NS * DKV_PITCH;
-  uint8_t* sPl = sPh + T128;
-  uint8_t* sDh = sPl + T128;
-  uint8_t* sDl = sDh + T128;
-  uint64_t* bars = (uint64_t*)(sDl + T128);
+  uint8_t* sSt = sV + T128;                 // [DKV_NS] stages
+  uint8_t* sPD = sSt + DKV_NS * DKV_PITCH;  // [2] x (P^T hi | P^T lo | dS^T hi | dS^T lo): the softmax warps fill one set
+                                            // while the dV / dK products of the previous tile still read the other
+  uint64_t* bars = (uint64_t*)(sPD + 8 * T128);
   uint64_t* kv_full = bars;
-  uint64_t* t_full = bars + 1;              // [4]
-  uint64_t* t_empty = t_full + DKV_NS;      // [4]
+  uint64_t* t_full = bars + 1;              // [DKV_NS]
+  uint64_t* t_empty = t_full + DKV_NS;      // [DKV_NS]
   uint64_t* sd_full = t_empty + DKV_NS;     // [2]
   uint64_t* sd_empty = sd_full + 2;         // [2]
-  uint64_t* pd_full = sd_empty + 2;
-  uint64_t* pd_empty = pd_full + 1;
-  uint64_t* acc_full = pd_empty + 1;
+  uint64_t* pd_full = sd_empty + 2;         // [2]
+  uint64_t* pd_empty = pd_full + 2;         // [2]
+  uint64_t* acc_full = pd_empty + 2;
   uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -631,7 +625,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
     mbar_init(kv_full, 1);
     for (int i = 0; i < DKV_NS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sd_full[i], 1); mbar_init(&sd_empty[i], 8); }
-    mbar_init(pd_full, 256); mbar_init(pd_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&pd_full[i], 256); mbar_init(&pd_empty[i], 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -678,14 +672,15 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
       issue_sd(0);
       for (int j = 0; j < nq; ++j) {
         if (j + 1 < nq) issue_sd(j + 1);
-        const int st = j % DKV_NS;
+        const int st = j % DKV_NS, pb = j & 1;
         uint8_t* s = sSt + st * DKV_PITCH;
-        mbar_wait(pd_full, j & 1, 34);
+        const uint32_t pd = smem_u32(sPD + pb * 4 * T128);
+        mbar_wait(&pd_full[pb], (j >> 1) & 1, 34);
         tcgen05_fence_after();
-        mma_tokens(tmem_base + 4 * BK + 64, smem_u32(sPh), smem_u32(sPl), smem_u32(s + T64), idesc_o, j > 0);   // dV += P^T dO
-        mma_tokens(tmem_base + 4 * BK, smem_u32(sDh), smem_u32(sDl), smem_u32(s), idesc_o, j > 0);            // dK += dS^T Q
+        mma_tokens(tmem_base + 4 * BK + 64, pd, pd + T128, smem_u32(s + T64), idesc_o, j > 0);            // dV += P^T dO
+        mma_tokens(tmem_base + 4 * BK, pd + 2 * T128, pd + 3 * T128, smem_u32(s), idesc_o, j > 0);        // dK += dS^T Q
         umma_commit(&t_empty[st]);
-        umma_commit(pd_empty);
+        umma_commit(&pd_empty[pb]);
       }
       umma_commit(acc_full);
     }
@@ -695,7 +690,6 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
     const int row = q * 32 + lane;
     const int ki = k0 + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t aPh = smem_u32(sPh), aPl = smem_u32(sPl), aDh = smem_u32(sDh), aDl = smem_u32(sDl);
     const float scale = rsqrtf((float)DK), scale2 = scale * LOG2E;
     const bool key_ok = ki < p.S && ((__ldg(p.maskbits + (int64_t)b * p.mask_words + (ki >> 5)) >> (ki & 31)) & 1u);
     const bool all_ok = __all_sync(0xffffffffu, key_ok);   // warp-uniform: no per-element selects for fully valid warps
@@ -733,14 +727,16 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
         split8(pv, ph[ch], pl[ch]);
         split8(dv, dh[ch], dl[ch]);
       }
-      mbar_wait(pd_empty, (j & 1) ^ 1, 36);   // the dV / dK products of the previous tile have released the P^T / dS^T tiles
+      const int pb = j & 1;
+      const uint32_t aPh = smem_u32(sPD + pb * 4 * T128), aPl = aPh + T128, aDh = aPh + 2 * T128, aDl = aPh + 3 * T128;
+      mbar_wait(&pd_empty[pb], ((j >> 1) & 1) ^ 1, 36);   // the dV / dK products of tile j - 2 have released this tile set
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         store_chunk(aPh, aPl, row, wg * 4 + ch, ph[ch], pl[ch]);
         store_chunk(aDh, aDl, row, wg * 4 + ch, dh[ch], dl[ch]);
       }
       fence_proxy_async_smem();
-      mbar_arrive(pd_full);
+      mbar_arrive(&pd_full[pb]);
     }
     mbar_wait(acc_full, 0, 37);
     tcgen05_fence_after();

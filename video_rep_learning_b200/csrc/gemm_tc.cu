@@ -221,15 +221,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int conv_rows = p.b_presplit ? BLOCK_M : BLOCK_M + BLOCK_N;
 #pragma unroll 1
         for (int r = ct; r < conv_rows; r += NUM_THREADS_SPLIT - NUM_THREADS) {
-          uint4* rowp = reinterpret_cast<uint4*>(tile + r * ROW_BYTES);
+          const uint32_t rowa = smem_u32(tile + r * ROW_BYTES);
           const int sw = r & 7;
-          float4 v[8];
+          uint4 v[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(rowp + (c ^ sw));
+          for (int c = 0; c < 8; ++c) v[c] = lds128(rowa + ((c ^ sw) << 4));
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float x[8] = {v[2 * c].x, v[2 * c].y, v[2 * c].z, v[2 * c].w,
-                                v[2 * c + 1].x, v[2 * c + 1].y, v[2 * c + 1].z, v[2 * c + 1].w};
+            const float x[8] = {__uint_as_float(v[2 * c].x), __uint_as_float(v[2 * c].y), __uint_as_float(v[2 * c].z),
+                                __uint_as_float(v[2 * c].w), __uint_as_float(v[2 * c + 1].x), __uint_as_float(v[2 * c + 1].y),
+                                __uint_as_float(v[2 * c + 1].z), __uint_as_float(v[2 * c + 1].w)};
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -239,8 +240,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               hi[j] = *reinterpret_cast<const uint32_t*>(&h);
               lo[j] = *reinterpret_cast<const uint32_t*>(&l);
             }
-            rowp[c ^ sw] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            rowp[(4 + c) ^ sw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            sts128(rowa + ((c ^ sw) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            sts128(rowa + (((4 + c) ^ sw) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
           }
         }
         fence_proxy_async_smem();
@@ -337,8 +338,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              sts128(smem_u32(sb) + lane * 128 + ((j ^ (lane & 7)) << 4),
+                     make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                __float_as_uint(v[4 * j + 3])));
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
