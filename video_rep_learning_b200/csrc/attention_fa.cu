@@ -191,6 +191,26 @@ __device__ __forceinline__ void mma_tokens(uint32_t tmem_d, uint32_t sa_hi, uint
   }
 }
 
+// the same product with the probabilities in TENSOR MEMORY (A operand of the "TS" MMA form): ta_hi / ta_lo = TMEM column of
+// the packed bf16 pairs (32 columns for 64 tokens; 8 columns per K = 16 step), written there by the softmax warps with
+// tcgen05.st -- no shared-memory store by 128 threads, no shared-memory operand read by the tensor core for A
+__device__ __forceinline__ void mma_tokens_ts(uint32_t tmem_d, uint32_t ta_hi, uint32_t ta_lo, uint32_t sb, uint32_t idesc, bool accumulate) {
+  const uint64_t db = make_smem_desc(sb, false, 64, 2);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t ob = (uint64_t)(128 * k);
+    umma_ts_f16(tmem_d, ta_lo + 8 * k, db + ob, idesc, (accumulate || k > 0) ? 1u : 0u);
+    umma_ts_f16(tmem_d, ta_hi + 8 * k, db + ob, idesc, 1u);
+  }
+}
+// eight fp32 values -> four packed bf16 pairs of the hi part and of the lo part
+__device__ __forceinline__ void split8u(const float* v, uint32_t* h, uint32_t* l) {
+  split2(v[0], v[1], h[0], l[0]);
+  split2(v[2], v[3], h[1], l[1]);
+  split2(v[4], v[5], h[2], l[2]);
+  split2(v[6], v[7], h[3], l[3]);
+}
+
 struct Params {
   int S, Sq, heads, H;
   int mask_words;
@@ -209,6 +229,7 @@ constexpr int FWD_THREADS = 192;   // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 
 constexpr int FWD_NK = 3, FWD_NV = 3;
 constexpr int FWD_SMEM = T128 + (FWD_NK + FWD_NV) * T64 + 2 * T128;   // Q | K ring | V ring | P hi, lo
 
+template <bool ATM>   // ATM: probabilities handed to the tensor core through tensor memory instead of shared memory
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
               const __grid_constant__ CUtensorMap map_v, const Params p) {
@@ -258,7 +279,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;   // columns: S0 [0,64) | S1 [64,128) | PV [128,192)
+  const uint32_t tmem_base = *tmem_slot;   // columns: S0 [0,64) | S1 [64,128) | PV [128,192) | P hi [192,224) | P lo [224,256)
   pdl_entry();
 
   if (warp == 0) {
@@ -295,7 +316,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         mbar_wait(p_full, j & 1, 15);
         mbar_wait(&v_full[sv], (j / FWD_NV) & 1, 16);
         tcgen05_fence_after();
-        mma_tokens(tmem_base + 2 * BK, smem_u32(sPh), smem_u32(sPl), smem_u32(sV + sv * T64), idesc_o, false);
+        if constexpr (ATM) mma_tokens_ts(tmem_base + 2 * BK, tmem_base + 192, tmem_base + 224, smem_u32(sV + sv * T64), idesc_o, false);
+        else mma_tokens(tmem_base + 2 * BK, smem_u32(sPh), smem_u32(sPl), smem_u32(sV + sv * T64), idesc_o, false);
         umma_commit(&v_empty[sv]);
         umma_commit(o_full);
       }
@@ -362,16 +384,31 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
         tcgen05_fence_before();
       }
+      if constexpr (ATM) {
+        // r[0..31] <- hi pairs, r[32..63] <- lo pairs (pair c = keys 2c, 2c+1), in place: pair c only reads r[2c], r[2c+1]
+        uint32_t lo[32];
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        float v[8];
+        for (int c = 0; c < 32; ++c) {
+          uint32_t hh;
+          split2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1]), hh, lo[c]);
+          r[c] = hh;
+        }
+        tmem_st32(lane_addr + 192, r);
+        tmem_st32(lane_addr + 224, lo);
+        tmem_st_wait();
+        tcgen05_fence_before();
+      } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * ch + e]);
-        uint4 hh, ll;
-        split8(v, hh, ll);
-        store_chunk(aPh, aPl, row, ch, hh, ll);
+        for (int ch = 0; ch < 8; ++ch) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * ch + e]);
+          uint4 hh, ll;
+          split8(v, hh, ll);
+          store_chunk(aPh, aPl, row, ch, hh, ll);
+        }
+        fence_proxy_async_smem();
       }
-      fence_proxy_async_smem();
       mbar_arrive(p_full);
       alpha_prev = alpha;
     }
@@ -412,6 +449,7 @@ constexpr int DQ_THREADS = 192;
 constexpr int DQ_NK = 3, DQ_NV = 2;   // K tiles live until the dQ product of their tile, V tiles only until dP
 constexpr int DQ_SMEM = 2 * T128 + (DQ_NK + DQ_NV) * T64 + 2 * T128;   // Q, G | K ring | V ring | dS hi, lo
 
+template <bool ATM>
 __global__ void __launch_bounds__(DQ_THREADS, 2)
 fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g,
                  const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, const Params p) {
@@ -464,7 +502,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;   // columns: S [0,64) | dP [64,128) | dQ [128,192)
+  const uint32_t tmem_base = *tmem_slot;   // columns: S [0,64) | dP [64,128) | dQ [128,192) | dS hi [192,224) | dS lo [224,256)
   pdl_entry();
 
   if (warp == 0) {
@@ -503,7 +541,8 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int sk = j % DQ_NK;
         mbar_wait(ds_full, j & 1, 26);
         tcgen05_fence_after();
-        mma_tokens(tmem_base + 2 * BK, smem_u32(sDh), smem_u32(sDl), smem_u32(sK + sk * T64), idesc_o, j > 0);   // dQ += dS K
+        if constexpr (ATM) mma_tokens_ts(tmem_base + 2 * BK, tmem_base + 192, tmem_base + 224, smem_u32(sK + sk * T64), idesc_o, j > 0);
+        else mma_tokens(tmem_base + 2 * BK, smem_u32(sDh), smem_u32(sDl), smem_u32(sK + sk * T64), idesc_o, j > 0);   // dQ += dS K
         umma_commit(&k_empty[sk]);
         umma_commit(ds_empty);
       }
@@ -524,7 +563,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     for (int j = 0; j < nt; ++j) {
       mbar_wait(sd_full, j & 1, 27);
       tcgen05_fence_after();
-      uint4 hh[8], ll[8];
+      uint32_t hh[32], ll[32];   // packed bf16 pairs of dS: pair c = keys 2c, 2c+1
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t rs_[32], rp[32];
@@ -548,13 +587,23 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (!full) pw = ((w >> c) & 1u) ? pw : 0.f;
             v[e] = pw * fmaf(__uint_as_float(rp[c]), scale, Dn);
           }
-          split8(v, hh[half * 4 + ch], ll[half * 4 + ch]);
+          split8u(v, hh + 4 * (half * 4 + ch), ll + 4 * (half * 4 + ch));
         }
       }
       mbar_wait(ds_empty, (j & 1) ^ 1, 28);   // the dQ product of the previous tile has released the dS tiles
+      if constexpr (ATM) {
+        tcgen05_fence_after();
+        tmem_st32(lane_addr + 192, hh);
+        tmem_st32(lane_addr + 224, ll);
+        tmem_st_wait();
+        tcgen05_fence_before();
+      } else {
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) store_chunk(aDh, aDl, row, ch, hh[ch], ll[ch]);
-      fence_proxy_async_smem();
+        for (int ch = 0; ch < 8; ++ch)
+          store_chunk(aDh, aDl, row, ch, make_uint4(hh[4 * ch], hh[4 * ch + 1], hh[4 * ch + 2], hh[4 * ch + 3]),
+                      make_uint4(ll[4 * ch], ll[4 * ch + 1], ll[4 * ch + 2], ll[4 * ch + 3]));
+        fence_proxy_async_smem();
+      }
       mbar_arrive(ds_full);
     }
     mbar_wait(acc_full, 0, 29);
@@ -589,6 +638,7 @@ constexpr int DKV_STAGE = 2 * T64 + 512;    // bytes landing per stage: Q, G til
 constexpr int DKV_PITCH = 2 * T64 + 1024;   // keeps every tile of every stage 1024-byte aligned
 constexpr int DKV_SMEM = 2 * T128 + DKV_NS * DKV_PITCH + 8 * T128;   // K, V | ring | 2 x (P^T hi, lo, dS^T hi, lo)
 
+template <bool ATM>
 __global__ void __launch_bounds__(DKV_THREADS, 1)
 fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                   const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g, const Params p) {
@@ -636,7 +686,8 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;   // columns: [S^T | dP^T] x 2 buffers = [0,256) | dK [256,320) | dV [320,384)
+  // columns: [S^T | dP^T] x 2 buffers = [0,256) | dK [256,320) | dV [320,384) | ATM: P^T hi, lo [384,448) | dS^T hi, lo [448,512)
+  const uint32_t tmem_base = *tmem_slot;
   pdl_entry();
 
   if (warp == 0) {
@@ -675,12 +726,21 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
         const int st = j % DKV_NS, pb = j & 1;
         uint8_t* s = sSt + st * DKV_PITCH;
         const uint32_t pd = smem_u32(sPD + pb * 4 * T128);
-        mbar_wait(&pd_full[pb], (j >> 1) & 1, 34);
-        tcgen05_fence_after();
-        mma_tokens(tmem_base + 4 * BK + 64, pd, pd + T128, smem_u32(s + T64), idesc_o, j > 0);            // dV += P^T dO
-        mma_tokens(tmem_base + 4 * BK, pd + 2 * T128, pd + 3 * T128, smem_u32(s), idesc_o, j > 0);        // dK += dS^T Q
-        umma_commit(&t_empty[st]);
-        umma_commit(&pd_empty[pb]);
+        if constexpr (ATM) {   // one probability set in tensor memory: barriers [0] only, one completion per tile
+          mbar_wait(&pd_full[0], j & 1, 34);
+          tcgen05_fence_after();
+          mma_tokens_ts(tmem_base + 4 * BK + 64, tmem_base + 384, tmem_base + 416, smem_u32(s + T64), idesc_o, j > 0);   // dV += P^T dO
+          mma_tokens_ts(tmem_base + 4 * BK, tmem_base + 448, tmem_base + 480, smem_u32(s), idesc_o, j > 0);              // dK += dS^T Q
+          umma_commit(&t_empty[st]);
+          umma_commit(&pd_empty[0]);
+        } else {
+          mbar_wait(&pd_full[pb], (j >> 1) & 1, 34);
+          tcgen05_fence_after();
+          mma_tokens(tmem_base + 4 * BK + 64, pd, pd + T128, smem_u32(s + T64), idesc_o, j > 0);            // dV += P^T dO
+          mma_tokens(tmem_base + 4 * BK, pd + 2 * T128, pd + 3 * T128, smem_u32(s), idesc_o, j > 0);        // dK += dS^T Q
+          umma_commit(&t_empty[st]);
+          umma_commit(&pd_empty[pb]);
+        }
       }
       umma_commit(acc_full);
     }
@@ -706,7 +766,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sd_empty[tb]);
-      uint4 ph[4], pl[4], dh[4], dl[4];
+      uint32_t ph[16], pl[16], dh[16], dl[16];   // packed bf16 pairs of this warpgroup's 32 queries
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         float pv[8], dv[8];
@@ -724,19 +784,33 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
             dv[4 * e4 + e] = pw * fmaf(__uint_as_float(rp[c]), scale, -Dx[e]);
           }
         }
-        split8(pv, ph[ch], pl[ch]);
-        split8(dv, dh[ch], dl[ch]);
+        split8u(pv, ph + 4 * ch, pl + 4 * ch);
+        split8u(dv, dh + 4 * ch, dl + 4 * ch);
       }
-      const int pb = j & 1;
-      const uint32_t aPh = smem_u32(sPD + pb * 4 * T128), aPl = aPh + T128, aDh = aPh + 2 * T128, aDl = aPh + 3 * T128;
-      mbar_wait(&pd_empty[pb], ((j >> 1) & 1) ^ 1, 36);   // the dV / dK products of tile j - 2 have released this tile set
+      if constexpr (ATM) {
+        mbar_wait(&pd_empty[0], (j & 1) ^ 1, 36);   // the dV / dK products of the previous tile have read the probabilities
+        tcgen05_fence_after();
+        tmem_st16(lane_addr + 384 + wg * 16, ph);
+        tmem_st16(lane_addr + 416 + wg * 16, pl);
+        tmem_st16(lane_addr + 448 + wg * 16, dh);
+        tmem_st16(lane_addr + 480 + wg * 16, dl);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&pd_full[0]);
+      } else {
+        const int pb = j & 1;
+        const uint32_t aPh = smem_u32(sPD + pb * 4 * T128), aPl = aPh + T128, aDh = aPh + 2 * T128, aDl = aPh + 3 * T128;
+        mbar_wait(&pd_empty[pb], ((j >> 1) & 1) ^ 1, 36);   // the dV / dK products of tile j - 2 have released this tile set
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        store_chunk(aPh, aPl, row, wg * 4 + ch, ph[ch], pl[ch]);
-        store_chunk(aDh, aDl, row, wg * 4 + ch, dh[ch], dl[ch]);
+        for (int ch = 0; ch < 4; ++ch) {
+          store_chunk(aPh, aPl, row, wg * 4 + ch, make_uint4(ph[4 * ch], ph[4 * ch + 1], ph[4 * ch + 2], ph[4 * ch + 3]),
+                      make_uint4(pl[4 * ch], pl[4 * ch + 1], pl[4 * ch + 2], pl[4 * ch + 3]));
+          store_chunk(aDh, aDl, row, wg * 4 + ch, make_uint4(dh[4 * ch], dh[4 * ch + 1], dh[4 * ch + 2], dh[4 * ch + 3]),
+                      make_uint4(dl[4 * ch], dl[4 * ch + 1], dl[4 * ch + 2], dl[4 * ch + 3]));
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&pd_full[pb]);
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&pd_full[pb]);
     }
     mbar_wait(acc_full, 0, 37);
     tcgen05_fence_after();
@@ -811,6 +885,15 @@ static int set_smem(K kernel, int bytes) {
 
 }  // namespace fa
 
+// MVF_ATTN_FA_TMEM: 1 (default) = probabilities through tensor memory ("TS" MMAs), 0 = through shared memory
+static bool attn_fa_tmem() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MVF_ATTN_FA_TMEM");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
 // MVF_ATTN_FA: 0 = never, 1 (default) = S > 64 when the caller allows split operands, 2 = every S (tests)
 static int attn_fa_mode() {
   const char* e = getenv("MVF_ATTN_FA");
@@ -856,7 +939,8 @@ int attention_fa_fwd(int B, int S, int heads, const void* qkv, const float* keym
   static bool configured = false;
   constexpr int smem = FWD_SMEM + 1024 + 256;
   if (!configured) {
-    MVF_TRY(set_smem(fa_fwd_kernel, smem));
+    MVF_TRY(set_smem(fa_fwd_kernel<true>, smem));
+    MVF_TRY(set_smem(fa_fwd_kernel<false>, smem));
     configured = true;
   }
   Params p;
@@ -864,7 +948,8 @@ int attention_fa_fwd(int B, int S, int heads, const void* qkv, const float* keym
   p.S = S; p.Sq = w.Sq; p.heads = heads; p.H = H;
   p.mask_words = w.mask_words; p.maskbits = mask;
   p.ctx = (float*)ctx; p.lse = lse;
-  launch_k(fa_fwd_kernel, dim3(cdiv(S, BQ), heads, B), FWD_THREADS, smem, st, mq, mk, mv, p);
+  if (attn_fa_tmem()) launch_k(fa_fwd_kernel<true>, dim3(cdiv(S, BQ), heads, B), FWD_THREADS, smem, st, mq, mk, mv, p);
+  else launch_k(fa_fwd_kernel<false>, dim3(cdiv(S, BQ), heads, B), FWD_THREADS, smem, st, mq, mk, mv, p);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }
@@ -911,8 +996,10 @@ int attention_fa_bwd(int B, int S, int heads, const void* qkv, const float* keym
   constexpr int smem_dq = DQ_SMEM + 1024 + 256;
   constexpr int smem_dkv = DKV_SMEM + 1024 + 256;
   if (!configured) {
-    MVF_TRY(set_smem(fa_bwd_dq_kernel, smem_dq));
-    MVF_TRY(set_smem(fa_bwd_dkv_kernel, smem_dkv));
+    MVF_TRY(set_smem(fa_bwd_dq_kernel<true>, smem_dq));
+    MVF_TRY(set_smem(fa_bwd_dq_kernel<false>, smem_dq));
+    MVF_TRY(set_smem(fa_bwd_dkv_kernel<true>, smem_dkv));
+    MVF_TRY(set_smem(fa_bwd_dkv_kernel<false>, smem_dkv));
     configured = true;
   }
   Params p;
@@ -921,9 +1008,11 @@ int attention_fa_bwd(int B, int S, int heads, const void* qkv, const float* keym
   p.mask_words = w.mask_words; p.maskbits = mask;
   p.L2 = L2; p.Dl = Dl;
   p.d_qkv = (float*)d_qkv;
-  launch_k(fa_bwd_dq_kernel, dim3(cdiv(S, BQ), heads, B), DQ_THREADS, smem_dq, st, mq128, mg128, mk64, mv64, p);
+  if (attn_fa_tmem()) launch_k(fa_bwd_dq_kernel<true>, dim3(cdiv(S, BQ), heads, B), DQ_THREADS, smem_dq, st, mq128, mg128, mk64, mv64, p);
+  else launch_k(fa_bwd_dq_kernel<false>, dim3(cdiv(S, BQ), heads, B), DQ_THREADS, smem_dq, st, mq128, mg128, mk64, mv64, p);
   MVF_CHECK_LAUNCH();
-  launch_k(fa_bwd_dkv_kernel, dim3(cdiv(S, BQ), heads, B), DKV_THREADS, smem_dkv, st, mk128, mv128, mq64, mg64, p);
+  if (attn_fa_tmem()) launch_k(fa_bwd_dkv_kernel<true>, dim3(cdiv(S, BQ), heads, B), DKV_THREADS, smem_dkv, st, mk128, mv128, mq64, mg64, p);
+  else launch_k(fa_bwd_dkv_kernel<false>, dim3(cdiv(S, BQ), heads, B), DKV_THREADS, smem_dkv, st, mk128, mv128, mq64, mg64, p);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }

@@ -581,6 +581,15 @@ struct Ctx {
     forked = true;
     return MVF_OK;
   }
+  // bias gradients collected so far: one batched column-sum launch on the side stream, without joining (the dY regions they
+  // read are never rewritten before the final join)
+  int flush_bias_sums() {
+    if (bias_sums.empty()) return MVF_OK;
+    MVF_TRY(fork());
+    MVF_TRY(colsum_batched(bias_sums.data(), (int)bias_sums.size(), side && forked ? side : st));
+    bias_sums.clear();
+    return MVF_OK;
+  }
   int join() {
     if (!bias_sums.empty()) {   // every dY region is still intact here (callers give each its own scratch region)
       MVF_TRY(colsum_batched(bias_sums.data(), (int)bias_sums.size(), side && forked ? side : st));
@@ -657,7 +666,7 @@ static int make_ctx(const mvf_head_desc* d, Ctx& c, bool proj, void* save, size_
   return MVF_OK;
 }
 
-static int pack_head_weights(Ctx& c) {
+static int pack_head_weights(Ctx& c, cudaStream_t on) {
   const Model& m = c.m;
   const mvf_head_desc& d = m.d;
   const int bf = m.act == MVF_BF16;
@@ -724,7 +733,7 @@ static int pack_head_weights(Ctx& c) {
   mat("w.emb", m.iWemb);
   split("w.emb", m.iWemb);
   if (d.final_mode == MVF_FINAL_LIN) { mat("w.lin", m.iWlin); split("w.lin", m.iWlin); }
-  return pack_params(e.data(), (int)e.size(), c.st);
+  return pack_params(e.data(), (int)e.size(), on);
 }
 
 static double bn_n_global(const Model& m, int64_t local_rows) {
@@ -741,7 +750,15 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
   if (ph1 > n_ph) ph1 = n_ph;
   for (int ph = ph0; ph < ph1; ++ph) {
     if (ph == 0) {
-      MVF_TRY(pack_head_weights(c));
+      // the packed / pre-split copies of the weights are first needed behind the streaming pooling pass: with folded pooling
+      // they are written on the side stream while that HBM-bound pass runs (joined below)
+      const bool pack_aside = m.fold && c.side != nullptr;
+      if (pack_aside) {
+        MVF_TRY(c.fork());
+        MVF_TRY(pack_head_weights(c, c.side));
+      } else {
+        MVF_TRY(pack_head_weights(c, st));
+      }
       float* attn = m.fwb ? nullptr : c.S.f("attn");
       if (m.fwb) {
         // FWBPooling (mvformer.py:455-462): ent[(f, e), c] = lin_conv(cls[f])[c*E + e]; with the weight rows regrouped
@@ -762,6 +779,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
           ProfScope ps(0, st);
           MVF_TRY(pool_fold_fwd(m.kvt, (int)m.F, d.P, d.E, d.C_in, tokens, c.S.f("wq"), attn, c.S.f("px"), st));
         }
+        if (pack_aside) MVF_TRY(c.join());
         {
           ProfScope ps(4, st);
           MVF_TRY(c.linear(MVF_F32, m.R, d.SPC, d.C_in, c.S.p("px"), d.C_in, c.P[m.iWv], d.C_in, c.P[m.ibv], c.S.p("ent32"),
@@ -1021,6 +1039,9 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
         const int64_t ldg = c.Lg.find("g.w.kv")->ld;
         float* gwk = c.G.f("g.w.kv");
         float* gwv = gwk + (size_t)d.SPC * ldg;
+        // the bias column sums of the chain so far go to the side stream now and overlap the GEMMs below; the side stream is
+        // joined BEFORE the streaming pass, which is HBM-bound on every SM and loses more to a concurrent kernel than it hides
+        MVF_TRY(c.flush_bias_sums());
         {
           ProfScope ps(3, st);
           // dEnt and, from the same pass, delta = <dEnt, ent - bv> (= <G, px>) for the streaming kernel
@@ -1032,6 +1053,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
           MVF_TRY(c.linear_dx(MVF_F32, m.R, d.SPC, d.C_in, c.W.p("dent"), d.SPC, c.P[m.iWv], d.C_in, c.W.p("G"), d.C_in));
           MVF_CHECK_CUDA(cudaMemsetAsync(c.W.p("dwq"), 0, (size_t)d.E * d.C_in * 4, st));
         }
+        MVF_TRY(c.join());
         {
           ProfScope ps(1, st);
           MVF_TRY(pool_fold_bwd(m.kvt, (int)m.F, d.P, d.E, d.C_in, tokens, c.W.f("G"), c.S.f("px"), c.S.f("attn"),
@@ -1360,7 +1382,10 @@ int mvf_head_forward(const mvf_head_desc* d, const float* const* params, float* 
   MVF_TRY(make_ctx(d, c, false, save, save_bytes, ws, ws_bytes, nullptr, params, (cudaStream_t)stream));
   MVF_REQUIRE((tokens != nullptr || d->pool_kind == MVF_POOLKIND_FWB) && out_emb != nullptr, MVF_ERR_BAD_ARG, "null tokens / output");
   MVF_REQUIRE(!d->has_mask || mask != nullptr, MVF_ERR_BAD_ARG, "has_mask set but mask is null");
-  return head_forward_impl(c, bn_running, bn_tracked, tokens, mask, out_emb, attn_out, phase_begin, phase_end);
+  MVF_TRY(side_acquire(c.st, &c.side, &c.side_dev));
+  int rc = head_forward_impl(c, bn_running, bn_tracked, tokens, mask, out_emb, attn_out, phase_begin, phase_end);
+  int rj = c.join();   // never leave forked work un-joined
+  return rc != MVF_OK ? rc : rj;
 }
 
 int mvf_head_backward(const mvf_head_desc* d, const float* const* params, const void* tokens, const float* mask,
