@@ -168,39 +168,41 @@ __global__ void __launch_bounds__(256) fa_stats_kernel(const float* __restrict__
 // the two MMA patterns
 // ---------------------------------------------------------------------------------------------------------------------
 // D[128 x N] = A[128 x 32] * B[N x 32]^T on row-split operands (contraction over d_k): hi*hi + hi*lo + lo*hi
-__device__ __forceinline__ void mma_rowsplit(uint32_t tmem_d, uint32_t sa, uint32_t sb, uint32_t idesc) {
+__device__ __forceinline__ void mma_rowsplit(uint32_t tmem_d, uint32_t sa, uint32_t sb, uint32_t idesc, uint32_t leader) {
   const uint64_t da = make_smem_desc(sa, true, 0, 2), db = make_smem_desc(sb, true, 0, 2);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const uint64_t hi = (uint64_t)(2 * j), lo = (uint64_t)(4 + 2 * j);   // 16-byte units inside the 128-byte row
-    umma<2>(tmem_d, da + lo, db + hi, idesc, j > 0 ? 1u : 0u);           // small terms first
-    umma<2>(tmem_d, da + hi, db + lo, idesc, 1u);
-    umma<2>(tmem_d, da + hi, db + hi, idesc, 1u);
+    umma_f16_p(tmem_d, da + lo, db + hi, idesc, j > 0 ? 1u : 0u, leader);   // small terms first
+    umma_f16_p(tmem_d, da + hi, db + lo, idesc, 1u, leader);
+    umma_f16_p(tmem_d, da + hi, db + hi, idesc, 1u, leader);
   }
 }
 // D[128 x 64] (+)= A[128 x 64 tokens] * X[64 tokens x (hi 32 | lo 32)]: A = hi and lo probability tiles (K-major), X = a
 // row-split tile used as an MN-major B operand (token rows are the K rows); columns 0..31 of D collect A x_hi, 32..63 A x_lo
-__device__ __forceinline__ void mma_tokens(uint32_t tmem_d, uint32_t sa_hi, uint32_t sa_lo, uint32_t sb, uint32_t idesc, bool accumulate) {
+__device__ __forceinline__ void mma_tokens(uint32_t tmem_d, uint32_t sa_hi, uint32_t sa_lo, uint32_t sb, uint32_t idesc, bool accumulate,
+                                           uint32_t leader) {
   const uint64_t dah = make_smem_desc(sa_hi, true, 0, 2), dal = make_smem_desc(sa_lo, true, 0, 2);
   const uint64_t db = make_smem_desc(sb, false, 64, 2);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {                                          // 4 x 16 tokens
     const uint64_t oa = (uint64_t)(2 * k), ob = (uint64_t)(128 * k);      // 32 bytes along an A row; 16 token rows of B
-    umma<2>(tmem_d, dal + oa, db + ob, idesc, (accumulate || k > 0) ? 1u : 0u);
-    umma<2>(tmem_d, dah + oa, db + ob, idesc, 1u);
+    umma_f16_p(tmem_d, dal + oa, db + ob, idesc, (accumulate || k > 0) ? 1u : 0u, leader);
+    umma_f16_p(tmem_d, dah + oa, db + ob, idesc, 1u, leader);
   }
 }
 
 // the same product with the probabilities in TENSOR MEMORY (A operand of the "TS" MMA form): ta_hi / ta_lo = TMEM column of
 // the packed bf16 pairs (32 columns for 64 tokens; 8 columns per K = 16 step), written there by the softmax warps with
 // tcgen05.st -- no shared-memory store by 128 threads, no shared-memory operand read by the tensor core for A
-__device__ __forceinline__ void mma_tokens_ts(uint32_t tmem_d, uint32_t ta_hi, uint32_t ta_lo, uint32_t sb, uint32_t idesc, bool accumulate) {
+__device__ __forceinline__ void mma_tokens_ts(uint32_t tmem_d, uint32_t ta_hi, uint32_t ta_lo, uint32_t sb, uint32_t idesc, bool accumulate,
+                                              uint32_t leader) {
   const uint64_t db = make_smem_desc(sb, false, 64, 2);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const uint64_t ob = (uint64_t)(128 * k);
-    umma_ts_f16(tmem_d, ta_lo + 8 * k, db + ob, idesc, (accumulate || k > 0) ? 1u : 0u);
-    umma_ts_f16(tmem_d, ta_hi + 8 * k, db + ob, idesc, 1u);
+    umma_ts_f16_p(tmem_d, ta_lo + 8 * k, db + ob, idesc, (accumulate || k > 0) ? 1u : 0u, leader);
+    umma_ts_f16_p(tmem_d, ta_hi + 8 * k, db + ob, idesc, 1u, leader);
   }
 }
 // eight fp32 values -> four packed bf16 pairs of the hi part and of the lo part
@@ -220,7 +222,9 @@ struct Params {
   float* ctx;          // forward output [B*S, H]
   float* lse;          // forward output [slab][S]
   float* d_qkv;        // backward output [B*S, 3H]
+  long long* dbg;      // MVF_FA_DBG=1: clock64() stamps of CTA 0 of the dK/dV kernel (debug aid, null otherwise)
 };
+#define FA_STAMP(slot, j) do { if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 24 && (threadIdx.x & 31) == 0) p.dbg[(j) * 16 + (slot)] = clock64(); } while (0)
 
 // =====================================================================================================================
 // forward
@@ -297,16 +301,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // every lane runs the protocol with warp-uniform operands; the elected lane issues (see umma_f16_p)
+    {
+      const uint32_t leader = elect_leader();
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0), sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t aQ = sb, aK = sb + T128, aV = aK + FWD_NK * T64, aPh = aV + FWD_NV * T64, aPl = aPh + T128;
       const uint32_t idesc_s = make_idesc(BK, true, true, 2), idesc_o = make_idesc(64, true, false, 2);
       auto issue_s = [&](int j) {
         const int st = j & 1, sk = j % FWD_NK;
         mbar_wait(&k_full[sk], (j / FWD_NK) & 1, 12);
         mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1, 13);
         tcgen05_fence_after();
-        mma_rowsplit(tmem_base + st * BK, smem_u32(sQ), smem_u32(sK + sk * T64), idesc_s);
-        umma_commit(&k_empty[sk]);
-        umma_commit(&s_full[st]);
+        mma_rowsplit(tb + st * BK, aQ, aK + sk * T64, idesc_s, leader);
+        umma_commit_p(&k_empty[sk], leader);
+        umma_commit_p(&s_full[st], leader);
       };
       mbar_wait(q_full, 0, 14);
       issue_s(0);
@@ -316,10 +324,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         mbar_wait(p_full, j & 1, 15);
         mbar_wait(&v_full[sv], (j / FWD_NV) & 1, 16);
         tcgen05_fence_after();
-        if constexpr (ATM) mma_tokens_ts(tmem_base + 2 * BK, tmem_base + 192, tmem_base + 224, smem_u32(sV + sv * T64), idesc_o, false);
-        else mma_tokens(tmem_base + 2 * BK, smem_u32(sPh), smem_u32(sPl), smem_u32(sV + sv * T64), idesc_o, false);
-        umma_commit(&v_empty[sv]);
-        umma_commit(o_full);
+        if constexpr (ATM) mma_tokens_ts(tb + 2 * BK, tb + 192, tb + 224, aV + sv * T64, idesc_o, false, leader);
+        else mma_tokens(tb + 2 * BK, aPh, aPl, aV + sv * T64, idesc_o, false, leader);
+        umma_commit_p(&v_empty[sv], leader);
+        umma_commit_p(o_full, leader);
       }
     }
   } else {
@@ -521,7 +529,10 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_leader();
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0), sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t aQ = sb, aG = sb + T128, aK = aG + T128, aV = aK + DQ_NK * T64, aDh = aV + DQ_NV * T64, aDl = aDh + T128;
       const uint32_t idesc_s = make_idesc(BK, true, true, 2), idesc_o = make_idesc(64, true, false, 2);
       auto issue_sd = [&](int j) {
         const int sk = j % DQ_NK, sv = j % DQ_NV;
@@ -529,10 +540,10 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         mbar_wait(&v_full[sv], (j / DQ_NV) & 1, 23);
         mbar_wait(sd_empty, (j & 1) ^ 1, 24);
         tcgen05_fence_after();
-        mma_rowsplit(tmem_base, smem_u32(sQ), smem_u32(sK + sk * T64), idesc_s);        // S = Q K^T
-        mma_rowsplit(tmem_base + BK, smem_u32(sG), smem_u32(sV + sv * T64), idesc_s);   // dP = dO V^T
-        umma_commit(&v_empty[sv]);
-        umma_commit(sd_full);
+        mma_rowsplit(tb, aQ, aK + sk * T64, idesc_s, leader);        // S = Q K^T
+        mma_rowsplit(tb + BK, aG, aV + sv * T64, idesc_s, leader);   // dP = dO V^T
+        umma_commit_p(&v_empty[sv], leader);
+        umma_commit_p(sd_full, leader);
       };
       mbar_wait(qg_full, 0, 25);
       issue_sd(0);
@@ -541,12 +552,12 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int sk = j % DQ_NK;
         mbar_wait(ds_full, j & 1, 26);
         tcgen05_fence_after();
-        if constexpr (ATM) mma_tokens_ts(tmem_base + 2 * BK, tmem_base + 192, tmem_base + 224, smem_u32(sK + sk * T64), idesc_o, j > 0);
-        else mma_tokens(tmem_base + 2 * BK, smem_u32(sDh), smem_u32(sDl), smem_u32(sK + sk * T64), idesc_o, j > 0);   // dQ += dS K
-        umma_commit(&k_empty[sk]);
-        umma_commit(ds_empty);
+        if constexpr (ATM) mma_tokens_ts(tb + 2 * BK, tb + 192, tb + 224, aK + sk * T64, idesc_o, j > 0, leader);   // dQ += dS K
+        else mma_tokens(tb + 2 * BK, aDh, aDl, aK + sk * T64, idesc_o, j > 0, leader);
+        umma_commit_p(&k_empty[sk], leader);
+        umma_commit_p(ds_empty, leader);
       }
-      umma_commit(acc_full);
+      umma_commit_p(acc_full, leader);
     }
   } else {
     const int q = warp & 3;
@@ -707,42 +718,51 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_leader();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0), sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t aK = sb, aV = sb + T128, aSt = aV + T128, aPD = aSt + DKV_NS * DKV_PITCH;
       const uint32_t idesc_s = make_idesc(BK, true, true, 2), idesc_o = make_idesc(64, true, false, 2);
       auto issue_sd = [&](int j) {
         const int tb = j & 1, st = j % DKV_NS;
-        uint8_t* s = sSt + st * DKV_PITCH;
+        const uint32_t s = aSt + st * DKV_PITCH;
+        FA_STAMP(0, j);
         mbar_wait(&t_full[st], (j / DKV_NS) & 1, 31);
+        FA_STAMP(1, j);
         mbar_wait(&sd_empty[tb], ((j >> 1) & 1) ^ 1, 32);
         tcgen05_fence_after();
-        mma_rowsplit(tmem_base + tb * 2 * BK, smem_u32(sK), smem_u32(s), idesc_s);              // S^T = K Q^T
-        mma_rowsplit(tmem_base + tb * 2 * BK + BK, smem_u32(sV), smem_u32(s + T64), idesc_s);   // dP^T = V dO^T
-        umma_commit(&sd_full[tb]);
+        FA_STAMP(2, j);
+        mma_rowsplit(tm + tb * 2 * BK, aK, s, idesc_s, leader);              // S^T = K Q^T
+        mma_rowsplit(tm + tb * 2 * BK + BK, aV, s + T64, idesc_s, leader);   // dP^T = V dO^T
+        umma_commit_p(&sd_full[tb], leader);
+        FA_STAMP(3, j);
       };
       mbar_wait(kv_full, 0, 33);
       issue_sd(0);
       for (int j = 0; j < nq; ++j) {
         if (j + 1 < nq) issue_sd(j + 1);
         const int st = j % DKV_NS, pb = j & 1;
-        uint8_t* s = sSt + st * DKV_PITCH;
-        const uint32_t pd = smem_u32(sPD + pb * 4 * T128);
+        const uint32_t s = aSt + st * DKV_PITCH;
+        const uint32_t pd = aPD + pb * 4 * T128;
         if constexpr (ATM) {   // one probability set in tensor memory: barriers [0] only, one completion per tile
           mbar_wait(&pd_full[0], j & 1, 34);
           tcgen05_fence_after();
-          mma_tokens_ts(tmem_base + 4 * BK + 64, tmem_base + 384, tmem_base + 416, smem_u32(s + T64), idesc_o, j > 0);   // dV += P^T dO
-          mma_tokens_ts(tmem_base + 4 * BK, tmem_base + 448, tmem_base + 480, smem_u32(s), idesc_o, j > 0);              // dK += dS^T Q
-          umma_commit(&t_empty[st]);
-          umma_commit(&pd_empty[0]);
+          FA_STAMP(4, j);
+          mma_tokens_ts(tm + 4 * BK + 64, tm + 384, tm + 416, s + T64, idesc_o, j > 0, leader);   // dV += P^T dO
+          mma_tokens_ts(tm + 4 * BK, tm + 448, tm + 480, s, idesc_o, j > 0, leader);              // dK += dS^T Q
+          umma_commit_p(&t_empty[st], leader);
+          umma_commit_p(&pd_empty[0], leader);
+          FA_STAMP(5, j);
         } else {
           mbar_wait(&pd_full[pb], (j >> 1) & 1, 34);
           tcgen05_fence_after();
-          mma_tokens(tmem_base + 4 * BK + 64, pd, pd + T128, smem_u32(s + T64), idesc_o, j > 0);            // dV += P^T dO
-          mma_tokens(tmem_base + 4 * BK, pd + 2 * T128, pd + 3 * T128, smem_u32(s), idesc_o, j > 0);        // dK += dS^T Q
-          umma_commit(&t_empty[st]);
-          umma_commit(&pd_empty[pb]);
+          mma_tokens(tm + 4 * BK + 64, pd, pd + T128, s + T64, idesc_o, j > 0, leader);            // dV += P^T dO
+          mma_tokens(tm + 4 * BK, pd + 2 * T128, pd + 3 * T128, s, idesc_o, j > 0, leader);        // dK += dS^T Q
+          umma_commit_p(&t_empty[st], leader);
+          umma_commit_p(&pd_empty[pb], leader);
         }
       }
-      umma_commit(acc_full);
+      umma_commit_p(acc_full, leader);
     }
   } else {
     const int q = warp & 3;
@@ -756,9 +776,11 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
     for (int j = 0; j < nq; ++j) {
       const int tb = j & 1, st = j % DKV_NS;
       const uint32_t sstat = smem_u32(sSt + st * DKV_PITCH + 2 * T64) + wg * 128;   // this warpgroup's 32 queries
+      if (threadIdx.x == 64) FA_STAMP(8, j);
       mbar_wait(&t_full[st], (j / DKV_NS) & 1, 38);      // the stage's L2 / D rows (bulk copies) are read by these threads
       mbar_wait(&sd_full[tb], (j >> 1) & 1, 35);
       tcgen05_fence_after();
+      if (threadIdx.x == 64) FA_STAMP(9, j);
       uint32_t rs_[32], rp[32];
       tmem_ld32(lane_addr + tb * 2 * BK + wg * 32, rs_);
       tmem_ld32(lane_addr + tb * 2 * BK + BK + wg * 32, rp);
@@ -766,6 +788,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sd_empty[tb]);
+      if (threadIdx.x == 64) FA_STAMP(10, j);
       uint32_t ph[16], pl[16], dh[16], dl[16];   // packed bf16 pairs of this warpgroup's 32 queries
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -788,8 +811,10 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
         split8u(dv, dh + 4 * ch, dl + 4 * ch);
       }
       if constexpr (ATM) {
+        if (threadIdx.x == 64) FA_STAMP(11, j);
         mbar_wait(&pd_empty[0], (j & 1) ^ 1, 36);   // the dV / dK products of the previous tile have read the probabilities
         tcgen05_fence_after();
+        if (threadIdx.x == 64) FA_STAMP(12, j);
         tmem_st16(lane_addr + 384 + wg * 16, ph);
         tmem_st16(lane_addr + 416 + wg * 16, pl);
         tmem_st16(lane_addr + 448 + wg * 16, dh);
@@ -797,6 +822,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
         tmem_st_wait();
         tcgen05_fence_before();
         mbar_arrive(&pd_full[0]);
+        if (threadIdx.x == 64) FA_STAMP(13, j);
       } else {
         const int pb = j & 1;
         const uint32_t aPh = smem_u32(sPD + pb * 4 * T128), aPl = aPh + T128, aDh = aPh + 2 * T128, aDl = aPh + 3 * T128;
@@ -1008,12 +1034,35 @@ int attention_fa_bwd(int B, int S, int heads, const void* qkv, const float* keym
   p.mask_words = w.mask_words; p.maskbits = mask;
   p.L2 = L2; p.Dl = Dl;
   p.d_qkv = (float*)d_qkv;
+  static int dbg_on = -1;
+  static long long* dbg_buf = nullptr;
+  if (dbg_on < 0) {
+    const char* e = getenv("MVF_FA_DBG");
+    dbg_on = (e && atoi(e) != 0) ? 1 : 0;
+    if (dbg_on && cudaMalloc(&dbg_buf, 24 * 16 * sizeof(long long)) != cudaSuccess) dbg_on = 0;   // debug aid only
+  }
+  if (dbg_on) {
+    cudaMemsetAsync(dbg_buf, 0, 24 * 16 * sizeof(long long), st);
+    p.dbg = dbg_buf;
+  }
   if (attn_fa_tmem()) launch_k(fa_bwd_dq_kernel<true>, dim3(cdiv(S, BQ), heads, B), DQ_THREADS, smem_dq, st, mq128, mg128, mk64, mv64, p);
   else launch_k(fa_bwd_dq_kernel<false>, dim3(cdiv(S, BQ), heads, B), DQ_THREADS, smem_dq, st, mq128, mg128, mk64, mv64, p);
   MVF_CHECK_LAUNCH();
   if (attn_fa_tmem()) launch_k(fa_bwd_dkv_kernel<true>, dim3(cdiv(S, BQ), heads, B), DKV_THREADS, smem_dkv, st, mk128, mv128, mq64, mg64, p);
   else launch_k(fa_bwd_dkv_kernel<false>, dim3(cdiv(S, BQ), heads, B), DKV_THREADS, smem_dkv, st, mk128, mv128, mq64, mg64, p);
   MVF_CHECK_LAUNCH();
+  if (dbg_on) {
+    long long h[24 * 16];
+    if (cudaStreamSynchronize(st) == cudaSuccess && cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      const long long t0 = h[0];
+      fprintf(stderr, "fa_bwd_dkv dbg (S=%d): clocks relative to the first stamp; MMA warp: sd{enter,t_full,sd_empty,issued} dvdk{pd_full,issued} | "
+              "softmax: enter sd_full ld_done compute_done pd_empty stored\n", S);
+      for (int j = 0; j < 24 && j * 64 < S; ++j)
+        fprintf(stderr, "  tile %2d: mma %7lld %7lld %7lld %7lld | %7lld %7lld || soft %7lld %7lld %7lld %7lld %7lld %7lld\n", j, h[j * 16 + 0] - t0,
+                h[j * 16 + 1] - t0, h[j * 16 + 2] - t0, h[j * 16 + 3] - t0, h[j * 16 + 4] - t0, h[j * 16 + 5] - t0, h[j * 16 + 8] - t0,
+                h[j * 16 + 9] - t0, h[j * 16 + 10] - t0, h[j * 16 + 11] - t0, h[j * 16 + 12] - t0, h[j * 16 + 13] - t0);
+    }
+  }
   return MVF_OK;
 }
 
