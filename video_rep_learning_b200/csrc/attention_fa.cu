@@ -318,8 +318,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       };
       mbar_wait(q_full, 0, 14);
       issue_s(0);
+      if (nt > 1) issue_s(1);
       for (int j = 0; j < nt; ++j) {
-        if (j + 1 < nt) issue_s(j + 1);
+        // two tiles ahead: S_{j+2} reuses the buffer of S_j, free as soon as the softmax warps have loaded tile j
+        if (j + 2 < nt) issue_s(j + 2);
         const int sv = j % FWD_NV;
         mbar_wait(p_full, j & 1, 15);
         mbar_wait(&v_full[sv], (j / FWD_NV) & 1, 16);
@@ -644,23 +646,25 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 // backward, rows = keys: dK, dV
 // =====================================================================================================================
 constexpr int DKV_THREADS = 320;   // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 columns 0..31, warps 6..9 columns 32..63
-constexpr int DKV_NS = 3;
+constexpr int DKV_NS_SMEM = 3, DKV_NS_TMEM = 6;   // ring depth: probabilities through shared memory / through tensor memory
 constexpr int DKV_STAGE = 2 * T64 + 512;    // bytes landing per stage: Q, G tiles (row-split) | L2[64], D[64]
 constexpr int DKV_PITCH = 2 * T64 + 1024;   // keeps every tile of every stage 1024-byte aligned
-constexpr int DKV_SMEM = 2 * T128 + DKV_NS * DKV_PITCH + 8 * T128;   // K, V | ring | 2 x (P^T hi, lo, dS^T hi, lo)
+constexpr int DKV_SMEM_SMEM = 2 * T128 + DKV_NS_SMEM * DKV_PITCH + 8 * T128;   // K, V | ring | 2 x (P^T hi, lo, dS^T hi, lo)
+constexpr int DKV_SMEM_TMEM = 2 * T128 + DKV_NS_TMEM * DKV_PITCH;             // K, V | ring
 
 template <bool ATM>
 __global__ void __launch_bounds__(DKV_THREADS, 1)
 fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                   const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g, const Params p) {
+  constexpr int DKV_NS = ATM ? DKV_NS_TMEM : DKV_NS_SMEM;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;
   uint8_t* sV = sK + T128;
   uint8_t* sSt = sV + T128;                 // [DKV_NS] stages
-  uint8_t* sPD = sSt + DKV_NS * DKV_PITCH;  // [2] x (P^T hi | P^T lo | dS^T hi | dS^T lo): the softmax warps fill one set
-                                            // while the dV / dK products of the previous tile still read the other
-  uint64_t* bars = (uint64_t*)(sPD + 8 * T128);
+  uint8_t* sPD = sSt + DKV_NS * DKV_PITCH;  // !ATM: [2] x (P^T hi | P^T lo | dS^T hi | dS^T lo): the softmax warps fill one
+                                            // set while the dV / dK products of the previous tile still read the other
+  uint64_t* bars = (uint64_t*)(sPD + (ATM ? 0 : 8 * T128));
   uint64_t* kv_full = bars;
   uint64_t* t_full = bars + 1;              // [DKV_NS]
   uint64_t* t_empty = t_full + DKV_NS;      // [DKV_NS]
@@ -739,8 +743,12 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_consta
       };
       mbar_wait(kv_full, 0, 33);
       issue_sd(0);
+      if (ATM && nq > 1) issue_sd(1);
       for (int j = 0; j < nq; ++j) {
-        if (j + 1 < nq) issue_sd(j + 1);
+        // ATM (deep ring): two tiles ahead -- S^T / dP^T of tile j+2 reuse the buffers of tile j, free once the softmax warps
+        // have loaded it; otherwise one tile ahead
+        if (ATM) { if (j + 2 < nq) issue_sd(j + 2); }
+        else if (j + 1 < nq) issue_sd(j + 1);
         const int st = j % DKV_NS, pb = j & 1;
         const uint32_t s = aSt + st * DKV_PITCH;
         const uint32_t pd = aPD + pb * 4 * T128;
@@ -1020,12 +1028,12 @@ int attention_fa_bwd(int B, int S, int heads, const void* qkv, const float* keym
   MVF_TRY(make_map_rs(&mg64, GS, S, slabs, BK));
   static bool configured = false;
   constexpr int smem_dq = DQ_SMEM + 1024 + 256;
-  constexpr int smem_dkv = DKV_SMEM + 1024 + 256;
+  constexpr int smem_dkv_t = DKV_SMEM_TMEM + 1024 + 256, smem_dkv_s = DKV_SMEM_SMEM + 1024 + 256;
   if (!configured) {
     MVF_TRY(set_smem(fa_bwd_dq_kernel<true>, smem_dq));
     MVF_TRY(set_smem(fa_bwd_dq_kernel<false>, smem_dq));
-    MVF_TRY(set_smem(fa_bwd_dkv_kernel<true>, smem_dkv));
-    MVF_TRY(set_smem(fa_bwd_dkv_kernel<false>, smem_dkv));
+    MVF_TRY(set_smem(fa_bwd_dkv_kernel<true>, smem_dkv_t));
+    MVF_TRY(set_smem(fa_bwd_dkv_kernel<false>, smem_dkv_s));
     configured = true;
   }
   Params p;
@@ -1048,8 +1056,8 @@ int attention_fa_bwd(int B, int S, int heads, const void* qkv, const float* keym
   if (attn_fa_tmem()) launch_k(fa_bwd_dq_kernel<true>, dim3(cdiv(S, BQ), heads, B), DQ_THREADS, smem_dq, st, mq128, mg128, mk64, mv64, p);
   else launch_k(fa_bwd_dq_kernel<false>, dim3(cdiv(S, BQ), heads, B), DQ_THREADS, smem_dq, st, mq128, mg128, mk64, mv64, p);
   MVF_CHECK_LAUNCH();
-  if (attn_fa_tmem()) launch_k(fa_bwd_dkv_kernel<true>, dim3(cdiv(S, BQ), heads, B), DKV_THREADS, smem_dkv, st, mk128, mv128, mq64, mg64, p);
-  else launch_k(fa_bwd_dkv_kernel<false>, dim3(cdiv(S, BQ), heads, B), DKV_THREADS, smem_dkv, st, mk128, mv128, mq64, mg64, p);
+  if (attn_fa_tmem()) launch_k(fa_bwd_dkv_kernel<true>, dim3(cdiv(S, BQ), heads, B), DKV_THREADS, smem_dkv_t, st, mk128, mv128, mq64, mg64, p);
+  else launch_k(fa_bwd_dkv_kernel<false>, dim3(cdiv(S, BQ), heads, B), DKV_THREADS, smem_dkv_s, st, mk128, mv128, mq64, mg64, p);
   MVF_CHECK_LAUNCH();
   if (dbg_on) {
     long long h[24 * 16];
