@@ -153,7 +153,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // Every lane runs the protocol with warp-uniform operands and the elected lane issues (umma_p): under a divergent
+    // `if (lane == 0)` every tcgen05.mma is wrapped in an ELECT / R2UR.BROADCAST / branch loop of ~100 clocks, as long as
+    // the tensor time of an N = 128 MMA -- it dominates the short GEMMs of the chain.
+    {
+      const uint32_t leader = elect_leader();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0), smem_a0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t idesc = SPLIT ? make_idesc(BLOCK_N, true, true, 2) : make_idesc(BLOCK_N, p.a_kmajor != 0, p.b_kmajor != 0, EB);
       // start-address advance (in 16 B units) per UMMA_K step inside a stage: 32 B along a K-major row,
       // UMMA_K rows of 128 B for an MN-major operand
@@ -170,12 +175,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t tmem_d = tmem_u + acc * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(SPLIT ? &conv_bar[stage] : &full_bar[stage], phase, 3);
           tcgen05_fence_after();
-          if (it == 0 && kb == kb0) MVF_STAMP(2);
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          if (it == 0 && kb == kb0 && lane == 0) MVF_STAMP(2);
+          const uint32_t sa = smem_a0 + stage * STAGE_BYTES;
           if constexpr (SPLIT) {
             // row = [hi k0..15 | hi k16..31 | lo k0..15 | lo k16..31] bf16, 32 bytes each: +2 descriptor units per slot
             const uint64_t da = make_smem_desc(sa, true, BLOCK_K, 2);
@@ -183,24 +188,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const uint64_t hi = (uint64_t)(2 * j), lo = (uint64_t)(4 + 2 * j);
-              umma<2>(tmem_d, da + lo, db + hi, idesc, (kb > kb0 || j > 0) ? 1u : 0u);   // small terms first
-              umma<2>(tmem_d, da + hi, db + lo, idesc, 1u);
-              umma<2>(tmem_d, da + hi, db + hi, idesc, 1u);
+              umma_p<2>(tmem_d, da + lo, db + hi, idesc, (kb > kb0 || j > 0) ? 1u : 0u, leader);   // small terms first
+              umma_p<2>(tmem_d, da + hi, db + lo, idesc, 1u, leader);
+              umma_p<2>(tmem_d, da + hi, db + hi, idesc, 1u, leader);
             }
           } else {
             const uint64_t da = make_smem_desc(sa, p.a_kmajor != 0, BLOCK_K, EB);
             const uint64_t db = make_smem_desc(sa + A_BYTES, p.b_kmajor != 0, BLOCK_K, EB);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              umma<EB>(tmem_d, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc,
-                       (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_p<EB>(tmem_d, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc, (kb > kb0 || k > 0) ? 1u : 0u, leader);
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          umma_commit_p(&empty_bar[stage], leader);  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        if (it == 0) MVF_STAMP(3);
+        umma_commit_p(&tmem_full[acc], leader);  // accumulator complete -> epilogue
+        if (it == 0 && lane == 0) MVF_STAMP(3);
       }
     }
   } else if (SPLIT && warp >= 8 && warp < 12) {

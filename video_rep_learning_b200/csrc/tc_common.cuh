@@ -154,6 +154,22 @@ __device__ __forceinline__ void umma_f16_p(uint32_t tmem_d, uint64_t desc_a, uin
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+template <int EB>
+__device__ __forceinline__ void umma_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                       uint32_t leader) {
+  if constexpr (EB == 2) umma_f16_p(tmem_d, desc_a, desc_b, idesc, accumulate, leader);
+  else umma_tf32_p(tmem_d, desc_a, desc_b, idesc, accumulate, leader);
+}
 __device__ __forceinline__ void umma_ts_f16_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
                                               uint32_t leader) {
   asm volatile(
