@@ -101,7 +101,8 @@ const char* mvf_last_error(void);
 int mvf_has_tcgen05(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t mvf_launch_count(void);
-/* Measurement aid: when enabled, CUDA events are recorded on the launching stream around the dominant kernels.
+/* Measurement aid: when enabled (1 = tags 0 and 1 only, 2 = every tag), CUDA events are recorded on the launching stream
+ * around the dominant kernels.
  * DENSE pooling: tag 0 K|V projection GEMM, 1 its weight-gradient GEMM, 2 cross-attention pooling fwd, 3 its bwd.
  * FOLDED pooling: tag 0 streaming pooling pass fwd, 1 streaming pass bwd, 2 the rest of the forward pooling block
  * (Wq fold, px Wv^T GEMM, dropout/one-hot), 3 the rest of its backward (dEnt, G and dWv GEMMs, dWk/dQ finish).

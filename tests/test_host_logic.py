@@ -206,3 +206,60 @@ def test_optimizer_tail_and_graph_step_have_no_cpu_path():
     from video_rep_learning_b200.algos import get_algo
     with pytest.raises(RuntimeError, match="CUDA"):
         GraphedTrainStep(m, get_algo(cfg), 2, 8, 9, 48, device=torch.device("cpu"))
+
+
+def test_eval_chunking_matches_reference_arithmetic():
+    """evaluate.py:45-55 (INT): equal chunks of ceil(L / ceil(L / FRAMES_PER_BATCH)) frames, clamped context windows."""
+    from video_rep_learning_b200.evaluate import chunk_steps
+    import math
+    for L, fpb in ((1500, 2000), (1500, 800), (2001, 1000), (7, 3), (1, 5)):
+        chunks = chunk_steps(L, fpb)
+        nb = int(math.ceil(float(L) / fpb))
+        per = int(math.ceil(float(L) / nb))
+        assert len(chunks) == nb and torch.equal(torch.cat(chunks), torch.arange(L))
+        assert all(len(c) == min(L - i * per, per) for i, c in enumerate(chunks))
+    c = chunk_steps(5, 10, num_contexts=2, context_stride=3)[0]
+    assert c.tolist() == [0, 0, 0, 1, 0, 2, 0, 3, 1, 4]            # steps - 3 clamped at 0, interleaved with the steps
+
+
+class _FakeViT(nn.Module):
+    """Just enough of a timm ViT for FeatureExtractor: .blocks, .patch_embed.num_patches, .forward_features."""
+
+    def __init__(self, width=8, depth=4, patches=9):
+        super().__init__()
+        self.embed = nn.Linear(3, width)
+        self.blocks = nn.ModuleList([nn.Linear(width, width) for _ in range(depth)])
+        self.patch_embed = nn.Module()
+        self.patch_embed.num_patches = patches
+        self.patches = patches
+
+    def forward_features(self, x):                       # x [n, 3, H, W] -> tokens [n, 1 + P, width]
+        n = x.shape[0]
+        t = self.embed(x.flatten(2)[:, :, :1 + self.patches].transpose(1, 2))
+        for b in self.blocks:
+            t = torch.tanh(b(t))
+        return t
+
+
+def test_feature_extractor_writes_hooked_tokens_straight_into_the_token_buffer():
+    """the hooked ViT block outputs land in the head's token buffer (CLS dropped, channel slices,
+    dtype cast) without a concatenated intermediate; same values as the reference's cat + drop-CLS + reshape."""
+    from video_rep_learning_b200.models.transformer import FeatureExtractor
+    torch.manual_seed(0)
+    vit = _FakeViT()
+    fx = FeatureExtractor(vit, [1, 3])
+    cfg = small_cfg(c_in=16)
+    cfg.MODEL.BASE_MODEL.FRAMES_PER_BATCH = 4
+    model = build_model(cfg, backbone=fx)
+    x = torch.randn(1, 6, 3, 4, 4)                        # one video, 6 frames -> two chunks of 4 + 2 frames
+    # reference-style path: cat of the hooked outputs, CLS dropped afterwards
+    toks, _cls = fx(x[0])
+    want = toks[:, 1:, :].reshape(1, 6, 9, 16)
+    buf = torch.full((1, 6, 9, 16), float("nan"), dtype=torch.bfloat16)
+    out = model.backbone_tokens(x, out=buf)
+    assert out.data_ptr() == buf.data_ptr()               # the producer wrote where the consumer reads
+    assert torch.equal(buf.float(), want.bfloat16().float())
+    assert fx._dest is None and not fx._feats              # nothing retained, hooks unbound again
+    # without a buffer it allocates one of the backbone's dtype and still goes through the hooks
+    out2 = model.backbone_tokens(x)
+    assert torch.equal(out2, want)

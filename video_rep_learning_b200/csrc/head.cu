@@ -49,7 +49,10 @@ struct ProfScope {
   int tag, slot;
   cudaStream_t st;
   ProfScope(int tag_, cudaStream_t st_) : tag(tag_), slot(-1), st(st_) {
-    if (!g_prof_on || tag < 0 || tag >= PROF_TAGS || g_prof_n[tag] >= PROF_CAP) return;
+    // level 1: the streaming pooling kernels only (two brackets per step); level 2: every tagged kernel group.  Inside a
+    // captured graph every bracket is a pair of event-record nodes, which also cuts the programmatic-dependent-launch overlap
+    // of the kernels around it -- so the timed graph of a ~1.6 ms step carries level 1 and the shares are read at level 2
+    if (!g_prof_on || tag < 0 || tag >= PROF_TAGS || g_prof_n[tag] >= PROF_CAP || (g_prof_on == 1 && tag > 1)) return;
     slot = g_prof_n[tag];
     if (!g_prof_init[tag][slot]) {
       if (cudaEventCreate(&g_prof_ev[tag][slot][0]) != cudaSuccess || cudaEventCreate(&g_prof_ev[tag][slot][1]) != cudaSuccess) {
@@ -1250,7 +1253,7 @@ const char* mvf_last_error(void) { return get_error(); }
 int mvf_has_tcgen05(void) { return tc_available() ? 1 : 0; }
 uint64_t mvf_launch_count(void) { return (uint64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 int mvf_profile_enable(int on) {
-  g_prof_on = on ? 1 : 0;
+  g_prof_on = on < 0 ? 0 : (on > 2 ? 2 : on);
   for (int t = 0; t < PROF_TAGS; ++t) g_prof_n[t] = 0;
   return MVF_OK;
 }

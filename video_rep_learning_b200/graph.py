@@ -80,7 +80,7 @@ class GraphedTrainStep:
             self.optimizer.step()
         return loss
 
-    def capture(self, profile: bool = False) -> "GraphedTrainStep":
+    def capture(self, profile: int = 0) -> "GraphedTrainStep":
         """Warm up eagerly on a side stream (lazy one-time work inside the library: kernel attributes, side streams,
         scratch buffers, NCCL communicators), then capture one step.  profile=True keeps the library's CUDA-event
         brackets around the dominant kernels in the graph (external event-record nodes, read with mvf_profile_read
@@ -136,7 +136,7 @@ class GraphedTrainStep:
             p.grad = None
         lib = L.lib()
         if profile:
-            lib.mvf_profile_enable(1)
+            lib.mvf_profile_enable(int(profile))   # 1: pooling kernels only, 2: every tagged kernel group (mvf_profile_enable)
         n0 = lib.mvf_launch_count()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

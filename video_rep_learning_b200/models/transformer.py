@@ -31,25 +31,43 @@ _TIMM_WIDTH = {
 
 
 class FeatureExtractor(nn.Module):
-    """Collects the token outputs of selected ViT blocks and concatenates them along channels
-    (role of transformer.py:306-333).  Returns (tokens [n, 1+P, C*k], cls [n, C])."""
+    """Collects the token outputs of selected ViT blocks (role of transformer.py:306-333).
+
+    The reference concatenates the k hooked block outputs along channels (`torch.cat`, one full write + read of the
+    largest tensor on the path) and `TransformerModel.forward` then copies the result again while dropping CLS and
+    re-laying it out.  Here the hooks write STRAIGHT into the head's token buffer: `bind(dest)` hands over the destination
+    slice [n, P, C*k] (token-major, CLS dropped, any dtype -- the bf16 conversion rides on the same copy) and every hook
+    stores its block's patch tokens into its own channel range of it as the block finishes.  Nothing else is materialised:
+    no concatenated tensor, no second copy.  Without a bound destination `forward` returns (tokens [n, 1+P, C*k], cls) like
+    the reference (one `torch.cat`), which is what third-party callers expect."""
 
     def __init__(self, vit: nn.Module, layers):
         super().__init__()
         self.vit = vit
         self.layers = [int(l) for l in layers]
         self._feats = {}
-        for l in self.layers:
-            vit.blocks[l].register_forward_hook(self._make_hook(l))
+        self._dest = None
+        for i, l in enumerate(self.layers):
+            vit.blocks[l].register_forward_hook(self._make_hook(i, l))
 
-    def _make_hook(self, l):
+    def bind(self, dest):
+        """dest: [n, P, C*k] view the next forward writes the patch tokens into (None: unbind)."""
+        self._dest = dest
+
+    def _make_hook(self, i, l):
         def hook(_m, _i, out):
-            self._feats[l] = out
+            if self._dest is not None:
+                C = out.shape[-1]
+                self._dest[:, :, i * C:(i + 1) * C].copy_(out[:, 1:, :])     # drop CLS, cast, place: one strided copy
+            else:
+                self._feats[l] = out
         return hook
 
     def forward(self, x):
         self._feats.clear()
         final = self.vit.forward_features(x)
+        if self._dest is not None:
+            return None, final[:, 0]
         toks = torch.cat([self._feats[l] for l in self.layers], dim=-1)
         return toks, final[:, 0]
 
@@ -101,29 +119,50 @@ class TransformerModel(nn.Module):
     def run_options(self) -> engine.RunOptions:
         return self.embed.run_options
 
-    def backbone_tokens(self, x: torch.Tensor, with_cls: bool = False):
+    def backbone_tokens(self, x: torch.Tensor, with_cls: bool = False, out: Optional[torch.Tensor] = None,
+                        dtype: Optional[torch.dtype] = None):
         """frames [BV,T,3,H,W] -> patch tokens [BV,T,P,C_in] (token-major, CLS dropped), chunked over frames like
-        transformer.py:175-189 (FRAMES_PER_BATCH), backbone in eval mode under no_grad.  with_cls: also the CLS embeddings
-        [BV*T, C] concatenated chunk by chunk exactly as transformer.py:200,217 does (chunk-major rows -- with T >
-        FRAMES_PER_BATCH that differs from the video-major order the head assumes; the reference's own behaviour is kept)."""
+        transformer.py:175-189 (FRAMES_PER_BATCH), backbone in eval mode under no_grad.
+        `out` (optional): the token buffer to fill -- e.g. graph.GraphedTrainStep.tokens, so the producer writes where the
+        captured step reads; `dtype`: element type of a freshly allocated buffer (default: the backbone's).  With the
+        package's FeatureExtractor the hooked ViT blocks write their patch tokens directly into that buffer (no concatenated
+        tensor, no second copy); any other backbone goes through one slice copy.
+        with_cls: also the CLS embeddings [BV*T, C] concatenated chunk by chunk exactly as transformer.py:200,217 does
+        (chunk-major rows -- with T > FRAMES_PER_BATCH that differs from the video-major order the head assumes; the
+        reference's own behaviour is kept)."""
         BV, T, c, h, w = x.shape
         fpb = self.cfg.MODEL.BASE_MODEL.FRAMES_PER_BATCH
-        out = None
         cls_chunks = []
         self.backbone.eval()
+        direct = isinstance(self.backbone, FeatureExtractor) and isinstance(self.res_finetune, nn.Identity)
+        if direct and out is None:
+            n_patches = getattr(getattr(self.backbone.vit, "patch_embed", None), "num_patches", None)
+            if n_patches is not None:
+                par = next(self.backbone.vit.parameters(), None)
+                out = torch.empty(BV, T, int(n_patches), int(self.cfg.MODEL.BASE_MODEL.OUT_CHANNEL),
+                                  dtype=dtype or (par.dtype if par is not None else x.dtype), device=x.device)
         for i in range(int(math.ceil(float(T) / fpb))):
             t0 = i * fpb
             t1 = min(T, t0 + fpb)
             cur = x[:, t0:t1].contiguous().view(-1, c, h, w)
-            with torch.no_grad():
-                toks, _cls = self.backbone(cur)
-            toks = self.res_finetune(toks)
+            if direct and out is not None and (BV == 1 or t1 - t0 == T):
+                # the frames of this chunk are one contiguous [n, P, C_in] block of the buffer: hooks write in place
+                self.backbone.bind(out[:, t0:t1].reshape(BV * (t1 - t0), out.shape[2], out.shape[3]))
+                try:
+                    with torch.no_grad():
+                        _, _cls = self.backbone(cur)
+                finally:
+                    self.backbone.bind(None)
+            else:
+                with torch.no_grad():
+                    toks, _cls = self.backbone(cur)
+                toks = self.res_finetune(toks)
+                n, ntok, C = toks.shape
+                if out is None:
+                    out = torch.empty(BV, T, ntok - 1, C, dtype=dtype or toks.dtype, device=toks.device)
+                out[:, t0:t1].copy_(toks[:, 1:, :].reshape(BV, t1 - t0, ntok - 1, C))   # drop CLS, keep token-major
             if with_cls:
                 cls_chunks.append(_cls)
-            n, ntok, C = toks.shape
-            if out is None:
-                out = torch.empty(BV, T, ntok - 1, C, dtype=toks.dtype, device=toks.device)
-            out[:, t0:t1] = toks[:, 1:, :].reshape(BV, t1 - t0, ntok - 1, C)   # drop CLS, keep token-major
         if with_cls:
             return out, torch.cat(cls_chunks, dim=0)
         return out
