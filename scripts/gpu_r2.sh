@@ -68,6 +68,32 @@ except Exception as e:
     print("   unreadable:", e)
 PY
       done ;;
+    scl)
+      timeout 300 python scripts/scl_bench.py > gpurun_out/scl_bench.txt 2>&1; echo "exit $?" | tee -a $S
+      python - <<'PY' | tee -a $S
+import json
+for l in open("gpurun_out/scl_bench.txt"):
+    try:
+        d = json.loads(l)
+        print("   pairs %6d T %3d D %3d masked %-5s  %8.4f ms  %7.1f GB/s  frac %.3f" % (d["pairs"], d["T"], d["D"], d["masked_frames"], d["ms"], d["GBps"], d["frac_of_measured_hbm"]))
+    except Exception:
+        pass
+PY
+      ;;
+    sclncu:*)
+      # sclncu:<Bv>:<T>:<D>:<masked>  launch list + full capture of the pair kernel for one SCL shape
+      spec=${stage#sclncu:}; IFS=: read bv tt dd mm <<< "$spec"
+      timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/scl_launches_${bv}_${tt}_${dd}_${mm}.csv python scripts/scl_one.py $bv $tt $dd $mm > /dev/null 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:scl_pair_mma -s 2 -c 1 -f -o gpurun_out/ncu_scl_pair_${bv}_${tt}_${dd}_${mm} python scripts/scl_one.py $bv $tt $dd $mm > gpurun_out/ncu_scl_pair_${bv}_${tt}_${dd}_${mm}.log 2>&1
+      echo "exit $?" | tee -a $S
+      python - gpurun_out/scl_launches_${bv}_${tt}_${dd}_${mm}.csv <<'PY' | tee -a $S
+import csv, sys
+rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
+h = rows[0]; ki = h.index("Kernel Name"); vi = h.index("Metric Value")
+for r in rows[1:][-8:]:
+    print("   %-70s %s" % (r[ki][:70], r[vi]))
+PY
+      ;;
     ref)
       timeout 900 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "exit $?" | tee -a $S ;;
     launches|launches4|launches5)

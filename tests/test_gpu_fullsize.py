@@ -94,5 +94,6 @@ def test_scl_named_shapes_match_oracle(Bv, T, D):
     L.check(lib.mvf_scl_fwd_bwd(L.ptr(ed), L.ptr(sl), L.ptr(st), L.ptr(mk), Bv, T, D, 0.1, 10.0, 0, 1, L.ptr(loss), L.ptr(dE),
                                 L.ptr(ws), nb, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
-    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
-    assert H.rel_l2(dE, e64.grad) < 1e-5
+    le, ge = abs(float(loss) - float(ref)) / abs(float(ref)), H.rel_l2(dE, e64.grad)
+    print(f"SCL {Bv} pairs x {T} frames x {D}: loss {le:.2e} gradient {ge:.2e} against the dense fp64 oracle")
+    assert le <= 1e-5 and ge < 1e-5

@@ -1,4 +1,4 @@
-"""GPU: fused SCL forward+gradient (csrc/scl.cu) through the algos/ interface against the reference goldens,
+"""GPU: fused SCL forward+gradient (csrc/scl.cu, csrc/scl_mma.cu) through the algos/ interface against the reference goldens,
 plus size-independent properties at BASELINE-scale batches."""
 import os
 
@@ -30,8 +30,9 @@ def test_scl_matches_reference_golden(name):
     loss, dE = _run(torch.from_numpy(z["embs"]), torch.from_numpy(z["seq_lens"]), torch.from_numpy(z["steps"]),
                     torch.from_numpy(z["masks"]), neg)
     # tolerance stated by the north star: 1e-5 relative in fp32 (the reference's own fp32-vs-fp64 gap is ~1e-7)
-    assert abs(loss - float(z["ref_loss_f64"])) / float(z["ref_loss_f64"]) < 1e-5
-    assert H.rel_l2(dE, torch.from_numpy(z["ref_dE_f64"])) < 1e-5
+    le, ge = abs(loss - float(z["ref_loss_f64"])) / float(z["ref_loss_f64"]), H.rel_l2(dE, torch.from_numpy(z["ref_dE_f64"]))
+    print(f"{name}: loss {le:.2e} gradient {ge:.2e} against the reference in fp64")
+    assert le < 1e-5 and ge < 1e-5
     assert abs(loss - float(z["ref_loss_f32"])) / float(z["ref_loss_f32"]) < 1e-5
 
 
@@ -113,18 +114,3 @@ def test_scl_properties_at_scale():
     idx = [0, 17, 255]
     lsub, gsub = O.scl_loss_pairs(e[idx].numpy(), seq_lens[idx].numpy(), steps[idx].numpy(), np.ones((3, 2, T)))
     assert H.rel_l2(ga[idx] * (Bv / 3.0), torch.from_numpy(gsub)) < 1e-5
-
-
-@pytest.mark.skipif(os.environ.get("MVF_SCL_TC", "0") in ("", "0"),
-                    reason="prototype tensor-core per-pair kernel (csrc/scl_tc.cu): runs only with MVF_SCL_TC=1")
-@pytest.mark.parametrize("Bv,T,D", [(5, 20, 128), (3, 32, 128), (4, 7, 64), (2, 20, 256)])
-def test_scl_tensor_core_prototype_against_closed_form(Bv, T, D):
-    """Round-2 work item: with MVF_SCL_TC=1 the per-pair statistics and gradients run on mma.sync (bf16 hi/lo operand
-    splits).  Checked against the per-pair closed form of the oracle; tolerance as for the tensor-core attention."""
-    g = torch.Generator().manual_seed(Bv * T + D)
-    e = torch.nn.functional.normalize(torch.randn(Bv, 2, T, D, generator=g), dim=-1)
-    _, seq_lens, steps, masks = O.synth_batch(Bv, T, 1, 1, seed=Bv + T)
-    loss, dE = _run(e, seq_lens, steps, masks)
-    lp, dEp = O.scl_loss_pairs(e.numpy(), seq_lens.numpy(), steps.numpy(), masks.numpy())
-    assert abs(loss - lp) <= 5e-5 * abs(lp)
-    assert float((dE.double() - torch.from_numpy(dEp)).norm()) <= 5e-5 * float(np.linalg.norm(dEp))

@@ -72,6 +72,25 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors are picked up by MVF_CHECK_LAUNCH
 }
+// the same with a thread-block cluster of `cluster_x` CTAs along x (gridDim.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+inline void launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- scalar conversion ---------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);

@@ -166,11 +166,14 @@ int attention_tc_bwd(int B, int S, int heads, const void* qkv, const float* keym
 
 // ---- scl.cu ----------------------------------------------------------------------------------------------------
 size_t scl_ws_bytes(int Bv, int T, int D);
-// scl_tc.cu: PROTOTYPE of the per-pair kernel on mma.sync (MVF_SCL_TC=1 only; not yet validated on a GPU)
-bool scl_pair_tc_enabled(int T, int D);
-int scl_pair_tc(const float* embs, const int64_t* seq_lens, const int64_t* steps, const float* masks, int Bv, int T, int D,
-                float tau, float two_var, const float* Mptr, const float* zext, float* c_out, float* loss_out, float* d_embs,
-                cudaStream_t st);
+// scl_mma.cu: the per-pair kernel and the cross passes on mma.sync (T <= 256, D <= 256, D % 4 == 0)
+struct SclWs;
+struct SclCrossJobs;
+bool scl_mma_supported(int T, int D);
+int scl_pair_mma(const float* embs, const int64_t* seq_lens, const int64_t* steps, const float* masks, int Bv, int T, int D,
+                 float tau, float two_var, const SclWs& w, int use_zext, float* loss_out, float* d_embs, cudaStream_t st);
+int scl_cross_mma(const float* embs, int N, int T2, int D, float tau, const SclCrossJobs& J, int grad, float* sum_out,
+                  float* vec_out, cudaStream_t st);
 int scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps, const float* masks, int Bv, int T,
                 int D, float temperature, float label_variance, int negative_type, int quirk, float* loss_out,
                 float* d_embs, void* ws, size_t ws_bytes, cudaStream_t st);
