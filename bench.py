@@ -387,10 +387,6 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
-        # --overlap: the chain's gradient all-reduce runs beside the pooling backward, which leaves --reserve-sms SMs free
-        # for it: keep NCCL's CTA count within that
-        if args.overlap:
-            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.reserve_sms))
         dist.init_process_group("nccl", device_id=dev)
     Bv, T, P, C_in = WL["videos_per_gpu"], WL["T"], WL["P"], WL["c_in"]
     E = WL["head"]["entities"]
@@ -432,7 +428,7 @@ def run_ours(args):
 
     lib = L.lib()
     head_opts = model.run_options
-    head_opts.overlap_grad_allreduce = bool(args.overlap)
+    head_opts.overlap_grad_allreduce = not args.no_overlap
     head_opts.pool_bwd_reserve_sms = args.reserve_sms
 
     def read_prof():
@@ -479,7 +475,7 @@ def run_ours(args):
         return dict(ms_step=max_over_ranks(ms_total) / steps, launches=launches, prof=prof, prof_steps=steps, clocks=clk,
                     loss=float(loss.item()))
 
-    def graph_region(pool_mode, steps, warmup, sample_clocks):
+    def graph_region(pool_mode, steps, warmup, sample_clocks, extras=True):
         """The same step captured once as a CUDA graph (video_rep_learning_b200.graph.GraphedTrainStep) and replayed:
         W untimed + K timed replays, tokens resident in HBM, CUDA events, max over ranks.  The library's event brackets
         around the dominant kernels are part of the graph (external event-record nodes); they are read after the timed
@@ -510,7 +506,7 @@ def run_ours(args):
         # `sustained`; `value` stays the exactly-K-steps figure of the contract)
         sustained = None
         n_sus = int(min(4000, math.ceil(1000.0 / max(ms_step, 1e-3))))
-        if n_sus > steps:
+        if extras and n_sus > steps:
             sync_all()
             ev0.record()
             for _ in range(n_sus):
@@ -521,7 +517,7 @@ def run_ours(args):
             sustained = dict(steps=n_sus, ms_per_step=sus_ms, value=world * Bv / (sus_ms / 1e3), unit=UNIT)
         clk = clocks.stop() if (sample_clocks and rank == 0) else None
         prof = {tag: [] for tag in range(N_TAGS)}
-        n_prof = min(steps, 20)
+        n_prof = min(steps, 20) if extras else 0
         for _ in range(n_prof):
             gs()
             torch.cuda.synchronize()
@@ -532,6 +528,31 @@ def run_ours(args):
         launches = gs.launches_per_step * steps
         gs.release()
         return dict(ms_step=ms_step, launches=launches, prof=prof, prof_steps=n_prof, clocks=clk, loss=final, sustained=sustained)
+
+    def comm_breakdown(steps=50):
+        """Several ranks: what the cross-rank steps cost inside the replayed graph, by difference -- the same step captured
+        again (a) without the gradient all-reduce and (b) also with rank-local BatchNorm statistics.  Diagnostic legs after the
+        timed region; their steps are not valid training steps and never enter `value`."""
+        from video_rep_learning_b200 import parallel as par
+        keep = (head_opts.allreduce_grads, head_opts.sync_bn)
+        out = {}
+        try:
+            head_opts.allreduce_grads = False
+            t_noar = graph_region(pool_default, steps, 5, False, extras=False)["ms_step"]
+            head_opts.sync_bn = False
+            t_local = graph_region(pool_default, steps, 5, False, extras=False)["ms_step"]
+        finally:
+            head_opts.allreduce_grads, head_opts.sync_bn = keep
+        fg = list(par.PeerFlatGrads._cache.values())
+        out["grad_allreduce"] = dict(us_per_step=1e3 * (ms_step - t_noar), calls_per_step=1,
+                                     via=("symmetric memory, " + ("NVSwitch multimem" if fg[0].mc_ptr else "peer loads/stores"))
+                                     if fg else "NCCL")
+        out["bn_exchange"] = dict(us_per_step=1e3 * (t_noar - t_local),
+                                  via="symmetric memory flags + peer loads" if par.PeerStats._cache else "NCCL")
+        out["ms_per_step"] = dict(full=ms_step, no_grad_allreduce=t_noar, rank_local=t_local)
+        out["note"] = ("graph replays of the same step without the gradient all-reduce / without any cross-rank call; "
+                       "differences of max-over-ranks step times")
+        return out
 
     pool_default = L.POOL_DENSE if args.pool == "dense" else L.POOL_FOLDED
     graph_note = None
@@ -641,6 +662,12 @@ def run_ours(args):
         del model0, params0
         torch.cuda.empty_cache()
 
+    comm = None
+    if world > 1 and not args.eager and graph_note and graph_note.startswith("one cudaGraphLaunch"):
+        try:
+            comm = comm_breakdown()
+        except Exception as e:
+            comm = dict(error=f"{type(e).__name__}: {str(e)[:200]}")
     ref_gpu = None
     if world == 1 and rank == 0 and not args.no_refgpu:
         ref_gpu = reference_gpu_run(dev, tokens_dev, seq_lens, steps, masks, max(3, min(args.steps, 10)))
@@ -844,6 +871,8 @@ def run_ours(args):
                        value=e2e_value, unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=k2,
                        note="pinned host tokens -> HBM on a copy stream (double buffered) + loss.item() per step", numa=numa),
                    gpu_launches=launches, clocks=clk)
+        if comm is not None:
+            out["cross_rank"] = comm
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -864,9 +893,9 @@ def main():
     ap.add_argument("--pool", default="folded", choices=["folded", "dense"],
                     help="entity pooling: folded (default product path) or dense (as written: K|V GEMM + attention)")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replays")
-    ap.add_argument("--overlap", action="store_true",
-                    help="multi-GPU: all-reduce the chain's gradients beside the pooling backward (measured slower; default off)")
-    ap.add_argument("--reserve-sms", type=int, default=16, help="SMs the pooling backward leaves to the overlapped all-reduce")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="multi-GPU: one gradient all-reduce at the end instead of summing the chain's gradients beside the pooling backward")
+    ap.add_argument("--reserve-sms", type=int, default=4, help="SMs the pooling backward leaves to the overlapped all-reduce")
     ap.add_argument("--no-dense", action="store_true", help="skip the short as-written (dense pooling) comparison leg")
     args = ap.parse_args()
     WL = WORKLOADS[args.workload]

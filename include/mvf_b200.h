@@ -258,13 +258,23 @@ int mvf_opt_adam_step(int32_t n_tensors, float* const* params, const float* cons
                       size_t ws_bytes, mvf_stream_t stream);
 
 /* Cross-rank sum of a small float64 buffer (BatchNorm statistics, replaces the SyncBatchNorm exchange of train.py:283)
- * over NVLink peer memory: bufs_dev = DEVICE array of `world` pointers to the ranks' symmetric buffers of
- * mvf_peer_buffer_bytes() bytes each (zero-filled before first use; e.g. torch.distributed._symmetric_memory),
+ * over NVLink peer memory: bufs_dev = DEVICE array of `world` (<= 16) pointers to the ranks' symmetric buffers of
+ * mvf_peer_buffer_bytes() bytes each (2 parities x 16 ranks x slot of 16-byte entries: n <= bytes / 512 values;
+ * zero-filled before first use; e.g. torch.distributed._symmetric_memory),
  * counter = this rank's device-resident exchange counter (starts at 0, advanced by the kernel: graph-replayable).
  * Every rank must call it the same number of times in the same order; the result is bitwise identical on all ranks. */
 size_t mvf_peer_buffer_bytes(void);
 int mvf_peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int32_t rank, int32_t world, uint32_t* counter,
                      mvf_stream_t stream);
+
+/* In-place SUM over the ranks of the flat fp32 gradient buffer (replaces DDP's all-reduce, train.py:286) through the same
+ * kind of symmetric memory: every rank's buffer holds n floats at data_off and mvf_peer_allreduce_flag_bytes() of flags at
+ * flag_off (zero before first use); mc_base = NVSwitch multicast address of the buffer (multimem.ld_reduce / multimem.st) or
+ * NULL (peer loads / stores); counters = 64 device words (start at 0); ctas <= 64 (0: default).  Each rank reduces and
+ * broadcasts its 1/world slice, so all ranks end with the bitwise identical sum.  Graph-replayable. */
+size_t mvf_peer_allreduce_flag_bytes(void);
+int mvf_peer_allreduce_f32(void* mc_base, void* const* bufs_dev, size_t data_off, size_t flag_off, int64_t n, int32_t rank,
+                           int32_t world, uint32_t* counters, int32_t ctas, mvf_stream_t stream);
 
 /* a5/a8 temporal self-attention core (utils.py:11-44 with the [B,1,1,S] key mask): qkv [B*S, 3*H]
  * (Q | K | V, head h at columns h*dk), keymask [B,S] fp32 or NULL -> ctx [B*S, H], lse [B,heads,S] fp32.

@@ -54,16 +54,18 @@ for stage in "$@"; do
     dist|dist4|dist5)
       # N = every GPU of the box: the driver's launch line, default and --overlap
       n=$(nvidia-smi -L | wc -l); wl=penn_cfg2; [ $stage = dist4 ] && wl=finegym_cfg4; [ $stage = dist5 ] && wl=long_cfg5
-      for v in "" "--overlap"; do
-        tag=${wl}_n${n}${v:+_overlap}
-        timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py \
-          --gpus $n --workload $wl --steps 50 --warmup 5 --no-cpu --no-refgpu --no-dense $v > gpurun_out/dist_$tag.json 2> gpurun_out/dist_$tag.err
+      for v in ${DIST_VARIANTS:-default nooverlap nccl}; do
+        tag=${wl}_n${n}_$v
+        ar=1; [ "$v" = nccl ] && ar=0
+        xo=""; [ "$v" = nooverlap ] && xo="--no-overlap"
+        MVF_PEER_AR=$ar timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py \
+          --gpus $n --workload $wl --steps 50 --warmup 5 --no-cpu --no-refgpu --no-dense $xo ${DIST_EXTRA:-} > gpurun_out/dist_$tag.json 2> gpurun_out/dist_$tag.err
         echo "$tag exit $? :: $(tail -c 400 gpurun_out/dist_$tag.json | tr '\n' ' ' | grep -o '"parity".*' | head -c 300)" | tee -a $S
         python - gpurun_out/dist_$tag.json <<'PY' | tee -a $S
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print("   n_gpus", d["n_gpus"], "value %.1f ms %.3f" % (d["value"], d["ms_per_step"]), "e2e", (d.get("e2e") or {}).get("value"), "clocks", d.get("clocks"))
+    print("   n_gpus", d["n_gpus"], "value %.1f ms %.3f" % (d["value"], d["ms_per_step"]), "e2e", (d.get("e2e") or {}).get("value"), "cross_rank", d.get("cross_rank"))
 except Exception as e:
     print("   unreadable:", e)
 PY
@@ -94,6 +96,10 @@ for r in rows[1:][-8:]:
     print("   %-70s %s" % (r[ki][:70], r[vi]))
 PY
       ;;
+    peer)
+      n=$(nvidia-smi -L | wc -l)
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29519 scripts/peer_bench.py > gpurun_out/peer_bench_n$n.json 2> gpurun_out/peer_bench_n$n.err
+      echo "exit $? :: $(tail -n 1 gpurun_out/peer_bench_n$n.json)" | tee -a $S ;;
     ref)
       timeout 900 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "exit $?" | tee -a $S ;;
     launches|launches4|launches5)

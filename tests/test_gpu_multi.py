@@ -75,3 +75,51 @@ def test_two_gpu_step_matches_syncbn_ddp_oracle(tmp_path):
     for k, v in nb.items():
         if v.is_floating_point():
             assert float((r0["bufs"][k].double() - v).abs().max()) < 1e-5, k
+
+
+def _allreduce_worker(rank, world, port, out_dir, multicast):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["MVF_PEER_MULTICAST"] = "1" if multicast else "0"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from video_rep_learning_b200 import parallel
+        dev = torch.device("cuda", rank)
+        res = {}
+        for n in (4, 1000, 4_800_003):
+            g = torch.Generator(device="cpu").manual_seed(100 * rank + n % 97)
+            x = torch.randn(n, generator=g)
+            for rep in range(3):                                  # the buffer and its exchange counters are reused every step
+                flat = parallel.flat_grad_buffer(n, dev)
+                obj = [o for o in parallel.PeerFlatGrads._cache.values() if o.owns(flat)]
+                assert obj, "symmetric-memory gradient buffer was not created"
+                flat.copy_(x.to(dev) * (rep + 1))
+                scale = parallel.finish_flat_grads_(flat)
+                torch.cuda.synchronize()
+                assert scale == 1.0 / world
+                res[(n, rep)] = flat.cpu().clone()
+            res[("mc", n)] = bool(obj[0].mc_ptr)
+        torch.save(res, os.path.join(out_dir, f"ar{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("multicast", [True, False], ids=["multimem", "peer_loads"])
+def test_two_gpu_flat_gradient_allreduce(tmp_path, multicast):
+    """mvf_peer_allreduce_f32 (NVSwitch multimem path and the peer load/store path): the in-place sum of the symmetric flat
+    buffer equals the sum of the ranks' inputs (one fp32 addition per element at world 2: exact) and is bitwise identical on
+    both ranks, call after call on the same buffer."""
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_allreduce_worker, args=(world, port, str(tmp_path), multicast), nprocs=world, join=True)
+    r = [torch.load(os.path.join(str(tmp_path), f"ar{k}.pt")) for k in range(world)]
+    for n in (4, 1000, 4_800_003):
+        xs = [torch.randn(n, generator=torch.Generator(device="cpu").manual_seed(100 * k + n % 97)) for k in range(world)]
+        for rep in range(3):
+            want = xs[0] * (rep + 1) + xs[1] * (rep + 1)
+            assert torch.equal(r[0][(n, rep)], r[1][(n, rep)])
+            assert torch.equal(r[0][(n, rep)], want), (n, rep, float((r[0][(n, rep)] - want).abs().max()))
+        print(f"n = {n}: multicast mapping {'present' if r[0][('mc', n)] else 'absent'}")

@@ -61,7 +61,6 @@ _PROTOS = {
     "mvf_ws_bytes": (_sz, [_pd]),
     "mvf_gpack_elems": (_sz, [_pd]),
     "mvf_gpack_pool_elems": (_sz, [_pd]),
-    "mvf_pool_bwd_reserve_sms": (C.c_int, [_i32]),
     "mvf_proj_save_bytes": (_sz, [_pd]),
     "mvf_proj_ws_bytes": (_sz, [_pd]),
     "mvf_save_lookup": (C.c_int, [_pd, C.c_char_p, C.POINTER(_sz), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
@@ -87,8 +86,11 @@ _PROTOS = {
     "mvf_opt_ws_bytes": (_sz, [_i32]),
     "mvf_opt_adam_step": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _f32, _f32, _i32, _f32, _f32, _vp, _vp,
                                     _sz, _vp]),
+    "mvf_pool_bwd_reserve_sms": (C.c_int, [_i32]),
     "mvf_peer_buffer_bytes": (_sz, []),
     "mvf_peer_sum_f64": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    "mvf_peer_allreduce_flag_bytes": (_sz, []),
+    "mvf_peer_allreduce_f32": (C.c_int, [_vp, _vp, _sz, _sz, _i64, _i32, _i32, _vp, _i32, _vp]),
     "mvf_attention_ws_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "mvf_attention_fwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mvf_attention_bwd": (C.c_int, [C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -1512,6 +1512,11 @@ int mvf_peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int32_t ra
                      mvf_stream_t stream) {
   return peer_sum_f64(local, n, bufs_dev, rank, world, counter, (cudaStream_t)stream);
 }
+size_t mvf_peer_allreduce_flag_bytes(void) { return peer_allreduce_flag_bytes(); }
+int mvf_peer_allreduce_f32(void* mc_base, void* const* bufs_dev, size_t data_off, size_t flag_off, int64_t n, int32_t rank,
+                           int32_t world, uint32_t* counters, int32_t ctas, mvf_stream_t stream) {
+  return peer_allreduce_f32(mc_base, bufs_dev, data_off, flag_off, n, rank, world, counters, ctas, (cudaStream_t)stream);
+}
 size_t mvf_attention_ws_bytes(int32_t B, int32_t S, int32_t heads, int32_t dk) { return attention_ws_bytes(B, S, heads, dk); }
 int mvf_attention_fwd(int dtype, int32_t B, int32_t S, int32_t heads, int32_t dk, const void* qkv, const float* keymask,
                       void* ctx, float* lse, void* ws, size_t ws_bytes, mvf_stream_t stream) {

@@ -141,6 +141,11 @@ int opt_adam_step(int n_tensors, float* const* params, const float* const* grads
 // ---- peer.cu: sum of small float64 buffers over NVLink peer memory (BatchNorm statistics across ranks) ----------------
 size_t peer_buffer_bytes();
 int peer_sum_f64(double* local, int64_t n, void* const* bufs_dev, int rank, int world, uint32_t* counter, cudaStream_t st);
+// in-place SUM over the ranks of n floats at data_off of every rank's symmetric buffer (mc_base: NVSwitch multicast address
+// of the buffer or null); flags at flag_off (peer_allreduce_flag_bytes(), zero before first use); counters: 64 device words
+size_t peer_allreduce_flag_bytes();
+int peer_allreduce_f32(void* mc_base, void* const* bufs_dev, size_t data_off, size_t flag_off, int64_t n, int rank, int world,
+                       uint32_t* counters, int ctas, cudaStream_t st);
 
 // ---- attention.cu --------------------------------------------------------------------------------------------
 // allow_split: the caller accepts operands split into bf16 hi + lo (2^-16 relative) -> tensor-core kernels of attention_tc.cu

@@ -59,13 +59,10 @@ class RunOptions:
     process_group: Optional[object] = None
     scl_quirk: bool = True          # keep the 1e-6 weight on masked columns (algos/scl.py:80)
     pool_mode: int = L.POOL_AUTO    # entity pooling: AUTO -> folded (no K|V tensors); POOL_DENSE = as written in the reference
-    overlap_grad_allreduce: bool = False  # several ranks: all-reduce the chain's gradients (12 of 19 MB) on a second stream
-                                          # while the pooling backward (the last ~0.23 ms of the step) still runs.
-                                          # Measured on 2 / 4 B200: 1.82 / 1.85 ms per step against 1.79 / 1.84 ms with one
-                                          # all-reduce at the end -- the SMs the HBM-bound pooling kernel gives up cost as
-                                          # much as the hidden transfer saves -- so it is off by default
-    pool_bwd_reserve_sms: int = 16        # SMs that kernel leaves to the collective while they overlap
-
+    overlap_grad_allreduce: bool = True   # several ranks, symmetric-memory gradient buffer: the chain's gradients are summed
+                                          # by a few CTAs (csrc/peer.cu) beside the pooling backward, the last ~0.25 ms of the
+                                          # step; only the pooling gradients wait for its end
+    pool_bwd_reserve_sms: int = 4         # SMs the pooling backward leaves to those CTAs (its persistent CTAs fill an SM)
 
 
 def _world(opts: RunOptions) -> int:
@@ -430,7 +427,8 @@ class HeadFn(torch.autograd.Function):
         with torch.cuda.device(tokens.device):
             d = plan.desc_with_seed(ctx.seed, cs.seed_dev, cs.cls_emb)
             ws = _scratch(tokens.device, plan.ws_bytes, "head")
-            gpack = torch.zeros(plan.gpack_elems, dtype=torch.float32, device=tokens.device)
+            gpack = parallel.flat_grad_buffer(plan.gpack_elems, tokens.device, cs.opts.process_group,
+                                              enabled=_world(cs.opts) > 1 and cs.opts.allreduce_grads)
             full = list(params) + [None] * (len(plan.param_names) - len(params))
             _run_head_backward(cs, plan, d, L.ptr_array(full), tokens, mask, d_emb.contiguous().float(), cs.head_save,
                                ws, gpack)
@@ -472,7 +470,8 @@ class ProjFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             d = plan.desc_with_seed(0)
             ws = _scratch(dev, plan.proj_ws_bytes, "proj")
-            gpack = torch.zeros(plan.gpack_elems, dtype=torch.float32, device=dev)
+            gpack = parallel.flat_grad_buffer(plan.gpack_elems, dev, cs.opts.process_group,
+                                              enabled=_world(cs.opts) > 1 and cs.opts.allreduce_grads)
             d_emb = torch.empty(d_out.shape, dtype=torch.float32, device=dev)
             full = ([None] * plan.n_head_params + params) if cs.project else [None] * len(plan.param_names)
             _run_proj_backward(cs, plan, d, L.ptr_array(full), d_out.contiguous().float(), cs.proj_save, ws, gpack, d_emb)
@@ -520,32 +519,36 @@ class ModelFn(torch.autograd.Function):
             d = plan.desc_with_seed(ctx.seed, cs.seed_dev, cs.cls_emb)
             ws = _scratch(dev, plan.ws_bytes, "head")
             pws = _scratch(dev, plan.proj_ws_bytes, "proj")
-            gpack = torch.zeros(plan.gpack_elems, dtype=torch.float32, device=dev)
+            gpack = parallel.flat_grad_buffer(plan.gpack_elems, dev, cs.opts.process_group,
+                                              enabled=_world(cs.opts) > 1 and cs.opts.allreduce_grads)
             d_emb = torch.empty(d_out.shape, dtype=torch.float32, device=dev)
             arr = ctx.param_ptrs
             _run_proj_backward(cs, plan, d, arr, d_out.contiguous().float(), cs.proj_save, pws, gpack, d_emb)
-            dist_world = _world(cs.opts)
-            split = plan.gpack_pool_elems
-            overlap = (dist_world > 1 and cs.opts.allreduce_grads and cs.opts.overlap_grad_allreduce
-                       and 0 < split < plan.gpack_elems)
-            if overlap:
+            # several ranks, symmetric-memory buffer: the chain's gradients (12 of 19 MB at the Penn shape, final before the
+            # pooling backward starts) are summed by a few CTAs on a second stream beside that HBM-bound kernel; only the
+            # pooling gradients are left for the end of the step
+            split = (plan.gpack_pool_elems + 3) // 4 * 4
+            peer = parallel.PeerFlatGrads.find(gpack) if (_world(cs.opts) > 1 and cs.opts.allreduce_grads) else None
+            # (only on the NVSwitch multimem path: plain peer loads / stores from a few CTAs are slower than the kernel they hide behind)
+            if peer is not None and peer[0].mc_ptr and cs.opts.overlap_grad_allreduce and 0 < split < plan.gpack_elems:
                 cur, comm = torch.cuda.current_stream(dev), _comm_stream(dev)
+
                 lib = L.lib()
+                reserve = max(1, int(cs.opts.pool_bwd_reserve_sms))
 
                 def start_chain_allreduce():
                     comm.wait_stream(cur)
                     with torch.cuda.stream(comm):
-                        parallel.finish_flat_grads_(gpack[split:], cs.opts.process_group)
-                    lib.mvf_pool_bwd_reserve_sms(int(cs.opts.pool_bwd_reserve_sms))
+                        parallel.finish_flat_grads_(gpack[split:], cs.opts.process_group, channel=1, ctas=reserve)
+                    lib.mvf_pool_bwd_reserve_sms(reserve)
 
                 try:
                     _run_head_backward(cs, plan, d, arr, tokens, mask, d_emb, cs.head_save, ws, gpack,
                                        before_pool=start_chain_allreduce)
                 finally:
                     lib.mvf_pool_bwd_reserve_sms(0)
-                grads_scale_from = split
                 cur.wait_stream(comm)
-                grads = _finish_grads(cs, plan, d, gpack, list(params), reduced_from=grads_scale_from)
+                grads = _finish_grads(cs, plan, d, gpack, list(params), reduced_from=split)
             else:
                 _run_head_backward(cs, plan, d, arr, tokens, mask, d_emb, cs.head_save, ws, gpack)
                 grads = _finish_grads(cs, plan, d, gpack, list(params))
