@@ -107,21 +107,11 @@ def test_fold_backward_equals_autograd_of_dense_formulation(F, P, E, C, SPC, dty
     assert float(d_bk.abs().max()) < 1e-9 * float(d_bv.abs().max())
 
 
-def test_fold_mma_and_cuda_core_paths_agree(monkeypatch):
-    """bf16 tokens with C_in % 16 == 0 run on mma.sync (pool_fold_mma.cu); MVF_FOLD_MMA=0 forces the CUDA-core kernels."""
-    F, P, E, C, SPC = 9, 196, 3, 2304, 384
-    X, qs, qb, Wk, Wv, bk, bv = _mk(F, P, E, C, SPC, torch.bfloat16, seed=3)
-    _, attn_m, px_m = _fold_forward(X, qs, qb, Wk)
-    monkeypatch.setenv("MVF_FOLD_MMA", "0")
-    _, attn_c, px_c = _fold_forward(X, qs, qb, Wk)
-    assert float((attn_m - attn_c).abs().max()) < 2e-6
-    assert float((px_m - px_c).abs().max() / px_c.abs().max()) < 5e-6
-
-
 @pytest.mark.parametrize("F,P,E,C", [(9, 196, 3, 2304), (301, 196, 3, 2304), (7, 50, 6, 384), (5, 30, 11, 768), (6, 9, 3, 48)])
-def test_fold_warp_specialised_and_first_generation_kernels_agree(monkeypatch, F, P, E, C):
-    """pool_fold_ws.cu (default) against pool_fold_mma.cu (MVF_FOLD_WS=0): forward outputs, and the backward pass with the
-    caller-supplied delta, with the in-kernel delta, and on the first-generation kernel."""
+def test_fold_tensor_core_and_cuda_core_kernels_agree(monkeypatch, F, P, E, C):
+    """pool_fold_ws.cu (bf16 tokens, C_in % 16 == 0: warp-specialised mma.sync kernels, the default) against the CUDA-core
+    kernels of pool_fold.cu (MVF_FOLD_WS=0): forward outputs, and the backward pass with the caller-supplied delta, with the
+    in-kernel delta, and on the CUDA-core kernel."""
     SPC = 64
     X, qs, qb, Wk, Wv, bk, bv = _mk(F, P, E, C, SPC, torch.bfloat16, seed=8)
     lib = L.lib()

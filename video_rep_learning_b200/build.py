@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvf_b200.so")
-SOURCES = ["head.cu", "elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "xattn.cu", "pool_fold.cu", "pool_fold_mma.cu", "pool_fold_ws.cu", "attention.cu", "attention_tc.cu", "attention_fa.cu", "scl.cu", "scl_mma.cu", "peer.cu", "optim.cu"]
+SOURCES = ["head.cu", "elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "xattn.cu", "pool_fold.cu", "pool_fold_ws.cu", "attention.cu", "attention_tc.cu", "attention_fa.cu", "scl.cu", "scl_mma.cu", "peer.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -114,12 +114,8 @@ int pool_fold_bwd(int dtype, int F, int P, int E, int C, const void* X, const fl
 // dWk += Q^T dWq / sqrt(SPC); dQ_s += dWq Wk^T / sqrt(SPC); dQ_b += column sums of dQ_s
 int fold_finish(const float* dWq, const float* q_s, const float* q_b, const float* Wk, int E, int SPC, int C, float* dWk,
                 int64_t ld_dwk, float* dQs, float* dQb, cudaStream_t st);
-// bf16 tokens, C % 16 == 0: the same two passes on mma.sync tensor cores (pool_fold_mma.cu); called by the two above
-bool pool_fold_mma_supported(int dtype, int C, int P);
-int pool_fold_mma_fwd(int F, int P, int E, int C, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st);
-int pool_fold_mma_bwd(int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,
-                      float* dWq, cudaStream_t st);
-// warp-specialised second generation of the same two passes (pool_fold_ws.cu): 8-token ring slots, mbarrier-only hand-offs
+// bf16 tokens, C % 16 == 0: the same two passes on mma.sync tensor cores, warp-specialised (pool_fold_ws.cu): 8-token ring
+// slots, mbarrier-only hand-offs; called by the two above
 bool pool_fold_ws_supported(int dtype, int C, int P);
 int pool_fold_ws_fwd(int F, int P, int E, int C, const void* X, const float* Wq, float* attn, float* px, cudaStream_t st);
 int pool_fold_ws_bwd(int F, int P, int E, int C, const void* X, const float* G, const float* px, const float* attn,

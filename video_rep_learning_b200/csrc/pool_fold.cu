@@ -689,15 +689,8 @@ bool pool_fold_supported(int dtype, int C, int E, int P) {
   return C > 0 && C % 8 == 0 && C / 8 <= 640 && E >= 1 && E <= MVF_MAX_ENTITIES && P >= 1;
 }
 
-// bf16 tokens with C_in % 16 == 0 run on the warp-level tensor cores (pool_fold_mma.cu); MVF_FOLD_MMA=0 forces the
+// bf16 tokens with C_in % 16 == 0 run on the warp-specialised tensor-core kernels of pool_fold_ws.cu; MVF_FOLD_WS=0 forces the
 // CUDA-core kernels of this file (A/B measurements, and the path fp32 tokens always take)
-static bool use_mma(int dtype, int C, int P) {
-  const char* e = getenv("MVF_FOLD_MMA");
-  if (e && atoi(e) == 0) return false;
-  return pool_fold_mma_supported(dtype, C, P);
-}
-
-// second-generation warp-specialised kernels (pool_fold_ws.cu) unless MVF_FOLD_WS=0
 static bool use_ws(int dtype, int C, int P) {
   const char* e = getenv("MVF_FOLD_WS");
   if (e && atoi(e) == 0) return false;
@@ -715,10 +708,7 @@ int pool_fold_fwd(int dtype, int F, int P, int E, int C, const void* X, const fl
                   cudaStream_t st) {
   MVF_TRY(fold_check(dtype, F, P, E, C, X));
   if (F == 0) return MVF_OK;
-  if (use_mma(dtype, C, P)) {
-    if (use_ws(dtype, C, P)) return pool_fold_ws_fwd(F, P, E, C, X, Wq, attn, px, st);
-    return pool_fold_mma_fwd(F, P, E, C, X, Wq, attn, px, st);
-  }
+  if (use_ws(dtype, C, P)) return pool_fold_ws_fwd(F, P, E, C, X, Wq, attn, px, st);
   for (int e0 = 0; e0 < E; e0 += 4) {   // entity passes of <= 4 (X is re-streamed per pass; E = 3 in every penn config)
     fold::Geom g{F, P, C, E, e0, 0, C * (dtype == MVF_BF16 ? 2 : 4)};
     const int ne = E - e0 < 4 ? E - e0 : 4;
@@ -732,10 +722,7 @@ int pool_fold_bwd(int dtype, int F, int P, int E, int C, const void* X, const fl
                   float* dWq, cudaStream_t st, const float* delta) {
   MVF_TRY(fold_check(dtype, F, P, E, C, X));
   if (F == 0) return MVF_OK;
-  if (use_mma(dtype, C, P)) {
-    if (use_ws(dtype, C, P)) return pool_fold_ws_bwd(F, P, E, C, X, G, px, attn, delta, dWq, st);
-    return pool_fold_mma_bwd(F, P, E, C, X, G, px, attn, dWq, st);
-  }
+  if (use_ws(dtype, C, P)) return pool_fold_ws_bwd(F, P, E, C, X, G, px, attn, delta, dWq, st);
   for (int e0 = 0; e0 < E; e0 += 4) {
     fold::Geom g{F, P, C, E, e0, 0, C * (dtype == MVF_BF16 ? 2 : 4)};
     const int ne = E - e0 < 4 ? E - e0 : 4;

@@ -1,10 +1,10 @@
-// Folded entity pooling for bf16 tokens, warp-specialised streaming version (second generation of pool_fold_mma.cu).
+// Folded entity pooling for bf16 tokens: warp-specialised streaming kernels on the warp-level tensor cores.
 //
-// Same mathematics, same single pass over the tokens, same mma.sync tensor-core contractions as pool_fold_mma.cu.  What
-// changes is the choreography.  The first version moved 16-token groups through a 2-slot ring and made all 12 compute
-// warps meet at a named barrier once per group, after which every warp redid the softmax bookkeeping: scores -> barrier
-// -> softmax -> pooling ran in lock step, the tensor pipe idled during the bookkeeping and only one group (74 KB) was ever
-// in flight per SM (measured: 56 % of the HBM copy bandwidth, issue slots 34 % busy, stalls = fixed-latency waits).
+// Same mathematics and the same single pass over the tokens as the CUDA-core kernels of pool_fold.cu; the contractions run
+// as mma.sync.  A first version moved 16-token groups through a 2-slot ring and made all 12 compute warps meet at a named
+// barrier once per group, after which every warp redid the softmax bookkeeping: scores -> barrier -> softmax -> pooling
+// ran in lock step, the tensor pipe idled during the bookkeeping and only one group (74 KB) was ever in flight per SM
+// (measured: 56 % of the HBM copy bandwidth, issue slots 34 % busy, stalls = fixed-latency waits).
 //
 // Here the ring holds 8-token slots (5 of them at C = 2304: two being consumed, three in flight = 110 KB per SM), and
 // three roles communicate through mbarriers only, so nobody waits in lock step:
