@@ -135,7 +135,7 @@ def test_fold_tensor_core_and_cuda_core_kernels_agree(monkeypatch, F, P, E, C):
     _, attn_m, px_m = _fold_forward(X, qs, qb, Wk)
     d_first = bwd(False)
     assert float((attn_w - attn_m).abs().max()) < 2e-6
-    assert float((px_w - px_m).abs().max() / px_m.abs().max()) < 5e-6
+    assert float((px_w - px_m).abs().max() / px_m.abs().max()) < 1e-5      # bf16 hi/lo tensor-core products vs fp32 FMA
     # fp64 reference of the streaming pass on the same operands
     dA = torch.einsum("fec,fpc->fep", G.view(F, E, C).double(), X.double())
     dS = attn_w.double() * (dA - delta.double().view(F, E, 1))

@@ -134,9 +134,60 @@ __global__ void posenc_add_kernel(const float* __restrict__ h3, const float* __r
     z[i] = v;
   }
 }
+// 16-byte version (H % 4 == 0, < 2^31 elements): no 64-bit divisions, four elements per thread
+__device__ __forceinline__ uint64_t seed_value(DropSeed s) { return s.base + (s.dev ? __ldg(s.dev) : 0ull); }
+__device__ __forceinline__ float4 drop4(float4 v, uint64_t sd, int site, uint64_t idx0, float p, float inv_keep) {
+  v.x *= drop_scale(sd, site, idx0, p, inv_keep);
+  v.y *= drop_scale(sd, site, idx0 + 1, p, inv_keep);
+  v.z *= drop_scale(sd, site, idx0 + 2, p, inv_keep);
+  v.w *= drop_scale(sd, site, idx0 + 3, p, inv_keep);
+  return v;
+}
+__global__ void __launch_bounds__(256)
+posenc_add_v4_kernel(const float4* __restrict__ h3, const float4* __restrict__ table, float4* __restrict__ z, int BV, int T,
+                     int E, int H4, float p, float inv_keep, DropSeed seed) {
+  pdl_entry();
+  const int total4 = BV * E * T * H4;
+  const uint64_t sd = seed_value(seed);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += gridDim.x * blockDim.x) {
+    const int row = q / H4, c4 = q - row * H4;   // row = b*E*T + e*T + t
+    const int be = row / T, t = row - be * T;
+    const int b = be / E, e = be - b * E;
+    const float4 a = h3[((b * T + t) * E + e) * H4 + c4], tb = table[t * H4 + c4];
+    float4 v = make_float4(a.x + tb.x, a.y + tb.y, a.z + tb.z, a.w + tb.w);
+    if (p > 0.f) v = drop4(v, sd, SITE_POS, (uint64_t)q * 4, p, inv_keep);
+    z[q] = v;
+  }
+}
+__global__ void __launch_bounds__(256)
+posenc_bwd_v4_kernel(const float4* __restrict__ dz, float4* __restrict__ dh3, int BV, int T, int E, int H4, float p,
+                     float inv_keep, DropSeed seed) {
+  pdl_entry();
+  const int total4 = BV * E * T * H4;
+  const uint64_t sd = seed_value(seed);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += gridDim.x * blockDim.x) {
+    const int row = q / H4, c4 = q - row * H4;
+    const int be = row / T, t = row - be * T;
+    const int b = be / E, e = be - b * E;
+    float4 v = dz[q];
+    if (p > 0.f) v = drop4(v, sd, SITE_POS, (uint64_t)q * 4, p, inv_keep);
+    dh3[((b * T + t) * E + e) * H4 + c4] = v;
+  }
+}
+static bool vec4_ok(int64_t total, int64_t inner, const void* a, const void* b, const void* c = nullptr) {
+  return (inner & 3) == 0 && total < (1ll << 31) && ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c)) & 15) == 0;
+}
+static int grid_for(int64_t work, int cap = 2368) { return (int)((work + 255) / 256 < cap ? (work + 255) / 256 : cap); }
+
 int posenc_add(const float* h3, const float* table, float* z, int BV, int T, int E, int H, float p, DropSeed seed,
                cudaStream_t st) {
   int64_t total = (int64_t)BV * E * T * H;
+  if (vec4_ok(total, H, h3, table, z)) {
+    launch_k(posenc_add_v4_kernel, grid_for(total / 4), 256, 0, st, (const float4*)h3, (const float4*)table, (float4*)z, BV, T, E,
+             H / 4, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+    MVF_CHECK_LAUNCH();
+    return MVF_OK;
+  }
   int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   launch_k(posenc_add_kernel, grid, 256, 0, st, h3, table, z, BV, T, E, H, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
   MVF_CHECK_LAUNCH();
@@ -164,6 +215,11 @@ int posenc_bwd(int dtype_out, const float* dz, void* dh3, int BV, int T, int E, 
   int64_t total = (int64_t)BV * E * T * H;
   int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (dtype_out == MVF_F32 && vec4_ok(total, H, dz, dh3)) {
+    launch_k(posenc_bwd_v4_kernel, grid_for(total / 4), 256, 0, st, (const float4*)dz, (float4*)dh3, BV, T, E, H / 4, p, ik, seed);
+    MVF_CHECK_LAUNCH();
+    return MVF_OK;
+  }
   if (dtype_out == MVF_BF16) launch_k(posenc_bwd_kernel<bf16>, grid, 256, 0, st, dz, (bf16*)dh3, BV, T, E, H, p, ik, seed);
   else launch_k(posenc_bwd_kernel<float>, grid, 256, 0, st, dz, (float*)dh3, BV, T, E, H, p, ik, seed);
   MVF_CHECK_LAUNCH();
@@ -608,9 +664,34 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, int64_t R, int C, c
     out[r * ld_out + c] = from_f<TO>(y);
   }
 }
+__global__ void __launch_bounds__(256)
+bn_apply_v4_kernel(const float4* __restrict__ x, int R, int C4, const float* __restrict__ mi, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, int relu, float* __restrict__ out, int ld_out, float p, float inv_keep,
+                   DropSeed seed, int site) {
+  pdl_entry();
+  const int total4 = R * C4, C = 4 * C4;
+  const uint64_t sd = seed_value(seed);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += gridDim.x * blockDim.x) {
+    const int r = q / C4, c = (q - r * C4) * 4;
+    const float4 xv = x[q], m = *reinterpret_cast<const float4*>(mi + c), is = *reinterpret_cast<const float4*>(mi + C + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    float4 y = make_float4((xv.x - m.x) * is.x * g.x + b.x, (xv.y - m.y) * is.y * g.y + b.y, (xv.z - m.z) * is.z * g.z + b.z,
+                           (xv.w - m.w) * is.w * g.w + b.w);
+    if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+    if (p > 0.f) y = drop4(y, sd, site, (uint64_t)q * 4, p, inv_keep);
+    *reinterpret_cast<float4*>(out + (int64_t)r * ld_out + c) = y;
+  }
+}
 int bn_apply(int dtype_out, const float* x, int64_t R, int C, const float* mi, const float* gamma, const float* beta,
              int relu, void* out, int64_t ld_out, float p, DropSeed seed, int site, cudaStream_t st) {
   int64_t total = R * C;
+  if (dtype_out == MVF_F32 && vec4_ok(total, C, x, out, mi) && (ld_out & 3) == 0 && ld_out < (1ll << 31) &&
+      ((((uintptr_t)gamma) | ((uintptr_t)beta)) & 15) == 0) {
+    launch_k(bn_apply_v4_kernel, grid_for(total / 4), 256, 0, st, (const float4*)x, (int)R, C / 4, mi, gamma, beta, relu, (float*)out,
+             (int)ld_out, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed, site);
+    MVF_CHECK_LAUNCH();
+    return MVF_OK;
+  }
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
   if (dtype_out == MVF_BF16)
@@ -689,10 +770,44 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ d_out, int64_t ld_
     dx[r * ld_dx + c] = from_f<TO>(g * is * (dy - s1 * inv_n - xh * s2 * inv_n));
   }
 }
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_v4_kernel(const float* __restrict__ d_out, int ld_d, const float4* __restrict__ x, int R, int C4,
+                       const float* __restrict__ mi, const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                       float p, float inv_keep, DropSeed seed, int site, const double* __restrict__ bsums, double n,
+                       float* __restrict__ dx, int ld_dx) {
+  pdl_entry();
+  const int total4 = R * C4, C = 4 * C4;
+  const float inv_n = (float)(1.0 / n);
+  const uint64_t sd = seed_value(seed);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += gridDim.x * blockDim.x) {
+    const int r = q / C4, c = (q - r * C4) * 4;
+    const float4 xv = x[q], m = *reinterpret_cast<const float4*>(mi + c), is = *reinterpret_cast<const float4*>(mi + C + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    float4 dy = *reinterpret_cast<const float4*>(d_out + (int64_t)r * ld_d + c);
+    if (p > 0.f) dy = drop4(dy, sd, site, (uint64_t)q * 4, p, inv_keep);
+    const float xh[4] = {(xv.x - m.x) * is.x, (xv.y - m.y) * is.y, (xv.z - m.z) * is.z, (xv.w - m.w) * is.w};
+    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w}, ii[4] = {is.x, is.y, is.z, is.w};
+    float d[4] = {dy.x, dy.y, dy.z, dy.w}, o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (relu && !(xh[k] * gg[k] + bb[k] > 0.f)) d[k] = 0.f;
+      const float s1 = (float)bsums[c + k], s2 = (float)bsums[C + c + k];
+      o[k] = gg[k] * ii[k] * (d[k] - s1 * inv_n - xh[k] * s2 * inv_n);
+    }
+    *reinterpret_cast<float4*>(dx + (int64_t)r * ld_dx + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
 int bn_bwd_apply(int dtype_out, const float* d_out, int64_t ld_d, const float* x, int64_t R, int C, const float* mi,
                  const float* gamma, const float* beta, int relu, float p, DropSeed seed, int site, const double* bsums,
                  double n_global, void* dx, int64_t ld_dx, cudaStream_t st) {
   int64_t total = R * C;
+  if (dtype_out == MVF_F32 && vec4_ok(total, C, x, dx, mi) && ((ld_d | ld_dx) & 3) == 0 && ld_d < (1ll << 31) && ld_dx < (1ll << 31) &&
+      ((((uintptr_t)gamma) | ((uintptr_t)beta) | ((uintptr_t)d_out)) & 15) == 0) {
+    launch_k(bn_bwd_apply_v4_kernel, grid_for(total / 4), 256, 0, st, d_out, (int)ld_d, (const float4*)x, (int)R, C / 4, mi, gamma, beta,
+             relu, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed, site, bsums, n_global, (float*)dx, (int)ld_dx);
+    MVF_CHECK_LAUNCH();
+    return MVF_OK;
+  }
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
   if (dtype_out == MVF_BF16)
@@ -787,10 +902,29 @@ __global__ void dropout_cast_kernel(const float* __restrict__ in, TO* __restrict
     out[(i / cols) * ld_out + (i % cols)] = from_f<TO>(v);
   }
 }
+__global__ void __launch_bounds__(256)
+dropout_cast_v4_kernel(const float4* __restrict__ in, float* __restrict__ out, int rows, int C4, int ld_out, float p,
+                       float inv_keep, DropSeed seed, int site) {
+  pdl_entry();
+  const int total4 = rows * C4;
+  const uint64_t sd = seed_value(seed);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += gridDim.x * blockDim.x) {
+    const int r = q / C4, c = (q - r * C4) * 4;
+    float4 v = in[q];
+    if (p > 0.f) v = drop4(v, sd, site, (uint64_t)q * 4, p, inv_keep);
+    *reinterpret_cast<float4*>(out + (int64_t)r * ld_out + c) = v;
+  }
+}
 int dropout_cast(int dtype_out, const float* in, void* out, int64_t rows, int cols, int64_t ld_out, float p,
                  DropSeed seed, int site, cudaStream_t st) {
   int64_t total = rows * cols;
   if (total == 0) return MVF_OK;
+  if (dtype_out == MVF_F32 && vec4_ok(total, cols, in, out) && (ld_out & 3) == 0 && ld_out < (1ll << 31)) {
+    launch_k(dropout_cast_v4_kernel, grid_for(total / 4), 256, 0, st, (const float4*)in, (float*)out, (int)rows, cols / 4, (int)ld_out,
+             p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed, site);
+    MVF_CHECK_LAUNCH();
+    return MVF_OK;
+  }
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
   float ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
   if (dtype_out == MVF_BF16)

@@ -486,18 +486,37 @@ fold_finish_kernel(const float* __restrict__ dWq, const float* __restrict__ q_s,
     qf[e] = e < E ? (q_s[e * SPC + j] + q_b[j]) * scale : 0.f;
     dot[e] = 0.f;
   }
-  for (int c = tid; c < C; c += blockDim.x) {
-    const float wk = Wk[(size_t)j * C + c];
-    float s = 0.f;
+  if ((C & 3) == 0 && (ld_dwk & 3) == 0 && ((((uintptr_t)Wk) | ((uintptr_t)dWq) | ((uintptr_t)dWk)) & 15) == 0) {
+    for (int c = 4 * tid; c < C; c += 4 * blockDim.x) {       // 16-byte path
+      const float4 wk = *reinterpret_cast<const float4*>(Wk + (size_t)j * C + c);
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int e = 0; e < MVF_MAX_ENTITIES; ++e) {
-      if (e < E) {
-        const float d = dWq[(size_t)e * C + c];
-        s = fmaf(qf[e], d, s);
-        dot[e] = fmaf(d, wk, dot[e]);
+      for (int e = 0; e < MVF_MAX_ENTITIES; ++e) {
+        if (e < E) {
+          const float4 d = *reinterpret_cast<const float4*>(dWq + (size_t)e * C + c);
+          s.x = fmaf(qf[e], d.x, s.x); s.y = fmaf(qf[e], d.y, s.y); s.z = fmaf(qf[e], d.z, s.z); s.w = fmaf(qf[e], d.w, s.w);
+          dot[e] = fmaf(d.x, wk.x, fmaf(d.y, wk.y, fmaf(d.z, wk.z, fmaf(d.w, wk.w, dot[e]))));
+        }
       }
+      float4* o = reinterpret_cast<float4*>(dWk + (size_t)j * ld_dwk + c);
+      float4 prev = *o;
+      prev.x += s.x; prev.y += s.y; prev.z += s.z; prev.w += s.w;
+      *o = prev;
     }
-    dWk[(size_t)j * ld_dwk + c] += s;
+  } else {
+    for (int c = tid; c < C; c += blockDim.x) {
+      const float wk = Wk[(size_t)j * C + c];
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < MVF_MAX_ENTITIES; ++e) {
+        if (e < E) {
+          const float d = dWq[(size_t)e * C + c];
+          s = fmaf(qf[e], d, s);
+          dot[e] = fmaf(d, wk, dot[e]);
+        }
+      }
+      dWk[(size_t)j * ld_dwk + c] += s;
+    }
   }
 #pragma unroll
   for (int e = 0; e < MVF_MAX_ENTITIES; ++e) {
@@ -535,6 +554,35 @@ __global__ void ent_finish_fwd_kernel(const float* __restrict__ ent, float* __re
     else if (one_hot && c - SPC == (int)(row % E)) v = 1.f;
     if (v != 0.f && p > 0.f && c < W) v *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + c), p, inv_keep);
     h0[i] = v;
+  }
+}
+// the same, four columns per thread (SPC % 4 == 0, ld % 4 == 0, < 2^31 elements)
+__global__ void __launch_bounds__(256)
+ent_finish_fwd_v4_kernel(const float* __restrict__ ent, float* __restrict__ h0, int ld4, int R, int SPC, int E, int one_hot,
+                         float p, float inv_keep, DropSeed seed) {
+  pdl_entry();
+  const int W = SPC + (one_hot ? E : 0);
+  const int total4 = R * ld4;
+  const uint64_t sd = seed.base + (seed.dev ? __ldg(seed.dev) : 0ull);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += gridDim.x * blockDim.x) {
+    const int row = q / ld4, c = (q - row * ld4) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c + 3 < SPC) {
+      const float4 e4 = *reinterpret_cast<const float4*>(ent + (int64_t)row * SPC + c);
+      v[0] = e4.x; v[1] = e4.y; v[2] = e4.z; v[3] = e4.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (c + k < SPC) v[k] = ent[(int64_t)row * SPC + c + k];
+        else if (one_hot && c + k - SPC == row % E) v[k] = 1.f;
+      }
+    }
+    if (p > 0.f) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (v[k] != 0.f && c + k < W) v[k] *= drop_scale(sd, SITE_FC0, (uint64_t)((int64_t)row * W + c + k), p, inv_keep);
+    }
+    *reinterpret_cast<float4*>(h0 + (int64_t)q * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 // dEnt[row, c] = drop'(d_h0[row, c]) for c < SPC
@@ -753,6 +801,13 @@ int ent_finish_fwd(const float* ent, float* h0, int64_t ld, int64_t R, int SPC, 
                    cudaStream_t st) {
   if (R <= 0) return MVF_OK;
   const int64_t total = R * ld;
+  if ((SPC & 3) == 0 && (ld & 3) == 0 && total < (1ll << 31) && ((((uintptr_t)ent) | ((uintptr_t)h0)) & 15) == 0) {
+    const int64_t work = total / 4;
+    launch_k(fold::ent_finish_fwd_v4_kernel, (int)((work + 255) / 256 < 2368 ? (work + 255) / 256 : 2368), 256, 0, st, ent, h0,
+             (int)(ld / 4), (int)R, SPC, E, one_hot, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+    MVF_CHECK_LAUNCH();
+    return MVF_OK;
+  }
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   launch_k(fold::ent_finish_fwd_kernel, blocks, 256, 0, st, ent, h0, ld, R, SPC, E, one_hot, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
   MVF_CHECK_LAUNCH();
