@@ -337,6 +337,20 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
   }
 }
 
+// z_out = z_in + drop(o), 16 bytes per thread (the residual add behind the last encoder sub-layer: no LayerNorm follows)
+__global__ void __launch_bounds__(256)
+resid_add_v4_kernel(const float4* __restrict__ z_in, const float4* __restrict__ o, float4* __restrict__ z_out, int total4, float p,
+                    float inv_keep, DropSeed seed, int site) {
+  pdl_entry();
+  const uint64_t sd = seed_value(seed);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += gridDim.x * blockDim.x) {
+    float4 ov = o[q];
+    if (p > 0.f) ov = drop4(ov, sd, site, (uint64_t)q * 4, p, inv_keep);
+    const float4 zi = z_in[q];
+    z_out[q] = make_float4(zi.x + ov.x, zi.y + ov.y, zi.z + ov.z, zi.w + ov.w);
+  }
+}
+
 template <typename TO>
 static bool ln_fwd_vec(const float* z_in, const float* o, float* z_out, TO* r, float* mean, float* rstd, const float* gamma,
                        const float* beta, int64_t rows, int H, float eps, float p, float ik, DropSeed seed, int site,
@@ -368,6 +382,12 @@ int ln_fwd(int dtype_out, const float* z_in, const float* o, float* z_out, void*
       MVF_CHECK_LAUNCH();
       return MVF_OK;
     }
+  }
+  if (r == nullptr && o != nullptr && rows > 0 && vec4_ok(rows * H, H, z_in, o, z_out)) {   // residual add only
+    launch_k(resid_add_v4_kernel, grid_for(rows * H / 4), 256, 0, st, (const float4*)z_in, (const float4*)o, (float4*)z_out,
+             (int)(rows * H / 4), p, ik, seed, site);
+    MVF_CHECK_LAUNCH();
+    return MVF_OK;
   }
   int grid = cdiv(rows, 8);
   if (dtype_out == MVF_BF16)
@@ -1010,9 +1030,39 @@ __global__ void entity_reduce_bwd_kernel(const float* __restrict__ dy, const int
     dz[i] = v;
   }
 }
+__global__ void __launch_bounds__(256)
+entity_reduce_bwd_v4_kernel(const float4* __restrict__ dy, const int4* __restrict__ argmax, float4* __restrict__ dz, int BV, int T,
+                            int E, int H4, int mode) {
+  pdl_entry();
+  const int total4 = BV * E * T * H4;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += gridDim.x * blockDim.x) {
+    const int row = q / H4, c4 = q - row * H4;
+    const int be = row / T, t = row - be * T;
+    const int b = be / E, e = be - b * E;
+    const int yi = (b * T + t) * H4 + c4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mode == MVF_FINAL_ONE) {
+      if (e == 0) v = dy[yi];
+    } else if (mode == MVF_FINAL_AVG) {
+      const float4 g = dy[yi];
+      v = make_float4(g.x / (float)E, g.y / (float)E, g.z / (float)E, g.w / (float)E);
+    } else {
+      const float4 g = dy[yi];
+      const int4 a = argmax[yi];
+      v = make_float4(a.x == e ? g.x : 0.f, a.y == e ? g.y : 0.f, a.z == e ? g.z : 0.f, a.w == e ? g.w : 0.f);
+    }
+    dz[q] = v;
+  }
+}
 int entity_reduce_bwd(const float* dy, const int32_t* argmax, float* dz, int BV, int T, int E, int H, int mode,
                       cudaStream_t st) {
   int64_t total = (int64_t)BV * E * T * H;
+  if (vec4_ok(total, H, dy, dz, argmax)) {
+    launch_k(entity_reduce_bwd_v4_kernel, grid_for(total / 4), 256, 0, st, (const float4*)dy, (const int4*)argmax, (float4*)dz, BV, T,
+             E, H / 4, mode);
+    MVF_CHECK_LAUNCH();
+    return MVF_OK;
+  }
   int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
   launch_k(entity_reduce_bwd_kernel, grid, 256, 0, st, dy, argmax, dz, BV, T, E, H, mode);
   MVF_CHECK_LAUNCH();

@@ -452,6 +452,7 @@ fold_prep_kernel(const float* __restrict__ q_s, const float* __restrict__ q_b, c
 #pragma unroll
   for (int e = 0; e < MVF_MAX_ENTITIES; ++e) acc[e] = 0.0;
   if (c < C) {
+#pragma unroll 4
     for (int j = js; j < SPC; j += PREP_SLICES) {
       const double wk = (double)Wk[(size_t)j * C + c];
 #pragma unroll
@@ -610,11 +611,28 @@ ent_finish_bwd_delta_kernel(const float* __restrict__ d_h0, int64_t ld, float* _
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
   float acc = 0.f;
-  for (int c = lane; c < SPC; c += 32) {
-    float v = d_h0[row * ld + c];
-    if (p > 0.f) v *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + c), p, inv_keep);
-    dEnt[row * SPC + c] = v;
-    acc = fmaf(v, ent[row * SPC + c] - bv[c], acc);
+  if ((SPC & 3) == 0 && (ld & 3) == 0 && ((((uintptr_t)d_h0) | ((uintptr_t)dEnt) | ((uintptr_t)ent) | ((uintptr_t)bv)) & 15) == 0) {
+    const uint64_t sd = seed.base + (seed.dev ? __ldg(seed.dev) : 0ull);
+    for (int c = 4 * lane; c < SPC; c += 128) {              // 16-byte path
+      float4 v = *reinterpret_cast<const float4*>(d_h0 + row * ld + c);
+      if (p > 0.f) {
+        const uint64_t i0 = (uint64_t)(row * W + c);
+        v.x *= drop_scale(sd, SITE_FC0, i0, p, inv_keep);
+        v.y *= drop_scale(sd, SITE_FC0, i0 + 1, p, inv_keep);
+        v.z *= drop_scale(sd, SITE_FC0, i0 + 2, p, inv_keep);
+        v.w *= drop_scale(sd, SITE_FC0, i0 + 3, p, inv_keep);
+      }
+      *reinterpret_cast<float4*>(dEnt + row * SPC + c) = v;
+      const float4 en = *reinterpret_cast<const float4*>(ent + row * SPC + c), b4 = *reinterpret_cast<const float4*>(bv + c);
+      acc = fmaf(v.x, en.x - b4.x, fmaf(v.y, en.y - b4.y, fmaf(v.z, en.z - b4.z, fmaf(v.w, en.w - b4.w, acc))));
+    }
+  } else {
+    for (int c = lane; c < SPC; c += 32) {
+      float v = d_h0[row * ld + c];
+      if (p > 0.f) v *= drop_scale(seed, SITE_FC0, (uint64_t)(row * W + c), p, inv_keep);
+      dEnt[row * SPC + c] = v;
+      acc = fmaf(v, ent[row * SPC + c] - bv[c], acc);
+    }
   }
   acc = warp_sum(acc);
   if (lane == 0) delta[row] = acc;
