@@ -89,7 +89,13 @@ def _worker(rank, world, port, out_dir):
         loss = _rank_loss(Pr, tokens[2 * v0:2 * v1], masks[2 * v0:2 * v1], seq_lens[v0:v1], steps[v0:v1])
         loss.backward()
         flat = torch.cat([Pr[k].grad.reshape(-1) for k in P])          # the "gpack" of this rank
-        scale = parallel.finish_flat_grads_(flat)
+        # the engine sums the buffer in two pieces (the chain's gradients beside the pooling backward, the pooling gradients at
+        # the end of the step, engine.py); off the symmetric-memory path both pieces are plain all-reduces
+        assert parallel.flat_grad_buffer(8, torch.device("cpu")).tolist() == [0.0] * 8      # gloo: an ordinary zeroed buffer
+        assert parallel.PeerFlatGrads.find(flat) is None
+        split = (flat.numel() // 3 + 3) // 4 * 4
+        scale = parallel.finish_flat_grads_(flat[split:], channel=1)
+        assert parallel.finish_flat_grads_(flat[:split], channel=0) == scale
         flat *= scale
         # descriptor world sizes (engine.py): BatchNorm divides its statistics by local_rows * bn_world, so bn_world must be 1
         # when the statistics are NOT exchanged (sync_bn=False), whatever the size of the group; the gradient all-reduce is

@@ -263,3 +263,21 @@ def test_feature_extractor_writes_hooked_tokens_straight_into_the_token_buffer()
     # without a buffer it allocates one of the backbone's dtype and still goes through the hooks
     out2 = model.backbone_tokens(x)
     assert torch.equal(out2, want)
+
+
+def test_symmetric_gradient_buffer_piece_arithmetic():
+    """parallel.PeerFlatGrads.range_of: which tensors count as (16-byte aligned) pieces of the symmetric flat buffer and
+    which float range the all-reduce kernel is given for them -- host arithmetic only, no symmetric memory needed."""
+    from video_rep_learning_b200 import parallel
+    obj = object.__new__(parallel.PeerFlatGrads)
+    backing = torch.zeros(1024 + 4)
+    obj.flat = backing[:1022]            # 1022 gradient floats, padded to 1024 inside the buffer
+    obj.elems = 1024
+    assert obj.range_of(obj.flat) == (0, 1024)                      # the whole buffer takes its zero padding along
+    assert obj.range_of(obj.flat[:512]) == (0, 512)
+    assert obj.range_of(obj.flat[512:]) == (512, 512)               # a tail piece reaches the padded end
+    assert obj.range_of(obj.flat[2:514]) is None                    # not 16-byte aligned
+    assert obj.range_of(obj.flat[:510]) is None                     # not a multiple of four floats
+    assert obj.range_of(torch.zeros(512)) is None                   # somebody else's memory
+    assert obj.range_of(obj.flat[:512].double()) is None
+    assert obj.owns(obj.flat[512:]) and not obj.owns(torch.zeros(4))
