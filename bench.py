@@ -802,7 +802,7 @@ def run_ours(args):
             sm_mhz = (clk or {}).get("sm_mhz") or 1900.0
             mufu_peak = 148 * 16 * sm_mhz * 1e6        # ex2 per second: 16 / clk / SM
             r = dict(bound="tensor", kernel="temporal self-attention forward (one launch per encoder layer)", achieved=achieved,
-                     peak=peaks["tflops_burst"], unit="TFLOP/s", frac=achieved / peaks["tflops_burst"], traffic=None,
+                     peak=peaks["tflops_burst"], unit="TFLOP/s", frac=achieved / peaks["tflops_burst"], traffic=traffic_of("attention_fwd_traffic.json"),
                      peak_source=f"{peaks['source']} bf16_tflops (burst)", ms_per_launch=f_ms, launches_timed=len(pr[6]),
                      flops_per_launch=f_flops,
                      sfu=dict(exp_per_launch=scores, achieved_gexp_s=scores / (f_ms * 1e-3) / 1e9, peak_gexp_s=mufu_peak / 1e9,

@@ -48,7 +48,7 @@ for stage in "$@"; do
     ncu:*)
       # ncu:<kernel regex>:<workload>  -> one full capture of the matching kernel
       spec=${stage#ncu:}; kre=${spec%%:*}; wl=${spec#*:}
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kre -s 6 -c 2 -f -o gpurun_out/ncu_${kre}_$wl \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kre -s 3 -c 2 -f -o gpurun_out/ncu_${kre}_$wl \
         python bench.py --workload $wl --eager --steps 2 --warmup 3 --no-e2e --no-cpu --no-dense --no-refgpu --no-parity > gpurun_out/ncu_${kre}_$wl.log 2>&1
       echo "exit $?" | tee -a $S ;;
     dist|dist4|dist5)
