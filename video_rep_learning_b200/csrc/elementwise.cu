@@ -702,6 +702,69 @@ bn_apply_v4_kernel(const float4* __restrict__ x, int R, int C4, const float* __r
     *reinterpret_cast<float4*>(out + (int64_t)r * ld_out + c) = y;
   }
 }
+// bn_finalize + bn_apply in one launch: every CTA derives mean / invstd of all C columns from the (all-reduced) double sums
+// into shared memory (2C floats); CTA 0 also stores them for backward and updates the running statistics.
+__global__ void __launch_bounds__(256)
+bn_finalize_apply_v4_kernel(const double* __restrict__ sums, double n, float eps, int training, float momentum,
+                            float* __restrict__ rmean, float* __restrict__ rvar, int64_t* __restrict__ tracked,
+                            float* __restrict__ mi_out, const float4* __restrict__ x, int R, int C4,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, int relu, float* __restrict__ out,
+                            int ld_out, float p, float inv_keep, DropSeed seed, int site) {
+  pdl_entry();
+  extern __shared__ __align__(16) float mis[];   // [2C]
+  const int C = 4 * C4;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, inv;
+    if (training) {
+      const double m = sums[c] / n;
+      double var = sums[C + c] / n - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      inv = (float)(1.0 / sqrt(var + (double)eps));
+      if (blockIdx.x == 0 && rmean) {
+        const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+        rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+        rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+      }
+    } else {
+      mean = rmean[c];
+      inv = 1.0f / sqrtf(rvar[c] + eps);
+    }
+    mis[c] = mean;
+    mis[C + c] = inv;
+    if (blockIdx.x == 0) { mi_out[c] = mean; mi_out[C + c] = inv; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && tracked) *tracked += 1;
+  __syncthreads();
+  const int total4 = R * C4;
+  const uint64_t sd = seed_value(seed);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += gridDim.x * blockDim.x) {
+    const int r = q / C4, c = (q - r * C4) * 4;
+    const float4 xv = x[q], m = *reinterpret_cast<const float4*>(mis + c), is = *reinterpret_cast<const float4*>(mis + C + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    float4 y = make_float4((xv.x - m.x) * is.x * g.x + b.x, (xv.y - m.y) * is.y * g.y + b.y, (xv.z - m.z) * is.z * g.z + b.z,
+                           (xv.w - m.w) * is.w * g.w + b.w);
+    if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+    if (p > 0.f) y = drop4(y, sd, site, (uint64_t)q * 4, p, inv_keep);
+    *reinterpret_cast<float4*>(out + (int64_t)r * ld_out + c) = y;
+  }
+}
+// returns MVF_OK when the fused launch was taken, MVF_ERR_UNSUPPORTED (no error string) when the caller must use the two kernels
+int bn_finalize_apply(const double* sums, int C, double n_global, float eps, int training, float momentum, float* rmean,
+                      float* rvar, int64_t* tracked, float* mi, int dtype_out, const float* x, int64_t R,
+                      const float* gamma, const float* beta, int relu, void* out, int64_t ld_out, float p, DropSeed seed, int site,
+                      cudaStream_t st) {
+  const int64_t total = R * C;
+  if (!(dtype_out == MVF_F32 && C <= 4096 && total > 0 && vec4_ok(total, C, x, out, mi) && (ld_out & 3) == 0 && ld_out < (1ll << 31) &&
+        ((((uintptr_t)gamma) | ((uintptr_t)beta)) & 15) == 0))
+    return MVF_ERR_UNSUPPORTED;
+  launch_k(bn_finalize_apply_v4_kernel, grid_for(total / 4, 1184), 256, (size_t)2 * C * sizeof(float), st, sums, n_global, eps, training,
+           momentum, rmean, rvar, tracked, mi, (const float4*)x, (int)R, C / 4, gamma, beta, relu, (float*)out, (int)ld_out, p,
+           p > 0.f ? 1.f / (1.f - p) : 1.f, seed, site);
+  MVF_CHECK_LAUNCH();
+  return MVF_OK;
+}
+
 int bn_apply(int dtype_out, const float* x, int64_t R, int C, const float* mi, const float* gamma, const float* beta,
              int relu, void* out, int64_t ld_out, float p, DropSeed seed, int site, cudaStream_t st) {
   int64_t total = R * C;
@@ -1114,7 +1177,8 @@ int entity_scatter_lin(const float* dzl, float* dz, int BV, int T, int E, int H,
 
 // F.normalize(x, dim=-1, eps=1e-12): y = x / max(||x||, eps)   (transformer.py:228)
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                         float* __restrict__ norm, int64_t rows, int D) {
+                                                         float* __restrict__ norm, int64_t rows, int D,
+                                                         float* __restrict__ y2) {
   pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -1123,11 +1187,15 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict
   for (int c = lane; c < D; c += 32) { float v = x[row * D + c]; s += v * v; }
   s = warp_sum(s);
   float n = fmaxf(sqrtf(s), 1e-12f);
-  for (int c = lane; c < D; c += 32) y[row * D + c] = x[row * D + c] / n;
+  for (int c = lane; c < D; c += 32) {
+    const float v = x[row * D + c] / n;
+    y[row * D + c] = v;
+    if (y2) y2[row * D + c] = v;      // the caller's output tensor (the saved copy stays for backward)
+  }
   if (lane == 0) norm[row] = n;
 }
-int l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int D, cudaStream_t st) {
-  launch_k(l2norm_fwd_kernel, cdiv(rows, 8), 256, 0, st, x, y, norm, rows, D);
+int l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int D, cudaStream_t st, float* y2) {
+  launch_k(l2norm_fwd_kernel, cdiv(rows, 8), 256, 0, st, x, y, norm, rows, D, y2);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
 }

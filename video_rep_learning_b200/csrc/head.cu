@@ -373,10 +373,13 @@ static void head_save_layout(const Model& m, Layout& L) {
   }
   L.add("h0", m.R, m.W0, A, m.ld0);
   L.add("ent32", m.R, d.SPC, RT_F32);
+  // the BatchNorm sum buffers of every layer are adjacent: one memset per forward call zeroes them all
   for (int i = 0; i < d.n_fc; ++i) {
-    L.add(fname(i, "x"), m.R, d.fc[i], RT_F32);
     L.add(fname(i, "sum"), 1, 2 * d.fc[i], RT_F64);
     L.add(fname(i, "bsum"), 1, 2 * d.fc[i], RT_F64);
+  }
+  for (int i = 0; i < d.n_fc; ++i) {
+    L.add(fname(i, "x"), m.R, d.fc[i], RT_F32);
     L.add(fname(i, "mi"), 1, 2 * d.fc[i], RT_F32);
     L.add(fname(i, "a"), m.R, d.fc[i], A);
   }
@@ -608,6 +611,15 @@ struct Ctx {
   // y = x W^T + b.  Forward GEMMs feed the softmax/temperature non-linearities of SCL: on the tensor-core backend they
   // run as bf16x3, with the weight taken from its pre-split copy `wsplit` (region "<name>.s") when there is one, and
   // K >= 512 contractions that cannot fill the machine are split along K (TMA reduce-add epilogue).
+  // one memset over the adjacent save regions first .. last (the BatchNorm sum buffers of a call)
+  int zero_span(const std::string& first, const std::string& last) const {
+    const Region* a = Ls.find(first);
+    const Region* b = Ls.find(last);
+    MVF_REQUIRE(a && b && b->off >= a->off, MVF_ERR_BAD_ARG, "zero_span: %s .. %s", first.c_str(), last.c_str());
+    const size_t esz = b->dtype == RT_F64 ? 8 : 4;
+    MVF_CHECK_CUDA(cudaMemsetAsync(S.base + a->off, 0, b->off - a->off + (size_t)b->rows * b->ld * esz, st));
+    return MVF_OK;
+  }
   int linear(int dtype_c, int64_t M, int64_t N, int64_t K, const void* x, int64_t ldx, const void* Wp, int64_t ldw,
              const float* bias, void* y, int64_t ldy, int flags = 0, const char* wsplit = nullptr) const {
     const int sk = (m.tc && !(flags & MVF_GEMM_RELU) && dtype_c == MVF_F32) ? 0 : 1;
@@ -751,6 +763,7 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
   cudaStream_t st = c.st;
   const int n_ph = d.n_fc + 1;
   if (ph1 > n_ph) ph1 = n_ph;
+  if (ph0 == 0 && d.training && d.n_fc > 0) MVF_TRY(c.zero_span(fname(0, "sum"), fname(d.n_fc - 1, "bsum")));
   for (int ph = ph0; ph < ph1; ++ph) {
     if (ph == 0) {
       // the packed / pre-split copies of the weights are first needed behind the streaming pooling pass: with folded pooling
@@ -816,22 +829,27 @@ static int head_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       float* rm = bn_running ? bn_running[2 * i] : nullptr;
       float* rv = bn_running ? bn_running[2 * i + 1] : nullptr;
       MVF_REQUIRE(d.training || (rm && rv), MVF_ERR_BAD_ARG, "eval mode needs BatchNorm running statistics");
-      MVF_TRY(bn_finalize(c.S.dbl(fname(i, "sum")), C, bn_n_global(m, m.R), d.bn_eps, d.training, d.bn_momentum, rm, rv,
-                          bn_tracked ? bn_tracked[i] : nullptr, c.S.f(fname(i, "mi")), st));
       // dropout of the NEXT FC layer is applied to this activation (fc_layers.{4i}: Dropout before Linear)
       const float pn = (i + 1 < d.n_fc) ? c.p : 0.f;
-      MVF_TRY(bn_apply(A, c.S.f(fname(i, "x")), m.R, C, c.S.f(fname(i, "mi")), c.P[m.iFcG[i]], c.P[m.iFcBeta[i]], 1,
-                       c.S.p(fname(i, "a")), C, pn, DropSeed(d.seed, d.seed_dev), SITE_FC0 + i + 1, st));
+      const int fused = bn_finalize_apply(c.S.dbl(fname(i, "sum")), C, bn_n_global(m, m.R), d.bn_eps, d.training, d.bn_momentum, rm,
+                                          rv, bn_tracked ? bn_tracked[i] : nullptr, c.S.f(fname(i, "mi")), A, c.S.f(fname(i, "x")),
+                                          m.R, c.P[m.iFcG[i]], c.P[m.iFcBeta[i]], 1, c.S.p(fname(i, "a")), C, pn,
+                                          DropSeed(d.seed, d.seed_dev), SITE_FC0 + i + 1, st);
+      if (fused == MVF_ERR_UNSUPPORTED) {
+        MVF_TRY(bn_finalize(c.S.dbl(fname(i, "sum")), C, bn_n_global(m, m.R), d.bn_eps, d.training, d.bn_momentum, rm, rv,
+                            bn_tracked ? bn_tracked[i] : nullptr, c.S.f(fname(i, "mi")), st));
+        MVF_TRY(bn_apply(A, c.S.f(fname(i, "x")), m.R, C, c.S.f(fname(i, "mi")), c.P[m.iFcG[i]], c.P[m.iFcBeta[i]], 1,
+                         c.S.p(fname(i, "a")), C, pn, DropSeed(d.seed, d.seed_dev), SITE_FC0 + i + 1, st));
+      } else {
+        MVF_TRY(fused);
+      }
       xin = c.S.p(fname(i, "a")); ldin = C; kin = C;
     }
     if (ph < d.n_fc) {
       const int C = d.fc[ph];
       MVF_TRY(c.linear(MVF_F32, m.R, C, kin, xin, ldin, c.S.p(fname(ph, "w")), c.S.ld(fname(ph, "w")), c.P[m.iFcB[ph]],
                        c.S.p(fname(ph, "x")), C, 0, fname(ph, "w").c_str()));
-      if (d.training) {
-        MVF_CHECK_CUDA(cudaMemsetAsync(c.S.p(fname(ph, "sum")), 0, (size_t)2 * C * 8, st));
-        MVF_TRY(bn_stats(c.S.f(fname(ph, "x")), m.R, C, c.S.dbl(fname(ph, "sum")), st));
-      }
+      if (d.training) MVF_TRY(bn_stats(c.S.f(fname(ph, "x")), m.R, C, c.S.dbl(fname(ph, "sum")), st));   // zeroed at phase 0
       continue;
     }
     // ---- last phase: video_emb, positional encoding, temporal encoder, entity reduction, embedding ----
@@ -909,6 +927,7 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
   // (n_fc + 1) so that a multi-GPU caller can start all-reducing the chain's gradients while it runs
   const int n_ph = d.n_fc + 2;
   if (ph1 > n_ph) ph1 = n_ph;
+  if (ph0 == 0 && d.n_fc > 0) MVF_TRY(c.zero_span(fname(0, "sum"), fname(d.n_fc - 1, "bsum")));   // the forward sums are spent
   for (int ph = ph0; ph < ph1; ++ph) {
     const void* d_in;   // gradient w.r.t. the output of the FC Linear handled in this phase (act dtype)
     int64_t ld_din;
@@ -994,7 +1013,6 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
       } else {
         const int i = d.n_fc - 1, C = d.fc[i];
         MVF_TRY(c.linear_dx(MVF_F32, m.R, m.Hin, C, c.W.p("dh3"), m.Hin, c.S.p("w.e"), c.S.ld("w.e"), c.W.p("da"), C));
-        MVF_CHECK_CUDA(cudaMemsetAsync(c.S.p(fname(i, "bsum")), 0, (size_t)2 * C * 8, st));
         MVF_TRY(bn_bwd_stats(c.W.f("da"), C, c.S.f(fname(i, "x")), m.R, C, c.S.f(fname(i, "mi")), c.P[m.iFcG[i]],
                              c.P[m.iFcBeta[i]], 1, 0.f, DropSeed(d.seed, d.seed_dev), SITE_FC0 + i + 1, c.S.dbl(fname(i, "bsum")),
                              c.G.f("g." + fname(i, "gamma")), c.G.f("g." + fname(i, "beta")), st));
@@ -1016,7 +1034,6 @@ static int head_backward_impl(Ctx& c, const void* tokens, const float* mask, con
       if (i > 0) {
         const int Cp = d.fc[i - 1];
         MVF_TRY(c.linear_dx(MVF_F32, m.R, C, Cp, d_in, ld_din, c.S.p(fname(i, "w")), c.S.ld(fname(i, "w")), c.W.p("da"), Cp));
-        MVF_CHECK_CUDA(cudaMemsetAsync(c.S.p(fname(i - 1, "bsum")), 0, (size_t)2 * Cp * 8, st));
         const float pp = c.p;  // activation i-1 was followed by the dropout of FC layer i
         MVF_TRY(bn_bwd_stats(c.W.f("da"), Cp, c.S.f(fname(i - 1, "x")), m.R, Cp, c.S.f(fname(i - 1, "mi")),
                              c.P[m.iFcG[i - 1]], c.P[m.iFcBeta[i - 1]], 1, pp, DropSeed(d.seed, d.seed_dev), SITE_FC0 + i,
@@ -1098,8 +1115,7 @@ static int proj_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
   if (!project) {
     // MODEL.L2_NORMALIZE without the projection head (evaluate.py path, transformer.py:229-230)
     if (ph0 == 0) {
-      MVF_TRY(l2norm_fwd(emb, c.S.f("ehat"), c.S.f("norm"), m.N, d.D, st));
-      MVF_CHECK_CUDA(cudaMemcpyAsync(out, c.S.p("ehat"), (size_t)m.N * d.D * 4, cudaMemcpyDeviceToDevice, st));
+      MVF_TRY(l2norm_fwd(emb, c.S.f("ehat"), c.S.f("norm"), m.N, d.D, st, out));
     }
     return MVF_OK;
   }
@@ -1123,22 +1139,28 @@ static int proj_forward_impl(Ctx& c, float* const* bn_running, int64_t* const* b
       MVF_TRY(cast_f32(A, emb, c.S.p("emb"), m.N * d.D, st));
       MVF_TRY(c.linear(MVF_F32, m.N, d.PS, d.D, c.S.p("emb"), d.D, c.S.p("w.p1"), d.D, c.P[m.ibp1], c.S.p("u1"), d.PS, 0, "w.p1"));
       if (d.training) {
-        MVF_CHECK_CUDA(cudaMemsetAsync(c.S.p("p.sum"), 0, (size_t)2 * d.PS * 8, st));
+        MVF_TRY(c.zero_span("p.sum", "p.bsum"));
         MVF_TRY(bn_stats(c.S.f("u1"), m.N, d.PS, c.S.dbl("p.sum"), st));
       }
     } else {
       float* rm = bn_running ? bn_running[2 * ibn] : nullptr;
       float* rv = bn_running ? bn_running[2 * ibn + 1] : nullptr;
       MVF_REQUIRE(d.training || (rm && rv), MVF_ERR_BAD_ARG, "eval mode needs BatchNorm running statistics");
-      MVF_TRY(bn_finalize(c.S.dbl("p.sum"), d.PS, bn_n_global(m, m.N), d.bn_eps, d.training, d.bn_momentum, rm, rv,
-                          bn_tracked ? bn_tracked[ibn] : nullptr, c.S.f("p.mi"), st));
-      MVF_TRY(bn_apply(A, c.S.f("u1"), m.N, d.PS, c.S.f("p.mi"), c.P[m.iGp], c.P[m.iBp], 1, c.S.p("a3"), d.PS, 0.f, 0, 0, st));
+      const int fused = bn_finalize_apply(c.S.dbl("p.sum"), d.PS, bn_n_global(m, m.N), d.bn_eps, d.training, d.bn_momentum, rm, rv,
+                                          bn_tracked ? bn_tracked[ibn] : nullptr, c.S.f("p.mi"), A, c.S.f("u1"), m.N, c.P[m.iGp],
+                                          c.P[m.iBp], 1, c.S.p("a3"), d.PS, 0.f, 0, 0, st);
+      if (fused == MVF_ERR_UNSUPPORTED) {
+        MVF_TRY(bn_finalize(c.S.dbl("p.sum"), d.PS, bn_n_global(m, m.N), d.bn_eps, d.training, d.bn_momentum, rm, rv,
+                            bn_tracked ? bn_tracked[ibn] : nullptr, c.S.f("p.mi"), st));
+        MVF_TRY(bn_apply(A, c.S.f("u1"), m.N, d.PS, c.S.f("p.mi"), c.P[m.iGp], c.P[m.iBp], 1, c.S.p("a3"), d.PS, 0.f, 0, 0, st));
+      } else {
+        MVF_TRY(fused);
+      }
       MVF_TRY(c.linear(MVF_F32, m.N, d.D, d.PS, c.S.p("a3"), d.PS, c.S.p("w.p2"), d.PS, c.P[m.ibp2], c.S.p("u"), d.D, 0, "w.p2"));
       if (project == 2) {  // MLPHead.forward on its own (resnet_c2d.py:122-126): no normalisation
         MVF_CHECK_CUDA(cudaMemcpyAsync(out, c.S.p("u"), (size_t)m.N * d.D * 4, cudaMemcpyDeviceToDevice, st));
       } else {
-        MVF_TRY(l2norm_fwd(c.S.f("u"), c.S.f("ehat"), c.S.f("norm"), m.N, d.D, st));
-        MVF_CHECK_CUDA(cudaMemcpyAsync(out, c.S.p("ehat"), (size_t)m.N * d.D * 4, cudaMemcpyDeviceToDevice, st));
+        MVF_TRY(l2norm_fwd(c.S.f("u"), c.S.f("ehat"), c.S.f("norm"), m.N, d.D, st, out));
       }
     }
   }

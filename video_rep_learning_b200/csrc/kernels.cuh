@@ -51,6 +51,12 @@ int bn_finalize(const double* sums, int C, double n_global, float eps, int train
 // out = drop(relu?(gamma*(x-mean)*invstd+beta))
 int bn_apply(int dtype_out, const float* x, int64_t R, int C, const float* mi, const float* gamma, const float* beta,
              int relu, void* out, int64_t ld_out, float p, DropSeed seed, int site, cudaStream_t st);
+// bn_finalize + bn_apply in one launch (fp32 output, 16-byte aligned rows, C <= 4096); MVF_ERR_UNSUPPORTED without an error
+// string when the shape does not qualify -- the caller then issues the two kernels
+int bn_finalize_apply(const double* sums, int C, double n_global, float eps, int training, float momentum, float* rmean,
+                      float* rvar, int64_t* tracked, float* mi, int dtype_out, const float* x, int64_t R,
+                      const float* gamma, const float* beta, int relu, void* out, int64_t ld_out, float p, DropSeed seed, int site,
+                      cudaStream_t st);
 // dy = d_out*drop*relu'(y); bsums[0:C]+=sum dy, [C:2C]+=sum dy*xhat; dgamma/dbeta accumulated from the LOCAL sums
 int bn_bwd_stats(const float* d_out, int64_t ld_d, const float* x, int64_t R, int C, const float* mi,
                  const float* gamma, const float* beta, int relu, float p, DropSeed seed, int site, double* bsums,
@@ -85,7 +91,7 @@ int entity_reduce_bwd(const float* dy, const int32_t* argmax, float* dz, int BV,
 int entity_gather_lin(int dtype_out, const float* z, void* zl, int BV, int T, int E, int H, cudaStream_t st);
 int entity_scatter_lin(const float* dzl, float* dz, int BV, int T, int E, int H, cudaStream_t st);
 // F.normalize (eps 1e-12) and its backward; norms saved
-int l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int D, cudaStream_t st);
+int l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int D, cudaStream_t st, float* y2 = nullptr);
 int l2norm_bwd(const float* dy, const float* y, const float* norm, void* dx, int dtype_out, int64_t rows, int D,
                cudaStream_t st);
 int dropout_mask_export(DropSeed seed, int site, int64_t rows, int64_t cols, float p, float* out, cudaStream_t st);
