@@ -70,6 +70,35 @@ def test_scl_edge_shapes_against_closed_form(Bv, T, D):
     assert float((dE.double() - torch.from_numpy(dEp)).norm()) <= 1e-5 * float(np.linalg.norm(dEp)) + floor
 
 
+@pytest.mark.parametrize("Bv,T,D,neg", [
+    (160, 40, 64, "single_noself"),     # one CTA per pair holding both views, S recomputed per pass (needs a batch >= the SM count)
+    (150, 96, 32, "single_noself"),     # the same at its largest T (12 warps)
+    (1, 256, 256, "single_noself"),     # largest shape: cluster of 8, partner view staged per pass (does not fit shared memory)
+    (2, 32, 128, "single_noself"),      # exactly one tile
+    (3, 64, 36, "single_noself"),       # channels padded to 64 inside the kernel
+    (5, 20, 128, "batch_noself"),       # batch negatives through the cross passes, T <= 32 kernel
+    (3, 48, 64, "batch_noself"),        # and through the cluster kernel
+])
+def test_scl_kernel_variants_against_dense_oracle(Bv, T, D, neg):
+    """Every shape class of scl_mma.cu (kernel variant chosen by T, D and the batch size) against the dense N x N oracle in
+    fp64 on a subsample of the videos' rows (loss exactly, gradient on all rows)."""
+    g = torch.Generator().manual_seed(Bv * 7 + T + D)
+    e = torch.nn.functional.normalize(torch.randn(Bv, 2, T, D, generator=g), dim=-1)
+    _, seq_lens, steps, masks = O.synth_batch(Bv, T, 1, 1, seed=Bv + T)
+    loss, dE = _run(e, seq_lens, steps, masks, neg=neg)
+    if neg == "single_noself":
+        lp, dEp = O.scl_loss_pairs(e.numpy(), seq_lens.numpy(), steps.numpy(), masks.numpy())
+        ref_l, ref_g = lp, torch.from_numpy(dEp)
+    else:
+        e64 = e.double().requires_grad_(True)
+        ref = O.scl_loss_dense(e64, seq_lens, steps, masks.double(), negative_type=neg)
+        ref.backward()
+        ref_l, ref_g = float(ref), e64.grad
+    le, ge = abs(loss - ref_l) / abs(ref_l), H.rel_l2(dE, ref_g)
+    print(f"SCL {Bv} x {T} x {D} {neg}: loss {le:.2e} gradient {ge:.2e}")
+    assert le < 1e-5 and ge < 1e-5
+
+
 def test_scl_all_frames_valid_and_fully_masked_video():
     Bv, T, D = 3, 20, 128
     g = torch.Generator().manual_seed(9)
