@@ -205,7 +205,9 @@ attn_tc_fwd_kernel(int S, int H, const float* __restrict__ qkv, const float* __r
 // =====================================================================================================================
 // backward: d_ctx [B*S, H] -> d_qkv [B*S, 3H]
 // =====================================================================================================================
-__global__ void __launch_bounds__(128)
+// Eight warps: warps 0-3 take the query orientation (dQ), warps 4-7 the key orientation (dK, dV) of the same 16-row blocks --
+// the two halves only share the staged operands, so the kernel's latency is one orientation, not the sum of both.
+__global__ void __launch_bounds__(256)
 attn_tc_bwd_kernel(int S, int H, const float* __restrict__ qkv, const float* __restrict__ keymask,
                    const float* __restrict__ ctx, const float* __restrict__ lse, const float* __restrict__ d_ctx,
                    float* __restrict__ d_qkv) {
@@ -219,10 +221,36 @@ attn_tc_bwd_kernel(int S, int H, const float* __restrict__ qkv, const float* __r
   const float* obase = ctx + (int64_t)b * S * H + h * DK;
   uint8_t *Qh = sm, *Ql = sm + MAT, *Kh = sm + 2 * MAT, *Kl = sm + 3 * MAT, *Vh = sm + 4 * MAT, *Vl = sm + 5 * MAT,
           *Gh = sm + 6 * MAT, *Gl = sm + 7 * MAT;
-  load_split(base, ld, S, Qh, Ql);
-  load_split(base + H, ld, S, Kh, Kl);
-  load_split(base + 2 * H, ld, S, Vh, Vl);
-  load_split(gbase, H, S, Gh, Gl);
+  {
+    // all eight 16-byte loads of a thread are issued before the first conversion (one memory round trip for the four operands)
+    static_assert(SP * 8 == 512, "two float4 per thread and operand at 256 threads");
+    const float* srcs[4] = {base, base + H, base + 2 * H, gbase};
+    const int64_t lds[4] = {ld, ld, ld, (int64_t)H};
+    uint8_t* his[4] = {Qh, Kh, Vh, Gh};
+    uint8_t* los[4] = {Ql, Kl, Vl, Gl};
+    float4 v[4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int idx = tid + u * 256, row = idx >> 3, c4 = idx & 7;
+        v[a][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < S) v[a][u] = *reinterpret_cast<const float4*>(srcs[a] + (int64_t)row * lds[a] + 4 * c4);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int idx = tid + u * 256, row = idx >> 3, c4 = idx & 7;
+        uint2 h, l;
+        split2(v[a][u].x, v[a][u].y, h.x, l.x);
+        split2(v[a][u].z, v[a][u].w, h.y, l.y);
+        *reinterpret_cast<uint2*>(his[a] + row * PITCH + c4 * 8) = h;
+        *reinterpret_cast<uint2*>(los[a] + row * PITCH + c4 * 8) = l;
+      }
+    }
+  }
   // delta_i = <dO_i, O_i>: eight consecutive lanes own one row
   for (int idx = tid; idx < SP * 8; idx += blockDim.x) {
     const int row = idx >> 3, c4 = idx & 7;
@@ -245,14 +273,15 @@ attn_tc_bwd_kernel(int S, int H, const float* __restrict__ qkv, const float* __r
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int row0 = warp * 16;
+  const int row0 = (warp & 3) * 16;
+  const bool keys_orientation = warp >= 4;
   if (row0 >= S) return;
   const float scale = 1.0f / sqrtf((float)DK);
   const float scale2 = scale * LOG2E;
   const int r0 = row0 + g, r1 = row0 + g + 8;
 
   // ---- phase A: rows = queries.  dQ_i = sum_j dS_ij K_j ----
-  {
+  if (!keys_orientation) {
     uint32_t ah[2][4], al[2][4];
     float sc[8][4], dp[8][4];
 #pragma unroll
@@ -284,7 +313,7 @@ attn_tc_bwd_kernel(int S, int H, const float* __restrict__ qkv, const float* __r
     }
   }
   // ---- phase B: rows = keys.  dV_j = sum_i P_ij dO_i, dK_j = sum_i dS_ij Q_i ----
-  {
+  else {
     uint32_t ah[2][4], al[2][4];
     float st[8][4], dpt[8][4];
 #pragma unroll
@@ -350,7 +379,7 @@ int attention_tc_fwd(int B, int S, int heads, const void* qkv, const float* keym
 }
 int attention_tc_bwd(int B, int S, int heads, const void* qkv, const float* keymask, const void* ctx, const float* lse,
                      const void* d_ctx, void* d_qkv, cudaStream_t st) {
-  launch_k(atc::attn_tc_bwd_kernel, dim3(heads, B), 128, 0, st, S, heads * atc::DK, (const float*)qkv, keymask, (const float*)ctx, lse,
+  launch_k(atc::attn_tc_bwd_kernel, dim3(heads, B), 256, 0, st, S, heads * atc::DK, (const float*)qkv, keymask, (const float*)ctx, lse,
            (const float*)d_ctx, (float*)d_qkv);
   MVF_CHECK_LAUNCH();
   return MVF_OK;
