@@ -58,7 +58,8 @@ for stage in "$@"; do
         tag=${wl}_n${n}_$v
         ar=1; [ "$v" = nccl ] && ar=0
         xo=""; [ "$v" = nooverlap ] && xo="--no-overlap"
-        MVF_PEER_AR=$ar timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py \
+        ctas=0; [ "$v" = ctas8 ] && ctas=8
+        MVF_PEER_AR_CTAS=$ctas MVF_PEER_AR=$ar timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py \
           --gpus $n --workload $wl --steps 50 --warmup 5 --no-cpu --no-refgpu --no-dense $xo ${DIST_EXTRA:-} > gpurun_out/dist_$tag.json 2> gpurun_out/dist_$tag.err
         echo "$tag exit $? :: $(tail -c 400 gpurun_out/dist_$tag.json | tr '\n' ' ' | grep -o '"parity".*' | head -c 300)" | tee -a $S
         python - gpurun_out/dist_$tag.json <<'PY' | tee -a $S

@@ -126,7 +126,7 @@ class PeerFlatGrads:
         mode = os.environ.get("MVF_PEER_MULTICAST", "auto")
         if mode == "0" or (mode == "auto" and self.world <= 2):
             self.mc_ptr = 0
-        self.ctas = int(os.environ.get("MVF_PEER_AR_CTAS", "0")) or (16 if self.mc_ptr else 64)
+        self.ctas = int(os.environ.get("MVF_PEER_AR_CTAS", "0")) or (8 if self.mc_ptr else 64)   # multimem: more CTAs are slower (8: 71 us, 16: 82 us at 8 GPUs)
         self.counters = torch.zeros(2 * 64, dtype=torch.int32, device=device)     # two channels (see sum_range)
         self.flat = self.buf[:elems * 4].view(torch.float32)
         torch.cuda.synchronize(device)
