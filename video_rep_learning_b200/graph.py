@@ -4,7 +4,7 @@ The eager step (models.TransformerModel.forward_tokens -> algos.SCL.compute_sequ
 ~125 kernels through six C-ABI calls plus PyTorch's autograd bookkeeping: ~1.8 ms of host time against ~2.2 ms of
 device time at BASELINE configs[1], and every extra collective of the multi-GPU protocol (BatchNorm statistics, the flat
 gradient all-reduce) adds host latency on top.  `GraphedTrainStep` captures exactly that launch sequence ONCE --
-including the library's side-stream fork/join, the NCCL collectives and the gradient scatter -- and replays it with one
+including the library's side-stream fork/join, the cross-rank exchanges (symmetric-memory kernels or NCCL) and the gradient scatter -- and replays it with one
 `cudaGraphLaunch` per step.  Nothing about the math changes: the same kernels run in the same order on the same
 buffers, which is what tests/test_gpu_graph.py checks (graph replay == eager step, bit for bit, dropout included).
 
