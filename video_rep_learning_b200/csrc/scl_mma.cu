@@ -111,22 +111,28 @@ __device__ __forceinline__ void stage_rows(uint8_t* hi, uint8_t* lo, int pitch, 
     uint8_t* dl = lo + c4 * 8;
     for (int rbase = r0; rbase < nrows; rbase += 8 * rstep) {
       float4 x[8];
+      unsigned valid = 0;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int row = rbase + u * rstep;
         x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < nrows) {
           const int64_t gr = rowof(row);
-          if (gr >= 0 && cin) x[u] = __ldg(reinterpret_cast<const float4*>(src + gr * D));
+          if (gr >= 0 && cin) {
+            x[u] = __ldg(reinterpret_cast<const float4*>(src + gr * D));
+            valid |= 1u << u;
+          }
         }
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int row = rbase + u * rstep;
         if (row < nrows) {
-          uint2 h, l;
-          split2(x[u].x, x[u].y, h.x, l.x);
-          split2(x[u].z, x[u].w, h.y, l.y);
+          uint2 h = make_uint2(0u, 0u), l = make_uint2(0u, 0u);
+          if (valid & (1u << u)) {                            // padded rows are stored as zeros without the conversion
+            split2(x[u].x, x[u].y, h.x, l.x);
+            split2(x[u].z, x[u].w, h.y, l.y);
+          }
           *reinterpret_cast<uint2*>(dh + row * pitch) = h;
           *reinterpret_cast<uint2*>(dl + row * pitch) = l;
         }
@@ -244,7 +250,8 @@ static __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1
 
 // BOTH: one CTA holds both views of the pair (warp = view * nbv + row block); else a cluster of 2 * chunks CTAs.
 // KEEP (BOTH, T <= 32): e^{l} of the single partner tile stays in registers through every pass.
-template <int NTD, bool BOTH, bool KEEP, int NTHR, int MINB>
+// NTVC (KEEP only): ceil(T / 8) as a compile-time constant, so that the guards of the padded 8-column tiles fold away.
+template <int NTD, bool BOTH, bool KEEP, int NTHR, int MINB, int NTVC = 0>
 __global__ void __launch_bounds__(NTHR, MINB) scl_pair_mma_kernel(const PairArgs A) {
   pdl_entry();
   extern __shared__ __align__(128) uint8_t sm[];
@@ -351,6 +358,10 @@ __global__ void __launch_bounds__(NTHR, MINB) scl_pair_mma_kernel(const PairArgs
 
   // every partner tile of one pass: body(c0, tile_hi, tile_lo, ntv); all threads of the CTA walk the staging barriers
   auto partner_pass = [&](auto&& body) {
+    if constexpr (KEEP) {
+      if (active) body(0, colbase_hi, colbase_lo, NTVC ? NTVC : min(4, (T + 7) >> 3));
+      return;
+    }
     for (int s0 = 0; s0 < Tp; s0 += CS) {
       if (!resident) {
         __syncthreads();
@@ -359,7 +370,8 @@ __global__ void __launch_bounds__(NTHR, MINB) scl_pair_mma_kernel(const PairArgs
       }
       if (active)
         for (int c0 = s0; c0 < min(s0 + CS, Tp); c0 += CT)
-          body(c0, colbase_hi + (uint32_t)((c0 - s0) * pitch), colbase_lo + (uint32_t)((c0 - s0) * pitch), min(4, (T - c0 + 7) >> 3));
+          body(c0, colbase_hi + (uint32_t)((c0 - s0) * pitch), colbase_lo + (uint32_t)((c0 - s0) * pitch),
+               NTVC ? NTVC : min(4, (T - c0 + 7) >> 3));
     }
   };
   // log2 of the Gaussian label weight of (row h, column index j of the thread); -inf when the column is masked
@@ -420,7 +432,7 @@ __global__ void __launch_bounds__(NTHR, MINB) scl_pair_mma_kernel(const PairArgs
     }
   };
   if (KEEP) {
-    if (active) pass_b(0, ex, min(4, (T + 7) >> 3));
+    if (active) pass_b(0, ex, NTVC ? NTVC : min(4, (T + 7) >> 3));
   } else {
     partner_pass([&](int c0, uint32_t th, uint32_t tl, int ntv) {
       float acc[4][4];
@@ -502,7 +514,7 @@ __global__ void __launch_bounds__(NTHR, MINB) scl_pair_mma_kernel(const PairArgs
   if constexpr (KEEP) {
     // one partner tile: every 16-channel slice of the gradient is complete after two k-steps and leaves at once
     if (active) {
-      const int ntv = min(4, (T + 7) >> 3);
+      const int ntv = NTVC ? NTVC : min(4, (T + 7) >> 3);
       coef_tile(0, ex, ntv);
       uint32_t ch[2][4], cl[2][4];
       coef_frags(ex, ch, cl);
@@ -687,8 +699,18 @@ int scl_pair_mma(const float* embs, const int64_t* seq_lens, const int64_t* step
   if (Tp == CT) {
     const size_t smem = 2 * tile_b + meta_bytes(2 * Tp);
     static size_t conf[2] = {48 * 1024, 48 * 1024};
-    return wide ? launch_pair(scl_pair_mma_kernel<32, true, true, 128, 2>, conf[0], Bv, 128, smem, 1, st, A)
-                : launch_pair(scl_pair_mma_kernel<16, true, true, 128, 4>, conf[1], Bv, 128, smem, 1, st, A);
+    static size_t confk[2][4] = {{48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024}, {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024}};
+    (void)conf;
+    switch ((T + 7) / 8) {
+      case 1: return wide ? launch_pair(scl_pair_mma_kernel<32, true, true, 128, 2, 1>, confk[0][0], Bv, 128, smem, 1, st, A)
+                          : launch_pair(scl_pair_mma_kernel<16, true, true, 128, 4, 1>, confk[1][0], Bv, 128, smem, 1, st, A);
+      case 2: return wide ? launch_pair(scl_pair_mma_kernel<32, true, true, 128, 2, 2>, confk[0][1], Bv, 128, smem, 1, st, A)
+                          : launch_pair(scl_pair_mma_kernel<16, true, true, 128, 4, 2>, confk[1][1], Bv, 128, smem, 1, st, A);
+      case 3: return wide ? launch_pair(scl_pair_mma_kernel<32, true, true, 128, 2, 3>, confk[0][2], Bv, 128, smem, 1, st, A)
+                          : launch_pair(scl_pair_mma_kernel<16, true, true, 128, 4, 3>, confk[1][2], Bv, 128, smem, 1, st, A);
+      default: return wide ? launch_pair(scl_pair_mma_kernel<32, true, true, 128, 2, 4>, confk[0][3], Bv, 128, smem, 1, st, A)
+                           : launch_pair(scl_pair_mma_kernel<16, true, true, 128, 4, 4>, confk[1][3], Bv, 128, smem, 1, st, A);
+    }
   }
   // one CTA per pair when both views fit and the batch fills the machine
   const size_t both_smem = (size_t)2 * Tp / CT * tile_b + meta_bytes(2 * Tp);
