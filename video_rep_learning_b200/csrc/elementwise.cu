@@ -9,7 +9,7 @@
 namespace mvf {
 
 // =========================================== pack / unpack ===========================================
-constexpr int PACK_CHUNK = 48;
+constexpr int PACK_CHUNK = 64;   // entries per launch (kernel parameter table: 2.6 KB)
 struct PackTable {
   int n;
   PackEntry e[PACK_CHUNK];
