@@ -360,18 +360,17 @@ __global__ void __launch_bounds__(NTHR, MINB) scl_pair_mma_kernel(const PairArgs
   auto partner_pass = [&](auto&& body) {
     if constexpr (KEEP) {
       if (active) body(0, colbase_hi, colbase_lo, NTVC ? NTVC : min(4, (T + 7) >> 3));
-      return;
-    }
-    for (int s0 = 0; s0 < Tp; s0 += CS) {
-      if (!resident) {
-        __syncthreads();
-        stage_cols(s0);
-        __syncthreads();
+    } else {
+      for (int s0 = 0; s0 < Tp; s0 += CS) {
+        if (!resident) {
+          __syncthreads();
+          stage_cols(s0);
+          __syncthreads();
+        }
+        if (active)
+          for (int c0 = s0; c0 < min(s0 + CS, Tp); c0 += CT)
+            body(c0, colbase_hi + (uint32_t)((c0 - s0) * pitch), colbase_lo + (uint32_t)((c0 - s0) * pitch), min(4, (T - c0 + 7) >> 3));
       }
-      if (active)
-        for (int c0 = s0; c0 < min(s0 + CS, Tp); c0 += CT)
-          body(c0, colbase_hi + (uint32_t)((c0 - s0) * pitch), colbase_lo + (uint32_t)((c0 - s0) * pitch),
-               NTVC ? NTVC : min(4, (T - c0 + 7) >> 3));
     }
   };
   // log2 of the Gaussian label weight of (row h, column index j of the thread); -inf when the column is masked
@@ -698,9 +697,7 @@ int scl_pair_mma(const float* embs, const int64_t* seq_lens, const int64_t* step
   const size_t tile_b = (size_t)CT * pitch * 2;              // 32 staged rows, hi + lo
   if (Tp == CT) {
     const size_t smem = 2 * tile_b + meta_bytes(2 * Tp);
-    static size_t conf[2] = {48 * 1024, 48 * 1024};
     static size_t confk[2][4] = {{48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024}, {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024}};
-    (void)conf;
     switch ((T + 7) / 8) {
       case 1: return wide ? launch_pair(scl_pair_mma_kernel<32, true, true, 128, 2, 1>, confk[0][0], Bv, 128, smem, 1, st, A)
                           : launch_pair(scl_pair_mma_kernel<16, true, true, 128, 4, 1>, confk[1][0], Bv, 128, smem, 1, st, A);
