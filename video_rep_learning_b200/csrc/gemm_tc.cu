@@ -560,7 +560,8 @@ int gemm_tc(int dtype_ab, int dtype_c, int a_kmajor, int b_kmajor, int64_t M, in
     // Measured in round 2 and not adopted (cfg2 step, 1.508 ms): smaller tiles for the forward chain alone -- it has no
     // side-stream GEMM beside it -- 120 CTAs no change, 148 / 240 CTAs +1.3 % / +1.6 %; eight converter warps (two threads
     // per stage row) +0 % in the step, +10 % on the stand-alone SPLIT3 GEMM; the A operand pre-split by a separate
-    // full-machine kernel (converter warps idle): +2.8 % -- the extra launch costs more than the ~2.5 us it takes off a GEMM.
+    // full-machine kernel (converter warps idle): +2.8 % -- the extra launch costs more than the ~2.5 us it takes off a GEMM;
+    // no split-K (and no output memset) for the K = 512 GEMMs: -0.3 %, within run-to-run noise.
     while (bn > 64 && (int64_t)cdiv(M, BLOCK_M) * cdiv(N, bn) * sk_est < fill_target) bn >>= 1;
   }
   Params p;
