@@ -857,7 +857,7 @@ def run_ours(args):
             cpu = dict(value=sample / cms, unit=UNIT, cores=threads, kind=kind,
                        sample=f"{sample} videos of {WL['name']} (fp32, dropout 0), {len(times)} timed iterations after 1 warm-up")
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                   ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                   ms_per_step=ms_step, higher_is_better=True, scaling="strong" if WL.get("strong") else "weak", vs_baseline=None, dtype="bf16",
                    data="synthetic",
                    config=workload_config(world),
                    as_written_tflops=whole, gflop_per_video_as_written=fl["total"] / 1e9, loss=final_loss,
@@ -896,9 +896,21 @@ def main():
     ap.add_argument("--no-overlap", action="store_true",
                     help="multi-GPU: one gradient all-reduce at the end instead of summing the chain's gradients beside the pooling backward")
     ap.add_argument("--reserve-sms", type=int, default=4, help="SMs the pooling backward leaves to the overlapped all-reduce")
+    ap.add_argument("--global-videos", type=int, default=0,
+                    help="strong scaling: total videos of the step, split evenly over the ranks (default: the workload's per-GPU shard on every rank)")
     ap.add_argument("--no-dense", action="store_true", help="skip the short as-written (dense pooling) comparison leg")
     args = ap.parse_args()
-    WL = WORKLOADS[args.workload]
+    WL = dict(WORKLOADS[args.workload])
+    if args.global_videos:
+        # strong scaling: a fixed global batch split over the ranks (BASELINE configs[2]: 256 Penn videos on 8 GPUs)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.global_videos % world:
+            raise SystemExit(f"--global-videos {args.global_videos} is not divisible by {world} ranks")
+        WL["videos_per_gpu"] = args.global_videos // world
+        WL["name"] = WL["name"].replace(f"bv{WORKLOADS[args.workload]['videos_per_gpu']}", f"bv{WL['videos_per_gpu']}")
+        WL["baseline_config"] += f"; global batch fixed at {args.global_videos} videos (strong scaling)"
+        WL["cpu_sample"] = min(WL["cpu_sample"], WL["videos_per_gpu"])
+        WL["strong"] = True
     if args.impl == "reference":
         run_reference_arm(args)
     elif args.impl == "reference-gpu":

@@ -101,6 +101,25 @@ PY
       n=$(nvidia-smi -L | wc -l)
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29519 scripts/peer_bench.py > gpurun_out/peer_bench_n$n.json 2> gpurun_out/peer_bench_n$n.err
       echo "exit $? :: $(tail -n 1 gpurun_out/peer_bench_n$n.json)" | tee -a $S ;;
+    strong)
+      # BASELINE configs[2]: 256 Penn videos in total, split over the box's GPUs (strong scaling)
+      n=$(nvidia-smi -L | wc -l)
+      if [ $n -gt 1 ]; then
+        timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29521 bench.py \
+          --gpus $n --global-videos 256 --steps 20 --warmup 5 --no-cpu --no-refgpu --no-dense --no-e2e > gpurun_out/strong_n$n.json 2> gpurun_out/strong_n$n.err
+      else
+        timeout 900 python bench.py --global-videos 256 --steps 20 --warmup 5 --no-cpu --no-refgpu --no-dense --no-e2e > gpurun_out/strong_n$n.json 2> gpurun_out/strong_n$n.err
+      fi
+      echo "exit $?" | tee -a $S
+      python - gpurun_out/strong_n$n.json <<'PY' | tee -a $S
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print("   n_gpus", d["n_gpus"], "videos/GPU", d["config"]["videos_per_gpu"], "value %.1f ms %.3f" % (d["value"], d["ms_per_step"]), d["scaling"], "parity ok", (d.get("parity") or {}).get("ok"))
+except Exception as e:
+    print("   unreadable:", e)
+PY
+      ;;
     ref)
       timeout 900 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "exit $?" | tee -a $S ;;
     launches|launches4|launches5)
