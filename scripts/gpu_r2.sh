@@ -52,7 +52,7 @@ for stage in "$@"; do
         python bench.py --workload $wl --eager --steps 2 --warmup 3 --no-e2e --no-cpu --no-dense --no-refgpu --no-parity > gpurun_out/ncu_${kre}_$wl.log 2>&1
       echo "exit $?" | tee -a $S ;;
     dist|dist4|dist5)
-      # N = every GPU of the box: the driver's launch line, default and --overlap
+      # N = every GPU of the box: the driver's launch line; variants: default, nooverlap, nccl, ctas8 (DIST_VARIANTS)
       n=$(nvidia-smi -L | wc -l); wl=penn_cfg2; [ $stage = dist4 ] && wl=finegym_cfg4; [ $stage = dist5 ] && wl=long_cfg5
       for v in ${DIST_VARIANTS:-default nooverlap nccl}; do
         tag=${wl}_n${n}_$v
