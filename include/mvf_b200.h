@@ -188,7 +188,9 @@ int mvf_unpack_grads(const mvf_head_desc* d, const float* gpack, float* const* g
 /* embs [Bv,2,T,D] fp32 unit rows; seq_lens [Bv,2] int64; steps [Bv,2,T] int64; masks [Bv,2,T] fp32.
  * loss_out: 1 fp32 (overwritten); d_embs [Bv,2,T,D] fp32 = d loss / d embs (overwritten; may be NULL).
  * quirk = 1 reproduces scl.py:80 exactly (every masked frame of the local batch enters every partition
- * sum with weight 1e-6); quirk = 0 keeps only the own-pair terms. ws: mvf_scl_ws_bytes bytes. */
+ * sum with weight 1e-6); quirk = 0 keeps only the own-pair terms. ws: mvf_scl_ws_bytes bytes.
+ * T <= 256, D <= 256, D % 4 == 0, embs 16-byte aligned (MVF_ERR_UNSUPPORTED / MVF_ERR_ALIGN otherwise).  The products run on
+ * the warp-level tensor cores with bf16 hi/lo operand splits: loss within 1e-6, gradient within 1e-5 of the fp64 evaluation. */
 size_t mvf_scl_ws_bytes(int32_t Bv, int32_t T, int32_t D);
 int mvf_scl_fwd_bwd(const float* embs, const int64_t* seq_lens, const int64_t* steps, const float* masks,
                     int32_t Bv, int32_t T, int32_t D, float temperature, float label_variance,
