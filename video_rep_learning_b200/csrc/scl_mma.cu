@@ -1,5 +1,5 @@
-// Sequence Contrastive Loss (algos/scl.py:52-105), NEGATIVE_TYPE single_noself: forward + gradient on the warp-level tensor
-// cores, T <= 256 frames per view, D <= 256 channels.
+// Sequence Contrastive Loss (algos/scl.py:52-105), NEGATIVE_TYPE single_noself / batch_noself: forward + gradient on the
+// warp-level tensor cores, T <= 256 frames per view, D <= 256 channels.
 //
 // Every product of the loss is a small matrix product between the two views of ONE video pair (logits S = E0 E1^T, gradients
 // dE0 = C E1, dE1 = C^T E0 with C = dloss/dS) or between a row block and the batch's masked frames (the scl.py:80 quirk: every
@@ -17,7 +17,7 @@
 //   BOTH + KEEP  T <= 32: one CTA (4 warps) holds both views; e^{l} stays in registers through all passes, the partner operand
 //                is the other view's panel (no second staging), row statistics cross through shared memory, every 16-channel
 //                slice of the gradient leaves as soon as its two k-steps are done (no D-wide accumulator);
-//   BOTH         T <= 96 (D <= 128) / 64: the same with S recomputed per pass;
+//   BOTH         T <= 96 (D <= 128) / T <= 64 (D <= 256), batch >= the SM count: the same with S recomputed per pass;
 //   cluster      the row blocks of a pair are spread over a thread-block cluster (2 views x 1/2/4 chunks, more chunks when the
 //                batch alone cannot fill the machine); each CTA stages the partner view once when it fits (else per pass in
 //                multiples of 32 columns), and the row statistics cross through global memory + one cluster barrier.
