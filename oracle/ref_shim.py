@@ -27,8 +27,13 @@ VENDORED_ROOT = os.path.join(_REPO, "baseline", "_ref", "CARL_MVF")
 # files of the reference that the hot path (and its samplers / configs) needs; copied verbatim by vendor_reference()
 VENDOR_FILES = ("models/utils.py", "models/mvformer.py", "models/resnet_c2d.py", "algos/scl.py",
                 "datasets/dataset_splits.py", "datasets/data_augment.py", "datasets/penn_action.py", "datasets/finegym.py",
-                "datasets/pouring.py", "configs_mvf/penn_mvf.yml", "configs_mvf/fg99_mvf.yml", "configs_mvf/k400_mvf.yml",
-                "configs_mvf/ablate_dinoB8_fwb3.yml")
+                "datasets/pouring.py") + tuple(
+    "configs_mvf/" + n for n in (
+        "penn_mvf.yml", "pouring_mvf.yml", "fg99_mvf.yml", "fg288_mvf.yml", "k400_mvf.yml", "k400_penn_mvf.yml",
+        "ablate_dinoB8_fwb3.yml", "ablate_dinoB8_fwb5.yml", "ablate_dinoB8_lstp1.yml", "ablate_dinoB8_lstp3.yml",
+        "ablate_dinoB8_lstp5.yml", "ablate_dinoB8_multi_lstp1.yml", "ablate_dinoB8_multi_lstp5.yml", "ablate_dinoB8_avg.yml",
+        "ablate_dinoB8_cls.yml", "ablate_dinoB8_max.yml", "ablate_rn50_lstp1.yml", "ablate_rn50_lstp3.yml",
+        "ablate_rn50_lstp5.yml", "ablate_rn50_max.yml"))
 
 
 def _default_root() -> str:

@@ -281,3 +281,39 @@ def test_symmetric_gradient_buffer_piece_arithmetic():
     assert obj.range_of(torch.zeros(512)) is None                   # somebody else's memory
     assert obj.range_of(obj.flat[:512].double()) is None
     assert obj.owns(obj.flat[512:]) and not obj.owns(torch.zeros(4))
+
+
+def test_every_shipped_mvformer_config_constructs_unmodified():
+    """configs_mvf/*.yml of the reference, read unchanged: the 15 files that select the MV-Former head (FUSION_TYPE: smart)
+    construct with a caller-supplied producer -- OUT_CHANNEL derived from NETWORK as transformer.py:40-56,119-133 does -- and map
+    to head shapes inside the supported envelope; the 5 late-fusion CARL ablations are rejected by name."""
+    import glob
+    from oracle import ref_shim
+    from video_rep_learning_b200.config import load_yaml
+    from video_rep_learning_b200.models import build_model
+    from video_rep_learning_b200.models.mvformer import head_spec_from_cfg
+    root = os.path.join(ref_shim.REF_ROOT, "configs_mvf")
+    files = sorted(glob.glob(os.path.join(root, "*.yml")))
+    if len(files) < 20:
+        pytest.skip("reference configs not available (neither /root/reference nor baseline/_ref)")
+    smart, late = {}, []
+    for y in files:
+        cfg = load_yaml(y)
+        em = cfg.MODEL.EMBEDDER_MODEL
+        if "FUSION_TYPE" in em and em.FUSION_TYPE == "smart":
+            model = build_model(cfg, backbone=DummyBackbone(16))
+            hs = head_spec_from_cfg(cfg)
+            assert model.embed.embedding_size == hs.emb
+            smart[os.path.basename(y)] = (hs.c_in, hs.n_entities, hs.fc_channels, hs.emb, hs.final, hs.one_hot, hs.pool_kind,
+                                          cfg.TRAIN.NUM_FRAMES)
+        else:
+            with pytest.raises(NotImplementedError, match="FUSION_TYPE"):
+                build_model(cfg, backbone=DummyBackbone(16))
+            late.append(os.path.basename(y))
+    assert len(smart) == 15 and len(late) == 5
+    assert smart["penn_mvf.yml"] == (2304, 3, (512, 512), 128, "one", "pool", "lstp", 80)
+    assert smart["fg99_mvf.yml"] == (2304, 6, (1536, 1536), 256, "avg", "pool", "lstp", 240)
+    assert smart["pouring_mvf.yml"][:2] == (768, 3) and smart["ablate_rn50_lstp5.yml"][:2] == (2048, 5)
+    assert smart["ablate_dinoB8_fwb5.yml"][6] == "fwb" and smart["ablate_dinoB8_fwb5.yml"][1] == 5
+    for name, (c_in, E, fc, emb, final, one_hot, kind, T) in smart.items():
+        assert c_in % 16 == 0 and 1 <= E <= 16 and emb in (128, 256) and T * E <= 16384, name

@@ -91,6 +91,15 @@ class TransformerModel(nn.Module):
         feats = [int(s) for s in str(_get(em, "SMART_FEATS", "11")).split(",")]
         if backbone is not None:
             self.backbone = backbone          # any module: frames [n,3,H,W] -> (tokens [n,1+P,C_in], cls [n,C])
+            # the shipped yml files carry no OUT_CHANNEL: the reference derives it from NETWORK (transformer.py:40-56, 90,
+            # 119-133), so an unmodified config works with a caller-supplied producer as well
+            if "OUT_CHANNEL" not in cfg.MODEL.BASE_MODEL:
+                if net.startswith("TIMM-") and net[5:] in _TIMM_WIDTH:
+                    cfg.MODEL.BASE_MODEL.OUT_CHANNEL = _TIMM_WIDTH[net[5:]] * len(feats)
+                elif "resnet" in net.lower():
+                    cfg.MODEL.BASE_MODEL.OUT_CHANNEL = 2048
+                else:
+                    raise ValueError(f"MODEL.BASE_MODEL.OUT_CHANNEL is not set and cannot be derived from NETWORK: {net}")
         elif net.startswith("TIMM-"):
             name = net[5:]
             if name not in _TIMM_WIDTH:
