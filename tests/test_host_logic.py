@@ -317,3 +317,29 @@ def test_every_shipped_mvformer_config_constructs_unmodified():
     assert smart["ablate_dinoB8_fwb5.yml"][6] == "fwb" and smart["ablate_dinoB8_fwb5.yml"][1] == 5
     for name, (c_in, E, fc, emb, final, one_hot, kind, T) in smart.items():
         assert c_in % 16 == 0 and 1 <= E <= 16 and emb in (128, 256) and T * E <= 16384, name
+
+
+def test_get_embeddings_dataset_mirrors_reference_contract():
+    """evaluate.get_embeddings_dataset (evaluate.py:27-81): same arguments and dictionary; chunks are concatenated in order and
+    frames with a negative label dropped.  A stand-in model (frame index -> embedding) keeps this on the host."""
+    from video_rep_learning_b200 import evaluate as E
+    from video_rep_learning_b200.config import mvf_cfg
+
+    class Stub(nn.Module):
+        def forward(self, x, num_steps):          # x: [1, n, 1] frame indices -> [1, n, 2]
+            assert x.shape[1] == num_steps
+            return torch.cat([x.float(), 2 * x.float()], dim=-1)
+
+    cfg = mvf_cfg(num_frames=8)
+    cfg.EVAL = dict(FRAMES_PER_BATCH=4)
+    cfg.DATA = dict(NUM_CONTEXTS=1, CONTEXT_STRIDE=1)
+    L = 10
+    video = torch.arange(L).view(1, L, 1)
+    labels = torch.tensor([[0, 1, -1, 1, 2, 2, -1, 3, 3, 3]])
+    loader = [(video, labels, torch.tensor([L]), torch.arange(L).view(1, L), None, ["vid0"])]
+    ds = E.get_embeddings_dataset(cfg, Stub(), loader)
+    assert set(ds) == {"embs", "labels", "seq_lens", "input_lens", "steps", "names"}
+    keep = [0, 1, 3, 4, 5, 7, 8, 9]
+    assert ds["embs"][0].shape == (8, 2) and ds["embs"][0][:, 0].tolist() == [float(k) for k in keep]
+    assert ds["labels"][0].tolist() == [0, 1, 1, 2, 2, 3, 3, 3]
+    assert ds["seq_lens"] == [L] and ds["input_lens"] == [L] and ds["names"] == ["vid0"] and ds["steps"][0].tolist() == list(range(L))

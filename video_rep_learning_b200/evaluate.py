@@ -49,3 +49,24 @@ def embed_video(cfg, model, video: torch.Tensor) -> torch.Tensor:
         feats = model(curr, num_steps)
         embs.append(feats[0].float().cpu())
     return torch.cat(embs, dim=0)
+
+
+def get_embeddings_dataset(cfg, model, data_loader) -> dict:
+    """Same name, arguments and return value as evaluate.py:27-81: one pass over a batch-size-1 loader of
+    (video, frame_label, seq_len, chosen_steps, video_masks, names); frames whose label is negative are dropped.
+    Returns {'embs', 'labels', 'seq_lens', 'input_lens', 'steps', 'names'} with numpy arrays per video."""
+    embs_list, labels_list, seq_lens_list, input_lens_list, steps_list, names_list = [], [], [], [], [], []
+    model.eval()
+    for video, frame_label, seq_len, chosen_steps, _video_masks, names in data_loader:
+        assert video.size(0) == 1                                             # evaluate.py:41
+        assert video.size(1) == frame_label.size(1) == int(seq_len.item())    # evaluate.py:42
+        embs = embed_video(cfg, model, video)
+        valid = frame_label[0] >= 0
+        embs_list.append(embs[valid.cpu()].numpy())
+        labels_list.append(frame_label[0][valid].cpu().numpy())
+        seq_lens_list.append(int(seq_len.item()))
+        input_lens_list.append(len(video[0]))
+        steps_list.append(chosen_steps[0].cpu().numpy())
+        names_list.append(names[0])
+    return {"embs": embs_list, "labels": labels_list, "seq_lens": seq_lens_list, "input_lens": input_lens_list,
+            "steps": steps_list, "names": names_list}
