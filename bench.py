@@ -2,7 +2,7 @@
 """Benchmark of the MV-Former training hot path (head + projection + SCL, forward + backward).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload penn_cfg2|finegym_cfg4|long_cfg5]
-                    [--impl ours|reference|reference-gpu]
+                    [--impl ours|reference|reference-gpu] [--global-videos G] [--no-overlap]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workloads (per-GPU shards of BASELINE.json configs; synthetic tokens, deterministic synthetic
@@ -23,7 +23,9 @@ inside the timed steps (event-record nodes of the graph); `parity` = loss / embe
 untimed dropout-free step on the bench's own inputs against the CPU oracle (and, across ranks, against a single-process
 run of the concatenated batch); `reference_gpu` = the reference's own PyTorch modules run eagerly on the same GPU on the
 same inputs (the like-for-like baseline a user of the reference runs today); `cpu_baseline` = the reference algorithm on
-this host's cores on a bounded sample.
+this host's cores on a bounded sample; `cross_rank` (N > 1) = what the gradient all-reduce and the BatchNorm exchanges cost
+inside the replayed graph, by difference against the same step captured without them.  `--global-videos G` fixes the global
+batch (strong scaling, `scaling: "strong"`); `--no-overlap` sums the whole gradient buffer at the end of the step.
 """
 from __future__ import annotations
 
