@@ -28,3 +28,21 @@ def test_reference_arm_prints_the_contract_line():
     e2e = d["e2e"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0 and e2e["unit"] == d["unit"]
     assert abs(e2e["value"] - d["value"]) < 1e-9
+
+
+def test_workloads_are_the_baseline_configs():
+    """bench.py's workloads are the per-GPU shards of BASELINE.json configs[1..4]."""
+    sys.path.insert(0, ROOT)
+    import bench
+    cfgs = json.load(open(os.path.join(ROOT, "BASELINE.json")))["configs"]
+    w = bench.WORKLOADS
+    assert "32 videos" in cfgs[1] and "20 frames" in cfgs[1] and "2 views" in cfgs[1]
+    assert (w["penn_cfg2"]["videos_per_gpu"], w["penn_cfg2"]["T"], w["penn_cfg2"]["head"]["entities"]) == (32, 20, 3)
+    assert "global batch 256" in cfgs[2] and 256 // 8 == w["penn_cfg2"]["videos_per_gpu"]      # --global-videos 256 at N = 2 / 4 / 8
+    assert "64 videos" in cfgs[3] and "80 frames" in cfgs[3] and "8 B200" in cfgs[3]
+    assert (w["finegym_cfg4"]["videos_per_gpu"] * 8, w["finegym_cfg4"]["T"], w["finegym_cfg4"]["head"]["entities"]) == (64, 80, 6)
+    assert "32 videos" in cfgs[4] and "240 frames" in cfgs[4] and "16 entity" in cfgs[4]
+    assert (w["long_cfg5"]["videos_per_gpu"] * 8, w["long_cfg5"]["T"], w["long_cfg5"]["head"]["entities"]) == (32, 240, 16)
+    for name, wl in w.items():          # ViT-B/16 x 3 feature layers: 196 patch tokens of 3 x 768 channels
+        assert (wl["P"], wl["c_in"]) == (196, 2304), name
+    assert bench.METRIC.startswith("training videos/sec") and bench.UNIT == "videos/s"
