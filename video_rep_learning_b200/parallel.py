@@ -76,7 +76,6 @@ class PeerStats:
     def get(cls, group, device: torch.device):
         """The exchange object of (group, device), created on first use; None when it cannot be set up (no symmetric
         memory on this system, capture in progress before the first eager step, MVF_PEER_BN=0) -> NCCL all-reduce."""
-        import os
         key = (id(group) if group is not None else 0, device.index)
         if key in cls._failed or os.environ.get("MVF_PEER_BN", "1") == "0":
             return None
@@ -99,8 +98,8 @@ class PeerStats:
 class PeerFlatGrads:
     """The flat gradient buffer of a step in symmetric memory, summed over the ranks in place by csrc/peer.cu
     (mvf_peer_allreduce_f32: NVSwitch multimem.ld_reduce / multimem.st when the buffer has a multicast mapping, peer loads
-    and stores otherwise) instead of an NCCL all-reduce.  One object per (group, device, size); `buffer()` hands out the
-    SAME tensor every step (the caller zeroes it), which also makes the launch CUDA-graph replayable."""
+    and stores otherwise) instead of an NCCL all-reduce.  One object per (group, device, size); `flat` is the SAME tensor
+    every step (flat_grad_buffer zeroes it), which also makes the launch CUDA-graph replayable."""
 
     _cache = {}
     _failed = set()
